@@ -1,0 +1,121 @@
+"""Oracle (test infrastructure): produce tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+    python -m oracle.make_golden
+Inputs are regenerated from seeds (oracle/synth.py, oracle/weights.py), so the fixtures hold
+only the reference's *outputs*.  tests/test_oracle_golden.py checks the oracle restatements
+against these vectors; the GPU tests check the CUDA path against the oracle and the vectors.
+"""
+import os
+import sys
+import numpy as np
+import torch
+
+from . import synth, weights, ref_shim, mel_oracle
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+MEL_CASES = [  # (name, kind, n_samples, clip index)
+    ("noise_full", "noise", synth.CLIP_SAMPLES, 0),
+    ("noise_8000", "noise", 8000, 1),
+    ("tone_8000", "tone", 8000, 2),
+    ("int16_8000", "int16", 8000, 3),
+    ("zeros_1000", "zeros", 1000, 4),
+    ("one_frame_400", "noise", 400, 5),
+    ("no_frame_399", "noise", 399, 6),
+    ("ragged_559", "noise", 559, 7),       # 1 frame, 159-sample tail dropped
+    ("two_frames_560", "noise", 560, 8),
+]
+
+MODEL_CASES = [  # (name, weight seed, weight mode, B, T, F, with real_pose)
+    ("stress_b2", 0, "stress", 2, 64, 64, True),
+    ("default_b1", 1, "default", 1, 64, 64, False),
+    ("stress_t32_f128", 2, "stress", 1, 32, 128, False),
+]
+
+
+def model_input(case_seed, B, T, F):
+    """Seeded mel-like input: N(-1.5, 1.5^2), roughly the spread of log-mel of 0.1*noise."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(777 + case_seed)
+    return -1.5 + 1.5 * torch.randn(B, T, F, generator=g, dtype=torch.float32)
+
+
+def real_pose_input(case_seed, B, T):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(888 + case_seed)
+    return torch.randn(B, T, synth.POSE_FEATS, generator=g, dtype=torch.float32)
+
+
+def main():
+    ref = ref_shim.import_reference()
+    mf, me, rm = ref["mel_features"], ref["motion_evaluation"], ref["real_motion_model"]
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+
+    # ---- mel: the reference log_mel_spectrogram with audio_repr's parameters -------------------
+    kw = mel_oracle.AUDIO_REPR_KW
+    out = {}
+    for name, kind, n, idx in MEL_CASES:
+        out[name] = mf.log_mel_spectrogram(synth.wav_clip(idx, n, kind), **kw)
+    w = mf.spectrogram_to_mel_matrix(num_mel_bins=64, num_spectrogram_bins=257, audio_sample_rate=16000,
+                                     lower_edge_hertz=125, upper_edge_hertz=7500)
+    r, c = np.nonzero(w)
+    out["melw_rows"], out["melw_cols"], out["melw_vals"] = r.astype(np.int32), c.astype(np.int32), w[r, c]
+    out["hann_400"] = mf.periodic_hann(400)
+    out["stft_mag_2000"] = mf.stft_magnitude(synth.wav_clip(9, 2000), fft_length=512, hop_length=160, window_length=400)
+    out["frames_shape_1000"] = np.array(mf.frame(synth.wav_clip(4, 1000), 400, 160).shape)
+    # default-parameter call (8 kHz, 20 mel bins, log_offset 0 is -inf prone -> use 1e-3)
+    out["default_params_4000"] = mf.log_mel_spectrogram(synth.wav_clip(10, 4000), log_offset=1e-3)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "mel_reference.npz"), **out)
+    print("mel goldens:", {k: v.shape for k, v in out.items()})
+
+    # ---- eval: compute_pck / compute_pck_radius / L1Loss ---------------------------------------
+    gt = synth.gt_pose_batch(0, 4)
+    pred = synth.noisy_pred_batch(0, 4)
+    gtf, prf = gt.reshape(-1, 2, 52), pred.reshape(-1, 2, 52)
+    ev = {"pck_alpha02": me.compute_pck(prf, gtf, 0.2), "pck_alpha01": me.compute_pck(prf, gtf, 0.1),
+          "radius_alpha02": me.compute_pck_radius(gtf, 0.2)[:, 0],
+          "pck_identity": me.compute_pck(gtf, gtf)}
+    tp, tg_ = torch.from_numpy(pred), torch.from_numpy(gt)
+    ev["l1_pose"] = np.array(torch.nn.L1Loss()(tp, tg_).item())
+    ev["l1_motion"] = np.array(torch.nn.L1Loss()(torch.diff(tp, n=1, dim=1), torch.diff(tg_, n=1, dim=1)).item())
+    # fp64 inputs keep fp64 arithmetic in the reference
+    ev["pck_alpha02_f64"] = me.compute_pck(prf.astype(np.float64), gtf.astype(np.float64), 0.2)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "eval_reference.npz"), **ev)
+    print("eval goldens:", {k: v.shape for k, v in ev.items()})
+
+    # ---- model: the reference SelfAttention_G (shim + D1), eval mode ---------------------------
+    torch.manual_seed(0)
+    model = rm.SelfAttention_G().eval()
+    ref_sd = model.state_dict()
+    con = weights.contract()
+    assert [n for n, _, _ in con] == list(ref_sd.keys()), "contract key order differs from the reference state_dict"
+    for n, shape, _ in con:
+        assert tuple(ref_sd[n].shape) == tuple(shape), (n, ref_sd[n].shape, shape)
+    n_params = sum(p.numel() for p in model.parameters())
+    print("contract ok:", len(con), "tensors,", n_params, "parameters")
+    mo = {"n_tensors": np.array(len(con)), "n_params": np.array(n_params)}
+    captured = {}
+    model.audio_encoder.register_forward_hook(lambda m, i, o: captured.__setitem__("enc", o.detach().clone()))
+    model.unet.register_forward_hook(lambda m, i, o: captured.__setitem__("unet", o.detach().clone()))
+    for name, seed, mode, B, T, F, with_pose in MODEL_CASES:
+        sd = weights.make_state_dict(seed, mode)
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        x = model_input(seed, B, T, F)
+        rp = real_pose_input(seed, B, T) if with_pose else None
+        with torch.no_grad():
+            pose, losses = model(x, real_pose=rp)
+        mo[name + "_pose"] = pose.numpy()
+        mo[name + "_losses"] = np.array([l.item() for l in losses], dtype=np.float64)
+        if name == "stress_b2":
+            mo[name + "_enc"] = captured["enc"].numpy()
+            mo[name + "_unet"] = captured["unet"].numpy()
+        print(name, pose.shape, mo[name + "_losses"], float(pose.abs().mean()))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "model_reference.npz"), **mo)
+    for f in sorted(os.listdir(GOLDEN_DIR)):
+        print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
+
+
+if __name__ == "__main__":
+    sys.exit(main())
