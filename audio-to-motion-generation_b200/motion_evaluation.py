@@ -1,0 +1,96 @@
+"""B200 drop-in for ``motion_evaluation.py`` of the reference: PCK and its radius, plus the fused
+L1 / PCK partial-sum evaluation the multi-GPU driver all-reduces.
+
+``compute_pck`` / ``compute_pck_radius`` keep the reference's signatures (motion_evaluation.py:4,17)
+and its numpy-in / numpy-out behaviour; arithmetic is numpy's fp32 operation order, reproduced on the
+GPU bit for bit by csrc/eval.cu (hit counts are identical to the reference for fp32 inputs).
+Inputs of another float width are converted to fp32 first (the reference would compute fp64 inputs in
+fp64; decision D7 in DESIGN.md).  torch tensors are accepted and yield torch tensors.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+K_JOINTS = 52            # the radius is tiled to 52 keypoints, motion_evaluation.py:22
+METRIC_FIELDS = ("pck_hits", "n_keypoints", "n_frames", "n_pose", "n_motion")
+
+
+def _frames_on_device(x, name):
+    """[N, 2, 52] (numpy / torch, any device) -> contiguous fp32 CUDA tensor."""
+    was_numpy = not isinstance(x, torch.Tensor)
+    t = torch.as_tensor(np.asarray(x)) if was_numpy else x
+    if t.dim() != 3 or t.shape[1] != 2 or t.shape[2] != K_JOINTS:
+        raise ValueError("%s must have shape [N, 2, %d], got %s" % (name, K_JOINTS, tuple(t.shape)))
+    t = t.to(device="cuda", dtype=torch.float32).contiguous()
+    return t, was_numpy
+
+
+def new_metrics(device="cuda"):
+    """Zeroed 64-byte accumulator (a2m_metrics) as an int64[8] CUDA tensor."""
+    return torch.zeros(8, dtype=torch.int64, device=device)
+
+
+def read_metrics(buf):
+    """Device accumulator -> dict (one 64-byte D2H copy)."""
+    host = buf.cpu()
+    out = {k: int(host[i]) for i, k in enumerate(METRIC_FIELDS)}
+    sums = host[5:7].view(torch.float64)
+    out["abs_pose"], out["abs_motion"] = float(sums[0]), float(sums[1])
+    return out
+
+
+def finalize_metrics(m):
+    """hits / keypoints and sum / n -- identical on every rank after the all-reduce."""
+    return {"pck": m["pck_hits"] / max(m["n_keypoints"], 1),
+            "l1_pose": m["abs_pose"] / max(m["n_pose"], 1),
+            "l1_motion": m["abs_motion"] / max(m["n_motion"], 1)}
+
+
+def evaluate_poses(pred, gt, alpha=0.2, accum=None, pck_per_frame=None, radius_per_frame=None):
+    """Fused evaluation of a batch of pose sequences [B, T, 104] (fp32 CUDA tensors): accumulates
+    PCK hits, |pred-gt| and |motion(pred)-motion(gt)| sums into ``accum`` (device, 64 bytes)."""
+    _cabi.require_cuda("evaluate_poses")
+    if pred.shape != gt.shape or pred.dim() != 3 or pred.shape[-1] != 2 * K_JOINTS:
+        raise ValueError("pred and gt must both be [B, T, %d]" % (2 * K_JOINTS))
+    pred = pred.to(device="cuda", dtype=torch.float32).contiguous()
+    gt = gt.to(device=pred.device, dtype=torch.float32).contiguous()
+    if accum is None:
+        accum = new_metrics(pred.device)
+    with torch.cuda.device(pred.device):
+        _cabi.check(_cabi.lib().a2m_eval_l1_pck_f32(
+            _cabi.ptr(pred), _cabi.ptr(gt), pred.shape[0], pred.shape[1], float(alpha),
+            _cabi.ptr(pck_per_frame), _cabi.ptr(radius_per_frame), _cabi.ptr(accum),
+            _cabi.stream_ptr(pred.device)))
+    return accum
+
+
+def _per_frame(pred, gt, alpha, want):
+    p, was_numpy = _frames_on_device(pred, "pred")
+    g, _ = _frames_on_device(gt, "gt")
+    if p.shape != g.shape:
+        raise ValueError("pred and gt differ in shape: %s vs %s" % (tuple(p.shape), tuple(g.shape)))
+    n = g.shape[0]
+    pck = torch.empty(n, dtype=torch.float64, device=g.device) if want == "pck" else None
+    rad = torch.empty(n, dtype=torch.float32, device=g.device) if want == "radius" else None
+    # every frame is its own "clip" of length 1: no motion term, per-frame outputs only
+    evaluate_poses(p.view(n, 1, 2 * K_JOINTS), g.view(n, 1, 2 * K_JOINTS), alpha, None, pck, rad)
+    return (pck if want == "pck" else rad), was_numpy
+
+
+def compute_pck(pred, gt, alpha=0.2):
+    """Per-sample fraction of the 52 keypoints with ||gt - pred||_2 <= alpha * max(bbox w, bbox h)
+    -> float64 [N] (motion_evaluation.py:4-14)."""
+    _cabi.require_cuda("compute_pck")
+    out, was_numpy = _per_frame(pred, gt, alpha, "pck")
+    return out.cpu().numpy() if was_numpy else out
+
+
+def compute_pck_radius(gt, alpha):
+    """alpha * max(|max x - min x|, |max y - min y|) per sample, tiled to [N, 52] (:17-23)."""
+    _cabi.require_cuda("compute_pck_radius")
+    out, was_numpy = _per_frame(gt, gt, alpha, "radius")
+    out = out[:, None].expand(-1, K_JOINTS)
+    return out.cpu().numpy().copy() if was_numpy else out.contiguous()

@@ -1,0 +1,104 @@
+/* liba2m_b200.so -- C ABI of the B200-native audio->pose hot path.
+ *
+ * The reference (Xukai-UoA/Audio-to-Motion-Generation) is pure Python with no FFI; its boundary is
+ * the Python call surface.  The Python drop-in modules of this repo bind the
+ * entry points below with ctypes; each entry point names the reference interface it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *   - return 0 = OK, <0 = argument / state error, >0 = cudaError_t (or 1000 + ncclResult_t);
+ *     a2m_last_error() returns a thread-local message for the last non-zero return.
+ *   - all data pointers are DEVICE pointers unless the name says host; the caller owns every buffer.
+ *   - work is enqueued on the caller's stream (cudaStream_t passed as void*); no hidden device syncs
+ *     except in the *_create functions.
+ *   - there is no CPU fallback: every compute entry point launches sm_100a kernels.
+ */
+#ifndef A2M_B200_H
+#define A2M_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A2M_VERSION 100            /* 0.1.0 */
+#define A2M_OK 0
+#define A2M_ERR_ARGUMENT (-1)
+#define A2M_ERR_STATE (-2)
+#define A2M_ERR_UNSUPPORTED (-3)
+#define A2M_ERR_PIPELINE (-4)      /* a kernel's bounded barrier wait expired (bug guard, never a hang) */
+
+int a2m_version(void);
+const char* a2m_last_error(void);
+/* Number of kernels this library has launched since load / since the last reset (bench.py's
+ * gpu_launches claim is read from here). */
+int64_t a2m_launch_count(void);
+void a2m_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * log-mel front end: replaces pose_video/mel_features.py:192-223 log_mel_spectrogram()
+ * (frame :21-45, periodic_hann :48-68, stft_magnitude :71-92, the np.dot with
+ * spectrogram_to_mel_matrix :114-189 and the log :223) for a batch of clips in one launch.
+ *
+ * The plan carries the constants the reference recomputes on every call: the periodic Hann window
+ * and the mel matrix, both computed by the caller on the host in fp64 with the reference formulas
+ * (the Python drop-in does that) and rounded to fp32 here.
+ *   window <= nfft, nfft in {256, 512, 1024}, hop >= 1, 1 <= n_mel <= 128,
+ *   mel_weights: host fp64 [nfft/2+1, n_mel] row-major with at most two (adjacent-column) non-zeros
+ *   per row -- true of every matrix spectrogram_to_mel_matrix can produce.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct a2m_mel_plan a2m_mel_plan;
+int a2m_mel_plan_create(int window, int hop, int nfft, int n_mel, const double* hann_host,
+                        const double* mel_weights_host, double log_offset, int device, a2m_mel_plan** out);
+void a2m_mel_plan_destroy(a2m_mel_plan* plan);
+/* 1 + floor((n_samples - window) / hop), mel_features.py:41-42; negative when the reference would raise */
+int64_t a2m_mel_num_frames(const a2m_mel_plan* plan, int64_t n_samples);
+/* wav: [n_clips] rows of n_samples fp32, row stride wav_stride elements;
+ * out: [n_clips, num_frames, n_mel] fp32 contiguous. */
+int a2m_logmel_f32(const a2m_mel_plan* plan, const float* wav, int64_t n_clips, int64_t n_samples,
+                   int64_t wav_stride, float* out, void* stream);
+/* |STFT| only (mel_features.py:71-92 stft_magnitude): out [n_clips, num_frames, nfft/2+1] fp32 */
+int a2m_stft_magnitude_f32(const a2m_mel_plan* plan, const float* wav, int64_t n_clips, int64_t n_samples,
+                           int64_t wav_stride, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * evaluation: replaces motion_evaluation.py:4-23 compute_pck()/compute_pck_radius() and the
+ * nn.L1Loss() metric of version5_model_train.py:264,367,467 (on poses and on pos_to_motion :208-213).
+ *
+ * pred, gt: [n_clips, frames_per_clip, 104] fp32, each frame = 52 x then 52 y (version5_model_train.py:301).
+ * Partial sums are ACCUMULATED into *accum (zero it first); they are what the ranks all-reduce.
+ * PCK arithmetic is numpy's fp32 order, bit for bit: radius = fl(max(w,h) * fl32(alpha)),
+ * hit = fl(sqrt(fl(fl(dx*dx) + fl(dy*dy)))) <= radius, no FMA contraction.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct a2m_metrics {
+    int64_t pck_hits;      /* keypoints within the radius */
+    int64_t n_keypoints;   /* 52 * n_frames */
+    int64_t n_frames;
+    int64_t n_pose;        /* elements behind abs_pose   */
+    int64_t n_motion;      /* elements behind abs_motion */
+    double abs_pose;       /* sum |pred - gt|                         (fp32 difference, fp64 sum) */
+    double abs_motion;     /* sum |diff_t(pred) - diff_t(gt)|                                      */
+    int64_t reserved;
+} a2m_metrics;             /* 64 bytes */
+
+int a2m_eval_l1_pck_f32(const float* pred, const float* gt, int64_t n_clips, int frames_per_clip, float alpha,
+                        double* pck_per_frame /* nullable [n_clips*frames_per_clip] */,
+                        float* radius_per_frame /* nullable [n_clips*frames_per_clip] */,
+                        a2m_metrics* accum /* device */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * the one collective of the path: sum the 64-byte partials over the ranks.
+ * NCCL is bound at run time (dlopen of the libnccl.so.2 already loaded by torch); the unique id is
+ * distributed by the caller (torch.distributed store).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct a2m_comm a2m_comm;
+int a2m_comm_unique_id(void* out128_host);
+int a2m_comm_init(const void* id128_host, int rank, int world, int device, a2m_comm** out);
+int a2m_allreduce_metrics(a2m_comm* comm, a2m_metrics* inout /* device */, void* stream);
+void a2m_comm_destroy(a2m_comm* comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A2M_B200_H */

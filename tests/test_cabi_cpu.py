@@ -1,0 +1,84 @@
+"""CPU: the C-ABI library builds, loads without a GPU and exports every symbol include/a2m_b200.h
+declares; host-side logic of the drop-in modules (no compute calls)."""
+import ctypes
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mel_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "a2m_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(a2m_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    cabi = importlib.import_module(pkg.__name__ + "._cabi")
+    lib = pkg.load_library()
+    names = declared_symbols()
+    assert len(names) >= 14
+    for name in names:
+        assert hasattr(lib, name), "liba2m_b200.so does not export %s" % name
+        assert name in cabi.SIGNATURES, "no ctypes signature for %s" % name
+    assert set(cabi.SIGNATURES) == set(names)
+    assert lib.a2m_version() == 100
+    assert ctypes.sizeof(cabi.Metrics) == 64
+
+
+def test_no_cpu_fallback(pkg):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    pkg.install_dropin()
+    from pose_video.mel_features import log_mel_spectrogram
+    from motion_evaluation import compute_pck
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        log_mel_spectrogram(np.zeros(1000, np.float32), audio_sample_rate=16000)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        compute_pck(np.zeros((1, 2, 52), np.float32), np.zeros((1, 2, 52), np.float32))
+
+
+def test_argument_errors_without_gpu(pkg):
+    lib = pkg.load_library()
+    out = ctypes.c_void_p()
+    hann = np.ones(400)
+    w = np.zeros((257, 64))
+    rc = lib.a2m_mel_plan_create(400, 160, 1024, 64, hann.ctypes.data_as(ctypes.c_void_p),
+                                 w.ctypes.data_as(ctypes.c_void_p), 0.01, 0, ctypes.byref(out))
+    assert rc == -3 and b"not supported" in lib.a2m_last_error()
+    rc = lib.a2m_mel_plan_create(600, 160, 512, 64, hann.ctypes.data_as(ctypes.c_void_p),
+                                 w.ctypes.data_as(ctypes.c_void_p), 0.01, 0, ctypes.byref(out))
+    assert rc == -1 and b"window" in lib.a2m_last_error()
+    assert lib.a2m_eval_l1_pck_f32(None, None, 4, 64, 0.2, None, None, None, None) == -1
+
+
+def test_host_tables_match_oracle(pkg):
+    mf = pkg.install_dropin()["pose_video.mel_features"]
+    np.testing.assert_array_equal(mf.periodic_hann(400), mel_oracle.hann(400))
+    np.testing.assert_array_equal(mf.spectrogram_to_mel_matrix(64, 257, 16000, 125, 7500),
+                                  mel_oracle.mel_matrix(64, 257, 16000, 125, 7500))
+    np.testing.assert_array_equal(mf.spectrogram_to_mel_matrix(), mel_oracle.mel_matrix())
+    x = np.arange(1000.0)
+    np.testing.assert_array_equal(mf.frame(x, 400, 160), mel_oracle.frames(x, 400, 160))
+    assert mf.frame(np.zeros(399), 400, 160).shape == (0, 400)
+    with pytest.raises(ValueError):
+        mf.frame(np.zeros(100), 400, 160)
+    with pytest.raises(ValueError):
+        mf.spectrogram_to_mel_matrix(64, 257, 16000, 125, 9000)
+    assert mf._geometry(16000, 0.025, 0.010) == (400, 160, 512)
+    assert mf.hertz_to_mel(700.0) == pytest.approx(1127.0 * np.log(2.0))
+
+
+def test_audio_repr_registry(pkg):
+    ar = pkg.install_dropin()["pose_video.audio_repr"]
+    assert ar.get_repr("log_mel_spect") is ar.log_mel_spectograms
+    assert ar.get_repr(ar.RAW) is ar.raw_repr and ar.SR == 16000
+    with pytest.raises(KeyError):
+        ar.get_repr("nope")
