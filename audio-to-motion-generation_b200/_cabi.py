@@ -30,6 +30,17 @@ class TensorDesc(ctypes.Structure):
                 ("shape", c_i64 * 4)]
 
 
+class GemmDesc(ctypes.Structure):
+    """a2m_gemm_desc"""
+    _fields_ = [("n_src", ctypes.c_int32), ("a_rank", ctypes.c_int32 * 2), ("a_ptr", c_void_p * 2),
+                ("a_dims", (c_i64 * 5) * 2), ("a_strides", (c_i64 * 5) * 2), ("box", ctypes.c_int32 * 4),
+                ("m_extent", ctypes.c_int32 * 4), ("n_taps", ctypes.c_int32), ("tap_src", ctypes.c_int32 * 24),
+                ("tap_off", (ctypes.c_int32 * 4) * 24), ("tap_channels", ctypes.c_int32 * 24),
+                ("tap_w_off", c_i64 * 24), ("N", ctypes.c_int32), ("act", ctypes.c_int32),
+                ("out_type", ctypes.c_int32), ("reserved", ctypes.c_int32), ("out_stride", c_i64 * 4),
+                ("out_base", c_i64)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/a2m_b200.h
 SIGNATURES = {
     "a2m_version": (c_int, []),
@@ -48,6 +59,8 @@ SIGNATURES = {
     "a2m_comm_init": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
     "a2m_allreduce_metrics": (c_int, [c_void_p, c_void_p, c_void_p]),
     "a2m_comm_destroy": (None, [c_void_p]),
+    "a2m_gemm_taps": (c_int, [ctypes.POINTER(GemmDesc), c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p,
+                              c_void_p]),
 }
 
 _lib = None

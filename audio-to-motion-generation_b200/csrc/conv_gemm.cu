@@ -1,0 +1,454 @@
+// Tap-offset implicit-GEMM convolution engine on the 5th-generation tensor cores (SURVEY.md K4/K5/K8,
+// and K2 for the 2-D encoder convolutions).  See conv_gemm.cuh for the formulation.
+//
+// One CTA computes a 128 x BLOCK_N output tile:
+//   warp 0    : TMA producer  -- per K block (one tap, 64 channels) a 5-D activation box (128 rows
+//               x 64 bf16, OOB rows zero-filled = halo / batch tail) and a 2-D weight box
+//               (BLOCK_N x 64 bf16), both 128B-swizzled, into a STAGES-deep shared-memory ring
+//   warp 1    : tcgen05.mma issuer (one elected thread), fp32 accumulator in TMEM; tcgen05.commit
+//               releases ring slots and finally signals the epilogue
+//   warps 2-5 : epilogue -- tcgen05.ld the accumulator (one TMEM lane = one output row per thread),
+//               + folded bias, LeakyReLU(0.2) / ReLU, bf16 (or fp32) vector stores, strided so
+//               ConvTranspose parities and the [B,T,104] pose layout are written in place
+// Two CTAs fit per SM (3 stages x 32 KB), so one CTA's epilogue overlaps the other's main loop.
+#include <cstring>
+#include <mutex>
+#include "conv_gemm.cuh"
+
+void a2m_count_launch();
+
+namespace a2m {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kStages = 3;
+constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB
+
+template <int BLOCK_N>
+struct Smem {
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = kStages * kStageBytes;
+    static constexpr int kTotal = kBarOffset + 128 + 1024;      // barriers + alignment slack
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads)
+conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restrict__ bias, void* __restrict__ out,
+                 int* __restrict__ err_flag) {
+    using S = Smem<BLOCK_N>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);      // 1024 B: SWIZZLE_128B atom
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* accum_bar = empty_bar + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+
+    // tile -> base coordinates in dims 1..4 (dim 1 fastest)
+    int base[4];
+    {
+        int t = blockIdx.x;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ti = t % p.tiles[i];
+            t /= p.tiles[i];
+            base[i] = ti * p.box[i];
+        }
+    }
+    const int n0 = blockIdx.y * BLOCK_N;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.a_map[0]);
+        tma_prefetch_desc(&p.a_map[1]);
+        tma_prefetch_desc(&p.b_map);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int kb = 0;
+            bool ok = true;
+            for (int t = 0; t < p.n_taps && ok; ++t) {
+                const CUtensorMap* amap = &p.a_map[p.tap_src[t]];
+                const int c1 = base[0] + p.tap_off[t][0], c2 = base[1] + p.tap_off[t][1];
+                const int c3 = base[2] + p.tap_off[t][2], c4 = base[3] + p.tap_off[t][3];
+                for (int ch = 0; ch < p.tap_chunks[t]; ++ch, ++kb) {
+                    const int s = kb % kStages;
+                    if (!mbar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1, err_flag, 1)) { ok = false; break; }
+                    mbar_expect_tx(&full_bar[s], S::kStageBytes);
+                    unsigned char* stage = smem + s * S::kStageBytes;
+                    tma_load_5d(stage, amap, &full_bar[s], ch * kBlockK, c1, c2, c3, c4);
+                    tma_load_5d(stage + kABytes, &p.b_map, &full_bar[s], kb * kBlockK, n0, 0, 0, 0);   // all maps are rank 5
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                const int s = kb % kStages;
+                if (!mbar_wait(&full_bar[s], (kb / kStages) & 1, err_flag, 2)) break;
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
+                const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    // 16 bf16 = 32 B along K inside the 128 B swizzle row
+                    umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                              (kb | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);          // slot reusable once these MMAs have read it
+            }
+            umma_commit(accum_bar);                  // accumulator complete
+        }
+    } else {
+        const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;
+        long long off = p.out_base;
+        bool valid = true;
+        {
+            int r = row;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ii = r % p.box[i];
+                r /= p.box[i];
+                const int c = base[i] + ii;
+                valid = valid && (c < p.m_extent[i]);
+                off += static_cast<long long>(c) * p.out_stride[i];
+            }
+        }
+        mbar_wait(accum_bar, 0, err_flag, 3);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            const int n = n0 + c0;
+            if (n >= p.N) break;                      // warp-uniform
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(v[j]);
+                if (bias != nullptr && n + j < p.N) x += __ldg(bias + n + j);
+                if (p.act == kActLeaky) x = x > 0.f ? x : kLeakySlope * x;
+                else if (p.act == kActRelu) x = fmaxf(x, 0.f);
+                f[j] = x;
+            }
+            if (!valid) continue;
+            if (p.out_type == kOutBf16) {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + off + n;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (n + j < p.N) {                // N % 8 == 0 is enforced by the planner
+                        uint4 q;
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+                        __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                        __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                        q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+                        q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(o + j) = q;
+                    }
+                }
+            } else {
+                float* o = reinterpret_cast<float*>(out) + off + n;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (n + j + 3 < p.N) {
+                        *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (n + j + e < p.N) o[j + e] = f[j + e];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing / BatchNorm folding (run once at model load)
+// ---------------------------------------------------------------------------------------------
+struct PackTaps {
+    int n_taps;
+    int k_start[kMaxTaps + 1];
+    long long w_off[kMaxTaps];
+};
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, long long sn, long long sc, PackTaps pt, int N,
+                                    long long K, const float* __restrict__ scale, __nv_bfloat16* __restrict__ dst) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<long long>(N) * K) return;
+    const int n = static_cast<int>(idx / K);
+    const int k = static_cast<int>(idx - static_cast<long long>(n) * K);
+    int t = 0;
+    while (t + 1 < pt.n_taps && k >= pt.k_start[t + 1]) ++t;
+    const int c = k - pt.k_start[t];
+    float v = w[n * sn + pt.w_off[t] + c * sc];
+    if (scale) v *= scale[n];
+    dst[idx] = __float2bfloat16_rn(v);
+}
+
+__global__ void fold_bn_kernel(const float* __restrict__ conv_bias, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ mean,
+                               const float* __restrict__ var, float eps, int N, float* __restrict__ scale_out,
+                               float* __restrict__ bias_out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float s = gamma[n] / sqrtf(var[n] + eps);
+    scale_out[n] = s;
+    bias_out[n] = ((conv_bias ? conv_bias[n] : 0.f) - mean[n]) * s + beta[n];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int make_map(CUtensorMap* map, const void* ptr, int rank, const long long* dims, const long long* strides,
+             const int* box, CUtensorMapL2promotion promo, const char* what) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) { a2m_set_error("cuTensorMapEncodeTiled is not available from the driver"); return A2M_ERR_STATE; }
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bdim[5], estr[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < 5; ++i) {
+        gdim[i] = i < rank ? static_cast<cuuint64_t>(dims[i]) : 1;
+        bdim[i] = static_cast<cuuint32_t>(box[i]);
+    }
+    long long last = 0;
+    for (int i = 1; i < 5; ++i) {
+        long long s = i < rank ? strides[i] * 2 : last;          // bytes
+        if (i >= rank && s == 0) s = 16;
+        if (s % 16 != 0 || s <= 0) { a2m_set_error("%s: stride of dim %d (%lld B) is not a positive multiple of 16", what, i, s); return A2M_ERR_ARGUMENT; }
+        gstr[i - 1] = static_cast<cuuint64_t>(s);
+        last = s * static_cast<long long>(gdim[i]);
+    }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) { a2m_set_error("%s: base pointer not 16-byte aligned", what); return A2M_ERR_ARGUMENT; }
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gdim, gstr, bdim, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        a2m_set_error("%s: cuTensorMapEncodeTiled failed (CUresult %d) dims=[%llu,%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u,%u]",
+                      what, (int)r, (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2],
+                      (unsigned long long)gdim[3], (unsigned long long)gdim[4], bdim[0], bdim[1], bdim[2], bdim[3], bdim[4]);
+        return A2M_ERR_ARGUMENT;
+    }
+    return A2M_OK;
+}
+
+template <int BLOCK_N>
+int launch_variant(const ConvGemmPlan& plan, int* err_flag, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Smem<BLOCK_N>::kTotal));
+        configured = true;
+    }
+    conv_gemm_kernel<BLOCK_N><<<plan.grid, kThreads, Smem<BLOCK_N>::kTotal, stream>>>(
+        plan.p, plan.bias, plan.out, err_flag);
+    a2m_count_launch();
+    A2M_LAUNCH_CHECK();
+    return A2M_OK;
+}
+
+}  // namespace
+
+long long conv_gemm_k(const ConvGemmDesc& d) {
+    long long k = 0;
+    for (const Tap& t : d.taps) k += t.channels;
+    return k;
+}
+
+int pack_weights(const float* w_src, long long w_stride_n, long long w_stride_c, const std::vector<Tap>& taps, int N,
+                 const float* scale, __nv_bfloat16* w_packed, cudaStream_t stream) {
+    A2M_ARG_CHECK(!taps.empty() && static_cast<int>(taps.size()) <= kMaxTaps, "pack_weights: %zu taps", taps.size());
+    PackTaps pt;
+    pt.n_taps = static_cast<int>(taps.size());
+    int k = 0;
+    for (int t = 0; t < pt.n_taps; ++t) { pt.k_start[t] = k; pt.w_off[t] = taps[t].w_off; k += taps[t].channels; }
+    pt.k_start[pt.n_taps] = k;
+    const long long total = static_cast<long long>(N) * k;
+    pack_weights_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(w_src, w_stride_n, w_stride_c,
+                                                                                         pt, N, k, scale, w_packed);
+    a2m_count_launch();
+    A2M_LAUNCH_CHECK();
+    return A2M_OK;
+}
+
+int fold_batchnorm(const float* conv_bias, const float* gamma, const float* beta, const float* mean, const float* var,
+                   float eps, int N, float* scale_out, float* bias_out, cudaStream_t stream) {
+    fold_bn_kernel<<<(N + 127) / 128, 128, 0, stream>>>(conv_bias, gamma, beta, mean, var, eps, N, scale_out, bias_out);
+    a2m_count_launch();
+    A2M_LAUNCH_CHECK();
+    return A2M_OK;
+}
+
+int conv_gemm_plan(const ConvGemmDesc& d, const void* w_packed, const float* bias, void* out, ConvGemmPlan* plan) {
+    A2M_ARG_CHECK(plan != nullptr, "conv_gemm_plan: NULL plan");
+    A2M_ARG_CHECK(d.n_src == 1 || d.n_src == 2, "conv_gemm_plan: n_src %d", d.n_src);
+    A2M_ARG_CHECK(!d.taps.empty() && static_cast<int>(d.taps.size()) <= kMaxTaps, "conv_gemm_plan: %zu taps (max %d)",
+                  d.taps.size(), kMaxTaps);
+    A2M_ARG_CHECK(d.N >= 1, "conv_gemm_plan: N %d", d.N);
+    A2M_ARG_CHECK(d.out_type == kOutF32 || d.N % 8 == 0, "conv_gemm_plan: bf16 output needs N %% 8 == 0 (N = %d)", d.N);
+    long long rows = 1;
+    for (int i = 0; i < 4; ++i) {
+        A2M_ARG_CHECK(d.box[i] >= 1 && d.box[i] <= 256 && d.m_extent[i] >= 1, "conv_gemm_plan: box/extent of dim %d", i + 1);
+        rows *= d.box[i];
+    }
+    A2M_ARG_CHECK(rows == kBlockM, "conv_gemm_plan: tile has %lld rows, must be %d", rows, kBlockM);
+
+    ConvGemmParams& p = plan->p;
+    memset(&p, 0, sizeof(p));
+    int box5[5] = {kBlockK, d.box[0], d.box[1], d.box[2], d.box[3]};
+    for (int s = 0; s < 2; ++s) {
+        const AView& v = d.a[s < d.n_src ? s : 0];
+        A2M_ARG_CHECK(v.ptr != nullptr && v.rank >= 2 && v.rank <= 5 && v.strides[0] == 1 && v.dims[0] % kBlockK == 0,
+                      "conv_gemm_plan: bad A view %d (rank %d, channels %lld)", s, v.rank, v.dims[0]);
+        const int rc = make_map(&p.a_map[s], v.ptr, v.rank, v.dims, v.strides, box5, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                "activation map");
+        if (rc != A2M_OK) return rc;
+    }
+    const long long K = conv_gemm_k(d);
+    int block_n = 128;
+    if (d.N <= 32) block_n = 32;
+    else if (d.N <= 64) block_n = 64;
+    {
+        long long wd[2] = {K, d.N}, ws[2] = {1, K};
+        int wb[5] = {kBlockK, block_n, 1, 1, 1};
+        const int rc = make_map(&p.b_map, w_packed, 2, wd, ws, wb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "weight map");
+        if (rc != A2M_OK) return rc;
+    }
+    p.n_taps = static_cast<int>(d.taps.size());
+    int kb = 0;
+    for (int t = 0; t < p.n_taps; ++t) {
+        const Tap& tp = d.taps[t];
+        A2M_ARG_CHECK(tp.src >= 0 && tp.src < d.n_src && tp.channels > 0 && tp.channels % kBlockK == 0 &&
+                          tp.channels <= d.a[tp.src].dims[0],
+                      "conv_gemm_plan: tap %d (src %d, channels %d)", t, tp.src, tp.channels);
+        p.tap_src[t] = tp.src;
+        p.tap_chunks[t] = tp.channels / kBlockK;
+        for (int i = 0; i < 4; ++i) p.tap_off[t][i] = tp.off[i];
+        kb += p.tap_chunks[t];
+    }
+    p.k_blocks = kb;
+    long long m_tiles = 1, m_valid = 1;
+    for (int i = 0; i < 4; ++i) {
+        p.box[i] = d.box[i];
+        p.m_extent[i] = d.m_extent[i];
+        p.tiles[i] = (d.m_extent[i] + d.box[i] - 1) / d.box[i];
+        p.out_stride[i] = d.out_stride[i];
+        m_tiles *= p.tiles[i];
+        m_valid *= d.m_extent[i];
+    }
+    p.out_base = d.out_base;
+    p.N = d.N;
+    p.act = d.act;
+    p.out_type = d.out_type;
+    A2M_ARG_CHECK(m_tiles <= 0x7fffffffLL, "conv_gemm_plan: too many M tiles");
+    plan->w_packed = w_packed;
+    plan->bias = bias;
+    plan->out = out;
+    plan->block_n = block_n;
+    plan->grid = dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>((d.N + block_n - 1) / block_n), 1);
+    plan->flops = 2 * m_valid * d.N * K;
+    return A2M_OK;
+}
+
+int conv_gemm_launch(const ConvGemmPlan& plan, int* err_flag, cudaStream_t stream) {
+    switch (plan.block_n) {
+        case 32: return launch_variant<32>(plan, err_flag, stream);
+        case 64: return launch_variant<64>(plan, err_flag, stream);
+        case 128: return launch_variant<128>(plan, err_flag, stream);
+        default: a2m_set_error("conv_gemm_launch: block_n %d", plan.block_n); return A2M_ERR_STATE;
+    }
+}
+
+}  // namespace a2m
+
+// ---------------------------------------------------------------------------------------------
+// C ABI: the generic operator, used directly by the unit tests (one layer vs the oracle's conv)
+// ---------------------------------------------------------------------------------------------
+extern "C" int a2m_gemm_taps(const a2m_gemm_desc* g, const float* w_src, int64_t w_stride_n, int64_t w_stride_c,
+                             const float* scale, const float* bias, void* out, void* stream) {
+    using namespace a2m;
+    A2M_ARG_CHECK(g != nullptr && w_src != nullptr && out != nullptr, "a2m_gemm_taps: NULL argument");
+    A2M_ARG_CHECK(g->n_taps >= 1 && g->n_taps <= kMaxTaps, "a2m_gemm_taps: n_taps %d (max %d)", g->n_taps, kMaxTaps);
+    ConvGemmDesc d;
+    d.n_src = g->n_src;
+    for (int s = 0; s < 2; ++s) {
+        d.a[s].ptr = g->a_ptr[s];
+        d.a[s].rank = g->a_rank[s];
+        for (int i = 0; i < 5; ++i) { d.a[s].dims[i] = g->a_dims[s][i]; d.a[s].strides[i] = g->a_strides[s][i]; }
+    }
+    for (int i = 0; i < 4; ++i) {
+        d.box[i] = g->box[i]; d.m_extent[i] = g->m_extent[i]; d.out_stride[i] = g->out_stride[i];
+    }
+    for (int t = 0; t < g->n_taps; ++t) {
+        Tap tp;
+        tp.src = g->tap_src[t];
+        for (int i = 0; i < 4; ++i) tp.off[i] = g->tap_off[t][i];
+        tp.channels = g->tap_channels[t];
+        tp.w_off = g->tap_w_off[t];
+        d.taps.push_back(tp);
+    }
+    d.N = g->N; d.out_base = g->out_base; d.act = g->act; d.out_type = g->out_type;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long K = conv_gemm_k(d);
+    __nv_bfloat16* wp = nullptr;
+    int* flag = nullptr;
+    A2M_CUDA_CHECK(cudaMalloc(&wp, static_cast<size_t>(d.N) * K * 2));
+    cudaError_t e = cudaMalloc(&flag, sizeof(int));
+    if (e != cudaSuccess) { cudaFree(wp); a2m_set_error("cudaMalloc failed"); return (int)e; }
+    cudaMemsetAsync(flag, 0, sizeof(int), s);
+    int rc = pack_weights(w_src, w_stride_n, w_stride_c, d.taps, d.N, scale, wp, s);
+    ConvGemmPlan plan;
+    if (rc == A2M_OK) rc = conv_gemm_plan(d, wp, bias, out, &plan);
+    if (rc == A2M_OK) rc = conv_gemm_launch(plan, flag, s);
+    int host_flag = 0;
+    e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaMemcpy(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(wp);
+    cudaFree(flag);
+    if (rc != A2M_OK) return rc;
+    if (e != cudaSuccess) { a2m_set_error("a2m_gemm_taps: %s", cudaGetErrorString(e)); return (int)e; }
+    if (host_flag != 0) {
+        a2m_set_error("a2m_gemm_taps: pipeline barrier wait expired (role %d)", host_flag);
+        return A2M_ERR_PIPELINE;
+    }
+    return A2M_OK;
+}

@@ -323,7 +323,7 @@ static int launch_logmel(const a2m_mel_plan* plan, const float* wav, int64_t n_c
                          int64_t wav_stride, float* out, void* stream, const char* who) {
     A2M_ARG_CHECK(plan != nullptr, "%s: plan is NULL", who);
     A2M_ARG_CHECK(n_clips >= 0 && n_samples >= 0, "%s: negative size", who);
-    A2M_ARG_CHECK(wav_stride >= n_samples, "%s: wav_stride %lld < n_samples %lld", who, (long long)wav_stride, (long long)n_samples);
+    A2M_ARG_CHECK(n_clips <= 1 || wav_stride >= n_samples, "%s: wav_stride %lld < n_samples %lld", who, (long long)wav_stride, (long long)n_samples);
     const int64_t frames = a2m_mel_num_frames(plan, n_samples);
     A2M_ARG_CHECK(frames >= 0, "%s: negative dimensions are not allowed (%lld samples, window %d)", who,
                   (long long)n_samples, plan->window);

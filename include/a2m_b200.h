@@ -98,6 +98,49 @@ int a2m_comm_init(const void* id128_host, int rank, int world, int device, a2m_c
 int a2m_allreduce_metrics(a2m_comm* comm, a2m_metrics* inout /* device */, void* stream);
 void a2m_comm_destroy(a2m_comm* comm);
 
+/* ------------------------------------------------------------------------------------------------
+ * the dense-contraction operator of the generator: tap-offset implicit GEMM on tcgen05 tensor cores
+ * (bf16 operands, fp32 TMEM accumulation).  Replaces what ConvNormRelu (model_layers.py:94-118),
+ * ConvTranspose1D (:200-215), the 1x1 convs of SelfAttention (:126-128) / final_conv (:334) and
+ * nn.Linear (real_motion_model.py:76,86,102,112) dispatch to cuDNN/cuBLAS in the reference:
+ *   D[m, n] = act( sum_taps sum_c A_src[coords(m) + tap_off, c] * W[n, tap, c] * scale[n] + bias[n] )
+ * A sources are channels-last bf16 tensors described as <= 5-D strided views (dim 0 = channels,
+ * multiple of 64); rows of one 128-row M tile are the box[] extents along dims 1..4; out-of-range
+ * coordinates read zeros (convolution halo, batch tail).  W is the reference's fp32 weight, addressed
+ * as w[n * w_stride_n + tap_w_off + c * w_stride_c]; it is packed to bf16 on the device.
+ * This entry point packs, launches and synchronises (it is the unit-test / diagnostic surface); the
+ * model handle below keeps packed weights and launch plans resident.
+ * ---------------------------------------------------------------------------------------------- */
+#define A2M_MAX_TAPS 24
+#define A2M_ACT_NONE 0
+#define A2M_ACT_LEAKY 1      /* LeakyReLU(0.2) */
+#define A2M_ACT_RELU 2
+#define A2M_OUT_BF16 0
+#define A2M_OUT_F32 1
+typedef struct a2m_gemm_desc {
+    int32_t n_src;                       /* 1 or 2 activation sources */
+    int32_t a_rank[2];
+    const void* a_ptr[2];                /* bf16, device */
+    int64_t a_dims[2][5];
+    int64_t a_strides[2][5];             /* elements; [0] == 1 */
+    int32_t box[4];                      /* product == 128 */
+    int32_t m_extent[4];                 /* output positions along dims 1..4 */
+    int32_t n_taps;
+    int32_t tap_src[A2M_MAX_TAPS];
+    int32_t tap_off[A2M_MAX_TAPS][4];
+    int32_t tap_channels[A2M_MAX_TAPS];
+    int64_t tap_w_off[A2M_MAX_TAPS];
+    int32_t N;
+    int32_t act;
+    int32_t out_type;
+    int32_t reserved;
+    int64_t out_stride[4];               /* elements */
+    int64_t out_base;
+} a2m_gemm_desc;
+int a2m_gemm_taps(const a2m_gemm_desc* desc, const float* w_src, int64_t w_stride_n, int64_t w_stride_c,
+                  const float* scale /* nullable [N] */, const float* bias /* nullable [N] */, void* out,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif
