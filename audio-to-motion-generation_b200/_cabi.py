@@ -26,7 +26,7 @@ class Metrics(ctypes.Structure):
 
 class TensorDesc(ctypes.Structure):
     """a2m_tensor_desc"""
-    _fields_ = [("name", ctypes.c_char_p), ("data", c_void_p), ("dtype", c_int), ("ndim", c_int),
+    _fields_ = [("name", ctypes.c_char_p), ("data", c_void_p), ("dtype", ctypes.c_int32), ("ndim", ctypes.c_int32),
                 ("shape", c_i64 * 4)]
 
 
@@ -59,6 +59,13 @@ SIGNATURES = {
     "a2m_comm_init": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
     "a2m_allreduce_metrics": (c_int, [c_void_p, c_void_p, c_void_p]),
     "a2m_comm_destroy": (None, [c_void_p]),
+    "a2m_model_create": (c_int, [ctypes.POINTER(TensorDesc), c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "a2m_model_destroy": (None, [c_void_p]),
+    "a2m_model_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "a2m_model_encoder_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p]),
+    "a2m_model_unet_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
+    "a2m_model_status": (c_int, [c_void_p]),
+    "a2m_model_gemm_flops": (c_i64, [c_void_p, c_i64, c_int, c_int]),
     "a2m_gemm_taps": (c_int, [ctypes.POINTER(GemmDesc), c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p,
                               c_void_p]),
 }

@@ -1,0 +1,104 @@
+"""Shared plumbing of the nn.Module drop-ins: turn a module's state_dict into an a2m_model handle
+(BatchNorm folded, weights packed to bf16 on the device) and keep it in sync with the parameters."""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+
+
+class NativeHandle:
+    """Owns one a2m_model*; destroyed with the Python object."""
+
+    def __init__(self, state, device):
+        descs = (_cabi.TensorDesc * len(state))()
+        keep = []                                   # tensors (possibly converted copies) alive during create
+        for i, (name, t) in enumerate(state.items()):
+            if t.dtype == torch.int64:
+                dtype = 1
+            else:
+                dtype = 0
+                if t.dtype != torch.float32:
+                    t = t.to(torch.float32)
+            t = t.to(device).contiguous()
+            keep.append(t)
+            descs[i].name = name.encode()
+            descs[i].data = t.data_ptr()
+            descs[i].dtype = dtype
+            descs[i].ndim = t.dim()
+            for k, s in enumerate(t.shape):
+                descs[i].shape[k] = s
+        out = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _cabi.check(_cabi.lib().a2m_model_create(descs, len(state), device.index, ctypes.byref(out)))
+        self.ptr = out
+        self.device = device
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr:
+            try:
+                _cabi.lib().a2m_model_destroy(ptr)
+            except Exception:
+                pass
+
+
+class NativeModule(nn.Module):
+    """Base of the generator-level drop-ins.  Inference only (eval() semantics --
+    BatchNorm running statistics, dropout off); forward raises while the module is in training mode."""
+
+    _state_prefix = ""              # prefix that maps this module's keys onto SelfAttention_G's names
+
+    def _native_state(self):
+        sd = self.state_dict()
+        skip = "num_batches_tracked"
+        return {self._state_prefix + k: v for k, v in sd.items() if not k.endswith(skip)}
+
+    def _fingerprint(self):
+        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+
+    def native(self):
+        """The packed device handle, rebuilt whenever a parameter or buffer changed."""
+        _cabi.require_cuda(type(self).__name__)
+        fp = self._fingerprint()
+        h = self.__dict__.get("_handle")
+        if h is None or self.__dict__.get("_handle_fp") != fp:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("%s: parameters are on %s; move the module to a CUDA device (.cuda()) -- "
+                                   "there is no CPU fallback" % (type(self).__name__, dev))
+            h = NativeHandle(self._native_state(), dev)
+            self.__dict__["_handle"], self.__dict__["_handle_fp"] = h, fp
+        return h
+
+    def repack(self):
+        """Force re-folding / re-packing of the weights on the next forward."""
+        self.__dict__.pop("_handle", None)
+
+    def check_device_status(self):
+        """Synchronise and raise if a kernel's bounded barrier wait expired (debug aid)."""
+        h = self.__dict__.get("_handle")
+        if h is not None:
+            _cabi.check(_cabi.lib().a2m_model_status(h.ptr))
+
+    def _require_eval(self):
+        if self.training:
+            raise RuntimeError("%s implements inference (eval-mode) semantics only: call .eval() first "
+                               "(SURVEY.md D3; BatchNorm batch statistics and dropout are not implemented)"
+                               % type(self).__name__)
+
+    def __getstate__(self):
+        d = super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__.copy()
+        d = dict(d)
+        d.pop("_handle", None)
+        d.pop("_handle_fp", None)
+        return d
+
+
+def as_input(x, device, shape_msg):
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x)
+    if x.dim() != 3:
+        raise ValueError(shape_msg % (tuple(x.shape),))
+    return x.to(device=device, dtype=torch.float32).contiguous()

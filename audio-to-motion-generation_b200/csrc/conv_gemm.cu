@@ -199,7 +199,8 @@ struct PackTaps {
 };
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, long long sn, long long sc, PackTaps pt, int N,
-                                    long long K, const float* __restrict__ scale, __nv_bfloat16* __restrict__ dst) {
+                                    long long K, const float* __restrict__ scale, __nv_bfloat16* __restrict__ dst,
+                                    long long dst_ld, long long dst_col) {
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= static_cast<long long>(N) * K) return;
     const int n = static_cast<int>(idx / K);
@@ -209,7 +210,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, long long sn, l
     const int c = k - pt.k_start[t];
     float v = w[n * sn + pt.w_off[t] + c * sc];
     if (scale) v *= scale[n];
-    dst[idx] = __float2bfloat16_rn(v);
+    dst[n * dst_ld + dst_col + k] = __float2bfloat16_rn(v);
 }
 
 __global__ void fold_bn_kernel(const float* __restrict__ conv_bias, const float* __restrict__ gamma,
@@ -295,7 +296,7 @@ long long conv_gemm_k(const ConvGemmDesc& d) {
 }
 
 int pack_weights(const float* w_src, long long w_stride_n, long long w_stride_c, const std::vector<Tap>& taps, int N,
-                 const float* scale, __nv_bfloat16* w_packed, cudaStream_t stream) {
+                 const float* scale, __nv_bfloat16* w_packed, cudaStream_t stream, long long dst_ld, long long dst_col) {
     A2M_ARG_CHECK(!taps.empty() && static_cast<int>(taps.size()) <= kMaxTaps, "pack_weights: %zu taps", taps.size());
     PackTaps pt;
     pt.n_taps = static_cast<int>(taps.size());
@@ -304,7 +305,8 @@ int pack_weights(const float* w_src, long long w_stride_n, long long w_stride_c,
     pt.k_start[pt.n_taps] = k;
     const long long total = static_cast<long long>(N) * k;
     pack_weights_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(w_src, w_stride_n, w_stride_c,
-                                                                                         pt, N, k, scale, w_packed);
+                                                                                         pt, N, k, scale, w_packed,
+                                                                                         dst_ld > 0 ? dst_ld : k, dst_col);
     a2m_count_launch();
     A2M_LAUNCH_CHECK();
     return A2M_OK;

@@ -86,8 +86,10 @@ long long conv_gemm_k(const ConvGemmDesc& d);
 // Pack fp32 weights to the engine's bf16 [n_pad, K] K-major layout (K order = taps x channels),
 // folding an optional per-output-channel scale (BatchNorm) into the rows.
 //   w element (n, tap, c) = w_src[n * w_stride_n + tap.w_off + c * w_stride_c]
+//   destination element (n, k) = w_packed[n * dst_ld + dst_col + k]   (dst_ld = 0 -> dense [N, K])
 int pack_weights(const float* w_src, long long w_stride_n, long long w_stride_c, const std::vector<Tap>& taps, int N,
-                 const float* scale /* nullable [N] */, __nv_bfloat16* w_packed, cudaStream_t stream);
+                 const float* scale /* nullable [N] */, __nv_bfloat16* w_packed, cudaStream_t stream,
+                 long long dst_ld = 0, long long dst_col = 0);
 
 // bias'[n] = (conv_bias[n] - mean[n]) * gamma[n] / sqrt(var[n] + eps) + beta[n];  scale[n] = gamma / sqrt(var + eps)
 int fold_batchnorm(const float* conv_bias, const float* gamma, const float* beta, const float* mean, const float* var,

@@ -1,0 +1,577 @@
+// Non-GEMM kernels of the generator forward: first encoder conv, time interpolation, self-attention,
+// channel attention, LayerNorm, the static-graph GAT / GraphConv tails and the pose losses.
+// See layers.cuh for the contracts and the reference lines each kernel restates.
+#include "layers.cuh"
+
+void a2m_count_launch();
+
+namespace a2m {
+
+namespace {
+
+__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeakySlope * x; }
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& q, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
+    uint4 q;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return q;
+}
+
+// ------------------------------------------------------------------------------------------ conv0
+__global__ void __launch_bounds__(256)
+conv0_kernel(const float* __restrict__ mel, int T, int F, const float* __restrict__ w, const float* __restrict__ bias,
+             __nv_bfloat16* __restrict__ out) {
+    extern __shared__ float s_rows[];                 // [4][F + 2], zero padded left/right
+    const int ho = blockIdx.x, b = blockIdx.y;
+    const int Ho = T / 2, Wo = F / 2, stride = F + 2;
+    for (int i = threadIdx.x; i < 4 * stride; i += blockDim.x) {
+        const int r = i / stride, col = i - r * stride - 1;
+        const int h = 2 * ho + r - 1;
+        float v = 0.f;
+        if (h >= 0 && h < T && col >= 0 && col < F) v = mel[(static_cast<long long>(b) * T + h) * F + col];
+        s_rows[i] = v;
+    }
+    const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    float wr[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wr[i] = w[c * 16 + i];
+    const float bc = bias[c];
+    __syncthreads();
+    __nv_bfloat16* o = out + ((static_cast<long long>(b) * Ho + ho) * Wo) * 64 + c;
+    for (int wo = grp; wo < Wo; wo += 4) {
+        float acc = bc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc = fmaf(s_rows[i * stride + 2 * wo + j], wr[i * 4 + j], acc);
+        o[static_cast<long long>(wo) * 64] = __float2bfloat16_rn(leaky(acc));
+    }
+}
+
+// ------------------------------------------------------------------------------------ time interp
+__global__ void time_interp_kernel(const float* __restrict__ in, int Hc, int T, int C, long long total,
+                                   __nv_bfloat16* __restrict__ out) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = static_cast<int>(idx % C);
+    const long long bt = idx / C;
+    const int t = static_cast<int>(bt % T);
+    const long long b = bt / T;
+    // torch upsample_bilinear2d, align_corners=False: src = scale * (dst + 0.5) - 0.5, clamped at 0
+    const float scale = static_cast<float>(Hc) / static_cast<float>(T);
+    float src = scale * (static_cast<float>(t) + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    const int i0 = static_cast<int>(src);
+    const int i1 = i0 + (i0 < Hc - 1 ? 1 : 0);
+    const float l1 = src - static_cast<float>(i0), l0 = 1.f - l1;
+    const float* row = in + b * Hc * C + c;
+    out[idx] = __float2bfloat16_rn(l0 * row[static_cast<long long>(i0) * C] + l1 * row[static_cast<long long>(i1) * C]);
+}
+
+// -------------------------------------------------------------------------------------- attention
+constexpr int kAttnMaxT = 64;
+__global__ void __launch_bounds__(256)
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ x,
+                 const __nv_bfloat16* __restrict__ res2, const float* __restrict__ gamma_p, int T, int C,
+                 __nv_bfloat16* __restrict__ out) {
+    extern __shared__ float s_attn[];
+    const int d = C / 8, ld = 2 * d + C, kstride = d + 1;
+    float* s_q = s_attn;                       // [T][d]
+    float* s_k = s_q + T * d;                  // [T][d+1]
+    float* s_p = s_k + T * kstride;            // [T][T]
+    const long long b = blockIdx.x;
+    const __nv_bfloat16* base = qkv + b * T * ld;
+    for (int i = threadIdx.x; i < T * d; i += blockDim.x) {
+        const int t = i / d, c = i - t * d;
+        s_q[i] = __bfloat162float(base[static_cast<long long>(t) * ld + c]);
+        s_k[t * kstride + c] = __bfloat162float(base[static_cast<long long>(t) * ld + d + c]);
+    }
+    __syncthreads();
+    for (int ij = threadIdx.x; ij < T * T; ij += blockDim.x) {
+        const int i = ij / T, j = ij - i * T;
+        const float* q = s_q + i * d;
+        const float* k = s_k + j * kstride;
+        float acc = 0.f;
+        for (int c = 0; c < d; ++c) acc = fmaf(q[c], k[c], acc);
+        s_p[ij] = acc;                          // no 1/sqrt(d): model_layers.py:140
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (int i = warp; i < T; i += n_warps) {
+        float* row = s_p + i * T;
+        float m = -INFINITY;
+        for (int j = lane; j < T; j += 32) m = fmaxf(m, row[j]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int j = lane; j < T; j += 32) { const float e = __expf(row[j] - m); row[j] = e; s += e; }
+        s = warp_sum(s);
+        const float inv = 1.f / s;
+        for (int j = lane; j < T; j += 32) row[j] *= inv;
+    }
+    __syncthreads();
+    const float gamma = *gamma_p;
+    const __nv_bfloat16* vbase = base + 2 * d;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float v[kAttnMaxT];
+#pragma unroll
+        for (int j = 0; j < kAttnMaxT; ++j) v[j] = j < T ? __bfloat162float(vbase[static_cast<long long>(j) * ld + c]) : 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float* p = s_p + t * T;
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < kAttnMaxT; ++j)
+                if (j < T) acc = fmaf(p[j], v[j], acc);
+            const long long o = (b * T + t) * C + c;
+            float r = gamma * acc + __bfloat162float(x[o]);
+            if (res2) r += __bfloat162float(res2[o]);
+            out[o] = __float2bfloat16_rn(r);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ channel attention
+__global__ void __launch_bounds__(1024)
+channel_attention_kernel(const __nv_bfloat16* __restrict__ x, int T, int C, int hidden, const float* __restrict__ w0,
+                         const float* __restrict__ b0, const float* __restrict__ w2, const float* __restrict__ b2,
+                         __nv_bfloat16* __restrict__ out) {
+    extern __shared__ float s_ca[];
+    float* s_avg = s_ca;                 // [C]
+    float* s_max = s_avg + C;            // [C]
+    float* s_h = s_max + C;              // [2][hidden]
+    const long long b = blockIdx.x;
+    const int c = threadIdx.x;           // blockDim.x == C
+    const __nv_bfloat16* xb = x + b * T * C;
+    float sum = 0.f, mx = -INFINITY;
+    for (int t = 0; t < T; ++t) {
+        const float v = __bfloat162float(xb[static_cast<long long>(t) * C + c]);
+        sum += v;
+        mx = fmaxf(mx, v);
+    }
+    s_avg[c] = sum / static_cast<float>(T);
+    s_max[c] = mx;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (int u = warp; u < 2 * hidden; u += n_warps) {
+        const int unit = u % hidden;
+        const float* src = u < hidden ? s_avg : s_max;
+        float acc = 0.f;
+        for (int k = lane; k < C; k += 32) acc = fmaf(w0[unit * C + k], src[k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) s_h[u] = fmaxf(acc + b0[unit], 0.f);
+    }
+    __syncthreads();
+    float za = b2[c], zm = b2[c];
+    for (int u = 0; u < hidden; ++u) {
+        const float w = w2[c * hidden + u];
+        za = fmaf(w, s_h[u], za);
+        zm = fmaf(w, s_h[hidden + u], zm);
+    }
+    const float scale = 1.f / (1.f + __expf(-za)) + 1.f / (1.f + __expf(-zm));      // sigmoid each, then add
+    __nv_bfloat16* ob = out + b * T * C;
+    for (int t = 0; t < T; ++t) {
+        const long long o = static_cast<long long>(t) * C + c;
+        ob[o] = __float2bfloat16_rn(__bfloat162float(xb[o]) * scale);
+    }
+}
+
+// -------------------------------------------------------------------------------------- layernorm
+__global__ void __launch_bounds__(256)
+layernorm256_kernel(const __nv_bfloat16* __restrict__ x, long long rows, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, __nv_bfloat16* __restrict__ out) {
+    const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float f[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(x + row * 256 + lane * 8), f);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += f[i];
+    const float mean = warp_sum(s) * (1.f / 256.f);
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float dlt = f[i] - mean; v = fmaf(dlt, dlt, v); }
+    const float rstd = rsqrtf(warp_sum(v) * (1.f / 256.f) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = (f[i] - mean) * rstd * gamma[lane * 8 + i] + beta[lane * 8 + i];
+    *reinterpret_cast<uint4*>(out + row * 256 + lane * 8) = float_to_bf16x8(f);
+}
+
+// ------------------------------------------------------------------------------------- GAT tail
+// CTA: `gpc` whole graphs (gpc * J <= 128 nodes).  Phase 1 stages h rows in shared memory and reduces
+// the per-node, per-head attention scalars; phase 2 (one warp per node) does the neighbour softmax,
+// the weighted aggregation, the head mean, bias, LayerNorm(64), LeakyReLU and the residual.
+constexpr int kGatNodesPerCta = 128;
+__global__ void __launch_bounds__(256)
+gat_aggregate_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ x_res, long long n_nodes,
+                     int J, int gpc, const int* __restrict__ nbr, const int* __restrict__ deg,
+                     const float* __restrict__ att_src, const float* __restrict__ att_dst,
+                     const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                     __nv_bfloat16* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char s_gat_raw[];
+    uint4* s_h = reinterpret_cast<uint4*>(s_gat_raw);                                   // [128][32] x 16 B
+    float* s_src = reinterpret_cast<float*>(s_gat_raw + kGatNodesPerCta * 512);         // [128][4]
+    float* s_dst = s_src + kGatNodesPerCta * 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nodes_here_max = gpc * J;
+    const long long node0 = static_cast<long long>(blockIdx.x) * nodes_here_max;
+    const int n_here = static_cast<int>(min(static_cast<long long>(nodes_here_max), n_nodes - node0));
+    // lane owns features [8*lane, 8*lane+8) of the 256-wide row: head = lane / 8
+    float as[8], ad[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { as[i] = att_src[lane * 8 + i]; ad[i] = att_dst[lane * 8 + i]; }
+    for (int n = warp; n < n_here; n += 8) {
+        const uint4 q = *reinterpret_cast<const uint4*>(h + (node0 + n) * 256 + lane * 8);
+        s_h[n * 32 + lane] = q;
+        float f[8];
+        bf16x8_to_float(q, f);
+        float ps = 0.f, pd = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ps = fmaf(f[i], as[i], ps); pd = fmaf(f[i], ad[i], pd); }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { ps += __shfl_xor_sync(0xffffffffu, ps, o); pd += __shfl_xor_sync(0xffffffffu, pd, o); }
+        if ((lane & 7) == 0) { s_src[n * 4 + (lane >> 3)] = ps; s_dst[n * 4 + (lane >> 3)] = pd; }
+    }
+    __syncthreads();
+    const int head = lane >> 3, sub = lane & 7;
+    for (int n = warp; n < n_here; n += 8) {
+        const int jloc = n % J, g0 = n - jloc;          // graph-local index, first node of this graph in the CTA
+        const int dg = deg[jloc];
+        const float di = s_dst[n * 4 + head];
+        float e[kMaxDeg + 1];
+        int idx[kMaxDeg + 1];
+        idx[0] = n;                                     // self loop
+        e[0] = leaky(s_src[n * 4 + head] + di);
+        float m = e[0];
+#pragma unroll
+        for (int k = 0; k < kMaxDeg; ++k) {
+            if (k < dg) {
+                idx[k + 1] = g0 + nbr[jloc * kMaxDeg + k];
+                e[k + 1] = leaky(s_src[idx[k + 1] * 4 + head] + di);
+                m = fmaxf(m, e[k + 1]);
+            }
+        }
+        float denom = 0.f;
+#pragma unroll
+        for (int k = 0; k <= kMaxDeg; ++k)
+            if (k <= dg) { e[k] = __expf(e[k] - m); denom += e[k]; }
+        const float inv = 1.f / denom;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k <= kMaxDeg; ++k) {
+            if (k <= dg) {
+                float f[8];
+                bf16x8_to_float(s_h[idx[k] * 32 + lane], f);
+                const float a = e[k] * inv;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, f[i], acc[i]);
+            }
+        }
+        // mean over the 4 heads (lanes sub, sub+8, sub+16, sub+24 hold the same output features)
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+            acc[i] = 0.25f * acc[i] + bias[sub * 8 + i];
+            s += acc[i];
+        }
+        // LayerNorm over the 64 features held by 8 lanes x 8 values
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.f / 64.f);
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float dlt = acc[i] - mean; v = fmaf(dlt, dlt, v); }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const float rstd = rsqrtf(v * (1.f / 64.f) + 1e-5f);
+        if (head == 0) {
+            float r[8];
+            bf16x8_to_float(*reinterpret_cast<const uint4*>(x_res + (node0 + n) * 64 + sub * 8), r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                r[i] += leaky((acc[i] - mean) * rstd * ln_w[sub * 8 + i] + ln_b[sub * 8 + i]);
+            *reinterpret_cast<uint4*>(out + (node0 + n) * 64 + sub * 8) = float_to_bf16x8(r);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------- GraphConv aggregation
+__global__ void __launch_bounds__(256)
+graph_gather_kernel(const __nv_bfloat16* __restrict__ x, long long n_nodes, int J, const int* __restrict__ nbr,
+                    const int* __restrict__ deg, __nv_bfloat16* __restrict__ agg) {
+    const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long node = gid >> 3;
+    if (node >= n_nodes) return;
+    const int sub = static_cast<int>(gid & 7);
+    const int jloc = static_cast<int>(node % J);
+    const long long g0 = node - jloc;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int dg = deg[jloc];
+    for (int k = 0; k < dg; ++k) {
+        float f[8];
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(x + (g0 + nbr[jloc * kMaxDeg + k]) * 64 + sub * 8), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+    *reinterpret_cast<uint4*>(agg + node * 64 + sub * 8) = float_to_bf16x8(acc);
+}
+
+__global__ void __launch_bounds__(256)
+ln64_act_res_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict__ x_res, long long rows,
+                    const float* __restrict__ ln_w, const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
+    const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long row = gid >> 3;
+    const bool live = row < rows;
+    const int sub = static_cast<int>(gid & 7);
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (live) {
+        const float4 a = *reinterpret_cast<const float4*>(y + row * 64 + sub * 8);
+        const float4 b = *reinterpret_cast<const float4*>(y + row * 64 + sub * 8 + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += f[i];
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / 64.f);
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float dlt = f[i] - mean; v = fmaf(dlt, dlt, v); }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v * (1.f / 64.f) + 1e-5f);
+    if (!live) return;
+    float r[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(x_res + row * 64 + sub * 8), r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] += leaky((f[i] - mean) * rstd * ln_w[sub * 8 + i] + ln_b[sub * 8 + i]);
+    *reinterpret_cast<uint4*>(out + row * 64 + sub * 8) = float_to_bf16x8(r);
+}
+
+// ------------------------------------------------------------------------------------ pose losses
+__global__ void __launch_bounds__(256)
+angle_loss_kernel(const float* __restrict__ pose, long long n_frames, const int* __restrict__ triples, int n_hand,
+                  int n_body, double* __restrict__ scratch) {
+    __shared__ float s_hand[8], s_body[8];
+    const long long f = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    float hand = 0.f, body = 0.f;
+    if (f < n_frames) {
+        const float* p = pose + f * 104;                 // interleaved (x, y) per joint: view(B,T,52,2)
+        const float pi = 3.14159265358979323846f;
+        for (int t = 0; t < n_hand + n_body; ++t) {
+            const int jp = triples[3 * t], jj = triples[3 * t + 1], jc = triples[3 * t + 2];
+            const float ax = p[2 * jj] - p[2 * jp], ay = p[2 * jj + 1] - p[2 * jp + 1];
+            const float bx = p[2 * jc] - p[2 * jj], by = p[2 * jc + 1] - p[2 * jj + 1];
+            const float th = atan2f(ax * by - ay * bx, ax * bx + ay * by);
+            const float lo = t < n_hand ? 0.f : -0.5f * pi;
+            const float pen = fmaxf(lo - th, 0.f) + fmaxf(th - pi, 0.f);
+            if (t < n_hand) hand += pen; else body += pen;
+        }
+    }
+    hand = warp_sum(hand);
+    body = warp_sum(body);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_hand[warp] = hand; s_body[warp] = body; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double h = 0.0, bsum = 0.0;
+        for (int w = 0; w < 8; ++w) { h += s_hand[w]; bsum += s_body[w]; }
+        atomicAdd(&scratch[0], h);
+        atomicAdd(&scratch[1], bsum);
+    }
+}
+
+__global__ void __launch_bounds__(64)
+bone_loss_kernel(const float* __restrict__ gen, const float* __restrict__ real, int T, const int* __restrict__ parents,
+                 double* __restrict__ scratch) {
+    __shared__ float s_sq[2];
+    const long long b = blockIdx.x;
+    const int j = threadIdx.x;                            // joint; bones are joints with a parent
+    float sq = 0.f;
+    if (j < 52 && parents[j] >= 0) {
+        const int par = parents[j];
+        float lg = 0.f, lr = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float* g = gen + (b * T + t) * 104;
+            const float* r = real + (b * T + t) * 104;
+            const float gx = g[2 * j] - g[2 * par], gy = g[2 * j + 1] - g[2 * par + 1];
+            const float rx = r[2 * j] - r[2 * par], ry = r[2 * j + 1] - r[2 * par + 1];
+            lg += sqrtf(gx * gx + gy * gy);
+            lr += sqrtf(rx * rx + ry * ry);
+        }
+        const float dlt = (lg - lr) / static_cast<float>(T);
+        sq = dlt * dlt;
+    }
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) s_sq[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(&scratch[2], static_cast<double>(s_sq[0]) + static_cast<double>(s_sq[1]));
+}
+
+__global__ void finalize_losses_kernel(const double* __restrict__ scratch, long long n_frames, long long n_clips,
+                                       int n_hand, int n_body, int n_bones, bool with_bone, float* __restrict__ out) {
+    const double hand = n_hand > 0 ? scratch[0] / (static_cast<double>(n_frames) * n_hand) : 0.0;
+    const double body = n_body > 0 ? scratch[1] / (static_cast<double>(n_frames) * n_body) : 0.0;
+    out[0] = static_cast<float>(0.7 * hand + 0.3 * body);
+    out[1] = with_bone ? static_cast<float>(scratch[2] / (static_cast<double>(n_clips) * n_bones)) : 0.f;
+}
+
+// ------------------------------------------------------------------------------- layout / dtype
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, long long n, __nv_bfloat16* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void ncw_to_btc_kernel(const float* __restrict__ in, int C, int T, __nv_bfloat16* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const long long b = blockIdx.z;
+    const int c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, t = t0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && t < T) ? in[(b * C + c) * T + t] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int t = t0 + i, c = c0 + threadIdx.x;
+        if (t < T && c < C) out[(b * T + t) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+}
+__global__ void btc_to_ncw_kernel(const __nv_bfloat16* __restrict__ in, int C, int T, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const long long b = blockIdx.z;
+    const int c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int t = t0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && t < T) ? __bfloat162float(in[(b * T + t) * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, t = t0 + threadIdx.x;
+        if (t < T && c < C) out[(b * C + c) * T + t] = tile[threadIdx.x][i];
+    }
+}
+
+}  // namespace
+
+#define A2M_AFTER_LAUNCH()  \
+    a2m_count_launch();     \
+    A2M_LAUNCH_CHECK();     \
+    return A2M_OK
+
+int launch_conv0(const float* mel, int B, int T, int F, const float* w_folded, const float* bias_folded,
+                 __nv_bfloat16* out, cudaStream_t stream) {
+    A2M_ARG_CHECK(T % 2 == 0 && F % 2 == 0 && B <= 65535, "conv0: T %d, F %d, B %d", T, F, B);
+    conv0_kernel<<<dim3(T / 2, B), 256, 4 * (F + 2) * sizeof(float), stream>>>(mel, T, F, w_folded, bias_folded, out);
+    A2M_AFTER_LAUNCH();
+}
+
+int launch_time_interp(const float* in, int B, int Hc, int T, int C, __nv_bfloat16* out, cudaStream_t stream) {
+    const long long total = static_cast<long long>(B) * T * C;
+    time_interp_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, Hc, T, C, total, out);
+    A2M_AFTER_LAUNCH();
+}
+
+int launch_attention(const __nv_bfloat16* qkv, const __nv_bfloat16* x, const __nv_bfloat16* res2, const float* gamma,
+                     int B, int T, int C, __nv_bfloat16* out, cudaStream_t stream) {
+    A2M_ARG_CHECK(T >= 1 && T <= kAttnMaxT, "attention: T = %d, this build supports T <= %d", T, kAttnMaxT);
+    A2M_ARG_CHECK(C % 8 == 0, "attention: C = %d", C);
+    const int d = C / 8;
+    const size_t smem = (static_cast<size_t>(T) * d + static_cast<size_t>(T) * (d + 1) + static_cast<size_t>(T) * T) * 4;
+    static bool configured = false;
+    if (!configured) {
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
+    }
+    A2M_ARG_CHECK(smem <= 160 * 1024, "attention: T %d x C %d needs %zu B of shared memory", T, C, smem);
+    attention_kernel<<<B, 256, smem, stream>>>(qkv, x, res2, gamma, T, C, out);
+    A2M_AFTER_LAUNCH();
+}
+
+int launch_channel_attention(const __nv_bfloat16* x, int B, int T, int C, int hidden, const float* w0, const float* b0,
+                             const float* w2, const float* b2, __nv_bfloat16* out, cudaStream_t stream) {
+    A2M_ARG_CHECK(C % 32 == 0 && C <= 1024 && hidden >= 1, "channel attention: C = %d hidden = %d", C, hidden);
+    channel_attention_kernel<<<B, C, (2 * C + 2 * hidden) * sizeof(float), stream>>>(x, T, C, hidden, w0, b0, w2, b2, out);
+    A2M_AFTER_LAUNCH();
+}
+
+int launch_layernorm(const __nv_bfloat16* x, long long rows, int C, const float* gamma, const float* beta,
+                     __nv_bfloat16* out, cudaStream_t stream) {
+    A2M_ARG_CHECK(C == 256, "layernorm: C = %d (this build implements 256)", C);
+    layernorm256_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, rows, gamma, beta, out);
+    A2M_AFTER_LAUNCH();
+}
+
+int launch_gat_aggregate(const __nv_bfloat16* h, const __nv_bfloat16* x_res, long long n_graphs, GraphTopo topo,
+                         const float* att_src, const float* att_dst, const float* bias, const float* ln_w,
+                         const float* ln_b, __nv_bfloat16* out, cudaStream_t stream) {
+    A2M_ARG_CHECK(topo.n_nodes >= 1 && topo.n_nodes <= kGatNodesPerCta, "gat: %d nodes per graph", topo.n_nodes);
+    const int gpc = kGatNodesPerCta / topo.n_nodes;
+    const size_t smem = kGatNodesPerCta * 512 + 2 * kGatNodesPerCta * 4 * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(gat_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long long ctas = (n_graphs + gpc - 1) / gpc;
+    gat_aggregate_kernel<<<static_cast<unsigned>(ctas), 256, smem, stream>>>(
+        h, x_res, n_graphs * topo.n_nodes, topo.n_nodes, gpc, topo.nbr, topo.deg, att_src, att_dst, bias, ln_w, ln_b, out);
+    A2M_AFTER_LAUNCH();
+}
+
+int launch_graph_gather(const __nv_bfloat16* x, long long n_graphs, GraphTopo topo, __nv_bfloat16* agg,
+                        cudaStream_t stream) {
+    const long long threads = n_graphs * topo.n_nodes * 8;
+    graph_gather_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(x, n_graphs * topo.n_nodes,
+                                                                                          topo.n_nodes, topo.nbr, topo.deg, agg);
+    A2M_AFTER_LAUNCH();
+}
+
+int launch_ln64_act_res(const float* y, const __nv_bfloat16* x_res, long long rows, const float* ln_w,
+                        const float* ln_b, __nv_bfloat16* out, cudaStream_t stream) {
+    const long long threads = rows * 8;
+    ln64_act_res_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(y, x_res, rows, ln_w, ln_b, out);
+    A2M_AFTER_LAUNCH();
+}
+
+int launch_pose_losses(const float* pose, const float* real_pose, int B, int T, const int* triples, int n_hand,
+                       int n_body, const int* parents, double* scratch, float* losses_out, cudaStream_t stream) {
+    const long long frames = static_cast<long long>(B) * T;
+    A2M_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), stream));
+    angle_loss_kernel<<<static_cast<unsigned>((frames + 255) / 256), 256, 0, stream>>>(pose, frames, triples, n_hand, n_body, scratch);
+    a2m_count_launch();
+    A2M_LAUNCH_CHECK();
+    if (real_pose) {
+        bone_loss_kernel<<<B, 64, 0, stream>>>(pose, real_pose, T, parents, scratch);
+        a2m_count_launch();
+        A2M_LAUNCH_CHECK();
+    }
+    finalize_losses_kernel<<<1, 1, 0, stream>>>(scratch, frames, B, n_hand, n_body, 51, real_pose != nullptr, losses_out);
+    A2M_AFTER_LAUNCH();
+}
+
+int launch_f32_to_bf16(const float* in, long long n, __nv_bfloat16* out, cudaStream_t stream) {
+    f32_to_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, n, out);
+    A2M_AFTER_LAUNCH();
+}
+int launch_ncw_to_btc(const float* in, int B, int C, int T, __nv_bfloat16* out, cudaStream_t stream) {
+    ncw_to_btc_kernel<<<dim3((T + 31) / 32, (C + 31) / 32, B), dim3(32, 8), 0, stream>>>(in, C, T, out);
+    A2M_AFTER_LAUNCH();
+}
+int launch_btc_to_ncw(const __nv_bfloat16* in, int B, int C, int T, float* out, cudaStream_t stream) {
+    btc_to_ncw_kernel<<<dim3((T + 31) / 32, (C + 31) / 32, B), dim3(32, 8), 0, stream>>>(in, C, T, out);
+    A2M_AFTER_LAUNCH();
+}
+
+}  // namespace a2m

@@ -1,0 +1,68 @@
+// Internal API of the non-GEMM kernels of the generator forward (csrc/layers.cu).  All activations
+// are channels-last bf16 ([B, T, C]); reductions, softmax, LayerNorm and the attention coefficients are
+// evaluated in fp32.
+#pragma once
+#include "a2m_common.cuh"
+
+namespace a2m {
+
+// AudioEncoder conv 0: Conv2d(1 -> 64, k4, s2, p1) + BatchNorm(eval) + LeakyReLU(0.2)  (model_layers.py:252)
+//   mel [B, T, F] fp32 -> out [B, T/2, F/2, 64] bf16.  w_folded [64][16] fp32 (BN scale folded), bias_folded [64].
+int launch_conv0(const float* mel, int B, int T, int F, const float* w_folded, const float* bias_folded,
+                 __nv_bfloat16* out, cudaStream_t stream);
+
+// F.interpolate(size=(T,1), mode='bilinear') + squeeze (model_layers.py:277-279) applied to the centre
+// column computed by the last encoder conv: in [B, Hc, C] fp32 -> out [B, T, C] bf16.
+int launch_time_interp(const float* in, int B, int Hc, int T, int C, __nv_bfloat16* out, cudaStream_t stream);
+
+// SelfAttention (model_layers.py:133-146) after the fused q|k|v 1x1-conv GEMM:
+//   qkv [B, T, 2*d + C] bf16 (q: d, k: d, v: C; d = C/8), x [B, T, C] bf16
+//   out = gamma * softmax(q k^T) v + x (+ res2 if given: the ResBlock skip, :190)
+int launch_attention(const __nv_bfloat16* qkv, const __nv_bfloat16* x, const __nv_bfloat16* res2, const float* gamma,
+                     int B, int T, int C, __nv_bfloat16* out, cudaStream_t stream);
+
+// ChannelAttention (model_layers.py:167-174): x * (sigmoid(mlp(avg_T x)) + sigmoid(mlp(max_T x))), C = 256, hidden 32
+int launch_channel_attention(const __nv_bfloat16* x, int B, int T, int C, int hidden, const float* w0, const float* b0,
+                             const float* w2, const float* b2, __nv_bfloat16* out, cudaStream_t stream);
+
+// LayerNorm over the last dim (256) of [rows, C] bf16 -> bf16 (real_motion_model.py:205,257)
+int launch_layernorm(const __nv_bfloat16* x, long long rows, int C, const float* gamma, const float* beta,
+                     __nv_bfloat16* out, cudaStream_t stream);
+
+// Static skeleton graph shared by every (clip, frame): neighbours by node (symmetric tree, no self loops)
+struct GraphTopo {
+    int n_nodes;
+    const int* nbr;      // device [n_nodes][kMaxDeg], -1 padded
+    const int* deg;      // device [n_nodes]
+};
+constexpr int kMaxDeg = 6;
+constexpr int kJointFeat = 64;
+constexpr int kGatHeads = 4;
+
+// GATConv(64,64,heads=4,concat=False) tail (real_motion_model.py:172-176 etc.) after the shared linear:
+//   h [n_graphs*J, 256] bf16 (= x W^T), x_res [n_graphs*J, 64] bf16
+//   out = LeakyReLU_0.2(LayerNorm_64(mean_heads(sum_j softmax_j(leaky(a_src.h_j + a_dst.h_i)) h_j) + bias)) + x_res
+int launch_gat_aggregate(const __nv_bfloat16* h, const __nv_bfloat16* x_res, long long n_graphs, GraphTopo topo,
+                         const float* att_src, const float* att_dst, const float* bias, const float* ln_w,
+                         const float* ln_b, __nv_bfloat16* out, cudaStream_t stream);
+
+// GraphConv aggregation: agg_i = sum_{j->i} x_j   ([n_graphs*J, 64] bf16 -> bf16)
+int launch_graph_gather(const __nv_bfloat16* x, long long n_graphs, GraphTopo topo, __nv_bfloat16* agg,
+                        cudaStream_t stream);
+
+// out = LeakyReLU_0.2(LayerNorm_64(y)) + x_res     ([rows, 64]; y fp32 from the GraphConv GEMM)
+int launch_ln64_act_res(const float* y, const __nv_bfloat16* x_res, long long rows, const float* ln_w,
+                        const float* ln_b, __nv_bfloat16* out, cudaStream_t stream);
+
+// Internal losses of SelfAttention_G.forward (real_motion_model.py:307-461) on pose [B, T, 104] fp32.
+// triples: device int [n][3] (hand first, joints already offset by 10, then body);
+// losses_out[0] = angle loss, losses_out[1] = bone loss (only if real_pose != NULL); scratch: 4 doubles.
+int launch_pose_losses(const float* pose, const float* real_pose, int B, int T, const int* triples, int n_hand,
+                       int n_body, const int* parents, double* scratch, float* losses_out, cudaStream_t stream);
+
+int launch_f32_to_bf16(const float* in, long long n, __nv_bfloat16* out, cudaStream_t stream);
+// [B, C, T] fp32 (reference NCW layout) <-> [B, T, C] bf16 for the AudioEncoder / UNet1D drop-in surfaces
+int launch_ncw_to_btc(const float* in, int B, int C, int T, __nv_bfloat16* out, cudaStream_t stream);
+int launch_btc_to_ncw(const __nv_bfloat16* in, int B, int C, int T, float* out, cudaStream_t stream);
+
+}  // namespace a2m

@@ -1,0 +1,819 @@
+// SelfAttention_G forward (real_motion_model.py:154-278, eval mode) as a resident launch program:
+// a2m_model_create folds BatchNorm, packs every weight to bf16 once and keeps it in HBM;
+// a2m_model_forward builds (and caches per input shape) an activation arena plus the list of kernel
+// launches -- tcgen05 implicit-GEMM convolutions / linears (conv_gemm.cu) and the small fused kernels
+// of layers.cu -- and enqueues them on the caller's stream.  Decisions D1 (up_attention before the
+// skip concat) and D3 (eval semantics) of SURVEY.md section 8 apply.
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include "conv_gemm.cuh"
+#include "layers.cuh"
+
+using namespace a2m;
+
+namespace {
+
+// pats/data_loading/skeleton.py:94-110
+const int kParents[52] = {-1, 0, 1, 2, 0, 4, 5, 0, 7, 7, 6, 10, 11, 12, 13, 10, 15, 16, 17, 10, 19, 20, 21, 10, 23, 24,
+                          25, 10, 27, 28, 29, 3, 31, 32, 33, 34, 31, 36, 37, 38, 31, 40, 41, 42, 31, 44, 45, 46, 31, 48,
+                          49, 50};
+constexpr int kBodyJoints = 10, kHandJoints = 42, kPoseFeats = 104, kBodyFeats = 20;
+constexpr float kBnEps = 1e-5f;
+
+struct Param {
+    const float* f32 = nullptr;
+    const long long* i64 = nullptr;
+    int ndim = 0;
+    long long shape[4] = {0, 0, 0, 0};
+    long long numel() const { long long n = 1; for (int i = 0; i < ndim; ++i) n *= shape[i]; return n; }
+};
+
+struct LayerW {                 // one packed GEMM layer
+    __nv_bfloat16* w = nullptr; // [N, K]
+    float* bias = nullptr;      // [N] folded (may be null)
+    int N = 0;
+    std::vector<Tap> taps;
+    int act = kActNone;
+};
+
+struct AttnW { LayerW qkv; const float* gamma = nullptr; int C = 0; };
+struct ChanW { const float *w0, *b0, *w2, *b2; int C, hidden; };
+struct GatW { LayerW lin; const float *att_src, *att_dst, *bias; };
+struct LnW { const float *w, *b; };
+struct ResW { LayerW c1, c2; AttnW attn; };
+
+struct DecoderW {
+    ResW pre_res; LayerW pre_conv; AttnW pre_attn; ChanW pre_chan; bool chan_first;
+    LayerW proj_in;
+    GatW gat[3]; LayerW gconv[2]; LnW ln64[5];
+    LayerW proj_out; LnW norm;
+    ResW post_res; LayerW post_conv; AttnW post_attn; ChanW post_chan; bool has_post_chan;
+    LayerW logits;
+    int joints;
+    int *nbr, *deg;             // device topology tables
+};
+
+struct ForwardPlan {
+    int B, T, F;
+    void* arena = nullptr;
+    std::vector<std::function<int(cudaStream_t)>> ops;
+    int enc_end = 0, unet_end = 0;              // op index ranges: [0,enc_end) encoder, [enc_end,unet_end) unet
+    float* mel_in = nullptr;                    // staging (fp32) used by the stage entry points
+    __nv_bfloat16 *enc_out = nullptr, *unet_out = nullptr;
+    float* pose_stage = nullptr;                // fp32 [B, T, 104] written by the two logits GEMMs
+    long long gemm_flops = 0;
+    ~ForwardPlan() { if (arena) cudaFree(arena); }
+};
+
+}  // namespace
+
+struct a2m_model {
+    int device = 0;
+    std::map<std::string, Param> params;
+    std::vector<void*> owned;                   // device allocations freed on destroy
+    // encoder
+    float *conv0_w = nullptr, *conv0_b = nullptr;
+    LayerW enc[5];                              // [1..4] used
+    // unet
+    LayerW ds[4], bott, up0_even, up0_odd, up1, up2_even, up2_odd, up3, final_conv;
+    AttnW bott_attn, up_attn;
+    DecoderW dec[2];
+    int* triples = nullptr; int n_hand_triples = 0, n_body_triples = 0;
+    int* parents = nullptr;
+    double* loss_scratch = nullptr;
+    int* err_flag = nullptr;
+    bool has_encoder = false, has_unet = false, has_decoders = false;
+    // per-forward mutable slots read by the op closures
+    const float* cur_mel = nullptr;
+    float* cur_pose = nullptr;
+    std::map<std::string, std::unique_ptr<ForwardPlan>> plans;
+    std::string build_error;
+};
+
+namespace {
+
+struct Builder {
+    a2m_model* m;
+    cudaStream_t s;
+    int rc = A2M_OK;
+
+    template <typename T>
+    T* alloc(size_t n) {
+        void* p = nullptr;
+        if (rc != A2M_OK) return nullptr;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T) + 256);
+        if (e != cudaSuccess) { a2m_set_error("model: cudaMalloc(%zu) failed: %s", n * sizeof(T), cudaGetErrorString(e)); rc = (int)e; return nullptr; }
+        m->owned.push_back(p);
+        return static_cast<T*>(p);
+    }
+    const Param* find(const std::string& name, bool required = true) {
+        auto it = m->params.find(name);
+        if (it == m->params.end()) {
+            if (required && rc == A2M_OK) { a2m_set_error("model: missing tensor '%s' in the state_dict", name.c_str()); rc = A2M_ERR_ARGUMENT; }
+            return nullptr;
+        }
+        return &it->second;
+    }
+    const float* f32(const std::string& name, long long numel) {
+        const Param* p = find(name);
+        if (!p) return nullptr;
+        if (!p->f32 || p->numel() != numel) {
+            if (rc == A2M_OK) { a2m_set_error("model: tensor '%s' has %lld elements, expected %lld fp32", name.c_str(), p->numel(), numel); rc = A2M_ERR_ARGUMENT; }
+            return nullptr;
+        }
+        return p->f32;
+    }
+    void check(int r) { if (rc == A2M_OK && r != A2M_OK) rc = r; }
+    // small fp32 tensors the kernels read directly: copied, so the handle never aliases caller memory
+    const float* keep(const std::string& name, long long numel) {
+        const float* src = f32(name, numel);
+        float* dst = alloc<float>(static_cast<size_t>(numel));
+        if (rc != A2M_OK) return nullptr;
+        cudaMemcpyAsync(dst, src, numel * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        return dst;
+    }
+
+    // BatchNorm(eval) folded into per-channel scale / bias; returns scale (device) and fills *bias
+    const float* fold_bn(const std::string& conv, const std::string& bn, int N, float** bias_out) {
+        float* scale = alloc<float>(N);
+        *bias_out = alloc<float>(N);
+        const float *cb = f32(conv + ".bias", N), *g = f32(bn + ".weight", N), *b = f32(bn + ".bias", N),
+                    *mu = f32(bn + ".running_mean", N), *var = f32(bn + ".running_var", N);
+        if (rc != A2M_OK) return nullptr;
+        check(fold_batchnorm(cb, g, b, mu, var, kBnEps, N, scale, *bias_out, s));
+        return scale;
+    }
+    void pack(LayerW& L, const float* w, long long sn, long long sc, const float* scale) {
+        if (rc != A2M_OK) return;
+        long long K = 0;
+        for (const Tap& t : L.taps) K += t.channels;
+        L.w = alloc<__nv_bfloat16>(static_cast<size_t>(L.N) * K);
+        if (rc != A2M_OK) return;
+        check(pack_weights(w, sn, sc, L.taps, L.N, scale, L.w, s));
+    }
+    static Tap tap(int src, int o1, int o2, int o3, int channels, long long w_off) {
+        Tap t; t.src = src; t.off[0] = o1; t.off[1] = o2; t.off[2] = o3; t.off[3] = 0; t.channels = channels; t.w_off = w_off;
+        return t;
+    }
+
+    // ConvNormRelu 1-D, k3 s1 p1 over one or two concatenated sources (model_layers.py:60-66,94-118)
+    void conv1d_k3(LayerW& L, const std::string& p, int c0, int c1, int N) {
+        const int ct = c0 + c1;
+        for (int j = 0; j < 3; ++j) L.taps.push_back(tap(0, j - 1, 0, 0, c0, j));
+        if (c1) for (int j = 0; j < 3; ++j) L.taps.push_back(tap(1, j - 1, 0, 0, c1, static_cast<long long>(c0) * 3 + j));
+        L.N = N; L.act = kActLeaky;
+        const float* scale = fold_bn(p + ".conv", p + ".norm", N, &L.bias);
+        pack(L, f32(p + ".conv.weight", static_cast<long long>(N) * ct * 3), ct * 3LL, 3, scale);
+    }
+    // ConvNormRelu 1-D downsample, k4 s2 p1: view [B, T/2, 2, C]; tap j reads input 2t + j - 1
+    void conv1d_k4s2(LayerW& L, const std::string& p, int C, int N) {
+        L.taps = {tap(0, 1, -1, 0, C, 0), tap(0, 0, 0, 0, C, 1), tap(0, 1, 0, 0, C, 2), tap(0, 0, 1, 0, C, 3)};
+        L.N = N; L.act = kActLeaky;
+        const float* scale = fold_bn(p + ".conv", p + ".norm", N, &L.bias);
+        pack(L, f32(p + ".conv.weight", static_cast<long long>(N) * C * 4), C * 4LL, 4, scale);
+    }
+    // ConvTranspose1D k3 s2 p1 op1 + BN + ReLU (model_layers.py:200-215) as two parity GEMMs:
+    //   out[2j] = W[:,:,1] x[j];  out[2j+1] = W[:,:,2] x[j] + W[:,:,0] x[j+1];  weight layout [C_in, C_out, 3]
+    void conv_transpose(LayerW& even, LayerW& odd, const std::string& p, int C, int N) {
+        float* bias = nullptr;
+        const float* scale = fold_bn(p + ".conv_transpose", p + ".bn", N, &bias);
+        const float* w = f32(p + ".conv_transpose.weight", static_cast<long long>(C) * N * 3);
+        even.taps = {tap(0, 0, 0, 0, C, 1)};
+        odd.taps = {tap(0, 0, 0, 0, C, 2), tap(0, 1, 0, 0, C, 0)};
+        even.N = odd.N = N; even.act = odd.act = kActRelu; even.bias = odd.bias = bias;
+        pack(even, w, 3, N * 3LL, scale);
+        pack(odd, w, 3, N * 3LL, scale);
+    }
+    // nn.Linear / Conv1d k1: weight [N, C]
+    void linear(LayerW& L, const std::string& wname, const std::string& bname, int C, int N, int act) {
+        L.taps = {tap(0, 0, 0, 0, C, 0)};
+        L.N = N; L.act = act;
+        if (!bname.empty()) L.bias = const_cast<float*>(keep(bname, N));
+        pack(L, f32(wname, static_cast<long long>(N) * C), C, 1, nullptr);
+    }
+    // SelfAttention: q | k | v 1x1 convs fused along N (model_layers.py:126-128)
+    void attention(AttnW& A, const std::string& p, int C) {
+        const int d = C / 8, N = 2 * d + C;
+        A.C = C;
+        A.gamma = keep(p + ".gamma", 1);
+        LayerW& L = A.qkv;
+        L.taps = {tap(0, 0, 0, 0, C, 0)};
+        L.N = N; L.act = kActNone;
+        L.w = alloc<__nv_bfloat16>(static_cast<size_t>(N) * C);
+        L.bias = alloc<float>(N);
+        const float *wq = f32(p + ".query_conv.weight", static_cast<long long>(d) * C), *wk = f32(p + ".key_conv.weight", static_cast<long long>(d) * C),
+                    *wv = f32(p + ".value_conv.weight", static_cast<long long>(C) * C);
+        const float *bq = f32(p + ".query_conv.bias", d), *bk = f32(p + ".key_conv.bias", d), *bv = f32(p + ".value_conv.bias", C);
+        if (rc != A2M_OK) return;
+        check(pack_weights(wq, C, 1, L.taps, d, nullptr, L.w, s));
+        check(pack_weights(wk, C, 1, L.taps, d, nullptr, L.w + static_cast<size_t>(d) * C, s));
+        check(pack_weights(wv, C, 1, L.taps, C, nullptr, L.w + static_cast<size_t>(2 * d) * C, s));
+        cudaMemcpyAsync(L.bias, bq, d * 4, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(L.bias + d, bk, d * 4, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(L.bias + 2 * d, bv, C * 4, cudaMemcpyDeviceToDevice, s);
+    }
+    void channel(ChanW& Cw, const std::string& p, int C) {
+        Cw.C = C; Cw.hidden = C / 8;
+        Cw.w0 = keep(p + ".fc.0.weight", static_cast<long long>(Cw.hidden) * C); Cw.b0 = keep(p + ".fc.0.bias", Cw.hidden);
+        Cw.w2 = keep(p + ".fc.2.weight", static_cast<long long>(C) * Cw.hidden); Cw.b2 = keep(p + ".fc.2.bias", C);
+    }
+    void resblock(ResW& R, const std::string& p, int C) {
+        conv1d_k3(R.c1, p + ".conv1", C, 0, C);
+        conv1d_k3(R.c2, p + ".conv2", C, 0, C);
+        attention(R.attn, p + ".attention", C);
+    }
+    void gat(GatW& G, const std::string& p) {
+        const Param* w = find(p + ".lin.weight", false);
+        std::string wname = p + ".lin.weight";
+        if (!w) {                                           // torch_geometric version-dependent key names
+            for (const char* alt : {".lin_src.weight", ".lin_l.weight"})
+                if (find(p + alt, false)) { wname = p + alt; break; }
+        }
+        linear(G.lin, wname, "", kJointFeat, kGatHeads * kJointFeat, kActNone);
+        G.att_src = keep(p + ".att_src", kGatHeads * kJointFeat);
+        G.att_dst = keep(p + ".att_dst", kGatHeads * kJointFeat);
+        G.bias = keep(p + ".bias", kJointFeat);
+    }
+    // GraphConv: lin_rel(sum_j x_j) + lin_root(x_i) = [agg | x] [W_rel | W_root]^T + b_rel  (two A sources)
+    void graph_conv(LayerW& L, const std::string& p) {
+        L.taps = {tap(0, 0, 0, 0, kJointFeat, 0), tap(1, 0, 0, 0, kJointFeat, 0)};
+        L.N = kJointFeat; L.act = kActNone;
+        L.w = alloc<__nv_bfloat16>(kJointFeat * 2 * kJointFeat);
+        L.bias = const_cast<float*>(keep(p + ".lin_rel.bias", kJointFeat));
+        const float *wr = f32(p + ".lin_rel.weight", kJointFeat * kJointFeat), *wo = f32(p + ".lin_root.weight", kJointFeat * kJointFeat);
+        if (rc != A2M_OK) return;
+        std::vector<Tap> one = {tap(0, 0, 0, 0, kJointFeat, 0)};
+        check(pack_weights(wr, kJointFeat, 1, one, kJointFeat, nullptr, L.w, s, 2 * kJointFeat, 0));
+        check(pack_weights(wo, kJointFeat, 1, one, kJointFeat, nullptr, L.w, s, 2 * kJointFeat, kJointFeat));
+    }
+    void topology(DecoderW& D, const std::string& buf, int J) {
+        const Param* p = find(buf);
+        if (!p) return;
+        if (!p->i64 || p->ndim != 2 || p->shape[0] != 2) { a2m_set_error("model: '%s' must be int64 [2, E]", buf.c_str()); rc = A2M_ERR_ARGUMENT; return; }
+        const long long E = p->shape[1];
+        std::vector<long long> e(2 * E);
+        cudaError_t err = cudaMemcpy(e.data(), p->i64, 2 * E * 8, cudaMemcpyDeviceToHost);
+        if (err != cudaSuccess) { a2m_set_error("model: reading '%s': %s", buf.c_str(), cudaGetErrorString(err)); rc = (int)err; return; }
+        std::vector<int> nbr(J * kMaxDeg, -1), deg(J, 0);
+        for (long long k = 0; k < E; ++k) {
+            const long long src = e[k], dst = e[E + k];                // row 0 = source j, row 1 = target i
+            if (src == dst) continue;
+            if (src < 0 || dst < 0 || src >= J || dst >= J || deg[dst] >= kMaxDeg) {
+                a2m_set_error("model: '%s' edge %lld->%lld outside a %d-node graph of degree <= %d", buf.c_str(), src, dst, J, kMaxDeg);
+                rc = A2M_ERR_UNSUPPORTED; return;
+            }
+            nbr[dst * kMaxDeg + deg[dst]++] = static_cast<int>(src);
+        }
+        D.nbr = alloc<int>(nbr.size()); D.deg = alloc<int>(deg.size());
+        if (rc != A2M_OK) return;
+        cudaMemcpy(D.nbr, nbr.data(), nbr.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(D.deg, deg.data(), deg.size() * 4, cudaMemcpyHostToDevice);
+    }
+    void decoder(DecoderW& D, const std::string& part, int J, int n_feat) {
+        const int C = 256;
+        D.joints = J;
+        const std::string pre = part + "_decoder_pre", post = part + "_decoder_post";
+        resblock(D.pre_res, pre + ".0", C);
+        conv1d_k3(D.pre_conv, pre + ".1", C, 0, C);
+        D.chan_first = part == "body";                              // real_motion_model.py:70-75 vs :96-101
+        channel(D.pre_chan, pre + (D.chan_first ? ".2" : ".3"), C);
+        attention(D.pre_attn, pre + (D.chan_first ? ".3" : ".2"), C);
+        linear(D.proj_in, part + "_proj_in.weight", part + "_proj_in.bias", C, J * kJointFeat, kActNone);
+        for (int i = 0; i < 3; ++i) gat(D.gat[i], part + "_gcn" + std::to_string(2 * i + 1));
+        for (int i = 0; i < 2; ++i) graph_conv(D.gconv[i], part + "_gcn" + std::to_string(2 * i + 2));
+        for (int i = 0; i < 5; ++i) {
+            D.ln64[i].w = keep(part + "_layer_norms." + std::to_string(i) + ".weight", kJointFeat);
+            D.ln64[i].b = keep(part + "_layer_norms." + std::to_string(i) + ".bias", kJointFeat);
+        }
+        linear(D.proj_out, part + "_proj_out.weight", part + "_proj_out.bias", J * kJointFeat, C, kActNone);
+        D.norm.w = keep(part + "_norm.weight", C); D.norm.b = keep(part + "_norm.bias", C);
+        resblock(D.post_res, post + ".0", C);
+        conv1d_k3(D.post_conv, post + ".1", C, 0, C);
+        attention(D.post_attn, post + ".2", C);
+        D.has_post_chan = part == "hand";
+        if (D.has_post_chan) channel(D.post_chan, post + ".3", C);
+        linear(D.logits, part + "_logits.weight", part + "_logits.bias", C, n_feat, kActNone);
+        topology(D, part + "_edge_index_template", J);
+    }
+    void encoder() {
+        // conv 0 (1 -> 64, k4 s2 p1): tiny, folded on the host into fp32 [64][16] + bias[64]
+        const std::string p = "audio_encoder.conv.0";
+        const float *w = f32(p + ".conv.weight", 64 * 16), *cb = f32(p + ".conv.bias", 64), *g = f32(p + ".norm.weight", 64),
+                    *b = f32(p + ".norm.bias", 64), *mu = f32(p + ".norm.running_mean", 64), *var = f32(p + ".norm.running_var", 64);
+        if (rc != A2M_OK) return;
+        std::vector<float> hw(64 * 16), hcb(64), hg(64), hb(64), hmu(64), hvar(64);
+        cudaMemcpy(hw.data(), w, hw.size() * 4, cudaMemcpyDeviceToHost); cudaMemcpy(hcb.data(), cb, 256, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hg.data(), g, 256, cudaMemcpyDeviceToHost); cudaMemcpy(hb.data(), b, 256, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hmu.data(), mu, 256, cudaMemcpyDeviceToHost); cudaMemcpy(hvar.data(), var, 256, cudaMemcpyDeviceToHost);
+        std::vector<float> fb(64);
+        for (int c = 0; c < 64; ++c) {
+            const float sc = hg[c] / sqrtf(hvar[c] + kBnEps);
+            for (int i = 0; i < 16; ++i) hw[c * 16 + i] *= sc;
+            fb[c] = (hcb[c] - hmu[c]) * sc + hb[c];
+        }
+        m->conv0_w = alloc<float>(64 * 16); m->conv0_b = alloc<float>(64);
+        if (rc != A2M_OK) return;
+        cudaMemcpy(m->conv0_w, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(m->conv0_b, fb.data(), 256, cudaMemcpyHostToDevice);
+        // convs 1, 2: k4x4 s2 p1; dims (C, pw, W/2, H/2, B), row parity = A source
+        const int cin[5] = {1, 64, 128, 256, 512}, cout[5] = {64, 128, 256, 512, 256};
+        const int par[4][2] = {{1, -1}, {0, 0}, {1, 0}, {0, 1}};   // kernel index -> (parity, shift)
+        for (int l = 1; l <= 2; ++l) {
+            LayerW& L = m->enc[l];
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j)
+                    L.taps.push_back(tap(par[i][0], par[j][0], par[j][1], par[i][1], cin[l], i * 4 + j));
+            L.N = cout[l]; L.act = kActLeaky;
+            const std::string q = "audio_encoder.conv." + std::to_string(l);
+            const float* scale = fold_bn(q + ".conv", q + ".norm", L.N, &L.bias);
+            pack(L, f32(q + ".conv.weight", static_cast<long long>(L.N) * cin[l] * 16), cin[l] * 16LL, 16, scale);
+        }
+        {   // conv 3: k3x3 s1 p1; dims (C, W, H, B)
+            LayerW& L = m->enc[3];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) L.taps.push_back(tap(0, j - 1, i - 1, 0, cin[3], i * 3 + j));
+            L.N = cout[3]; L.act = kActLeaky;
+            const std::string q = "audio_encoder.conv.3";
+            const float* scale = fold_bn(q + ".conv", q + ".norm", L.N, &L.bias);
+            pack(L, f32(q + ".conv.weight", static_cast<long long>(L.N) * cin[3] * 9), cin[3] * 9LL, 9, scale);
+        }
+        {   // conv 4: k(3,8) p(1,3); only the centre output column survives the (T,1) resize, so the W
+            // offset of every tap is fixed up at plan time (depends on F): off[0] = j + (w_centre - 3)
+            LayerW& L = m->enc[4];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 8; ++j) L.taps.push_back(tap(0, j, i - 1, 0, cin[4], i * 8 + j));
+            L.N = cout[4]; L.act = kActLeaky;
+            const std::string q = "audio_encoder.conv.4";
+            const float* scale = fold_bn(q + ".conv", q + ".norm", L.N, &L.bias);
+            pack(L, f32(q + ".conv.weight", static_cast<long long>(L.N) * cin[4] * 24), cin[4] * 24LL, 24, scale);
+        }
+    }
+    void unet() {
+        const int c = 256;
+        conv1d_k3(m->ds[0], "unet.downsample_layers.0", c, 0, 2 * c);
+        conv1d_k4s2(m->ds[1], "unet.downsample_layers.1", 2 * c, 2 * c);
+        conv1d_k3(m->ds[2], "unet.downsample_layers.2", 2 * c, 0, 4 * c);
+        conv1d_k4s2(m->ds[3], "unet.downsample_layers.3", 4 * c, 4 * c);
+        conv1d_k3(m->bott, "unet.bottleneck", 4 * c, 0, 8 * c);
+        attention(m->bott_attn, "unet.bottleneck_attention", 8 * c);
+        conv_transpose(m->up0_even, m->up0_odd, "unet.upsample_layers.0", 8 * c, 4 * c);
+        attention(m->up_attn, "unet.up_attention", 4 * c);
+        conv1d_k3(m->up1, "unet.upsample_layers.1", 4 * c, 4 * c, 4 * c);
+        conv_transpose(m->up2_even, m->up2_odd, "unet.upsample_layers.2", 4 * c, 2 * c);
+        conv1d_k3(m->up3, "unet.upsample_layers.3", 2 * c, 2 * c, 2 * c);
+        linear(m->final_conv, "unet.final_conv.weight", "unet.final_conv.bias", 2 * c, c, kActNone);
+    }
+    void losses() {
+        // real_motion_model.py:280-304: (parent, joint, first child) triples; hand joints are offset by 10
+        std::vector<int> t;
+        int nh = 0, nb = 0;
+        for (int i = 0; i < kHandJoints; ++i) {
+            const int par = kParents[i + 10] >= 10 ? kParents[i + 10] - 10 : -1;
+            if (par == -1) continue;
+            for (int j = i + 1; j < kHandJoints; ++j)
+                if (kParents[j + 10] - 10 == i) { t.insert(t.end(), {par + 10, i + 10, j + 10}); ++nh; break; }
+        }
+        for (int i = 0; i < kBodyJoints; ++i) {
+            const int par = kParents[i] < kBodyJoints ? kParents[i] : -1;
+            if (par == -1) continue;
+            for (int j = i + 1; j < kBodyJoints; ++j)
+                if (kParents[j] == i) { t.insert(t.end(), {par, i, j}); ++nb; break; }
+        }
+        m->n_hand_triples = nh; m->n_body_triples = nb;
+        m->triples = alloc<int>(t.size()); m->parents = alloc<int>(52); m->loss_scratch = alloc<double>(4);
+        m->err_flag = alloc<int>(1);
+        if (rc != A2M_OK) return;
+        cudaMemcpy(m->triples, t.data(), t.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(m->parents, kParents, 52 * 4, cudaMemcpyHostToDevice);
+        cudaMemset(m->err_flag, 0, 4);
+    }
+};
+
+int pow2_at_least(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+}  // namespace
+
+// The plan is built in two passes over the same code: pass 0 sizes the arena, pass 1 emits the ops
+// with real pointers.
+namespace {
+
+struct Bufs {
+    size_t off = 0;
+    unsigned char* base = nullptr;
+    template <typename T>
+    T* get(size_t n) {
+        const size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += bytes;
+        return p;
+    }
+};
+
+struct Emit {
+    a2m_model* m;
+    ForwardPlan* P;
+    bool dry;
+    int rc = A2M_OK;
+
+    void gemm(const LayerW& L, std::vector<Tap> taps, const AView* views, int n_src, const int box[4], const int ext[4],
+              void* out, const long long ostride[4], long long obase, int out_type) {
+        if (dry || rc != A2M_OK) return;
+        ConvGemmDesc d;
+        d.n_src = n_src;
+        for (int s = 0; s < n_src; ++s) d.a[s] = views[s];
+        for (int i = 0; i < 4; ++i) { d.box[i] = box[i]; d.m_extent[i] = ext[i]; d.out_stride[i] = ostride[i]; }
+        d.taps = std::move(taps);
+        d.N = L.N; d.out_base = obase; d.act = L.act; d.out_type = out_type;
+        auto plan = std::make_shared<ConvGemmPlan>();
+        rc = conv_gemm_plan(d, L.w, L.bias, out, plan.get());
+        if (rc != A2M_OK) return;
+        P->gemm_flops += plan->flops;
+        int* flag = m->err_flag;
+        P->ops.push_back([plan, flag](cudaStream_t s) { return conv_gemm_launch(*plan, flag, s); });
+    }
+    // rows = (L, B) of a [B, L, C] tensor; taps shift along L
+    void conv_rows(const LayerW& L, const __nv_bfloat16* a0, int c0, const __nv_bfloat16* a1, int c1, int len, int B,
+                   void* out, long long out_row_stride, long long out_clip_stride, long long obase, int out_type) {
+        AView v[2];
+        v[0].ptr = a0; v[0].rank = 3; v[0].dims[0] = c0; v[0].dims[1] = len; v[0].dims[2] = B;
+        v[0].strides[0] = 1; v[0].strides[1] = c0; v[0].strides[2] = static_cast<long long>(len) * c0;
+        if (a1) { v[1] = v[0]; v[1].ptr = a1; v[1].dims[0] = c1; v[1].strides[1] = c1; v[1].strides[2] = static_cast<long long>(len) * c1; }
+        const int lt = std::min(128, pow2_at_least(len));
+        const int box[4] = {lt, 128 / lt, 1, 1}, ext[4] = {len, B, 1, 1};
+        const long long os[4] = {out_row_stride, out_clip_stride, 0, 0};
+        gemm(L, L.taps, v, a1 ? 2 : 1, box, ext, out, os, obase, out_type);
+    }
+    void conv_k3(const LayerW& L, const __nv_bfloat16* a0, int c0, const __nv_bfloat16* a1, int c1, int len, int B,
+                 __nv_bfloat16* out) {
+        conv_rows(L, a0, c0, a1, c1, len, B, out, L.N, static_cast<long long>(len) * L.N, 0, kOutBf16);
+    }
+    void conv_k4s2(const LayerW& L, const __nv_bfloat16* a, int C, int len, int B, __nv_bfloat16* out) {
+        const int lo = len / 2;
+        AView v;
+        v.ptr = a; v.rank = 4; v.dims[0] = C; v.dims[1] = 2; v.dims[2] = lo; v.dims[3] = B;
+        v.strides[0] = 1; v.strides[1] = C; v.strides[2] = 2LL * C; v.strides[3] = static_cast<long long>(len) * C;
+        const int lt = std::min(128, pow2_at_least(lo));
+        const int box[4] = {1, lt, 128 / lt, 1}, ext[4] = {1, lo, B, 1};
+        const long long os[4] = {0, L.N, static_cast<long long>(lo) * L.N, 0};
+        gemm(L, L.taps, &v, 1, box, ext, out, os, 0, kOutBf16);
+    }
+    void conv_transpose(const LayerW& even, const LayerW& odd, const __nv_bfloat16* a, int C, int len, int B,
+                        __nv_bfloat16* out) {
+        const int N = even.N;
+        conv_rows(even, a, C, nullptr, 0, len, B, out, 2LL * N, 2LL * len * N, 0, kOutBf16);
+        conv_rows(odd, a, C, nullptr, 0, len, B, out, 2LL * N, 2LL * len * N, N, kOutBf16);
+    }
+    void linear_rows(const LayerW& L, const __nv_bfloat16* a0, const __nv_bfloat16* a1, int C, long long rows, void* out,
+                     long long ldc, long long col, int out_type) {
+        AView v[2];
+        v[0].ptr = a0; v[0].rank = 2; v[0].dims[0] = C; v[0].dims[1] = rows; v[0].strides[0] = 1; v[0].strides[1] = C;
+        if (a1) { v[1] = v[0]; v[1].ptr = a1; }
+        const int box[4] = {128, 1, 1, 1}, ext[4] = {static_cast<int>(rows), 1, 1, 1};
+        const long long os[4] = {ldc, 0, 0, 0};
+        gemm(L, L.taps, v, a1 ? 2 : 1, box, ext, out, os, col, out_type);
+    }
+    void op(std::function<int(cudaStream_t)> f) { if (!dry && rc == A2M_OK) P->ops.push_back(std::move(f)); }
+
+    void attention(const AttnW& A, const __nv_bfloat16* x, const __nv_bfloat16* res2, int len, int B, __nv_bfloat16* qkv,
+                   __nv_bfloat16* out) {
+        const int C = A.C, ld = 2 * (C / 8) + C;
+        linear_rows(A.qkv, x, nullptr, C, static_cast<long long>(B) * len, qkv, ld, 0, kOutBf16);
+        const float* gamma = A.gamma;
+        op([=](cudaStream_t s) { return launch_attention(qkv, x, res2, gamma, B, len, C, out, s); });
+    }
+    void channel(const ChanW& W, const __nv_bfloat16* x, int len, int B, __nv_bfloat16* out) {
+        op([=](cudaStream_t s) { return launch_channel_attention(x, B, len, W.C, W.hidden, W.w0, W.b0, W.w2, W.b2, out, s); });
+    }
+    // ResBlock (model_layers.py:185-190): x -> conv1 -> conv2 -> attention -> + x
+    void resblock(const ResW& R, const __nv_bfloat16* x, int len, int B, __nv_bfloat16* t1, __nv_bfloat16* t2,
+                  __nv_bfloat16* qkv, __nv_bfloat16* out) {
+        conv_k3(R.c1, x, 256, nullptr, 0, len, B, t1);
+        conv_k3(R.c2, t1, 256, nullptr, 0, len, B, t2);
+        attention(R.attn, t2, x, len, B, qkv, out);
+    }
+};
+
+int build_plan(a2m_model* m, ForwardPlan* P) {
+    const int B = P->B, T = P->T, F = P->F;
+    const int H1 = T / 2, W1 = F / 2, H2 = T / 4, W2 = F / 4, H3 = T / 8, W3 = F / 8;
+    const int w_out = W3 - 1;                                   // conv 4: W + 2*3 - 8 + 1
+    A2M_ARG_CHECK(w_out >= 1 && (w_out % 2) == 1, "model: F = %d gives an even number (%d) of encoder output columns; "
+                  "only odd widths (F/8 even) are implemented", F, w_out);
+    const int w_centre = (w_out - 1) / 2;
+    Bufs bufs;
+    for (int pass = 0; pass < 2; ++pass) {
+        Emit E{m, P, pass == 0};
+        if (pass == 1) {
+            P->ops.clear();
+            cudaError_t e = cudaMalloc(&P->arena, bufs.off + 256);
+            if (e != cudaSuccess) { a2m_set_error("model: arena cudaMalloc(%zu) failed: %s", bufs.off, cudaGetErrorString(e)); return (int)e; }
+            bufs.base = static_cast<unsigned char*>(P->arena);
+        }
+        bufs.off = 0;
+        const size_t BT = static_cast<size_t>(B) * T;
+        auto* mel_stage = bufs.get<float>(BT * F);
+        auto* a0 = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * H1 * W1 * 64);
+        auto* a1 = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * H2 * W2 * 128);
+        auto* a2 = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * H3 * W3 * 256);
+        auto* a3 = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * H3 * W3 * 512);
+        auto* a4 = bufs.get<float>(static_cast<size_t>(B) * H3 * 256);
+        auto* e0 = bufs.get<__nv_bfloat16>(BT * 256);
+        auto* s0 = bufs.get<__nv_bfloat16>(BT * 512);
+        auto* u1 = bufs.get<__nv_bfloat16>(BT / 2 * 512);
+        auto* s1 = bufs.get<__nv_bfloat16>(BT / 2 * 1024);
+        auto* u3 = bufs.get<__nv_bfloat16>(BT / 4 * 1024);
+        auto* u4 = bufs.get<__nv_bfloat16>(BT / 4 * 2048);
+        auto* qkvb = bufs.get<__nv_bfloat16>(BT / 4 * 2560);
+        auto* u5 = bufs.get<__nv_bfloat16>(BT / 4 * 2048);
+        auto* u6 = bufs.get<__nv_bfloat16>(BT / 2 * 1024);
+        auto* qkvu = bufs.get<__nv_bfloat16>(BT / 2 * 1280);
+        auto* u7 = bufs.get<__nv_bfloat16>(BT / 2 * 1024);
+        auto* u8 = bufs.get<__nv_bfloat16>(BT / 2 * 1024);
+        auto* u9 = bufs.get<__nv_bfloat16>(BT * 512);
+        auto* u10 = bufs.get<__nv_bfloat16>(BT * 512);
+        auto* r = bufs.get<__nv_bfloat16>(BT * 256);
+        auto* pose_stage = bufs.get<float>(BT * kPoseFeats);
+        P->mel_in = mel_stage; P->enc_out = e0; P->unet_out = r; P->pose_stage = pose_stage;
+
+        // ---------------- AudioEncoder (model_layers.py:267-280) ----------------
+        if (m->has_encoder) {
+            a2m_model* mm = m;
+            E.op([=](cudaStream_t s) { return launch_conv0(mm->cur_mel, B, T, F, mm->conv0_w, mm->conv0_b, a0, s); });
+            auto conv2d_s2 = [&](const LayerW& L, const __nv_bfloat16* in, int H, int W, int C, __nv_bfloat16* out) {
+                const int Ho = H / 2, Wo = W / 2;
+                AView v[2];
+                for (int ph = 0; ph < 2; ++ph) {
+                    v[ph].ptr = in + static_cast<size_t>(ph) * W * C; v[ph].rank = 5;
+                    const long long dims[5] = {C, 2, Wo, Ho, B}, str[5] = {1, C, 2LL * C, 2LL * W * C, static_cast<long long>(H) * W * C};
+                    for (int i = 0; i < 5; ++i) { v[ph].dims[i] = dims[i]; v[ph].strides[i] = str[i]; }
+                }
+                const int wb = std::min(128, pow2_at_least(Wo)), hb = std::min(128 / wb, pow2_at_least(Ho));
+                const int box[4] = {1, wb, hb, 128 / (wb * hb)}, ext[4] = {1, Wo, Ho, B};
+                const long long os[4] = {0, L.N, static_cast<long long>(Wo) * L.N, static_cast<long long>(Ho) * Wo * L.N};
+                E.gemm(L, L.taps, v, 2, box, ext, out, os, 0, kOutBf16);
+            };
+            conv2d_s2(m->enc[1], a0, H1, W1, 64, a1);
+            conv2d_s2(m->enc[2], a1, H2, W2, 128, a2);
+            {   // conv 3
+                AView v; v.ptr = a2; v.rank = 4;
+                const long long dims[4] = {256, W3, H3, B}, str[4] = {1, 256, 256LL * W3, 256LL * W3 * H3};
+                for (int i = 0; i < 4; ++i) { v.dims[i] = dims[i]; v.strides[i] = str[i]; }
+                const int wb = std::min(128, pow2_at_least(W3)), hb = std::min(128 / wb, pow2_at_least(H3));
+                const int box[4] = {wb, hb, 128 / (wb * hb), 1}, ext[4] = {W3, H3, B, 1};
+                const long long os[4] = {512, 512LL * W3, 512LL * W3 * H3, 0};
+                E.gemm(m->enc[3], m->enc[3].taps, &v, 1, box, ext, a3, os, 0, kOutBf16);
+            }
+            {   // conv 4, centre column only -> fp32 [B, H3, 256]
+                AView v; v.ptr = a3; v.rank = 4;
+                const long long dims[4] = {512, W3, H3, B}, str[4] = {1, 512, 512LL * W3, 512LL * W3 * H3};
+                for (int i = 0; i < 4; ++i) { v.dims[i] = dims[i]; v.strides[i] = str[i]; }
+                std::vector<Tap> taps = m->enc[4].taps;
+                for (Tap& t : taps) t.off[0] += w_centre - 3;
+                const int hb = std::min(128, pow2_at_least(H3));
+                const int box[4] = {1, hb, 128 / hb, 1}, ext[4] = {1, H3, B, 1};
+                const long long os[4] = {0, 256, 256LL * H3, 0};
+                E.gemm(m->enc[4], taps, &v, 1, box, ext, a4, os, 0, kOutF32);
+            }
+            E.op([=](cudaStream_t s) { return launch_time_interp(a4, B, H3, T, 256, e0, s); });
+        }
+        if (pass == 1) P->enc_end = static_cast<int>(P->ops.size());
+
+        // ---------------- UNet1D (model_layers.py:341-374, D1) ----------------
+        if (m->has_unet) {
+        E.conv_k3(m->ds[0], e0, 256, nullptr, 0, T, B, s0);
+        E.conv_k4s2(m->ds[1], s0, 512, T, B, u1);
+        E.conv_k3(m->ds[2], u1, 512, nullptr, 0, T / 2, B, s1);
+        E.conv_k4s2(m->ds[3], s1, 1024, T / 2, B, u3);
+        E.conv_k3(m->bott, u3, 1024, nullptr, 0, T / 4, B, u4);
+        E.attention(m->bott_attn, u4, nullptr, T / 4, B, qkvb, u5);
+        E.conv_transpose(m->up0_even, m->up0_odd, u5, 2048, T / 4, B, u6);
+        E.attention(m->up_attn, u6, nullptr, T / 2, B, qkvu, u7);            // D1: before the concat
+        E.conv_k3(m->up1, u7, 1024, s1, 1024, T / 2, B, u8);
+        E.conv_transpose(m->up2_even, m->up2_odd, u8, 1024, T / 2, B, u9);
+        E.conv_k3(m->up3, u9, 512, s0, 512, T, B, u10);
+        E.linear_rows(m->final_conv, u10, nullptr, 512, static_cast<long long>(BT), r, 256, 0, kOutBf16);
+        }
+        if (pass == 1) P->unet_end = static_cast<int>(P->ops.size());
+
+        // ---------------- decoders (real_motion_model.py:160-262) ----------------
+        for (int part = 0; part < 2 && m->has_decoders; ++part) {
+            const DecoderW& D = m->dec[part];
+            const int J = D.joints;
+            const size_t nodes = BT * J;
+            auto* t1 = bufs.get<__nv_bfloat16>(BT * 256);
+            auto* t2 = bufs.get<__nv_bfloat16>(BT * 256);
+            auto* t3 = bufs.get<__nv_bfloat16>(BT * 256);
+            auto* t4 = bufs.get<__nv_bfloat16>(BT * 256);
+            auto* qkv = bufs.get<__nv_bfloat16>(BT * 320);
+            auto* xa = bufs.get<__nv_bfloat16>(nodes * 64);
+            auto* xb = bufs.get<__nv_bfloat16>(nodes * 64);
+            auto* hbuf = bufs.get<__nv_bfloat16>(nodes * 256);
+            auto* agg = bufs.get<__nv_bfloat16>(nodes * 64);
+            auto* ybuf = bufs.get<float>(nodes * 64);
+            E.resblock(D.pre_res, r, T, B, t1, t2, qkv, t3);
+            E.conv_k3(D.pre_conv, t3, 256, nullptr, 0, T, B, t1);
+            if (D.chan_first) {
+                E.channel(D.pre_chan, t1, T, B, t2);
+                E.attention(D.pre_attn, t2, nullptr, T, B, qkv, t3);
+            } else {
+                E.attention(D.pre_attn, t1, nullptr, T, B, qkv, t2);
+                E.channel(D.pre_chan, t2, T, B, t3);
+            }
+            E.linear_rows(D.proj_in, t3, nullptr, 256, static_cast<long long>(BT), xa, static_cast<long long>(J) * 64, 0, kOutBf16);
+            GraphTopo topo{J, D.nbr, D.deg};
+            __nv_bfloat16 *cur = xa, *nxt = xb;
+            for (int layer = 0; layer < 5; ++layer) {
+                const LnW ln = D.ln64[layer];
+                const long long n_graphs = static_cast<long long>(BT);
+                if (layer % 2 == 0) {
+                    const GatW& G = D.gat[layer / 2];
+                    E.linear_rows(G.lin, cur, nullptr, 64, static_cast<long long>(nodes), hbuf, 256, 0, kOutBf16);
+                    const __nv_bfloat16* c = cur; __nv_bfloat16* n = nxt;
+                    E.op([=](cudaStream_t s) { return launch_gat_aggregate(hbuf, c, n_graphs, topo, G.att_src, G.att_dst, G.bias, ln.w, ln.b, n, s); });
+                } else {
+                    const LayerW& L = D.gconv[layer / 2];
+                    const __nv_bfloat16* c = cur; __nv_bfloat16* n = nxt;
+                    E.op([=](cudaStream_t s) { return launch_graph_gather(c, n_graphs, topo, agg, s); });
+                    E.linear_rows(L, agg, cur, 64, static_cast<long long>(nodes), ybuf, 64, 0, kOutF32);
+                    E.op([=](cudaStream_t s) { return launch_ln64_act_res(ybuf, c, static_cast<long long>(nodes), ln.w, ln.b, n, s); });
+                }
+                std::swap(cur, nxt);
+            }
+            E.linear_rows(D.proj_out, cur, nullptr, J * 64, static_cast<long long>(BT), t1, 256, 0, kOutBf16);
+            {
+                const LnW nw = D.norm;
+                E.op([=](cudaStream_t s) { return launch_layernorm(t1, static_cast<long long>(BT), 256, nw.w, nw.b, t2, s); });
+            }
+            E.resblock(D.post_res, t2, T, B, t1, t3, qkv, t4);
+            E.conv_k3(D.post_conv, t4, 256, nullptr, 0, T, B, t1);
+            E.attention(D.post_attn, t1, nullptr, T, B, qkv, t2);
+            const __nv_bfloat16* last = t2;
+            if (D.has_post_chan) { E.channel(D.post_chan, t2, T, B, t3); last = t3; }
+            // logits: fp32 straight into pose[B, T, 104] at this branch's column block
+            E.linear_rows(D.logits, last, nullptr, 256, static_cast<long long>(BT), pose_stage, kPoseFeats,
+                          part == 0 ? 0 : kBodyFeats, kOutF32);
+        }
+        if (E.rc != A2M_OK) return E.rc;
+    }
+    return A2M_OK;
+}
+
+ForwardPlan* get_plan(a2m_model* m, int B, int T, int F, int* rc_out) {
+    char key[64];
+    snprintf(key, sizeof(key), "%d:%d:%d", B, T, F);
+    auto it = m->plans.find(key);
+    if (it != m->plans.end()) { *rc_out = A2M_OK; return it->second.get(); }
+    std::unique_ptr<ForwardPlan> P(new ForwardPlan());
+    P->B = B; P->T = T; P->F = F;
+    *rc_out = build_plan(m, P.get());
+    if (*rc_out != A2M_OK) return nullptr;
+    ForwardPlan* raw = P.get();
+    if (m->plans.size() >= 8) m->plans.clear();          // bound the cache: shapes rarely change
+    m->plans[key] = std::move(P);
+    return raw;
+}
+
+int check_shape(long long B, int T, int F, const char* who) {
+    A2M_ARG_CHECK(B >= 1 && B <= 65535, "%s: batch %lld out of range [1, 65535]", who, (long long)B);
+    A2M_ARG_CHECK(T >= 8 && T % 8 == 0, "%s: T = %d; the time axis must be a multiple of 8 (three stride-2 encoder "
+                  "stages; the reference itself needs T %% 4 == 0 for the UNet skip concat)", who, T);
+    A2M_ARG_CHECK(T <= 64, "%s: T = %d; this build implements T <= 64 (attention tile)", who, T);
+    A2M_ARG_CHECK(F >= 16 && F % 8 == 0, "%s: F = %d; the mel axis must be a multiple of 8 and >= 16", who, F);
+    return A2M_OK;
+}
+
+int run_ops(ForwardPlan* P, int lo, int hi, cudaStream_t s) {
+    for (int i = lo; i < hi; ++i) {
+        const int rc = P->ops[i](s);
+        if (rc != A2M_OK) return rc;
+    }
+    return A2M_OK;
+}
+
+}  // namespace
+
+extern "C" int a2m_model_create(const a2m_tensor_desc* tensors, int n_tensors, int device, a2m_model** out) {
+    A2M_ARG_CHECK(out != nullptr && tensors != nullptr && n_tensors > 0, "a2m_model_create: NULL argument");
+    *out = nullptr;
+    A2M_CUDA_CHECK(cudaSetDevice(device));
+    std::unique_ptr<a2m_model> m(new a2m_model());
+    m->device = device;
+    for (int i = 0; i < n_tensors; ++i) {
+        const a2m_tensor_desc& t = tensors[i];
+        A2M_ARG_CHECK(t.name != nullptr && t.ndim >= 0 && t.ndim <= 4, "a2m_model_create: bad descriptor %d", i);
+        Param p;
+        p.ndim = t.ndim;
+        for (int k = 0; k < t.ndim; ++k) p.shape[k] = t.shape[k];
+        if (t.dtype == A2M_DTYPE_F32) p.f32 = static_cast<const float*>(t.data);
+        else if (t.dtype == A2M_DTYPE_I64) p.i64 = static_cast<const long long*>(t.data);
+        else { a2m_set_error("a2m_model_create: tensor '%s' has unsupported dtype %d", t.name, t.dtype); return A2M_ERR_ARGUMENT; }
+        m->params[t.name] = p;
+    }
+    Builder b{m.get(), nullptr};
+    // a full SelfAttention_G state_dict has all three sections; the standalone AudioEncoder / UNet1D
+    // drop-in modules pass only their own
+    m->has_encoder = m->params.count("audio_encoder.conv.0.conv.weight") > 0;
+    m->has_unet = m->params.count("unet.final_conv.weight") > 0;
+    m->has_decoders = m->params.count("body_logits.weight") > 0;
+    A2M_ARG_CHECK(m->has_encoder || m->has_unet || m->has_decoders, "a2m_model_create: no known section in the state_dict");
+    if (m->has_encoder) b.encoder();
+    if (m->has_unet) b.unet();
+    if (m->has_decoders) {
+        b.decoder(m->dec[0], "body", kBodyJoints, kBodyFeats);
+        b.decoder(m->dec[1], "hand", kHandJoints, kPoseFeats - kBodyFeats);
+    }
+    b.losses();
+    cudaError_t e = cudaDeviceSynchronize();
+    if (b.rc == A2M_OK && e != cudaSuccess) { a2m_set_error("a2m_model_create: %s", cudaGetErrorString(e)); b.rc = (int)e; }
+    if (b.rc != A2M_OK) {
+        for (void* p : m->owned) cudaFree(p);
+        return b.rc;
+    }
+    m->params.clear();                       // the caller's tensors are not referenced after this point
+    *out = m.release();
+    return A2M_OK;
+}
+
+extern "C" void a2m_model_destroy(a2m_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    m->plans.clear();
+    for (void* p : m->owned) cudaFree(p);
+    delete m;
+}
+
+extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t B, int T, int F, float* pose, float* losses,
+                                 const float* real_pose, void* stream) {
+    A2M_ARG_CHECK(m != nullptr && mel != nullptr && pose != nullptr, "a2m_model_forward: NULL argument");
+    A2M_ARG_CHECK(m->has_encoder && m->has_unet && m->has_decoders, "a2m_model_forward: the handle was created from a partial state_dict");
+    int rc = check_shape(B, T, F, "a2m_model_forward");
+    if (rc != A2M_OK) return rc;
+    ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc);
+    if (!P) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    m->cur_mel = mel;
+    rc = run_ops(P, 0, static_cast<int>(P->ops.size()), s);
+    if (rc != A2M_OK) return rc;
+    float* stage = P->pose_stage;
+    A2M_CUDA_CHECK(cudaMemcpyAsync(pose, stage, static_cast<size_t>(B) * T * kPoseFeats * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (losses) {
+        rc = launch_pose_losses(stage, real_pose, static_cast<int>(B), T, m->triples, m->n_hand_triples, m->n_body_triples,
+                                m->parents, m->loss_scratch, losses, s);
+        if (rc != A2M_OK) return rc;
+    }
+    return A2M_OK;
+}
+
+extern "C" int a2m_model_encoder_forward(a2m_model* m, const float* mel, int64_t B, int T, int F, float* out_nct, void* stream) {
+    A2M_ARG_CHECK(m != nullptr && mel != nullptr && out_nct != nullptr, "a2m_model_encoder_forward: NULL argument");
+    A2M_ARG_CHECK(m->has_encoder, "a2m_model_encoder_forward: no audio_encoder.* tensors in the state_dict");
+    int rc = check_shape(B, T, F, "a2m_model_encoder_forward");
+    if (rc != A2M_OK) return rc;
+    ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc);
+    if (!P) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    m->cur_mel = mel;
+    rc = run_ops(P, 0, P->enc_end, s);
+    if (rc != A2M_OK) return rc;
+    return launch_btc_to_ncw(P->enc_out, static_cast<int>(B), 256, T, out_nct, s);
+}
+
+extern "C" int a2m_model_unet_forward(a2m_model* m, const float* x_nct, int64_t B, int T, float* out_nct, void* stream) {
+    A2M_ARG_CHECK(m != nullptr && x_nct != nullptr && out_nct != nullptr, "a2m_model_unet_forward: NULL argument");
+    A2M_ARG_CHECK(m->has_unet, "a2m_model_unet_forward: no unet.* tensors in the state_dict");
+    int rc = check_shape(B, T, 64, "a2m_model_unet_forward");
+    if (rc != A2M_OK) return rc;
+    ForwardPlan* P = get_plan(m, static_cast<int>(B), T, 64, &rc);
+    if (!P) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rc = launch_ncw_to_btc(x_nct, static_cast<int>(B), 256, T, P->enc_out, s);
+    if (rc != A2M_OK) return rc;
+    rc = run_ops(P, P->enc_end, P->unet_end, s);
+    if (rc != A2M_OK) return rc;
+    return launch_btc_to_ncw(P->unet_out, static_cast<int>(B), 256, T, out_nct, s);
+}
+
+extern "C" int a2m_model_status(a2m_model* m) {
+    A2M_ARG_CHECK(m != nullptr, "a2m_model_status: NULL");
+    int flag = 0;
+    A2M_CUDA_CHECK(cudaDeviceSynchronize());
+    A2M_CUDA_CHECK(cudaMemcpy(&flag, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag != 0) {
+        cudaMemset(m->err_flag, 0, sizeof(int));
+        a2m_set_error("a2m_model_status: a conv_gemm pipeline barrier wait expired (role %d)", flag);
+        return A2M_ERR_PIPELINE;
+    }
+    return A2M_OK;
+}
+
+extern "C" int64_t a2m_model_gemm_flops(a2m_model* m, int64_t B, int T, int F) {
+    if (!m) return -1;
+    int rc = A2M_OK;
+    if (check_shape(B, T, F, "a2m_model_gemm_flops") != A2M_OK) return -1;
+    ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc);
+    return P ? P->gemm_flops : -1;
+}

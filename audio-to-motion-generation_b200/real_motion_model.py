@@ -1,0 +1,169 @@
+"""B200 drop-in for ``real_motion_model.py`` of the reference: the ``SelfAttention_G`` generator.
+
+Same constructor and ``forward(audio, real_pose=None) -> (pose [B, T, 104], [losses])`` contract
+(real_motion_model.py:22,154-278) and the same 340 state_dict keys, so reference
+checkpoints load with ``load_state_dict``.  The forward is one native launch program (csrc/model.cu):
+tcgen05 implicit-GEMM convolutions / linears in bf16 with fp32 accumulation, fused attention, the
+static-skeleton GAT / GraphConv layers (restated from torch_geometric's documented semantics -- PyG is
+not a dependency here), and the angle / bone losses.
+
+Differences from the reference, all deliberate: inference (eval) semantics only (D3);
+``UNet1D.up_attention`` before the skip concat (D1); no Skeleton2D / CSV side effects -- the skeleton is
+the constant parent list of pats/data_loading/skeleton.py:94-110 (D5).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from ._native_module import NativeModule, as_input
+from .model_layers import (AudioEncoder, UNet1D, ResBlock, ConvNormRelu, ChannelAttention, SelfAttention,
+                           _Block)
+
+# pats/data_loading/skeleton.py:94-110
+SKELETON_PARENTS = [-1, 0, 1, 2, 0, 4, 5, 0, 7, 7, 6,
+                    10, 11, 12, 13, 10, 15, 16, 17, 10, 19, 20, 21, 10, 23, 24, 25, 10, 27, 28, 29,
+                    3,
+                    31, 32, 33, 34, 31, 36, 37, 38, 31, 40, 41, 42, 31, 44, 45, 46, 31, 48, 49, 50]
+SKELETON_JOINT_NAMES = (
+    ['Neck', 'RShoulder', 'RElbow', 'RWrist', 'LShoulder', 'LElbow', 'LWrist', 'Nose', 'REye', 'LEye'] +
+    [side + 'Hand' + part for side in 'LR'
+     for part in ['Root'] + [f + str(i) for f in ('Thumb', 'Index', 'Middle', 'Ring', 'Little') for i in range(1, 5)]])
+
+
+class _Lin(nn.Module):
+    def __init__(self, cin, cout, bias):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin))
+        nn.init.xavier_uniform_(self.weight)
+        self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
+
+
+class GATConv(_Block):
+    """Parameter container with torch_geometric's GATConv key names (att_src, att_dst, bias, lin.weight);
+    semantics implemented natively: heads averaged (concat=False), self loops, LeakyReLU(0.2) logits."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True):
+        super().__init__()
+        if concat or (in_channels, out_channels, heads) != (64, 64, 4):
+            raise NotImplementedError("the native path implements GATConv(64, 64, heads=4, concat=False)")
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        self.lin = _Lin(in_channels, heads * out_channels, bias=False)
+        nn.init.xavier_uniform_(self.att_src)
+        nn.init.xavier_uniform_(self.att_dst)
+
+
+class GraphConv(_Block):
+    """torch_geometric GraphConv key names (lin_rel.{weight,bias}, lin_root.weight), aggr='add'."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.lin_rel = _Lin(in_channels, out_channels, bias=True)
+        self.lin_root = _Lin(in_channels, out_channels, bias=False)
+
+
+def _edge_index(parents, lo, count):
+    """Undirected parent/child edges among joints [lo, lo+count) re-indexed from 0
+    (real_motion_model.py:43-60); row 0 = source, row 1 = target."""
+    edges = []
+    for i, par in enumerate(parents[lo:lo + count]):
+        par -= lo
+        if 0 <= par < count:
+            edges += [[par, i], [i, par]]
+    return torch.tensor(edges, dtype=torch.long).t().contiguous()
+
+
+class SelfAttention_G(NativeModule):
+    '''
+    input_shape:  (N, time, frequency)
+    output_shape: (N, time, pose_feats)
+    '''
+
+    def __init__(self, time_steps=64, in_channels=256, out_channels=256, out_feats=104, p=0.2):
+        super().__init__()
+        if (in_channels, out_channels, out_feats) != (256, 256, 104):
+            raise NotImplementedError("the native generator implements in/out channels 256 and 104 pose features")
+        self.audio_encoder = AudioEncoder(output_feats=time_steps, p=p)
+        self.unet = UNet1D(input_channels=in_channels, output_channels=out_channels, p=p)
+        self.body_feats, self.hand_feats = 20, out_feats - 20
+        self.num_body_joints, self.num_hand_joints, self.joint_feat_dim = 10, 42, 64
+        self.parents, self.joint_names = list(SKELETON_PARENTS), list(SKELETON_JOINT_NAMES)
+        self.joint_subset = list(range(out_feats // 2))
+        self.body_edge_index = _edge_index(self.parents, 0, self.num_body_joints)
+        self.hand_edge_index = _edge_index(self.parents, 10, self.num_hand_joints)
+        self.register_buffer('body_edge_index_template', self.body_edge_index)
+        self.register_buffer('hand_edge_index_template', self.hand_edge_index)
+        for part, joints, feats in (("body", self.num_body_joints, self.body_feats),
+                                    ("hand", self.num_hand_joints, self.hand_feats)):
+            pre = [ResBlock(out_channels, type='1d', p=p),
+                   ConvNormRelu(out_channels, out_channels, type='1d', leaky=True, downsample=False, p=p)]
+            pre += [ChannelAttention(out_channels), SelfAttention(out_channels)] if part == "body" else \
+                [SelfAttention(out_channels), ChannelAttention(out_channels)]
+            setattr(self, part + "_decoder_pre", nn.Sequential(*pre))
+            setattr(self, part + "_proj_in", nn.Linear(out_channels, joints * self.joint_feat_dim))
+            for li in range(1, 6):
+                layer = GATConv(64, 64, heads=4, concat=False) if li % 2 else GraphConv(64, 64)
+                setattr(self, "%s_gcn%d" % (part, li), layer)
+            setattr(self, part + "_layer_norms", nn.ModuleList([nn.LayerNorm(64) for _ in range(5)]))
+            setattr(self, part + "_relu", nn.LeakyReLU(0.2))
+            setattr(self, part + "_dropout", nn.Dropout(p=p))
+            setattr(self, part + "_proj_out", nn.Linear(joints * self.joint_feat_dim, out_channels))
+            setattr(self, part + "_norm", nn.LayerNorm(out_channels))
+            post = [ResBlock(out_channels, type='1d', p=p),
+                    ConvNormRelu(out_channels, out_channels, type='1d', leaky=True, downsample=False, p=p),
+                    SelfAttention(out_channels)]
+            if part == "hand":
+                post.append(ChannelAttention(out_channels))
+            setattr(self, part + "_decoder_post", nn.Sequential(*post))
+            setattr(self, part + "_logits", nn.Conv1d(out_channels, feats, kernel_size=1, stride=1))
+        self.hand_triples = self._triples(10, self.num_hand_joints)
+        self.body_triples = self._triples(0, self.num_body_joints)
+
+    def _triples(self, lo, count):
+        """(parent, joint, first child) per joint that has both (real_motion_model.py:280-304)."""
+        local = [p - lo if lo <= p < lo + count else -1 for p in self.parents[lo:lo + count]]
+        out = []
+        for i, par in enumerate(local):
+            if par == -1:
+                continue
+            child = next((j for j in range(i + 1, count) if local[j] == i), None)
+            if child is not None:
+                out.append((par, i, child))
+        return out
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # torch_geometric renamed GATConv's linear over versions (lin / lin_src+lin_dst / lin_l+lin_r)
+        for part in ("body", "hand"):
+            for li in (1, 3, 5):
+                base = "%s%s_gcn%d." % (prefix, part, li)
+                for alt in ("lin_src.weight", "lin_l.weight"):
+                    if base + alt in state_dict and base + "lin.weight" not in state_dict:
+                        state_dict[base + "lin.weight"] = state_dict.pop(base + alt)
+                for dup in ("lin_dst.weight", "lin_r.weight"):
+                    state_dict.pop(base + dup, None)
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def forward(self, audio, real_pose=None):
+        """audio [B, T, F] (log-mel) -> (pose [B, T, 104] fp32, [angle_loss]) or
+        (pose, [bone_loss, angle_loss]) when real_pose [B, T, 104] is given."""
+        self._require_eval()
+        h = self.native()
+        x = as_input(audio, h.device, "SelfAttention_G expects audio [B, T, F], got %s")
+        B, T, F = x.shape
+        if T % 4 != 0:
+            raise ValueError("SelfAttention_G needs T %% 4 == 0 (UNet1D skip concats), got T = %d" % T)
+        rp = None
+        if real_pose is not None:
+            rp = as_input(real_pose, h.device, "real_pose must be [B, T, 104], got %s")
+            if tuple(rp.shape) != (B, T, 104):
+                raise ValueError("real_pose must be [%d, %d, 104], got %s" % (B, T, tuple(rp.shape)))
+        pose = torch.empty((B, T, 104), dtype=torch.float32, device=h.device)
+        losses = torch.empty(2, dtype=torch.float32, device=h.device)
+        with torch.cuda.device(h.device):
+            _cabi.check(_cabi.lib().a2m_model_forward(h.ptr, _cabi.ptr(x), B, T, F, _cabi.ptr(pose), _cabi.ptr(losses),
+                                                      _cabi.ptr(rp), _cabi.stream_ptr(h.device)))
+        internal = [losses[1], losses[0]] if rp is not None else [losses[0]]
+        return pose, internal

@@ -141,6 +141,44 @@ int a2m_gemm_taps(const a2m_gemm_desc* desc, const float* w_src, int64_t w_strid
                   const float* scale /* nullable [N] */, const float* bias /* nullable [N] */, void* out,
                   void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * the generator: replaces real_motion_model.py:16-278 SelfAttention_G (eval-mode forward) together
+ * with the model_layers.py classes it instantiates (AudioEncoder :219-280, UNet1D :283-374 with
+ * decision D1, ResBlock/ConvNormRelu/SelfAttention/ChannelAttention/ConvTranspose1D) and the
+ * torch_geometric GATConv/GraphConv layers it calls (real_motion_model.py:78-82,104-108).
+ *
+ * a2m_model_create takes the state_dict (reference key names) as device
+ * tensors: fp32 parameters / buffers and the two int64 edge templates; it folds BatchNorm running
+ * statistics into the conv weights, packs every matrix to bf16 in the tcgen05 K-major layout and
+ * copies the small fp32 vectors, so the caller's tensors are not referenced afterwards.
+ * ---------------------------------------------------------------------------------------------- */
+#define A2M_DTYPE_F32 0
+#define A2M_DTYPE_I64 1
+typedef struct a2m_tensor_desc {
+    const char* name;
+    const void* data;        /* device */
+    int32_t dtype;
+    int32_t ndim;            /* <= 4 */
+    int64_t shape[4];
+} a2m_tensor_desc;
+typedef struct a2m_model a2m_model;
+int a2m_model_create(const a2m_tensor_desc* tensors, int n_tensors, int device, a2m_model** out);
+void a2m_model_destroy(a2m_model* model);
+/* mel [B, T, F] fp32 -> pose [B, T, 104] fp32 (columns 0..19 body, 20..103 hand);
+ * losses (nullable, device float[2]): [0] = 0.7*hand + 0.3*body angle penalty (:359-461),
+ * [1] = bone-length MSE against real_pose (:307-347) when real_pose != NULL, else 0.
+ * T multiple of 8, T <= 64; F multiple of 16 with F/8 even; 1 <= B <= 65535. */
+int a2m_model_forward(a2m_model* model, const float* mel, int64_t B, int T, int F, float* pose, float* losses,
+                      const float* real_pose /* nullable [B, T, 104] */, void* stream);
+/* AudioEncoder.forward (model_layers.py:267-280): mel [B, T, F] -> [B, 256, T] fp32 (reference NCW layout) */
+int a2m_model_encoder_forward(a2m_model* model, const float* mel, int64_t B, int T, int F, float* out_nct, void* stream);
+/* UNet1D.forward (model_layers.py:341-374, D1): [B, 256, T] fp32 -> [B, 256, T] fp32 */
+int a2m_model_unet_forward(a2m_model* model, const float* x_nct, int64_t B, int T, float* out_nct, void* stream);
+/* Synchronises the device and reports whether any kernel's bounded barrier wait expired. */
+int a2m_model_status(a2m_model* model);
+/* Algorithmic FLOPs (2*M*N*K over valid rows) of the tensor-core GEMMs one forward of this shape launches. */
+int64_t a2m_model_gemm_flops(a2m_model* model, int64_t B, int T, int F);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,120 @@
+"""GPU parity of the native generator (SelfAttention_G drop-in -> a2m_model_* C ABI) against the oracle
+and the reference goldens.  Tolerance (north_star / D8): sum|a-b| / sum|b| <= 1e-2 vs the fp32 reference
+(bf16 tensor-core operands, fp32 accumulation)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_oracle, weights
+from oracle.make_golden import MODEL_CASES, model_input, real_pose_input
+
+pytestmark = pytest.mark.gpu
+
+REL_L1 = 1e-2
+
+
+def rel_l1(got, ref):
+    got, ref = got.detach().float().cpu(), torch.as_tensor(ref).float()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert torch.isfinite(got).all()
+    return ((got - ref).abs().sum() / ref.abs().sum()).item()
+
+
+@pytest.fixture(scope="module")
+def mods(pkg):
+    return pkg.install_dropin()
+
+
+@pytest.fixture(scope="module")
+def stress_model(mods):
+    m = mods["real_motion_model"].SelfAttention_G().cuda().eval()
+    m.load_state_dict(weights.make_state_dict(0, "stress"))
+    return m
+
+
+def test_encoder_matches_reference(stress_model, golden):
+    x = model_input(0, 2, 64, 64)
+    got = stress_model.audio_encoder(x.cuda())
+    stress_model.audio_encoder.check_device_status()
+    assert got.shape == (2, 256, 64)
+    assert rel_l1(got, golden["model"]["stress_b2_enc"]) <= REL_L1
+
+
+def test_unet_matches_reference(stress_model, golden):
+    enc = torch.from_numpy(golden["model"]["stress_b2_enc"])
+    got = stress_model.unet(enc.cuda())
+    stress_model.unet.check_device_status()
+    assert rel_l1(got, golden["model"]["stress_b2_unet"]) <= REL_L1
+
+
+@pytest.mark.parametrize("name,seed,mode,B,T,F,with_pose", MODEL_CASES)
+def test_generator_matches_reference_golden(mods, golden, name, seed, mode, B, T, F, with_pose):
+    m = mods["real_motion_model"].SelfAttention_G().cuda().eval()
+    m.load_state_dict(weights.make_state_dict(seed, mode))
+    x = model_input(seed, B, T, F)
+    rp = real_pose_input(seed, B, T) if with_pose else None
+    pose, losses = m(x.cuda(), real_pose=None if rp is None else rp.cuda())
+    m.check_device_status()
+    assert pose.shape == (B, T, 104) and pose.dtype == torch.float32 and pose.is_cuda
+    err = rel_l1(pose, golden["model"][name + "_pose"])
+    assert err <= REL_L1, err
+    ref_losses = golden["model"][name + "_losses"]
+    assert len(losses) == len(ref_losses)
+    # losses are evaluated on the bf16-path poses: compare with the oracle losses of the SAME poses (tight)
+    o_losses = [model_oracle.angle_loss(pose.cpu())]
+    if with_pose:
+        o_losses = [model_oracle.bone_loss(rp, pose.cpu())] + o_losses
+    np.testing.assert_allclose([l.item() for l in losses], [l.item() for l in o_losses], rtol=1e-4, atol=1e-6)
+    # and with the reference's own numbers (loose: they inherit the pose tolerance)
+    np.testing.assert_allclose([l.item() for l in losses], ref_losses, rtol=5e-2, atol=5e-3)
+
+
+def test_generator_vs_oracle_other_seed(mods):
+    sd = weights.make_state_dict(7, "stress")
+    m = mods["real_motion_model"].SelfAttention_G().cuda().eval()
+    m.load_state_dict(sd)
+    x = model_input(7, 3, 64, 64)
+    pose, _ = m(x.cuda())
+    ref, _ = model_oracle.generator_forward(sd, x)
+    assert rel_l1(pose, ref) <= REL_L1
+
+
+def test_batch_invariance_and_config2_size(stress_model):
+    """BASELINE config 2 (B = 256, T = 64, F = 64): each clip's pose is independent of the batch it is in."""
+    x = model_input(11, 8, 64, 64).cuda().repeat(32, 1, 1)
+    pose, _ = stress_model(x)
+    stress_model.check_device_status()
+    assert pose.shape == (256, 64, 104)
+    assert torch.equal(pose[:8], pose[248:])
+    small, _ = stress_model(x[:5])
+    assert torch.equal(small, pose[:5])
+    again, _ = stress_model(x)
+    assert torch.equal(again, pose)
+
+
+def test_error_behaviour(mods, stress_model):
+    with pytest.raises(ValueError):
+        stress_model(torch.zeros(1, 62, 64, device="cuda"))            # T % 4 != 0 (reference: opaque cat error)
+    with pytest.raises(ValueError):
+        stress_model(torch.zeros(64, 64, device="cuda"))
+    fresh = mods["real_motion_model"].SelfAttention_G().cuda()
+    with pytest.raises(RuntimeError, match="eval"):
+        fresh(torch.zeros(1, 64, 64, device="cuda"))
+    cpu_model = mods["real_motion_model"].SelfAttention_G().eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cpu_model(torch.zeros(1, 64, 64))
+    with pytest.raises(NotImplementedError):
+        mods["model_layers"].ConvNormRelu(4, 4)(torch.zeros(1, 4, 8))
+
+
+def test_weight_update_repacks(mods):
+    m = mods["real_motion_model"].SelfAttention_G().cuda().eval()
+    m.load_state_dict(weights.make_state_dict(3, "stress"))
+    x = model_input(3, 1, 64, 64).cuda()
+    a, _ = m(x)
+    m.load_state_dict(weights.make_state_dict(4, "stress"))
+    b, _ = m(x)
+    assert not torch.equal(a, b)
+    sd = weights.make_state_dict(4, "stress")
+    ref, _ = model_oracle.generator_forward(sd, x.cpu())
+    assert rel_l1(b, ref) <= REL_L1
