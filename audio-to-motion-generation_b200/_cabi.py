@@ -61,11 +61,14 @@ SIGNATURES = {
     "a2m_comm_destroy": (None, [c_void_p]),
     "a2m_model_create": (c_int, [ctypes.POINTER(TensorDesc), c_int, c_int, ctypes.POINTER(c_void_p)]),
     "a2m_model_destroy": (None, [c_void_p]),
-    "a2m_model_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "a2m_model_forward": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
     "a2m_model_encoder_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p]),
     "a2m_model_unet_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "a2m_model_status": (c_int, [c_void_p]),
     "a2m_model_gemm_flops": (c_i64, [c_void_p, c_i64, c_int, c_int]),
+    "a2m_model_profile": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p]),
     "a2m_gemm_taps": (c_int, [ctypes.POINTER(GemmDesc), c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p,
                               c_void_p]),
 }

@@ -96,9 +96,15 @@ class NativeModule(nn.Module):
         return d
 
 
-def as_input(x, device, shape_msg):
+def as_input(x, device, shape_msg, keep_strides=False):
+    """fp32 tensor on `device`; contiguous unless keep_strides and the tensor is a row-strided view
+    (unit inner stride, rows ordered) that the native kernels can read in place."""
     if not isinstance(x, torch.Tensor):
         x = torch.as_tensor(x)
     if x.dim() != 3:
         raise ValueError(shape_msg % (tuple(x.shape),))
-    return x.to(device=device, dtype=torch.float32).contiguous()
+    x = x.to(device=device, dtype=torch.float32)
+    if keep_strides and x.stride(2) == 1 and x.stride(1) >= x.shape[2] and \
+            (x.shape[0] == 1 or x.stride(0) >= x.stride(1)):
+        return x
+    return x.contiguous()

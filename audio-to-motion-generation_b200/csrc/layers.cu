@@ -30,16 +30,17 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
 
 // ------------------------------------------------------------------------------------------ conv0
 __global__ void __launch_bounds__(256)
-conv0_kernel(const float* __restrict__ mel, int T, int F, const float* __restrict__ w, const float* __restrict__ bias,
-             __nv_bfloat16* __restrict__ out) {
+conv0_kernel(const float* __restrict__ mel, long long stride_b, long long stride_t, int T, int F,
+             const float* __restrict__ w, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
     extern __shared__ float s_rows[];                 // [4][F + 2], zero padded left/right
-    const int ho = blockIdx.x, b = blockIdx.y;
+    const int ho = blockIdx.x;
+    const long long b = blockIdx.y;
     const int Ho = T / 2, Wo = F / 2, stride = F + 2;
     for (int i = threadIdx.x; i < 4 * stride; i += blockDim.x) {
         const int r = i / stride, col = i - r * stride - 1;
         const int h = 2 * ho + r - 1;
         float v = 0.f;
-        if (h >= 0 && h < T && col >= 0 && col < F) v = mel[(static_cast<long long>(b) * T + h) * F + col];
+        if (h >= 0 && h < T && col >= 0 && col < F) v = mel[b * stride_b + h * stride_t + col];
         s_rows[i] = v;
     }
     const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;
@@ -48,7 +49,7 @@ conv0_kernel(const float* __restrict__ mel, int T, int F, const float* __restric
     for (int i = 0; i < 16; ++i) wr[i] = w[c * 16 + i];
     const float bc = bias[c];
     __syncthreads();
-    __nv_bfloat16* o = out + ((static_cast<long long>(b) * Ho + ho) * Wo) * 64 + c;
+    __nv_bfloat16* o = out + ((b * Ho + ho) * Wo) * 64 + c;
     for (int wo = grp; wo < Wo; wo += 4) {
         float acc = bc;
 #pragma unroll
@@ -470,10 +471,11 @@ __global__ void btc_to_ncw_kernel(const __nv_bfloat16* __restrict__ in, int C, i
     A2M_LAUNCH_CHECK();     \
     return A2M_OK
 
-int launch_conv0(const float* mel, int B, int T, int F, const float* w_folded, const float* bias_folded,
-                 __nv_bfloat16* out, cudaStream_t stream) {
+int launch_conv0(const float* mel, long long stride_b, long long stride_t, int B, int T, int F, const float* w_folded,
+                 const float* bias_folded, __nv_bfloat16* out, cudaStream_t stream) {
     A2M_ARG_CHECK(T % 2 == 0 && F % 2 == 0 && B <= 65535, "conv0: T %d, F %d, B %d", T, F, B);
-    conv0_kernel<<<dim3(T / 2, B), 256, 4 * (F + 2) * sizeof(float), stream>>>(mel, T, F, w_folded, bias_folded, out);
+    conv0_kernel<<<dim3(T / 2, B), 256, 4 * (F + 2) * sizeof(float), stream>>>(mel, stride_b, stride_t, T, F, w_folded,
+                                                                                 bias_folded, out);
     A2M_AFTER_LAUNCH();
 }
 

@@ -7,9 +7,10 @@
 namespace a2m {
 
 // AudioEncoder conv 0: Conv2d(1 -> 64, k4, s2, p1) + BatchNorm(eval) + LeakyReLU(0.2)  (model_layers.py:252)
-//   mel [B, T, F] fp32 -> out [B, T/2, F/2, 64] bf16.  w_folded [64][16] fp32 (BN scale folded), bias_folded [64].
-int launch_conv0(const float* mel, int B, int T, int F, const float* w_folded, const float* bias_folded,
-                 __nv_bfloat16* out, cudaStream_t stream);
+//   mel [B, T, F] fp32 (element strides stride_b, stride_t, 1: the D2 adapter slice is read in place)
+//   -> out [B, T/2, F/2, 64] bf16.  w_folded [64][16] fp32 (BN scale folded), bias_folded [64].
+int launch_conv0(const float* mel, long long stride_b, long long stride_t, int B, int T, int F, const float* w_folded,
+                 const float* bias_folded, __nv_bfloat16* out, cudaStream_t stream);
 
 // F.interpolate(size=(T,1), mode='bilinear') + squeeze (model_layers.py:277-279) applied to the centre
 // column computed by the last encoder conv: in [B, Hc, C] fp32 -> out [B, T, C] bf16.

@@ -61,6 +61,7 @@ struct ForwardPlan {
     int B, T, F;
     void* arena = nullptr;
     std::vector<std::function<int(cudaStream_t)>> ops;
+    std::vector<int> op_is_gemm;                // parallel to ops
     int enc_end = 0, unet_end = 0;              // op index ranges: [0,enc_end) encoder, [enc_end,unet_end) unet
     float* mel_in = nullptr;                    // staging (fp32) used by the stage entry points
     __nv_bfloat16 *enc_out = nullptr, *unet_out = nullptr;
@@ -89,6 +90,7 @@ struct a2m_model {
     bool has_encoder = false, has_unet = false, has_decoders = false;
     // per-forward mutable slots read by the op closures
     const float* cur_mel = nullptr;
+    long long cur_stride_b = 0, cur_stride_t = 0;
     float* cur_pose = nullptr;
     std::map<std::string, std::unique_ptr<ForwardPlan>> plans;
     std::string build_error;
@@ -434,6 +436,7 @@ struct Emit {
         P->gemm_flops += plan->flops;
         int* flag = m->err_flag;
         P->ops.push_back([plan, flag](cudaStream_t s) { return conv_gemm_launch(*plan, flag, s); });
+        P->op_is_gemm.push_back(1);
     }
     // rows = (L, B) of a [B, L, C] tensor; taps shift along L
     void conv_rows(const LayerW& L, const __nv_bfloat16* a0, int c0, const __nv_bfloat16* a1, int c1, int len, int B,
@@ -476,7 +479,9 @@ struct Emit {
         const long long os[4] = {ldc, 0, 0, 0};
         gemm(L, L.taps, v, a1 ? 2 : 1, box, ext, out, os, col, out_type);
     }
-    void op(std::function<int(cudaStream_t)> f) { if (!dry && rc == A2M_OK) P->ops.push_back(std::move(f)); }
+    void op(std::function<int(cudaStream_t)> f) {
+        if (!dry && rc == A2M_OK) { P->ops.push_back(std::move(f)); P->op_is_gemm.push_back(0); }
+    }
 
     void attention(const AttnW& A, const __nv_bfloat16* x, const __nv_bfloat16* res2, int len, int B, __nv_bfloat16* qkv,
                    __nv_bfloat16* out) {
@@ -509,6 +514,8 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
         Emit E{m, P, pass == 0};
         if (pass == 1) {
             P->ops.clear();
+            P->op_is_gemm.clear();
+            P->gemm_flops = 0;
             cudaError_t e = cudaMalloc(&P->arena, bufs.off + 256);
             if (e != cudaSuccess) { a2m_set_error("model: arena cudaMalloc(%zu) failed: %s", bufs.off, cudaGetErrorString(e)); return (int)e; }
             bufs.base = static_cast<unsigned char*>(P->arena);
@@ -542,7 +549,7 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
         // ---------------- AudioEncoder (model_layers.py:267-280) ----------------
         if (m->has_encoder) {
             a2m_model* mm = m;
-            E.op([=](cudaStream_t s) { return launch_conv0(mm->cur_mel, B, T, F, mm->conv0_w, mm->conv0_b, a0, s); });
+            E.op([=](cudaStream_t s) { return launch_conv0(mm->cur_mel, mm->cur_stride_b, mm->cur_stride_t, B, T, F, mm->conv0_w, mm->conv0_b, a0, s); });
             auto conv2d_s2 = [&](const LayerW& L, const __nv_bfloat16* in, int H, int W, int C, __nv_bfloat16* out) {
                 const int Ho = H / 2, Wo = W / 2;
                 AView v[2];
@@ -746,8 +753,8 @@ extern "C" void a2m_model_destroy(a2m_model* m) {
     delete m;
 }
 
-extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t B, int T, int F, float* pose, float* losses,
-                                 const float* real_pose, void* stream) {
+extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t mel_stride_b, int64_t mel_stride_t, int64_t B,
+                                 int T, int F, float* pose, float* losses, const float* real_pose, void* stream) {
     A2M_ARG_CHECK(m != nullptr && mel != nullptr && pose != nullptr, "a2m_model_forward: NULL argument");
     A2M_ARG_CHECK(m->has_encoder && m->has_unet && m->has_decoders, "a2m_model_forward: the handle was created from a partial state_dict");
     int rc = check_shape(B, T, F, "a2m_model_forward");
@@ -755,7 +762,9 @@ extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t B, int 
     ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc);
     if (!P) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    m->cur_mel = mel;
+    A2M_ARG_CHECK(mel_stride_t >= F && (B == 1 || mel_stride_b >= mel_stride_t), "a2m_model_forward: mel strides (%lld, %lld)",
+                  (long long)mel_stride_b, (long long)mel_stride_t);
+    m->cur_mel = mel; m->cur_stride_b = mel_stride_b; m->cur_stride_t = mel_stride_t;
     rc = run_ops(P, 0, static_cast<int>(P->ops.size()), s);
     if (rc != A2M_OK) return rc;
     float* stage = P->pose_stage;
@@ -776,7 +785,7 @@ extern "C" int a2m_model_encoder_forward(a2m_model* m, const float* mel, int64_t
     ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc);
     if (!P) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    m->cur_mel = mel;
+    m->cur_mel = mel; m->cur_stride_b = static_cast<long long>(T) * F; m->cur_stride_t = F;
     rc = run_ops(P, 0, P->enc_end, s);
     if (rc != A2M_OK) return rc;
     return launch_btc_to_ncw(P->enc_out, static_cast<int>(B), 256, T, out_nct, s);
@@ -816,4 +825,46 @@ extern "C" int64_t a2m_model_gemm_flops(a2m_model* m, int64_t B, int T, int F) {
     if (check_shape(B, T, F, "a2m_model_gemm_flops") != A2M_OK) return -1;
     ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc);
     return P ? P->gemm_flops : -1;
+}
+
+// Per-op CUDA-event timing of the forward program (bench.py's roofline leg): every launch is
+// bracketed by events on `stream`; returns per-iteration averages in out_ms = {all ops, tensor-core
+// GEMM ops, other ops} and the number of GEMM launches per forward.
+extern "C" int a2m_model_profile(a2m_model* m, const float* mel, int64_t mel_stride_b, int64_t mel_stride_t, int64_t B, int T,
+                                 int F, int iters, float* out_ms_host, int* n_gemm_host, void* stream) {
+    A2M_ARG_CHECK(m != nullptr && mel != nullptr && out_ms_host != nullptr && iters >= 1, "a2m_model_profile: bad argument");
+    A2M_ARG_CHECK(m->has_encoder && m->has_unet && m->has_decoders, "a2m_model_profile: partial handle");
+    int rc = check_shape(B, T, F, "a2m_model_profile");
+    if (rc != A2M_OK) return rc;
+    ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc);
+    if (!P) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    m->cur_mel = mel; m->cur_stride_b = mel_stride_b; m->cur_stride_t = mel_stride_t;
+    const int n = static_cast<int>(P->ops.size());
+    std::vector<cudaEvent_t> ev(2 * n);
+    for (auto& e : ev) A2M_CUDA_CHECK(cudaEventCreate(&e));
+    double gemm = 0.0, other = 0.0;
+    int n_gemm = 0;
+    for (int i = 0; i < n; ++i) n_gemm += P->op_is_gemm[i];
+    for (int it = 0; it < iters && rc == A2M_OK; ++it) {
+        for (int i = 0; i < n && rc == A2M_OK; ++i) {
+            cudaEventRecord(ev[2 * i], s);
+            rc = P->ops[i](s);
+            cudaEventRecord(ev[2 * i + 1], s);
+        }
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { a2m_set_error("a2m_model_profile: %s", cudaGetErrorString(e)); rc = (int)e; break; }
+        for (int i = 0; i < n; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
+            (P->op_is_gemm[i] ? gemm : other) += ms;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc != A2M_OK) return rc;
+    out_ms_host[0] = static_cast<float>((gemm + other) / iters);
+    out_ms_host[1] = static_cast<float>(gemm / iters);
+    out_ms_host[2] = static_cast<float>(other / iters);
+    if (n_gemm_host) *n_gemm_host = n_gemm;
+    return A2M_OK;
 }

@@ -1,0 +1,151 @@
+"""The composed hot path: waveform -> log-mel -> (adapter D2) -> SelfAttention_G -> L1 / PCK partials,
+clip-sharded over the GPUs of one box with a single 64-byte all-reduce at the end.
+
+Nothing in the reference connects these stages; this module is the composition the
+build defines, written against the drop-in modules of this package:
+
+    mel    = audio_repr.log_mel_spectograms(wav)            # [B, 425, 64]
+    x      = mel[:, 0:384:6, :]                             # D2: the reference's strided-slice feed, in place
+    pose,_ = SelfAttention_G(x)                             # [B, 64, 104]
+    motion_evaluation.evaluate_poses(pose, gt, accum=...)   # PCK hits, |d pose|, |d motion| partial sums
+
+One process per GPU (torchrun); ranks own contiguous clip ranges; weights are replicated; the only
+collective is ``allreduce_metrics`` (NCCL over NVLink through liba2m_b200's run-time binding).
+"""
+import ctypes
+
+import torch
+
+from . import _cabi, motion_evaluation
+from .pose_video import audio_repr
+
+ADAPTER_STRIDE = 6          # dataUtils.py:654 strided slice, fs_ratio = 6 (audio.py:177)
+POSE_FRAMES = 64
+CLIP_SAMPLES = 68267        # 64 / 15 s at 16 kHz -> 425 mel frames
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous clip range [lo, hi) of `rank`: rank r takes [r*ceil(n/W), (r+1)*ceil(n/W))."""
+    per = -(-n_items // world)
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
+
+
+def adapter(logmel, frames=POSE_FRAMES, stride=ADAPTER_STRIDE):
+    """D2: [B, >=frames*stride, F] -> strided view [B, frames, F] (no copy)."""
+    span = frames * stride
+    if logmel.shape[1] < span - stride + 1:
+        raise ValueError("log-mel has %d frames, the adapter needs at least %d" % (logmel.shape[1], span - stride + 1))
+    return logmel[:, 0:span:stride, :]
+
+
+class Communicator:
+    """NCCL communicator owned by liba2m_b200 (a2m_comm_*); the unique id travels over torch.distributed."""
+
+    def __init__(self, rank, world, device):
+        import torch.distributed as dist
+        self.rank, self.world = rank, world
+        ident = (ctypes.c_char * 128)()
+        if rank == 0:
+            _cabi.check(_cabi.lib().a2m_comm_unique_id(ctypes.cast(ident, ctypes.c_void_p)))
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0)
+        buf = (ctypes.c_char * 128).from_buffer_copy(box[0])
+        out = ctypes.c_void_p()
+        _cabi.check(_cabi.lib().a2m_comm_init(ctypes.cast(buf, ctypes.c_void_p), rank, world, device.index,
+                                              ctypes.byref(out)))
+        self.ptr, self.device = out, device
+
+    def allreduce(self, accum):
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().a2m_allreduce_metrics(self.ptr, _cabi.ptr(accum), _cabi.stream_ptr(self.device)))
+
+    def close(self):
+        if self.ptr:
+            _cabi.lib().a2m_comm_destroy(self.ptr)
+            self.ptr = None
+
+
+def allreduce_metrics(accum, comm=None):
+    """Sum the 64-byte partials over the ranks.  CUDA accumulators go through NCCL (a2m_allreduce_metrics);
+    host accumulators (the CPU/gloo tests of the sharding logic) through torch.distributed."""
+    if comm is not None and accum.is_cuda:
+        comm.allreduce(accum)
+        return accum
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if accum.is_cuda:
+            raise RuntimeError("CUDA accumulator without a Communicator: create one with Communicator(rank, world, device)")
+        counts = accum[:5].clone()
+        sums = accum[5:7].view(torch.float64).clone()
+        dist.all_reduce(counts)
+        dist.all_reduce(sums)
+        accum[:5] = counts
+        accum[5:7] = sums.view(torch.int64)
+    return accum
+
+
+class AudioToPosePipeline:
+    """mel -> generator -> evaluation on one GPU.  `model` is a SelfAttention_G drop-in in eval mode on `device`."""
+
+    def __init__(self, model, alpha=0.2, comm=None):
+        self.model = model
+        self.alpha = alpha
+        self.comm = comm
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("AudioToPosePipeline needs the model on a CUDA device; there is no CPU fallback")
+        self.accum = motion_evaluation.new_metrics(self.device)
+        self._copy_stream = torch.cuda.Stream(self.device)
+
+    def reset(self):
+        self.accum.zero_()
+
+    def generate(self, wav):
+        """wav [B, N] fp32 CUDA tensor -> pose [B, 64, 104] fp32."""
+        logmel = audio_repr.log_mel_spectograms(wav)
+        pose, _ = self.model(adapter(logmel))
+        return pose
+
+    def step(self, wav, gt_pose):
+        """One batch, inputs already on the device: accumulates the metric partials, returns the poses."""
+        pose = self.generate(wav)
+        motion_evaluation.evaluate_poses(pose, gt_pose, self.alpha, accum=self.accum)
+        return pose
+
+    def run_host_batches(self, batches):
+        """End-to-end over HOST batches [(wav_pinned [B,N], gt_pinned [B,64,104]), ...]: the H2D copy of batch
+        i+1 (side stream) overlaps the kernels of batch i; returns the number of clips processed."""
+        main = torch.cuda.current_stream(self.device)
+        clips = 0
+        staged = None
+        it = iter(batches)
+
+        def stage(pair):
+            with torch.cuda.stream(self._copy_stream):
+                w = pair[0].to(self.device, non_blocking=True)
+                g = pair[1].to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            return w, g, ev
+
+        nxt = next(it, None)
+        if nxt is not None:
+            staged = stage(nxt)
+        while staged is not None:
+            w, g, ev = staged
+            nxt = next(it, None)
+            staged = stage(nxt) if nxt is not None else None
+            main.wait_event(ev)
+            self.step(w, g)
+            w.record_stream(main)
+            g.record_stream(main)
+            clips += w.shape[0]
+        return clips
+
+    def finish(self):
+        """All-reduce (if sharded) and read the 64-byte result: {'pck', 'l1_pose', 'l1_motion', counts...}."""
+        allreduce_metrics(self.accum, self.comm)
+        m = motion_evaluation.read_metrics(self.accum)
+        m.update(motion_evaluation.finalize_metrics(m))
+        return m

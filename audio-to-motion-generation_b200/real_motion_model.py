@@ -151,7 +151,7 @@ class SelfAttention_G(NativeModule):
         (pose, [bone_loss, angle_loss]) when real_pose [B, T, 104] is given."""
         self._require_eval()
         h = self.native()
-        x = as_input(audio, h.device, "SelfAttention_G expects audio [B, T, F], got %s")
+        x = as_input(audio, h.device, "SelfAttention_G expects audio [B, T, F], got %s", keep_strides=True)
         B, T, F = x.shape
         if T % 4 != 0:
             raise ValueError("SelfAttention_G needs T %% 4 == 0 (UNet1D skip concats), got T = %d" % T)
@@ -163,7 +163,8 @@ class SelfAttention_G(NativeModule):
         pose = torch.empty((B, T, 104), dtype=torch.float32, device=h.device)
         losses = torch.empty(2, dtype=torch.float32, device=h.device)
         with torch.cuda.device(h.device):
-            _cabi.check(_cabi.lib().a2m_model_forward(h.ptr, _cabi.ptr(x), B, T, F, _cabi.ptr(pose), _cabi.ptr(losses),
-                                                      _cabi.ptr(rp), _cabi.stream_ptr(h.device)))
+            _cabi.check(_cabi.lib().a2m_model_forward(h.ptr, _cabi.ptr(x), x.stride(0), x.stride(1), B, T, F,
+                                                      _cabi.ptr(pose), _cabi.ptr(losses), _cabi.ptr(rp),
+                                                      _cabi.stream_ptr(h.device)))
         internal = [losses[1], losses[0]] if rp is not None else [losses[0]]
         return pose, internal

@@ -164,12 +164,15 @@ typedef struct a2m_tensor_desc {
 typedef struct a2m_model a2m_model;
 int a2m_model_create(const a2m_tensor_desc* tensors, int n_tensors, int device, a2m_model** out);
 void a2m_model_destroy(a2m_model* model);
-/* mel [B, T, F] fp32 -> pose [B, T, 104] fp32 (columns 0..19 body, 20..103 hand);
+/* mel [B, T, F] fp32, element strides (mel_stride_b, mel_stride_t, 1) so a strided slice of a longer
+ * log-mel (the D2 adapter logmel[:, 0:384:6, :]) is consumed in place
+ * -> pose [B, T, 104] fp32 contiguous (columns 0..19 body, 20..103 hand);
  * losses (nullable, device float[2]): [0] = 0.7*hand + 0.3*body angle penalty (:359-461),
  * [1] = bone-length MSE against real_pose (:307-347) when real_pose != NULL, else 0.
  * T multiple of 8, T <= 64; F multiple of 16 with F/8 even; 1 <= B <= 65535. */
-int a2m_model_forward(a2m_model* model, const float* mel, int64_t B, int T, int F, float* pose, float* losses,
-                      const float* real_pose /* nullable [B, T, 104] */, void* stream);
+int a2m_model_forward(a2m_model* model, const float* mel, int64_t mel_stride_b, int64_t mel_stride_t, int64_t B, int T,
+                      int F, float* pose, float* losses, const float* real_pose /* nullable [B, T, 104] */,
+                      void* stream);
 /* AudioEncoder.forward (model_layers.py:267-280): mel [B, T, F] -> [B, 256, T] fp32 (reference NCW layout) */
 int a2m_model_encoder_forward(a2m_model* model, const float* mel, int64_t B, int T, int F, float* out_nct, void* stream);
 /* UNet1D.forward (model_layers.py:341-374, D1): [B, 256, T] fp32 -> [B, 256, T] fp32 */
@@ -178,6 +181,11 @@ int a2m_model_unet_forward(a2m_model* model, const float* x_nct, int64_t B, int 
 int a2m_model_status(a2m_model* model);
 /* Algorithmic FLOPs (2*M*N*K over valid rows) of the tensor-core GEMMs one forward of this shape launches. */
 int64_t a2m_model_gemm_flops(a2m_model* model, int64_t B, int T, int F);
+/* Measurement aid: runs the forward `iters` times with CUDA events around every launch (synchronising)
+ * and returns host floats out_ms[3] = per-forward milliseconds in {all launches, tcgen05 GEMM launches,
+ * other launches}; n_gemm (nullable) = GEMM launches per forward. */
+int a2m_model_profile(a2m_model* model, const float* mel, int64_t mel_stride_b, int64_t mel_stride_t, int64_t B, int T,
+                      int F, int iters, float* out_ms_host, int* n_gemm_host, void* stream);
 
 #ifdef __cplusplus
 }
