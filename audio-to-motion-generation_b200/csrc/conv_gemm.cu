@@ -289,6 +289,13 @@ int launch_variant(const ConvGemmPlan& plan, int* err_flag, cudaStream_t stream)
 
 }  // namespace
 
+// 2-D bf16 weight matrix [n_rows, k] (K-major) as a 128B-swizzled TMA map with box (64, box_rows)
+int make_weight_map(CUtensorMap* map, const void* w, long long n_rows, long long k, int box_rows) {
+    long long wd[2] = {k, n_rows}, ws[2] = {1, k};
+    int wb[5] = {kBlockK, box_rows, 1, 1, 1};
+    return make_map(map, w, 2, wd, ws, wb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "weight map");
+}
+
 long long conv_gemm_k(const ConvGemmDesc& d) {
     long long k = 0;
     for (const Tap& t : d.taps) k += t.channels;

@@ -208,160 +208,6 @@ layernorm256_kernel(const __nv_bfloat16* __restrict__ x, long long rows, const f
     *reinterpret_cast<uint4*>(out + row * 256 + lane * 8) = float_to_bf16x8(f);
 }
 
-// ------------------------------------------------------------------------------------- GAT tail
-// CTA: `gpc` whole graphs (gpc * J <= 128 nodes).  Phase 1 stages h rows in shared memory and reduces
-// the per-node, per-head attention scalars; phase 2 (one warp per node) does the neighbour softmax,
-// the weighted aggregation, the head mean, bias, LayerNorm(64), LeakyReLU and the residual.
-constexpr int kGatNodesPerCta = 128;
-__global__ void __launch_bounds__(256)
-gat_aggregate_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ x_res, long long n_nodes,
-                     int J, int gpc, const int* __restrict__ nbr, const int* __restrict__ deg,
-                     const float* __restrict__ att_src, const float* __restrict__ att_dst,
-                     const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                     __nv_bfloat16* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char s_gat_raw[];
-    uint4* s_h = reinterpret_cast<uint4*>(s_gat_raw);                                   // [128][32] x 16 B
-    float* s_src = reinterpret_cast<float*>(s_gat_raw + kGatNodesPerCta * 512);         // [128][4]
-    float* s_dst = s_src + kGatNodesPerCta * 4;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nodes_here_max = gpc * J;
-    const long long node0 = static_cast<long long>(blockIdx.x) * nodes_here_max;
-    const int n_here = static_cast<int>(min(static_cast<long long>(nodes_here_max), n_nodes - node0));
-    // lane owns features [8*lane, 8*lane+8) of the 256-wide row: head = lane / 8
-    float as[8], ad[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { as[i] = att_src[lane * 8 + i]; ad[i] = att_dst[lane * 8 + i]; }
-    for (int n = warp; n < n_here; n += 8) {
-        const uint4 q = *reinterpret_cast<const uint4*>(h + (node0 + n) * 256 + lane * 8);
-        s_h[n * 32 + lane] = q;
-        float f[8];
-        bf16x8_to_float(q, f);
-        float ps = 0.f, pd = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { ps = fmaf(f[i], as[i], ps); pd = fmaf(f[i], ad[i], pd); }
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) { ps += __shfl_xor_sync(0xffffffffu, ps, o); pd += __shfl_xor_sync(0xffffffffu, pd, o); }
-        if ((lane & 7) == 0) { s_src[n * 4 + (lane >> 3)] = ps; s_dst[n * 4 + (lane >> 3)] = pd; }
-    }
-    __syncthreads();
-    const int head = lane >> 3, sub = lane & 7;
-    for (int n = warp; n < n_here; n += 8) {
-        const int jloc = n % J, g0 = n - jloc;          // graph-local index, first node of this graph in the CTA
-        const int dg = deg[jloc];
-        const float di = s_dst[n * 4 + head];
-        float e[kMaxDeg + 1];
-        int idx[kMaxDeg + 1];
-        idx[0] = n;                                     // self loop
-        e[0] = leaky(s_src[n * 4 + head] + di);
-        float m = e[0];
-#pragma unroll
-        for (int k = 0; k < kMaxDeg; ++k) {
-            if (k < dg) {
-                idx[k + 1] = g0 + nbr[jloc * kMaxDeg + k];
-                e[k + 1] = leaky(s_src[idx[k + 1] * 4 + head] + di);
-                m = fmaxf(m, e[k + 1]);
-            }
-        }
-        float denom = 0.f;
-#pragma unroll
-        for (int k = 0; k <= kMaxDeg; ++k)
-            if (k <= dg) { e[k] = __expf(e[k] - m); denom += e[k]; }
-        const float inv = 1.f / denom;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int k = 0; k <= kMaxDeg; ++k) {
-            if (k <= dg) {
-                float f[8];
-                bf16x8_to_float(s_h[idx[k] * 32 + lane], f);
-                const float a = e[k] * inv;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, f[i], acc[i]);
-            }
-        }
-        // mean over the 4 heads (lanes sub, sub+8, sub+16, sub+24 hold the same output features)
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
-            acc[i] = 0.25f * acc[i] + bias[sub * 8 + i];
-            s += acc[i];
-        }
-        // LayerNorm over the 64 features held by 8 lanes x 8 values
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float mean = s * (1.f / 64.f);
-        float v = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { const float dlt = acc[i] - mean; v = fmaf(dlt, dlt, v); }
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const float rstd = rsqrtf(v * (1.f / 64.f) + 1e-5f);
-        if (head == 0) {
-            float r[8];
-            bf16x8_to_float(*reinterpret_cast<const uint4*>(x_res + (node0 + n) * 64 + sub * 8), r);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                r[i] += leaky((acc[i] - mean) * rstd * ln_w[sub * 8 + i] + ln_b[sub * 8 + i]);
-            *reinterpret_cast<uint4*>(out + (node0 + n) * 64 + sub * 8) = float_to_bf16x8(r);
-        }
-    }
-}
-
-// -------------------------------------------------------------------------- GraphConv aggregation
-__global__ void __launch_bounds__(256)
-graph_gather_kernel(const __nv_bfloat16* __restrict__ x, long long n_nodes, int J, const int* __restrict__ nbr,
-                    const int* __restrict__ deg, __nv_bfloat16* __restrict__ agg) {
-    const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long node = gid >> 3;
-    if (node >= n_nodes) return;
-    const int sub = static_cast<int>(gid & 7);
-    const int jloc = static_cast<int>(node % J);
-    const long long g0 = node - jloc;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const int dg = deg[jloc];
-    for (int k = 0; k < dg; ++k) {
-        float f[8];
-        bf16x8_to_float(*reinterpret_cast<const uint4*>(x + (g0 + nbr[jloc * kMaxDeg + k]) * 64 + sub * 8), f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += f[i];
-    }
-    *reinterpret_cast<uint4*>(agg + node * 64 + sub * 8) = float_to_bf16x8(acc);
-}
-
-__global__ void __launch_bounds__(256)
-ln64_act_res_kernel(const float* __restrict__ y, const __nv_bfloat16* __restrict__ x_res, long long rows,
-                    const float* __restrict__ ln_w, const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
-    const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long row = gid >> 3;
-    const bool live = row < rows;
-    const int sub = static_cast<int>(gid & 7);
-    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (live) {
-        const float4 a = *reinterpret_cast<const float4*>(y + row * 64 + sub * 8);
-        const float4 b = *reinterpret_cast<const float4*>(y + row * 64 + sub * 8 + 4);
-        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += f[i];
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * (1.f / 64.f);
-    float v = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { const float dlt = f[i] - mean; v = fmaf(dlt, dlt, v); }
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const float rstd = rsqrtf(v * (1.f / 64.f) + 1e-5f);
-    if (!live) return;
-    float r[8];
-    bf16x8_to_float(*reinterpret_cast<const uint4*>(x_res + row * 64 + sub * 8), r);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] += leaky((f[i] - mean) * rstd * ln_w[sub * 8 + i] + ln_b[sub * 8 + i]);
-    *reinterpret_cast<uint4*>(out + row * 64 + sub * 8) = float_to_bf16x8(r);
-}
-
 // ------------------------------------------------------------------------------------ pose losses
 __global__ void __launch_bounds__(256)
 angle_loss_kernel(const float* __restrict__ pose, long long n_frames, const int* __restrict__ triples, int n_hand,
@@ -512,38 +358,6 @@ int launch_layernorm(const __nv_bfloat16* x, long long rows, int C, const float*
                      __nv_bfloat16* out, cudaStream_t stream) {
     A2M_ARG_CHECK(C == 256, "layernorm: C = %d (this build implements 256)", C);
     layernorm256_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, rows, gamma, beta, out);
-    A2M_AFTER_LAUNCH();
-}
-
-int launch_gat_aggregate(const __nv_bfloat16* h, const __nv_bfloat16* x_res, long long n_graphs, GraphTopo topo,
-                         const float* att_src, const float* att_dst, const float* bias, const float* ln_w,
-                         const float* ln_b, __nv_bfloat16* out, cudaStream_t stream) {
-    A2M_ARG_CHECK(topo.n_nodes >= 1 && topo.n_nodes <= kGatNodesPerCta, "gat: %d nodes per graph", topo.n_nodes);
-    const int gpc = kGatNodesPerCta / topo.n_nodes;
-    const size_t smem = kGatNodesPerCta * 512 + 2 * kGatNodesPerCta * 4 * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        A2M_CUDA_CHECK(cudaFuncSetAttribute(gat_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    const long long ctas = (n_graphs + gpc - 1) / gpc;
-    gat_aggregate_kernel<<<static_cast<unsigned>(ctas), 256, smem, stream>>>(
-        h, x_res, n_graphs * topo.n_nodes, topo.n_nodes, gpc, topo.nbr, topo.deg, att_src, att_dst, bias, ln_w, ln_b, out);
-    A2M_AFTER_LAUNCH();
-}
-
-int launch_graph_gather(const __nv_bfloat16* x, long long n_graphs, GraphTopo topo, __nv_bfloat16* agg,
-                        cudaStream_t stream) {
-    const long long threads = n_graphs * topo.n_nodes * 8;
-    graph_gather_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(x, n_graphs * topo.n_nodes,
-                                                                                          topo.n_nodes, topo.nbr, topo.deg, agg);
-    A2M_AFTER_LAUNCH();
-}
-
-int launch_ln64_act_res(const float* y, const __nv_bfloat16* x_res, long long rows, const float* ln_w,
-                        const float* ln_b, __nv_bfloat16* out, cudaStream_t stream) {
-    const long long threads = rows * 8;
-    ln64_act_res_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(y, x_res, rows, ln_w, ln_b, out);
     A2M_AFTER_LAUNCH();
 }
 

@@ -2,6 +2,7 @@
 // are channels-last bf16 ([B, T, C]); reductions, softmax, LayerNorm and the attention coefficients are
 // evaluated in fp32.
 #pragma once
+#include <memory>
 #include "a2m_common.cuh"
 
 namespace a2m {
@@ -40,20 +41,19 @@ constexpr int kMaxDeg = 6;
 constexpr int kJointFeat = 64;
 constexpr int kGatHeads = 4;
 
-// GATConv(64,64,heads=4,concat=False) tail (real_motion_model.py:172-176 etc.) after the shared linear:
-//   h [n_graphs*J, 256] bf16 (= x W^T), x_res [n_graphs*J, 64] bf16
-//   out = LeakyReLU_0.2(LayerNorm_64(mean_heads(sum_j softmax_j(leaky(a_src.h_j + a_dst.h_i)) h_j) + bias)) + x_res
-int launch_gat_aggregate(const __nv_bfloat16* h, const __nv_bfloat16* x_res, long long n_graphs, GraphTopo topo,
-                         const float* att_src, const float* att_dst, const float* bias, const float* ln_w,
-                         const float* ln_b, __nv_bfloat16* out, cudaStream_t stream);
-
-// GraphConv aggregation: agg_i = sum_{j->i} x_j   ([n_graphs*J, 64] bf16 -> bf16)
-int launch_graph_gather(const __nv_bfloat16* x, long long n_graphs, GraphTopo topo, __nv_bfloat16* agg,
-                        cudaStream_t stream);
-
-// out = LeakyReLU_0.2(LayerNorm_64(y)) + x_res     ([rows, 64]; y fp32 from the GraphConv GEMM)
-int launch_ln64_act_res(const float* y, const __nv_bfloat16* x_res, long long rows, const float* ln_w,
-                        const float* ln_b, __nv_bfloat16* out, cudaStream_t stream);
+// Fused five-layer GNN stack (csrc/gnn_fused.cu): GAT, GraphConv, GAT, GraphConv, GAT, each followed by
+// LayerNorm(64) -> LeakyReLU(0.2) -> + residual, x_in/x_out [n_graphs * J, 64] bf16.
+struct GnnFusedWeights {
+    const __nv_bfloat16* gat_w[3];      // [256, 64] bf16 (lin.weight)
+    const float *att_src[3], *att_dst[3], *gat_bias[3];
+    const __nv_bfloat16* gc_w[2];       // [64, 128] bf16 = [W_rel | W_root]
+    const float* gc_bias[2];
+    const float *ln_w[5], *ln_b[5];
+};
+struct GnnFusedPlan;
+int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_graphs, const __nv_bfloat16* x_in,
+                   __nv_bfloat16* x_out, std::shared_ptr<GnnFusedPlan>* out);
+int gnn_fused_launch(const GnnFusedPlan& plan, int* err_flag, cudaStream_t stream);
 
 // Internal losses of SelfAttention_G.forward (real_motion_model.py:307-461) on pose [B, T, 104] fp32.
 // triples: device int [n][3] (hand first, joints already offset by 10, then body);

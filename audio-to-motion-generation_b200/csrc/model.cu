@@ -618,9 +618,6 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
             auto* qkv = bufs.get<__nv_bfloat16>(BT * 320);
             auto* xa = bufs.get<__nv_bfloat16>(nodes * 64);
             auto* xb = bufs.get<__nv_bfloat16>(nodes * 64);
-            auto* hbuf = bufs.get<__nv_bfloat16>(nodes * 256);
-            auto* agg = bufs.get<__nv_bfloat16>(nodes * 64);
-            auto* ybuf = bufs.get<float>(nodes * 64);
             E.resblock(D.pre_res, r, T, B, t1, t2, qkv, t3);
             E.conv_k3(D.pre_conv, t3, 256, nullptr, 0, T, B, t1);
             if (D.chan_first) {
@@ -632,24 +629,20 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
             }
             E.linear_rows(D.proj_in, t3, nullptr, 256, static_cast<long long>(BT), xa, static_cast<long long>(J) * 64, 0, kOutBf16);
             GraphTopo topo{J, D.nbr, D.deg};
-            __nv_bfloat16 *cur = xa, *nxt = xb;
-            for (int layer = 0; layer < 5; ++layer) {
-                const LnW ln = D.ln64[layer];
-                const long long n_graphs = static_cast<long long>(BT);
-                if (layer % 2 == 0) {
-                    const GatW& G = D.gat[layer / 2];
-                    E.linear_rows(G.lin, cur, nullptr, 64, static_cast<long long>(nodes), hbuf, 256, 0, kOutBf16);
-                    const __nv_bfloat16* c = cur; __nv_bfloat16* n = nxt;
-                    E.op([=](cudaStream_t s) { return launch_gat_aggregate(hbuf, c, n_graphs, topo, G.att_src, G.att_dst, G.bias, ln.w, ln.b, n, s); });
-                } else {
-                    const LayerW& L = D.gconv[layer / 2];
-                    const __nv_bfloat16* c = cur; __nv_bfloat16* n = nxt;
-                    E.op([=](cudaStream_t s) { return launch_graph_gather(c, n_graphs, topo, agg, s); });
-                    E.linear_rows(L, agg, cur, 64, static_cast<long long>(nodes), ybuf, 64, 0, kOutF32);
-                    E.op([=](cudaStream_t s) { return launch_ln64_act_res(ybuf, c, static_cast<long long>(nodes), ln.w, ln.b, n, s); });
+            if (!E.dry && E.rc == A2M_OK) {
+                GnnFusedWeights gw;
+                for (int i = 0; i < 3; ++i) {
+                    gw.gat_w[i] = D.gat[i].lin.w; gw.att_src[i] = D.gat[i].att_src; gw.att_dst[i] = D.gat[i].att_dst;
+                    gw.gat_bias[i] = D.gat[i].bias;
                 }
-                std::swap(cur, nxt);
+                for (int i = 0; i < 2; ++i) { gw.gc_w[i] = D.gconv[i].w; gw.gc_bias[i] = D.gconv[i].bias; }
+                for (int i = 0; i < 5; ++i) { gw.ln_w[i] = D.ln64[i].w; gw.ln_b[i] = D.ln64[i].b; }
+                std::shared_ptr<GnnFusedPlan> gp;
+                E.rc = gnn_fused_plan(gw, topo, static_cast<long long>(BT), xa, xb, &gp);
+                int* flag = m->err_flag;
+                if (E.rc == A2M_OK) E.op([gp, flag](cudaStream_t s) { return gnn_fused_launch(*gp, flag, s); });
             }
+            __nv_bfloat16* cur = xb;
             E.linear_rows(D.proj_out, cur, nullptr, J * 64, static_cast<long long>(BT), t1, 256, 0, kOutBf16);
             {
                 const LnW nw = D.norm;
