@@ -81,60 +81,113 @@ __global__ void time_interp_kernel(const float* __restrict__ in, int Hc, int T, 
 }
 
 // -------------------------------------------------------------------------------------- attention
-constexpr int kAttnMaxT = 64;
-__global__ void __launch_bounds__(256)
+// One CTA per clip.  q, k staged as fp32 in shared memory; S = q k^T register-tiled 4x4 per thread;
+// softmax by one warp per row, written TRANSPOSED (P^T[j][t]) so that the P.V loop reads, for a fixed
+// source step j, the weights of all T output steps as broadcast 16-byte loads; each thread owns one
+// channel and keeps its T accumulators in registers (T FMAs per 1 global + T/4 shared loads).
+template <int T>
+__global__ void __launch_bounds__(256, 2)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ x,
-                 const __nv_bfloat16* __restrict__ res2, const float* __restrict__ gamma_p, int T, int C,
+                 const __nv_bfloat16* __restrict__ res2, const float* __restrict__ gamma_p, int C,
                  __nv_bfloat16* __restrict__ out) {
-    extern __shared__ float s_attn[];
-    const int d = C / 8, ld = 2 * d + C, kstride = d + 1;
-    float* s_q = s_attn;                       // [T][d]
-    float* s_k = s_q + T * d;                  // [T][d+1]
-    float* s_p = s_k + T * kstride;            // [T][T]
+    extern __shared__ __align__(16) float s_attn[];
+    const int d = C / 8, ld = 2 * d + C, qs = d + 4;              // row stride d+4: 16 B aligned, conflict-free
+    float* s_q = s_attn;                       // [T][d+4]
+    float* s_k = s_q + T * qs;                 // [T][d+4]
+    float* s_p = s_k + T * qs;                 // S [T][T+1], then P^T [T][T]
     const long long b = blockIdx.x;
     const __nv_bfloat16* base = qkv + b * T * ld;
-    for (int i = threadIdx.x; i < T * d; i += blockDim.x) {
-        const int t = i / d, c = i - t * d;
-        s_q[i] = __bfloat162float(base[static_cast<long long>(t) * ld + c]);
-        s_k[t * kstride + c] = __bfloat162float(base[static_cast<long long>(t) * ld + d + c]);
+    for (int i = threadIdx.x; i < T * (d / 8); i += blockDim.x) {          // 8 bf16 per 16-byte load
+        const int t = i / (d / 8), c8 = i - t * (d / 8);
+        float f[8];
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * ld + c8 * 8), f);
+        *reinterpret_cast<float4*>(s_q + t * qs + c8 * 8) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(s_q + t * qs + c8 * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * ld + d + c8 * 8), f);
+        *reinterpret_cast<float4*>(s_k + t * qs + c8 * 8) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(s_k + t * qs + c8 * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
     }
     __syncthreads();
-    for (int ij = threadIdx.x; ij < T * T; ij += blockDim.x) {
-        const int i = ij / T, j = ij - i * T;
-        const float* q = s_q + i * d;
-        const float* k = s_k + j * kstride;
-        float acc = 0.f;
-        for (int c = 0; c < d; ++c) acc = fmaf(q[c], k[c], acc);
-        s_p[ij] = acc;                          // no 1/sqrt(d): model_layers.py:140
+    constexpr int kTiles = (T / 4) * (T / 4);                     // 4x4 output tiles of S
+    for (int tile = threadIdx.x; tile < kTiles; tile += blockDim.x) {
+        const int i0 = (tile / (T / 4)) * 4, j0 = (tile % (T / 4)) * 4;
+        float acc[4][4] = {};
+        for (int c = 0; c < d; c += 4) {
+            float4 qv[4], kv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                qv[a] = *reinterpret_cast<const float4*>(s_q + (i0 + a) * qs + c);
+                kv[a] = *reinterpret_cast<const float4*>(s_k + (j0 + a) * qs + c);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    acc[a][e] += qv[a].x * kv[e].x + qv[a].y * kv[e].y + qv[a].z * kv[e].z + qv[a].w * kv[e].w;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s_p[(i0 + a) * (T + 1) + j0 + e] = acc[a][e];     // no 1/sqrt(d): model_layers.py:140
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-    for (int i = warp; i < T; i += n_warps) {
-        float* row = s_p + i * T;
+    // softmax over j for each row i; results kept in registers, then written transposed after a barrier
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kPerLane = (T + 31) / 32, kRowsPerWarp = (T + 7) / 8;
+    float pr[kRowsPerWarp][kPerLane];
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int i = warp + rr * 8;
         float m = -INFINITY;
-        for (int j = lane; j < T; j += 32) m = fmaxf(m, row[j]);
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) {
+            const int j = lane + 32 * u;
+            pr[rr][u] = (i < T && j < T) ? s_p[i * (T + 1) + j] : -INFINITY;
+            m = fmaxf(m, pr[rr][u]);
+        }
         m = warp_max(m);
         float s = 0.f;
-        for (int j = lane; j < T; j += 32) { const float e = __expf(row[j] - m); row[j] = e; s += e; }
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) { pr[rr][u] = __expf(pr[rr][u] - m); s += pr[rr][u]; }
         s = warp_sum(s);
         const float inv = 1.f / s;
-        for (int j = lane; j < T; j += 32) row[j] *= inv;
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) pr[rr][u] *= inv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int i = warp + rr * 8;
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) {
+            const int j = lane + 32 * u;
+            if (i < T && j < T) s_p[j * T + i] = pr[rr][u];      // P^T[j][i]
+        }
     }
     __syncthreads();
     const float gamma = *gamma_p;
     const __nv_bfloat16* vbase = base + 2 * d;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float v[kAttnMaxT];
+        float acc[T];
 #pragma unroll
-        for (int j = 0; j < kAttnMaxT; ++j) v[j] = j < T ? __bfloat162float(vbase[static_cast<long long>(j) * ld + c]) : 0.f;
+        for (int t = 0; t < T; ++t) acc[t] = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < T; ++j) {
+            const float v = __bfloat162float(vbase[static_cast<long long>(j) * ld + c]);
+            const float4* pt = reinterpret_cast<const float4*>(s_p + j * T);
+#pragma unroll
+            for (int t4 = 0; t4 < T / 4; ++t4) {
+                const float4 p4 = pt[t4];
+                acc[4 * t4] = fmaf(p4.x, v, acc[4 * t4]);
+                acc[4 * t4 + 1] = fmaf(p4.y, v, acc[4 * t4 + 1]);
+                acc[4 * t4 + 2] = fmaf(p4.z, v, acc[4 * t4 + 2]);
+                acc[4 * t4 + 3] = fmaf(p4.w, v, acc[4 * t4 + 3]);
+            }
+        }
+#pragma unroll
         for (int t = 0; t < T; ++t) {
-            const float* p = s_p + t * T;
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < kAttnMaxT; ++j)
-                if (j < T) acc = fmaf(p[j], v[j], acc);
             const long long o = (b * T + t) * C + c;
-            float r = gamma * acc + __bfloat162float(x[o]);
+            float r = gamma * acc[t] + __bfloat162float(x[o]);
             if (res2) r += __bfloat162float(res2[o]);
             out[o] = __float2bfloat16_rn(r);
         }
@@ -331,20 +384,37 @@ int launch_time_interp(const float* in, int B, int Hc, int T, int C, __nv_bfloat
     A2M_AFTER_LAUNCH();
 }
 
-int launch_attention(const __nv_bfloat16* qkv, const __nv_bfloat16* x, const __nv_bfloat16* res2, const float* gamma,
-                     int B, int T, int C, __nv_bfloat16* out, cudaStream_t stream) {
-    A2M_ARG_CHECK(T >= 1 && T <= kAttnMaxT, "attention: T = %d, this build supports T <= %d", T, kAttnMaxT);
-    A2M_ARG_CHECK(C % 8 == 0, "attention: C = %d", C);
+template <int T>
+static int launch_attention_t(const __nv_bfloat16* qkv, const __nv_bfloat16* x, const __nv_bfloat16* res2,
+                              const float* gamma, int B, int C, __nv_bfloat16* out, cudaStream_t stream) {
     const int d = C / 8;
-    const size_t smem = (static_cast<size_t>(T) * d + static_cast<size_t>(T) * (d + 1) + static_cast<size_t>(T) * T) * 4;
+    const size_t smem = (2 * static_cast<size_t>(T) * (d + 4) + static_cast<size_t>(T) * (T + 1)) * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        A2M_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         configured = true;
     }
-    A2M_ARG_CHECK(smem <= 160 * 1024, "attention: T %d x C %d needs %zu B of shared memory", T, C, smem);
-    attention_kernel<<<B, 256, smem, stream>>>(qkv, x, res2, gamma, T, C, out);
+    A2M_ARG_CHECK(smem <= 100 * 1024, "attention: T %d x C %d needs %zu B of shared memory", T, C, smem);
+    attention_kernel<T><<<B, 256, smem, stream>>>(qkv, x, res2, gamma, C, out);
     A2M_AFTER_LAUNCH();
+}
+
+int launch_attention(const __nv_bfloat16* qkv, const __nv_bfloat16* x, const __nv_bfloat16* res2, const float* gamma,
+                     int B, int T, int C, __nv_bfloat16* out, cudaStream_t stream) {
+    A2M_ARG_CHECK(C % 64 == 0, "attention: C = %d must be a multiple of 64", C);
+    switch (T) {
+        case 8: return launch_attention_t<8>(qkv, x, res2, gamma, B, C, out, stream);
+        case 16: return launch_attention_t<16>(qkv, x, res2, gamma, B, C, out, stream);
+        case 24: return launch_attention_t<24>(qkv, x, res2, gamma, B, C, out, stream);
+        case 32: return launch_attention_t<32>(qkv, x, res2, gamma, B, C, out, stream);
+        case 40: return launch_attention_t<40>(qkv, x, res2, gamma, B, C, out, stream);
+        case 48: return launch_attention_t<48>(qkv, x, res2, gamma, B, C, out, stream);
+        case 56: return launch_attention_t<56>(qkv, x, res2, gamma, B, C, out, stream);
+        case 64: return launch_attention_t<64>(qkv, x, res2, gamma, B, C, out, stream);
+        default:
+            a2m_set_error("attention: T = %d; this build implements T in {8, 16, ..., 64}", T);
+            return A2M_ERR_UNSUPPORTED;
+    }
 }
 
 int launch_channel_attention(const __nv_bfloat16* x, int B, int T, int C, int hidden, const float* w0, const float* b0,

@@ -16,8 +16,10 @@ def label(full):
     m = re.search(r"conv_gemm_kernel<(?:\(int\))?(\d+)", full)
     if m:
         return "conv_gemm_kernel<%s>" % m.group(1)
+    m = re.search(r"([A-Za-z_0-9]+_kernel)", full)
+    if m:
+        return m.group(1)
     name = re.sub(r"\(.*", "", full)
-    name = re.sub(r"<.*", "", name)
     return name.split("::")[-1][:48]
 
 
