@@ -69,6 +69,9 @@ SIGNATURES = {
     "a2m_model_gemm_flops": (c_i64, [c_void_p, c_i64, c_int, c_int]),
     "a2m_model_profile": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p]),
+    "a2m_model_profile_ops": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_void_p, c_int,
+                                      c_void_p, c_void_p]),
+    "a2m_model_op_name": (ctypes.c_char_p, [c_void_p, c_i64, c_int, c_int, c_int, c_void_p]),
     "a2m_gemm_taps": (c_int, [ctypes.POINTER(GemmDesc), c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p,
                               c_void_p]),
 }

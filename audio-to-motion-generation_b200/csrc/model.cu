@@ -62,6 +62,8 @@ struct ForwardPlan {
     void* arena = nullptr;
     std::vector<std::function<int(cudaStream_t)>> ops;
     std::vector<int> op_is_gemm;                // parallel to ops
+    std::vector<std::string> op_name;           // parallel to ops (measurement aid)
+    std::vector<long long> op_flops;            // parallel to ops: 2*M*N*K for GEMMs, 0 otherwise
     int enc_end = 0, unet_end = 0;              // op index ranges: [0,enc_end) encoder, [enc_end,unet_end) unet
     float* mel_in = nullptr;                    // staging (fp32) used by the stage entry points
     __nv_bfloat16 *enc_out = nullptr, *unet_out = nullptr;
@@ -420,6 +422,7 @@ struct Emit {
     ForwardPlan* P;
     bool dry;
     int rc = A2M_OK;
+    std::string tag;                            // label of the ops emitted next (per-op profile)
 
     void gemm(const LayerW& L, std::vector<Tap> taps, const AView* views, int n_src, const int box[4], const int ext[4],
               void* out, const long long ostride[4], long long obase, int out_type) {
@@ -437,6 +440,8 @@ struct Emit {
         int* flag = m->err_flag;
         P->ops.push_back([plan, flag](cudaStream_t s) { return conv_gemm_launch(*plan, flag, s); });
         P->op_is_gemm.push_back(1);
+        P->op_name.push_back(tag + ".gemm");
+        P->op_flops.push_back(plan->flops);
     }
     // rows = (L, B) of a [B, L, C] tensor; taps shift along L
     void conv_rows(const LayerW& L, const __nv_bfloat16* a0, int c0, const __nv_bfloat16* a1, int c1, int len, int B,
@@ -480,7 +485,10 @@ struct Emit {
         gemm(L, L.taps, v, a1 ? 2 : 1, box, ext, out, os, col, out_type);
     }
     void op(std::function<int(cudaStream_t)> f) {
-        if (!dry && rc == A2M_OK) { P->ops.push_back(std::move(f)); P->op_is_gemm.push_back(0); }
+        if (!dry && rc == A2M_OK) {
+            P->ops.push_back(std::move(f)); P->op_is_gemm.push_back(0);
+            P->op_name.push_back(tag); P->op_flops.push_back(0);
+        }
     }
 
     void attention(const AttnW& A, const __nv_bfloat16* x, const __nv_bfloat16* res2, int len, int B, __nv_bfloat16* qkv,
@@ -515,6 +523,8 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
         if (pass == 1) {
             P->ops.clear();
             P->op_is_gemm.clear();
+            P->op_name.clear();
+            P->op_flops.clear();
             P->gemm_flops = 0;
             cudaError_t e = cudaMalloc(&P->arena, bufs.off + 256);
             if (e != cudaSuccess) { a2m_set_error("model: arena cudaMalloc(%zu) failed: %s", bufs.off, cudaGetErrorString(e)); return (int)e; }
@@ -549,6 +559,7 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
         // ---------------- AudioEncoder (model_layers.py:267-280) ----------------
         if (m->has_encoder) {
             a2m_model* mm = m;
+            E.tag = "enc.conv0";
             E.op([=](cudaStream_t s) { return launch_conv0(mm->cur_mel, mm->cur_stride_b, mm->cur_stride_t, B, T, F, mm->conv0_w, mm->conv0_b, a0, s); });
             auto conv2d_s2 = [&](const LayerW& L, const __nv_bfloat16* in, int H, int W, int C, __nv_bfloat16* out) {
                 const int Ho = H / 2, Wo = W / 2;
@@ -563,8 +574,11 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
                 const long long os[4] = {0, L.N, static_cast<long long>(Wo) * L.N, static_cast<long long>(Ho) * Wo * L.N};
                 E.gemm(L, L.taps, v, 2, box, ext, out, os, 0, kOutBf16);
             };
+            E.tag = "enc.conv1";
             conv2d_s2(m->enc[1], a0, H1, W1, 64, a1);
+            E.tag = "enc.conv2";
             conv2d_s2(m->enc[2], a1, H2, W2, 128, a2);
+            E.tag = "enc.conv3";
             {   // conv 3
                 AView v; v.ptr = a2; v.rank = 4;
                 const long long dims[4] = {256, W3, H3, B}, str[4] = {1, 256, 256LL * W3, 256LL * W3 * H3};
@@ -574,6 +588,7 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
                 const long long os[4] = {512, 512LL * W3, 512LL * W3 * H3, 0};
                 E.gemm(m->enc[3], m->enc[3].taps, &v, 1, box, ext, a3, os, 0, kOutBf16);
             }
+            E.tag = "enc.conv4";
             {   // conv 4, centre column only -> fp32 [B, H3, 256]
                 AView v; v.ptr = a3; v.rank = 4;
                 const long long dims[4] = {512, W3, H3, B}, str[4] = {1, 512, 512LL * W3, 512LL * W3 * H3};
@@ -585,23 +600,36 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
                 const long long os[4] = {0, 256, 256LL * H3, 0};
                 E.gemm(m->enc[4], taps, &v, 1, box, ext, a4, os, 0, kOutF32);
             }
+            E.tag = "enc.interp";
             E.op([=](cudaStream_t s) { return launch_time_interp(a4, B, H3, T, 256, e0, s); });
         }
         if (pass == 1) P->enc_end = static_cast<int>(P->ops.size());
 
         // ---------------- UNet1D (model_layers.py:341-374, D1) ----------------
         if (m->has_unet) {
+        E.tag = "unet.ds0";
         E.conv_k3(m->ds[0], e0, 256, nullptr, 0, T, B, s0);
+        E.tag = "unet.ds1";
         E.conv_k4s2(m->ds[1], s0, 512, T, B, u1);
+        E.tag = "unet.ds2";
         E.conv_k3(m->ds[2], u1, 512, nullptr, 0, T / 2, B, s1);
+        E.tag = "unet.ds3";
         E.conv_k4s2(m->ds[3], s1, 1024, T / 2, B, u3);
+        E.tag = "unet.bottleneck";
         E.conv_k3(m->bott, u3, 1024, nullptr, 0, T / 4, B, u4);
+        E.tag = "unet.bott_attn";
         E.attention(m->bott_attn, u4, nullptr, T / 4, B, qkvb, u5);
+        E.tag = "unet.up0";
         E.conv_transpose(m->up0_even, m->up0_odd, u5, 2048, T / 4, B, u6);
+        E.tag = "unet.up_attn";
         E.attention(m->up_attn, u6, nullptr, T / 2, B, qkvu, u7);            // D1: before the concat
+        E.tag = "unet.up1";
         E.conv_k3(m->up1, u7, 1024, s1, 1024, T / 2, B, u8);
+        E.tag = "unet.up2";
         E.conv_transpose(m->up2_even, m->up2_odd, u8, 1024, T / 2, B, u9);
+        E.tag = "unet.up3";
         E.conv_k3(m->up3, u9, 512, s0, 512, T, B, u10);
+        E.tag = "unet.final";
         E.linear_rows(m->final_conv, u10, nullptr, 512, static_cast<long long>(BT), r, 256, 0, kOutBf16);
         }
         if (pass == 1) P->unet_end = static_cast<int>(P->ops.size());
@@ -618,8 +646,12 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
             auto* qkv = bufs.get<__nv_bfloat16>(BT * 320);
             auto* xa = bufs.get<__nv_bfloat16>(nodes * 64);
             auto* xb = bufs.get<__nv_bfloat16>(nodes * 64);
+            const std::string dn = part == 0 ? "body" : "hand";
+            E.tag = dn + ".pre_res";
             E.resblock(D.pre_res, r, T, B, t1, t2, qkv, t3);
+            E.tag = dn + ".pre_conv";
             E.conv_k3(D.pre_conv, t3, 256, nullptr, 0, T, B, t1);
+            E.tag = dn + ".pre_attn_chan";
             if (D.chan_first) {
                 E.channel(D.pre_chan, t1, T, B, t2);
                 E.attention(D.pre_attn, t2, nullptr, T, B, qkv, t3);
@@ -627,7 +659,9 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
                 E.attention(D.pre_attn, t1, nullptr, T, B, qkv, t2);
                 E.channel(D.pre_chan, t2, T, B, t3);
             }
+            E.tag = dn + ".proj_in";
             E.linear_rows(D.proj_in, t3, nullptr, 256, static_cast<long long>(BT), xa, static_cast<long long>(J) * 64, 0, kOutBf16);
+            E.tag = dn + ".gnn";
             GraphTopo topo{J, D.nbr, D.deg};
             if (!E.dry && E.rc == A2M_OK) {
                 GnnFusedWeights gw;
@@ -643,16 +677,22 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
                 if (E.rc == A2M_OK) E.op([gp, flag](cudaStream_t s) { return gnn_fused_launch(*gp, flag, s); });
             }
             __nv_bfloat16* cur = xb;
+            E.tag = dn + ".proj_out";
             E.linear_rows(D.proj_out, cur, nullptr, J * 64, static_cast<long long>(BT), t1, 256, 0, kOutBf16);
             {
+                E.tag = dn + ".norm";
                 const LnW nw = D.norm;
                 E.op([=](cudaStream_t s) { return launch_layernorm(t1, static_cast<long long>(BT), 256, nw.w, nw.b, t2, s); });
             }
+            E.tag = dn + ".post_res";
             E.resblock(D.post_res, t2, T, B, t1, t3, qkv, t4);
+            E.tag = dn + ".post_conv";
             E.conv_k3(D.post_conv, t4, 256, nullptr, 0, T, B, t1);
+            E.tag = dn + ".post_attn";
             E.attention(D.post_attn, t1, nullptr, T, B, qkv, t2);
             const __nv_bfloat16* last = t2;
             if (D.has_post_chan) { E.channel(D.post_chan, t2, T, B, t3); last = t3; }
+            E.tag = dn + ".logits";
             // logits: fp32 straight into pose[B, T, 104] at this branch's column block
             E.linear_rows(D.logits, last, nullptr, 256, static_cast<long long>(BT), pose_stage, kPoseFeats,
                           part == 0 ? 0 : kBodyFeats, kOutF32);
@@ -821,24 +861,21 @@ extern "C" int64_t a2m_model_gemm_flops(a2m_model* m, int64_t B, int T, int F) {
 }
 
 // Per-op CUDA-event timing of the forward program (bench.py's roofline leg): every launch is
-// bracketed by events on `stream`; returns per-iteration averages in out_ms = {all ops, tensor-core
-// GEMM ops, other ops} and the number of GEMM launches per forward.
-extern "C" int a2m_model_profile(a2m_model* m, const float* mel, int64_t mel_stride_b, int64_t mel_stride_t, int64_t B, int T,
-                                 int F, int iters, float* out_ms_host, int* n_gemm_host, void* stream) {
-    A2M_ARG_CHECK(m != nullptr && mel != nullptr && out_ms_host != nullptr && iters >= 1, "a2m_model_profile: bad argument");
+// bracketed by events on `stream`; per_op (nullable, n entries) receives each launch's average ms.
+namespace {
+int profile_impl(a2m_model* m, const float* mel, int64_t mel_stride_b, int64_t mel_stride_t, int64_t B, int T, int F,
+                 int iters, ForwardPlan** plan_out, std::vector<double>* per_op, cudaStream_t s) {
+    A2M_ARG_CHECK(m != nullptr && mel != nullptr && iters >= 1, "a2m_model_profile: bad argument");
     A2M_ARG_CHECK(m->has_encoder && m->has_unet && m->has_decoders, "a2m_model_profile: partial handle");
     int rc = check_shape(B, T, F, "a2m_model_profile");
     if (rc != A2M_OK) return rc;
     ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc);
     if (!P) return rc;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     m->cur_mel = mel; m->cur_stride_b = mel_stride_b; m->cur_stride_t = mel_stride_t;
     const int n = static_cast<int>(P->ops.size());
     std::vector<cudaEvent_t> ev(2 * n);
     for (auto& e : ev) A2M_CUDA_CHECK(cudaEventCreate(&e));
-    double gemm = 0.0, other = 0.0;
-    int n_gemm = 0;
-    for (int i = 0; i < n; ++i) n_gemm += P->op_is_gemm[i];
+    per_op->assign(n, 0.0);
     for (int it = 0; it < iters && rc == A2M_OK; ++it) {
         for (int i = 0; i < n && rc == A2M_OK; ++i) {
             cudaEventRecord(ev[2 * i], s);
@@ -850,14 +887,52 @@ extern "C" int a2m_model_profile(a2m_model* m, const float* mel, int64_t mel_str
         for (int i = 0; i < n; ++i) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
-            (P->op_is_gemm[i] ? gemm : other) += ms;
+            (*per_op)[i] += ms / iters;
         }
     }
     for (auto& e : ev) cudaEventDestroy(e);
+    *plan_out = P;
+    return rc;
+}
+}  // namespace
+
+extern "C" int a2m_model_profile(a2m_model* m, const float* mel, int64_t mel_stride_b, int64_t mel_stride_t, int64_t B, int T,
+                                 int F, int iters, float* out_ms_host, int* n_gemm_host, void* stream) {
+    A2M_ARG_CHECK(out_ms_host != nullptr, "a2m_model_profile: NULL output");
+    ForwardPlan* P = nullptr;
+    std::vector<double> per_op;
+    const int rc = profile_impl(m, mel, mel_stride_b, mel_stride_t, B, T, F, iters, &P, &per_op, static_cast<cudaStream_t>(stream));
     if (rc != A2M_OK) return rc;
-    out_ms_host[0] = static_cast<float>((gemm + other) / iters);
-    out_ms_host[1] = static_cast<float>(gemm / iters);
-    out_ms_host[2] = static_cast<float>(other / iters);
+    double gemm = 0.0, other = 0.0;
+    int n_gemm = 0;
+    for (size_t i = 0; i < per_op.size(); ++i) {
+        (P->op_is_gemm[i] ? gemm : other) += per_op[i];
+        n_gemm += P->op_is_gemm[i];
+    }
+    out_ms_host[0] = static_cast<float>(gemm + other);
+    out_ms_host[1] = static_cast<float>(gemm);
+    out_ms_host[2] = static_cast<float>(other);
     if (n_gemm_host) *n_gemm_host = n_gemm;
     return A2M_OK;
+}
+
+extern "C" int a2m_model_profile_ops(a2m_model* m, const float* mel, int64_t mel_stride_b, int64_t mel_stride_t, int64_t B,
+                                     int T, int F, int iters, float* out_ms_host, int capacity, int* n_ops_host, void* stream) {
+    A2M_ARG_CHECK(out_ms_host != nullptr && n_ops_host != nullptr && capacity >= 1, "a2m_model_profile_ops: bad argument");
+    ForwardPlan* P = nullptr;
+    std::vector<double> per_op;
+    const int rc = profile_impl(m, mel, mel_stride_b, mel_stride_t, B, T, F, iters, &P, &per_op, static_cast<cudaStream_t>(stream));
+    if (rc != A2M_OK) return rc;
+    *n_ops_host = static_cast<int>(per_op.size());
+    for (int i = 0; i < capacity && i < *n_ops_host; ++i) out_ms_host[i] = static_cast<float>(per_op[i]);
+    return A2M_OK;
+}
+
+extern "C" const char* a2m_model_op_name(a2m_model* m, int64_t B, int T, int F, int index, int64_t* flops_host) {
+    if (!m || check_shape(B, T, F, "a2m_model_op_name") != A2M_OK) return nullptr;
+    int rc = A2M_OK;
+    ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc);
+    if (!P || index < 0 || index >= static_cast<int>(P->op_name.size())) return nullptr;
+    if (flops_host) *flops_host = P->op_flops[index];
+    return P->op_name[index].c_str();
 }

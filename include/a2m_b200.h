@@ -186,6 +186,12 @@ int64_t a2m_model_gemm_flops(a2m_model* model, int64_t B, int T, int F);
  * other launches}; n_gemm (nullable) = GEMM launches per forward. */
 int a2m_model_profile(a2m_model* model, const float* mel, int64_t mel_stride_b, int64_t mel_stride_t, int64_t B, int T,
                       int F, int iters, float* out_ms_host, int* n_gemm_host, void* stream);
+/* Same, per launch: out_ms_host[min(capacity, n_ops)] = average ms of each launch of one forward, in launch
+ * order; a2m_model_op_name(i) labels launch i (e.g. "unet.up1.gemm") and reports its algorithmic FLOPs
+ * (0 for the non-GEMM kernels).  The returned string lives as long as the handle's plan for that shape. */
+int a2m_model_profile_ops(a2m_model* model, const float* mel, int64_t mel_stride_b, int64_t mel_stride_t, int64_t B,
+                          int T, int F, int iters, float* out_ms_host, int capacity, int* n_ops_host, void* stream);
+const char* a2m_model_op_name(a2m_model* model, int64_t B, int T, int F, int index, int64_t* flops_host /* nullable */);
 
 #ifdef __cplusplus
 }
