@@ -65,6 +65,7 @@ SIGNATURES = {
                                   c_void_p]),
     "a2m_model_encoder_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p]),
     "a2m_model_unet_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
+    "a2m_model_gnn_forward": (c_int, [c_void_p, c_int, c_void_p, c_i64, c_void_p, c_void_p]),
     "a2m_model_status": (c_int, [c_void_p]),
     "a2m_model_gemm_flops": (c_i64, [c_void_p, c_i64, c_int, c_int]),
     "a2m_model_profile": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -61,6 +61,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
         }
     }
     const int n0 = blockIdx.y * BLOCK_N;
+    const int kb_lo = static_cast<int>(static_cast<long long>(blockIdx.z) * p.k_blocks / p.split_k);
+    const int kb_hi = static_cast<int>(static_cast<long long>(blockIdx.z + 1) * p.k_blocks / p.split_k);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.a_map[0]);
@@ -88,8 +90,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
                 const int c1 = base[0] + p.tap_off[t][0], c2 = base[1] + p.tap_off[t][1];
                 const int c3 = base[2] + p.tap_off[t][2], c4 = base[3] + p.tap_off[t][3];
                 for (int ch = 0; ch < p.tap_chunks[t]; ++ch, ++kb) {
-                    const int s = kb % kStages;
-                    if (!mbar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1, err_flag, 1)) { ok = false; break; }
+                    if (kb < kb_lo || kb >= kb_hi) continue;
+                    const int lk = kb - kb_lo;
+                    const int s = lk % kStages;
+                    if (!mbar_wait(&empty_bar[s], ((lk / kStages) & 1) ^ 1, err_flag, 1)) { ok = false; break; }
                     mbar_expect_tx(&full_bar[s], S::kStageBytes);
                     unsigned char* stage = smem + s * S::kStageBytes;
                     tma_load_5d(stage, amap, &full_bar[s], ch * kBlockK, c1, c2, c3, c4);
@@ -100,7 +104,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
-            for (int kb = 0; kb < p.k_blocks; ++kb) {
+            for (int kb = 0; kb < kb_hi - kb_lo; ++kb) {
                 const int s = kb % kStages;
                 if (!mbar_wait(&full_bar[s], (kb / kStages) & 1, err_flag, 2)) break;
                 tc_fence_after();
@@ -132,8 +136,55 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
                 off += static_cast<long long>(c) * p.out_stride[i];
             }
         }
+        off += static_cast<long long>(blockIdx.z) * p.split_stride;     // split-K: one fp32 partial plane per split
         mbar_wait(accum_bar, 0, err_flag, 3);
         tc_fence_after();
+        if (BLOCK_N >= 64 && p.c_tma) {
+            // bf16 output through shared memory + TMA store: the (now idle) operand ring is reused as
+            // [128 rows][64 cols] 128B-swizzled sub-tiles, so global writes are whole 128-byte rows.
+            tma_prefetch_desc(&p.c_map);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+                const int n = n0 + c0;
+                if (n >= p.N) break;                  // uniform over the epilogue warps
+                unsigned char* st = smem + (c0 >> 6) * 16384;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0 + hf * 32, v);
+                    tmem_ld_wait();
+                    const int nn = n + hf * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float x = __uint_as_float(v[j + e]);
+                            if (bias != nullptr && nn + j + e < p.N) x += __ldg(bias + nn + j + e);
+                            if (p.act == kActLeaky) x = x > 0.f ? x : kLeakySlope * x;
+                            else if (p.act == kActRelu) x = fmaxf(x, 0.f);
+                            f[e] = x;
+                        }
+                        uint4 q;
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]);
+                        __nv_bfloat162 h1 = __floats2bfloat162_rn(f[2], f[3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]);
+                        __nv_bfloat162 h3 = __floats2bfloat162_rn(f[6], f[7]);
+                        q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+                        q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+                        const int chunk = hf * 4 + (j >> 3);
+                        *reinterpret_cast<uint4*>(st + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
+                    }
+                }
+                fence_proxy_async_smem();
+                named_barrier(1, 128);
+                if (warp == 2 && lane == 0) {
+                    tma_store_5d(&p.c_map, st, n, base[0], base[1], base[2], base[3]);
+                    tma_store_commit();
+                }
+            }
+            if (warp == 2 && lane == 0) tma_store_wait_read();
+        } else {
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
             const int n = n0 + c0;
@@ -145,12 +196,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 float x = __uint_as_float(v[j]);
-                if (bias != nullptr && n + j < p.N) x += __ldg(bias + n + j);
+                if (bias != nullptr && n + j < p.N && blockIdx.z == 0) x += __ldg(bias + n + j);
                 if (p.act == kActLeaky) x = x > 0.f ? x : kLeakySlope * x;
                 else if (p.act == kActRelu) x = fmaxf(x, 0.f);
                 f[j] = x;
             }
             if (!valid) continue;
+
             if (p.out_type == kOutBf16) {
                 __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + off + n;
 #pragma unroll
@@ -179,6 +231,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
                     }
                 }
             }
+        }
         }
     }
     tc_fence_before();
@@ -362,6 +415,25 @@ int conv_gemm_plan(const ConvGemmDesc& d, const void* w_packed, const float* bia
         const int rc = make_map(&p.b_map, w_packed, 2, wd, ws, wb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "weight map");
         if (rc != A2M_OK) return rc;
     }
+    p.c_tma = 0;
+    if (d.out_type == kOutBf16 && block_n >= 64) {
+        // output as a strided 5-D view: dim 0 = channels, dims 1..4 = the M coordinates
+        long long cd[5], cs[5];
+        cd[0] = d.N; cs[0] = 1;
+        bool ok = (d.out_base % 8) == 0;
+        for (int i = 0; i < 4; ++i) {
+            cd[i + 1] = d.m_extent[i];
+            cs[i + 1] = d.m_extent[i] > 1 ? d.out_stride[i] : 8;      // extent-1 dims: any legal stride
+            ok = ok && cs[i + 1] > 0 && (cs[i + 1] % 8) == 0;
+        }
+        if (ok) {
+            int cb[5] = {64, d.box[0], d.box[1], d.box[2], d.box[3]};
+            const int rc = make_map(&p.c_map, static_cast<__nv_bfloat16*>(out) + d.out_base, 5, cd, cs, cb,
+                                    CU_TENSOR_MAP_L2_PROMOTION_NONE, "output map");
+            if (rc != A2M_OK) return rc;
+            p.c_tma = 1;
+        }
+    }
     p.n_taps = static_cast<int>(d.taps.size());
     int kb = 0;
     for (int t = 0; t < p.n_taps; ++t) {
@@ -388,12 +460,18 @@ int conv_gemm_plan(const ConvGemmDesc& d, const void* w_packed, const float* bia
     p.N = d.N;
     p.act = d.act;
     p.out_type = d.out_type;
+    A2M_ARG_CHECK(d.split_k >= 1 && d.split_k <= 64 && d.split_k <= kb, "conv_gemm_plan: split_k %d (k blocks %d)", d.split_k, kb);
+    A2M_ARG_CHECK(d.split_k == 1 || (d.out_type == kOutF32 && d.act == kActNone),
+                  "conv_gemm_plan: split-K needs an fp32 output without activation");
+    p.split_k = d.split_k;
+    p.split_stride = d.split_stride;
     A2M_ARG_CHECK(m_tiles <= 0x7fffffffLL, "conv_gemm_plan: too many M tiles");
     plan->w_packed = w_packed;
     plan->bias = bias;
     plan->out = out;
     plan->block_n = block_n;
-    plan->grid = dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>((d.N + block_n - 1) / block_n), 1);
+    plan->grid = dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>((d.N + block_n - 1) / block_n),
+                      static_cast<unsigned>(d.split_k));
     plan->flops = 2 * m_valid * d.N * K;
     return A2M_OK;
 }

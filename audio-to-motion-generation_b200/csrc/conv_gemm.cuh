@@ -49,12 +49,17 @@ struct ConvGemmDesc {
     long long out_base;
     int act;
     int out_type;
+    int split_k = 1;            // > 1: K blocks split over gridDim.z; split z writes its fp32 partial sums at
+    long long split_stride = 0; // out + z * split_stride (act must be none; bias added by split 0); the consumer
+                                // sums the planes in a fixed order (deterministic, batch-invariant)
 };
 
 // Device-side launch record (kernel parameter), built once per (layer, batch size).
 struct ConvGemmParams {
     CUtensorMap a_map[2];
     CUtensorMap b_map;
+    CUtensorMap c_map;          // bf16 output as a 5-D strided view (TMA store epilogue); valid iff c_tma
+    int c_tma;
     int n_taps;
     int tap_src[kMaxTaps];
     int tap_chunks[kMaxTaps];
@@ -68,6 +73,8 @@ struct ConvGemmParams {
     int k_blocks;
     int act;
     int out_type;
+    int split_k;
+    long long split_stride;
 };
 
 struct ConvGemmPlan {

@@ -7,13 +7,19 @@
 //     j in N(i) + {i}, alpha = softmax_j(e_ij), out_i = mean_heads(sum_j alpha_ij h_j) + bias
 //   GraphConv(64, 64), aggr = add:        out_i = W_rel (sum_{j in N(i)} x_j) + b_rel + W_root x_i
 //
-// One persistent CTA per SM keeps all five weight matrices resident in shared memory (128 KB, loaded
-// once with TMA in the 128B-swizzled K-major layout) and walks over tiles of whole graphs (<= 128 node
-// rows: 3 hand graphs or 12 body graphs).  Per layer the shared linear runs on the tensor cores
-// (tcgen05.mma, A = the bf16 node tile in shared memory, D = [128 x 256] fp32 in TMEM); the epilogue
-// threads (2 per node) read their TMEM lane, reduce the attention scalars, stage h as bf16 in shared
-// memory, and do the neighbour softmax / aggregation / head mean / LayerNorm / residual with the
-// residual stream held in fp32 registers across all five layers.
+// Everything that is a contraction runs on the tensor cores, including the neighbourhood aggregation:
+// a tile is 128 node rows = whole graphs (3 hand graphs or 12 body graphs), and per layer
+//   GAT:   [H | S] = X [W | U]^T           (tcgen05, N = 256 + 16; U = W^T a_src / W^T a_dst folded at load, so the
+//                                           attention logits s_src, s_dst come out of the same MMA, hi + lo split)
+//          P^h     = softmax rows (fp32, CUDA cores; <= 7 entries per row) scattered as bf16 into a dense
+//                    block-diagonal [128 x 128] matrix in shared memory (zeros elsewhere, written once)
+//          OUT     = sum_h P^h H^h          (tcgen05, A = P^h K-major, B = H^h staged as bf16 in shared memory and
+//                                           read MN-major; the head mean is folded into P)
+//   GraphConv: AGG = Adj X (tcgen05, B = the node tile itself read MN-major), OUT = AGG W_rel^T + X W_root^T
+// The epilogue threads (4 per node row, 16 features each, residual stream in fp32 registers) do the softmax,
+// bias, LayerNorm, LeakyReLU and residual.  One persistent CTA per SM; node tiles arrive by TMA (double
+// buffered, prefetched one tile ahead) and leave by TMA store; per-layer weights stream through one 34 KB
+// shared-memory buffer by TMA, prefetched as soon as the MMA that reads the previous layer's has completed.
 #include <cuda.h>
 #include <cstring>
 #include "conv_gemm.cuh"
@@ -25,23 +31,26 @@ namespace a2m {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kRows = 128;
-constexpr int kHStride = 528;                         // bytes per staged h row (512 + 16: conflict-free 16 B accesses)
-constexpr int kOffW = 0;                              // 3 x 32 KB GAT + 2 x 16 KB GraphConv
-constexpr int kOffX = 131072;                         // node tile, bf16 [128][64] SW128
-constexpr int kOffH = kOffX + 16384;                  // h rows (GAT) / aggregated tile (GraphConv)
-constexpr int kOffS = kOffH + kRows * kHStride;       // s_src, s_dst [128][4] fp32 each
-constexpr int kOffLn = kOffS + 2 * kRows * 4 * 4;     // LayerNorm partials [128][2][2] fp32
-constexpr int kOffTopo = kOffLn + kRows * 2 * 2 * 4;  // nbr [J][6], deg [J]
+constexpr int kGatRows = 272;                          // 256 W rows + 16 folded attention rows
+constexpr int kOffW = 0;                               // per-layer weights: GAT 34816 B / GraphConv 16384 B
+constexpr int kOffX = 34816;                           // node tile, bf16 [128][64] SW128, x 2 buffers
+constexpr int kOffH = kOffX + 2 * 16384;               // GAT: H^h tiles (4 x 16 KB); GraphConv: AGG tile
+constexpr int kOffP = kOffH + 4 * 16384;               // attention / adjacency matrices, 2 x [128][128] bf16
+constexpr int kOffS = kOffP + 2 * 32768;               // s_src [128][4] fp32
+constexpr int kOffLn = kOffS + kRows * 4 * 4;          // LayerNorm partials [128][4][2] fp32
+constexpr int kOffTopo = kOffLn + kRows * 4 * 2 * 4;   // nbr [48][6], deg [48]
 constexpr int kOffBar = kOffTopo + 48 * kMaxDeg * 4 + 48 * 4;
 constexpr int kSmemBytes = kOffBar + 64 + 1024;
+constexpr uint32_t kColS = 256, kColOut = 288;         // TMEM columns: H [0,256), S [256,272), OUT [288,352)
+static_assert(kOffX % 1024 == 0 && kOffH % 1024 == 0 && kOffP % 1024 == 0, "swizzled tiles need 1024 B alignment");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 struct GnnParams {
-    CUtensorMap w_gat[3];
-    CUtensorMap w_gc[2];
-    const float* att_src[3];
-    const float* att_dst[3];
+    CUtensorMap w_gat[3];                // [272][64] bf16, box 64 x 136
+    CUtensorMap w_gc[2];                 // [64][128] bf16, box 64 x 64
+    CUtensorMap x_in, x_out;             // [rows][64] bf16, box 64 x rows_per_tile
     const float* gat_bias[3];
     const float* gc_bias[2];
     const float* ln_w[5];
@@ -50,282 +59,357 @@ struct GnnParams {
     const int* deg;
     int J, gpc;
     long long n_graphs;
-    const __nv_bfloat16* x_in;
-    __nv_bfloat16* x_out;
 };
 
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeakySlope * x; }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
-// byte offset of 16-byte chunk `c` (8 features) of row r in a [128][64] bf16 SW128 K-major tile
+// byte offset of 16-byte chunk `c` (8 features) of row r in a [128][64] bf16 SW128 tile
 __device__ __forceinline__ int sw128_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
-
-// LayerNorm(64) over the two 32-feature halves of a node held by threads (r, 0) and (r, 1)
-__device__ __forceinline__ void layernorm_pair(float (&v)[32], float* s_ln, int r, int half, const float* __restrict__ w,
-                                               const float* __restrict__ b) {
-    float s = 0.f, q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) { s += v[i]; q = fmaf(v[i], v[i], q); }
-    s_ln[(r * 2 + half) * 2] = s;
-    s_ln[(r * 2 + half) * 2 + 1] = q;
-    __syncthreads();
-    const float ts = s + s_ln[(r * 2 + (half ^ 1)) * 2], tq = q + s_ln[(r * 2 + (half ^ 1)) * 2 + 1];
-    const float mean = ts * (1.f / 64.f);
-    const float rstd = rsqrtf(fmaxf(tq * (1.f / 64.f) - mean * mean, 0.f) + 1e-5f);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * __ldg(w + half * 32 + i) + __ldg(b + half * 32 + i);
+// byte offset of element (row r, column col) of a [128][128] bf16 matrix stored as two K-major SW128 chunks
+__device__ __forceinline__ int p_off(int r, int col) {
+    return (col >> 6) * 16384 + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2;
 }
+__device__ __forceinline__ uint32_t idesc_b_mn(uint32_t m, uint32_t n) { return umma_idesc_bf16(m, n) | (1u << 16); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    unsigned char* s_x = smem + kOffX;
     unsigned char* s_h = smem + kOffH;
+    unsigned char* s_p = smem + kOffP;
     float* s_src = reinterpret_cast<float*>(smem + kOffS);
-    float* s_dst = s_src + kRows * 4;
     float* s_ln = reinterpret_cast<float*>(smem + kOffLn);
     int* s_nbr = reinterpret_cast<int*>(smem + kOffTopo);
     int* s_deg = s_nbr + 48 * kMaxDeg;
     uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint64_t* mma_bar = w_bar + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+    uint64_t* x_bar = w_bar + 2;                       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int r = tid & 127, half = tid >> 7, quad = warp & 3;
+    const int r = tid & 127, q = tid >> 7, quad = warp & 3;
     const int J = p.J, rows_per_tile = p.gpc * J;
+    const long long n_rows = p.n_graphs * J;
+    const long long n_tiles = (p.n_graphs + p.gpc - 1) / p.gpc;
+    const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;    // >= 1 by construction of the grid
+    const uint32_t tile_bytes = static_cast<uint32_t>(rows_per_tile) * 128u;
+
+    auto load_weights = [&](int layer) {               // one thread
+        if ((layer & 1) == 0) {
+            mbar_expect_tx(w_bar, kGatRows * 128);
+            tma_load_5d(smem + kOffW, &p.w_gat[layer >> 1], w_bar, 0, 0, 0, 0, 0);
+            tma_load_5d(smem + kOffW + 136 * 128, &p.w_gat[layer >> 1], w_bar, 0, 136, 0, 0, 0);
+        } else {
+            mbar_expect_tx(w_bar, 16384);
+            tma_load_5d(smem + kOffW, &p.w_gc[layer >> 1], w_bar, 0, 0, 0, 0, 0);            // W_rel  (k 0..63)
+            tma_load_5d(smem + kOffW + 8192, &p.w_gc[layer >> 1], w_bar, 64, 0, 0, 0, 0);    // W_root (k 64..127)
+        }
+    };
 
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) tma_prefetch_desc(&p.w_gat[i]);
         for (int i = 0; i < 2; ++i) tma_prefetch_desc(&p.w_gc[i]);
+        tma_prefetch_desc(&p.x_in);
+        tma_prefetch_desc(&p.x_out);
         mbar_init(w_bar, 1);
         mbar_init(mma_bar, 1);
+        mbar_init(&x_bar[0], 1);
+        mbar_init(&x_bar[1], 1);
         mbar_fence_init();
-        // all five weight matrices, once per CTA
-        mbar_expect_tx(w_bar, 131072);
-        for (int i = 0; i < 3; ++i) tma_load_5d(smem + kOffW + i * 32768, &p.w_gat[i], w_bar, 0, 0, 0, 0, 0);
-        for (int i = 0; i < 2; ++i) {
-            tma_load_5d(smem + kOffW + 98304 + i * 16384, &p.w_gc[i], w_bar, 0, 0, 0, 0, 0);          // W_rel  (k 0..63)
-            tma_load_5d(smem + kOffW + 98304 + i * 16384 + 8192, &p.w_gc[i], w_bar, 64, 0, 0, 0, 0);  // W_root (k 64..127)
-        }
+        load_weights(0);
+        mbar_expect_tx(&x_bar[0], tile_bytes);
+        tma_load_5d(smem + kOffX, &p.x_in, &x_bar[0], 0, static_cast<int>(blockIdx.x * static_cast<long long>(rows_per_tile)), 0, 0, 0);
     }
-    if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     for (int i = tid; i < J * kMaxDeg; i += kThreads) s_nbr[i] = p.nbr[i];
     for (int i = tid; i < J; i += kThreads) s_deg[i] = p.deg[i];
+    {   // zero the attention matrices (only the static neighbour positions are ever rewritten) and the rows of
+        // the node tiles that TMA never writes (rows_per_tile .. 127): 0 x garbage must not become NaN
+        uint4 z = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < 2 * 32768 / 16; i += kThreads) reinterpret_cast<uint4*>(s_p)[i] = z;
+        for (int i = tid; i < 2 * 16384 / 16; i += kThreads) {
+            const int row = (i & 1023) >> 3;
+            if (row >= rows_per_tile) reinterpret_cast<uint4*>(smem + kOffX)[i] = z;
+        }
+    }
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    mbar_wait(w_bar, 0, err_flag, 11);      // bounded; on expiry the flag is set and the CTA still runs to completion
-    uint32_t mma_parity = 0;
-    const uint32_t idesc_gat = umma_idesc_bf16(128, 256), idesc_gc = umma_idesc_bf16(128, 64);
-    const uint32_t x_addr = smem_u32(s_x), h_addr = smem_u32(s_h), w_addr = smem_u32(smem + kOffW);
+    const uint32_t idesc_h = umma_idesc_bf16(128, 256), idesc_s = umma_idesc_bf16(128, 16);
+    const uint32_t idesc_agg = idesc_b_mn(128, 64), idesc_gc = umma_idesc_bf16(128, 64);
+    const uint32_t w_addr = smem_u32(smem + kOffW), h_addr = smem_u32(s_h), p_addr = smem_u32(s_p);
 
-    const long long n_tiles = (p.n_graphs + p.gpc - 1) / p.gpc;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // static per-thread topology: the node this row holds, its neighbours' rows and their positions in P
+    const bool valid_row = r < rows_per_tile;
+    const int jloc = r % J, g0 = r - jloc;
+    const int dg = valid_row ? s_deg[jloc] : 0;
+    int idx[kMaxDeg + 1], pofs[kMaxDeg + 1];
+    idx[0] = r;
+#pragma unroll
+    for (int k = 0; k < kMaxDeg; ++k) idx[k + 1] = k < dg ? g0 + s_nbr[jloc * kMaxDeg + k] : r;
+#pragma unroll
+    for (int k = 0; k <= kMaxDeg; ++k) pofs[k] = p_off(r, idx[k]);
+
+    uint32_t mma_parity = 0, w_parity = 0;
+    for (long long it = 0; it < my_tiles; ++it) {
+        const long long tile = blockIdx.x + it * gridDim.x;
         const long long row0 = tile * rows_per_tile;
-        const long long rows_left = p.n_graphs * J - row0;
-        const int n_here = static_cast<int>(rows_left < rows_per_tile ? rows_left : rows_per_tile);
-        const bool live = r < n_here;
-        const int jloc = r % J, g0 = r - jloc;
-        const int dg = live ? s_deg[jloc] : 0;
-
-        // ---- load this thread's 32 features (fp32 residual stream in registers + bf16 MMA operand tile)
-        float x[32];
-        {
-            uint4 q[4] = {};
-            if (live) {
-                const uint4* src = reinterpret_cast<const uint4*>(p.x_in + (row0 + r) * 64 + half * 32);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) q[c] = __ldg(src + c);
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                *reinterpret_cast<uint4*>(s_x + sw128_off(r, half * 4 + c)) = q[c];
-                const uint32_t u[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { x[c * 8 + 2 * e] = bf_lo(u[e]); x[c * 8 + 2 * e + 1] = bf_hi(u[e]); }
-            }
+        const int buf = static_cast<int>(it & 1);
+        unsigned char* s_x = smem + kOffX + buf * 16384;
+        const uint32_t x_addr = smem_u32(s_x);
+        const bool live = valid_row && row0 + r < n_rows;
+        if (tid == 0 && it + 1 < my_tiles) {           // prefetch the next tile into the other buffer
+            tma_store_wait_read();                     // ... once the store that last read it has drained
+            mbar_expect_tx(&x_bar[buf ^ 1], tile_bytes);
+            tma_load_5d(smem + kOffX + (buf ^ 1) * 16384, &p.x_in, &x_bar[buf ^ 1], 0,
+                        static_cast<int>((tile + gridDim.x) * rows_per_tile), 0, 0, 0);
         }
-        fence_async_smem();
-        __syncthreads();
+        mbar_wait(&x_bar[buf], static_cast<uint32_t>((it >> 1) & 1), err_flag, 10);
+        // residual stream: this thread's 16 features in fp32 registers
+        float x[16];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const uint4 u = *reinterpret_cast<const uint4*>(s_x + sw128_off(r, q * 2 + c));
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { x[c * 8 + 2 * e] = bf_lo(w4[e]); x[c * 8 + 2 * e + 1] = bf_hi(w4[e]); }
+        }
 
 #pragma unroll 1
         for (int layer = 0; layer < 5; ++layer) {
-            float v[32];
+            float v[16];
+            const bool more_weights = !(layer == 4 && it + 1 == my_tiles);
+            mbar_wait(w_bar, w_parity, err_flag, 11);
+            w_parity ^= 1;
             if ((layer & 1) == 0) {
                 // ================= GATConv =================
                 const int gi = layer >> 1;
                 if (tid == 0) {
                     tc_fence_after();
-                    const uint32_t wa = w_addr + gi * 32768;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base, umma_desc_sw128(x_addr + k * 32), umma_desc_sw128(wa + k * 32), idesc_gat, k != 0);
+                    for (int k = 0; k < 4; ++k) {
+                        umma_bf16(tmem_base, umma_desc_sw128(x_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc_h, k != 0);
+                        umma_bf16(tmem_base + kColS, umma_desc_sw128(x_addr + k * 32), umma_desc_sw128(w_addr + 32768 + k * 32),
+                                  idesc_s, k != 0);
+                    }
                     umma_commit(mma_bar);
                 }
                 mbar_wait(mma_bar, mma_parity, err_flag, 12);
                 mma_parity ^= 1;
                 tc_fence_after();
-                // phase A: my node's h for heads {2*half, 2*half+1}: attention scalars + bf16 staging
-                const float* a_src = p.att_src[gi];
-                const float* a_dst = p.att_dst[gi];
-#pragma unroll 1
-                for (int hh = 0; hh < 2; ++hh) {
-                    float ps = 0.f, pd = 0.f;
-#pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int col0 = half * 128 + hh * 64 + cc * 32;
-                        uint32_t t[32];
-                        tmem_ld_32x32(tmem_lane + col0, t);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float f = __uint_as_float(t[i]);
-                            ps = fmaf(f, __ldg(a_src + col0 + i), ps);
-                            pd = fmaf(f, __ldg(a_dst + col0 + i), pd);
-                        }
-                        unsigned char* hrow = s_h + r * kHStride + col0 * 2;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            uint4 q;
-                            q.x = pack_bf16(__uint_as_float(t[c * 8]), __uint_as_float(t[c * 8 + 1]));
-                            q.y = pack_bf16(__uint_as_float(t[c * 8 + 2]), __uint_as_float(t[c * 8 + 3]));
-                            q.z = pack_bf16(__uint_as_float(t[c * 8 + 4]), __uint_as_float(t[c * 8 + 5]));
-                            q.w = pack_bf16(__uint_as_float(t[c * 8 + 6]), __uint_as_float(t[c * 8 + 7]));
-                            *reinterpret_cast<uint4*>(hrow + c * 16) = q;
-                        }
+                if (tid == 0 && more_weights) load_weights((layer + 1) % 5);
+                // ---- phase A: attention logits of my node, my head's H row staged as bf16 (MMA B operand)
+                float s_dst_q;
+                {
+                    uint32_t t[16];
+                    tmem_ld_32x16(tmem_lane + kColS, t);
+                    tmem_ld_wait();
+                    s_dst_q = __uint_as_float(t[4 + q]) + __uint_as_float(t[12 + q]);
+                    if (q == 0) {
+                        *reinterpret_cast<float4*>(s_src + r * 4) =
+                            make_float4(__uint_as_float(t[0]) + __uint_as_float(t[8]), __uint_as_float(t[1]) + __uint_as_float(t[9]),
+                                        __uint_as_float(t[2]) + __uint_as_float(t[10]), __uint_as_float(t[3]) + __uint_as_float(t[11]));
                     }
-                    s_src[r * 4 + half * 2 + hh] = ps;
-                    s_dst[r * 4 + half * 2 + hh] = pd;
+                }
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    uint32_t t[32];
+                    tmem_ld_32x32(tmem_lane + q * 64 + cc * 32, t);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(t[c * 8]), __uint_as_float(t[c * 8 + 1]));
+                        o.y = pack_bf16(__uint_as_float(t[c * 8 + 2]), __uint_as_float(t[c * 8 + 3]));
+                        o.z = pack_bf16(__uint_as_float(t[c * 8 + 4]), __uint_as_float(t[c * 8 + 5]));
+                        o.w = pack_bf16(__uint_as_float(t[c * 8 + 6]), __uint_as_float(t[c * 8 + 7]));
+                        *reinterpret_cast<uint4*>(s_h + q * 16384 + sw128_off(r, cc * 4 + c)) = o;
+                    }
                 }
                 tc_fence_before();
+                fence_proxy_async_smem();
                 __syncthreads();
-                // phase B: softmax over {self} + neighbours per head, weighted aggregation of my 32 features
-                float alpha[kMaxDeg + 1][4];
-                int idx[kMaxDeg + 1];
-                idx[0] = r;
-#pragma unroll
-                for (int k = 0; k < kMaxDeg; ++k) idx[k + 1] = k < dg ? g0 + s_nbr[jloc * kMaxDeg + k] : r;
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const float di = s_dst[r * 4 + h];
+                // ---- softmax over {self} + neighbours for head q (the head mean 1/4 is folded in)
+                float alpha[kMaxDeg + 1];
+                {
                     float m = -INFINITY;
 #pragma unroll
                     for (int k = 0; k <= kMaxDeg; ++k) {
-                        alpha[k][h] = k <= dg ? leaky(s_src[idx[k] * 4 + h] + di) : -INFINITY;
-                        m = fmaxf(m, alpha[k][h]);
+                        alpha[k] = k <= dg ? leaky(s_src[idx[k] * 4 + q] + s_dst_q) : -INFINITY;
+                        m = fmaxf(m, alpha[k]);
                     }
                     float den = 0.f;
 #pragma unroll
-                    for (int k = 0; k <= kMaxDeg; ++k) { alpha[k][h] = k <= dg ? __expf(alpha[k][h] - m) : 0.f; den += alpha[k][h]; }
-                    const float inv = 0.25f / den;                      // softmax normaliser and the head mean
+                    for (int k = 0; k <= kMaxDeg; ++k) { alpha[k] = k <= dg ? __expf(alpha[k] - m) : 0.f; den += alpha[k]; }
+                    const float inv = 0.25f / den;
 #pragma unroll
-                    for (int k = 0; k <= kMaxDeg; ++k) alpha[k][h] *= inv;
+                    for (int k = 0; k <= kMaxDeg; ++k) alpha[k] *= inv;
                 }
+                // ---- two rounds over the two P buffers: heads {0,1}, then heads {2,3}
+#pragma unroll 1
+                for (int round = 0; round < 2; ++round) {
+                    if ((q >> 1) == round) {
+                        unsigned char* pb = s_p + (q & 1) * 32768;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0.f;
-#pragma unroll
-                for (int k = 0; k <= kMaxDeg; ++k) {
-                    if (k <= dg) {
-                        const unsigned char* hrow = s_h + idx[k] * kHStride + half * 64;
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const float a = alpha[k][h];
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const uint4 q = *reinterpret_cast<const uint4*>(hrow + h * 128 + c * 16);
-                                v[c * 8 + 0] = fmaf(a, bf_lo(q.x), v[c * 8 + 0]); v[c * 8 + 1] = fmaf(a, bf_hi(q.x), v[c * 8 + 1]);
-                                v[c * 8 + 2] = fmaf(a, bf_lo(q.y), v[c * 8 + 2]); v[c * 8 + 3] = fmaf(a, bf_hi(q.y), v[c * 8 + 3]);
-                                v[c * 8 + 4] = fmaf(a, bf_lo(q.z), v[c * 8 + 4]); v[c * 8 + 5] = fmaf(a, bf_hi(q.z), v[c * 8 + 5]);
-                                v[c * 8 + 6] = fmaf(a, bf_lo(q.w), v[c * 8 + 6]); v[c * 8 + 7] = fmaf(a, bf_hi(q.w), v[c * 8 + 7]);
-                            }
-                        }
+                        for (int k = 0; k <= kMaxDeg; ++k)
+                            if (k <= dg) *reinterpret_cast<__nv_bfloat16*>(pb + pofs[k]) = __float2bfloat16_rn(alpha[k]);
                     }
-                }
-                const float* gb = p.gat_bias[gi];
+                    fence_proxy_async_smem();
+                    __syncthreads();
+                    if (tid == 0) {
+                        tc_fence_after();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += __ldg(gb + half * 32 + i);
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int h = round * 2 + hh;
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk)
+                                umma_bf16(tmem_base + kColOut,
+                                          umma_desc_sw128(p_addr + hh * 32768 + (kk >> 2) * 16384 + (kk & 3) * 32),
+                                          umma_desc_sw128(h_addr + h * 16384 + kk * 2048), idesc_agg, (h | kk) != 0);
+                        }
+                        umma_commit(mma_bar);
+                    }
+                    mbar_wait(mma_bar, mma_parity, err_flag, 13);
+                    mma_parity ^= 1;
+                }
+                tc_fence_after();
+                {
+                    uint32_t t[16];
+                    tmem_ld_32x16(tmem_lane + kColOut + q * 16, t);
+                    tmem_ld_wait();
+                    const float* gb = p.gat_bias[gi];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(t[i]) + __ldg(gb + q * 16 + i);
+                }
             } else {
                 // ================= GraphConv =================
                 const int ci = layer >> 1;
-                // aggregated neighbour tile (bf16, SW128) into the h buffer
-                float agg[32];
+                if (q == 0) {                              // adjacency (no self loops) into P buffer 0
+                    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+                    *reinterpret_cast<__nv_bfloat16*>(s_p + pofs[0]) = zero;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) agg[i] = 0.f;
-#pragma unroll
-                for (int k = 0; k < kMaxDeg; ++k) {
-                    if (k < dg) {
-                        const int j = g0 + s_nbr[jloc * kMaxDeg + k];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const uint4 q = *reinterpret_cast<const uint4*>(s_x + sw128_off(j, half * 4 + c));
-                            agg[c * 8 + 0] += bf_lo(q.x); agg[c * 8 + 1] += bf_hi(q.x); agg[c * 8 + 2] += bf_lo(q.y); agg[c * 8 + 3] += bf_hi(q.y);
-                            agg[c * 8 + 4] += bf_lo(q.z); agg[c * 8 + 5] += bf_hi(q.z); agg[c * 8 + 6] += bf_lo(q.w); agg[c * 8 + 7] += bf_hi(q.w);
-                        }
-                    }
+                    for (int k = 1; k <= kMaxDeg; ++k)
+                        if (k <= dg) *reinterpret_cast<__nv_bfloat16*>(s_p + pofs[k]) = one;
                 }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint4 q;
-                    q.x = pack_bf16(agg[c * 8], agg[c * 8 + 1]); q.y = pack_bf16(agg[c * 8 + 2], agg[c * 8 + 3]);
-                    q.z = pack_bf16(agg[c * 8 + 4], agg[c * 8 + 5]); q.w = pack_bf16(agg[c * 8 + 6], agg[c * 8 + 7]);
-                    *reinterpret_cast<uint4*>(s_h + sw128_off(r, half * 4 + c)) = q;
-                }
-                fence_async_smem();
+                fence_proxy_async_smem();
                 __syncthreads();
                 if (tid == 0) {
                     tc_fence_after();
-                    const uint32_t wa = w_addr + 98304 + ci * 16384;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)       // W_rel . agg
-                        umma_bf16(tmem_base, umma_desc_sw128(h_addr + k * 32), umma_desc_sw128(wa + k * 32), idesc_gc, k != 0);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)       // + W_root . x
-                        umma_bf16(tmem_base, umma_desc_sw128(x_addr + k * 32), umma_desc_sw128(wa + 8192 + k * 32), idesc_gc, 1);
+                    for (int kk = 0; kk < 8; ++kk)       // AGG = Adj . X
+                        umma_bf16(tmem_base + kColOut, umma_desc_sw128(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32),
+                                  umma_desc_sw128(x_addr + kk * 2048), idesc_agg, kk != 0);
                     umma_commit(mma_bar);
                 }
-                mbar_wait(mma_bar, mma_parity, err_flag, 13);
+                mbar_wait(mma_bar, mma_parity, err_flag, 14);
                 mma_parity ^= 1;
                 tc_fence_after();
-                uint32_t t[32];
-                tmem_ld_32x32(tmem_lane + half * 32, t);
-                tmem_ld_wait();
+                {
+                    uint32_t t[16];
+                    tmem_ld_32x16(tmem_lane + kColOut + q * 16, t);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(t[c * 8]), __uint_as_float(t[c * 8 + 1]));
+                        o.y = pack_bf16(__uint_as_float(t[c * 8 + 2]), __uint_as_float(t[c * 8 + 3]));
+                        o.z = pack_bf16(__uint_as_float(t[c * 8 + 4]), __uint_as_float(t[c * 8 + 5]));
+                        o.w = pack_bf16(__uint_as_float(t[c * 8 + 6]), __uint_as_float(t[c * 8 + 7]));
+                        *reinterpret_cast<uint4*>(s_h + sw128_off(r, q * 2 + c)) = o;
+                    }
+                }
                 tc_fence_before();
-                const float* cb = p.gc_bias[ci];
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(t[i]) + __ldg(cb + half * 32 + i);
+                    for (int k = 0; k < 4; ++k)           // W_rel . agg
+                        umma_bf16(tmem_base, umma_desc_sw128(h_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc_gc, k != 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)           // + W_root . x
+                        umma_bf16(tmem_base, umma_desc_sw128(x_addr + k * 32), umma_desc_sw128(w_addr + 8192 + k * 32), idesc_gc, 1);
+                    umma_commit(mma_bar);
+                }
+                mbar_wait(mma_bar, mma_parity, err_flag, 15);
+                mma_parity ^= 1;
+                tc_fence_after();
+                if (tid == 0 && more_weights) load_weights((layer + 1) % 5);
+                {
+                    uint32_t t[16];
+                    tmem_ld_32x16(tmem_lane + q * 16, t);
+                    tmem_ld_wait();
+                    const float* cb = p.gc_bias[ci];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(t[i]) + __ldg(cb + q * 16 + i);
+                }
             }
-            // ---- LayerNorm(64) -> LeakyReLU -> + residual; refresh the bf16 operand tile
-            layernorm_pair(v, s_ln, r, half, p.ln_w[layer], p.ln_b[layer]);
+            // ---- LayerNorm(64) over the four 16-feature quarters of the node -> LeakyReLU -> + residual
+            {
+                float s = 0.f, sq = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] += leaky(v[i]);
+                for (int i = 0; i < 16; ++i) { s += v[i]; sq = fmaf(v[i], v[i], sq); }
+                *reinterpret_cast<float2*>(s_ln + (r * 4 + q) * 2) = make_float2(s, sq);
+                __syncthreads();
+                const float4 a = *reinterpret_cast<const float4*>(s_ln + r * 8);
+                const float4 b = *reinterpret_cast<const float4*>(s_ln + r * 8 + 4);
+                const float mean = (a.x + a.z + b.x + b.z) * (1.f / 64.f);
+                const float rstd = rsqrtf(fmaxf((a.y + a.w + b.y + b.w) * (1.f / 64.f) - mean * mean, 0.f) + 1e-5f);
+                const float* lw = p.ln_w[layer];
+                const float* lb = p.ln_b[layer];
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    x[i] += leaky((v[i] - mean) * rstd * __ldg(lw + q * 16 + i) + __ldg(lb + q * 16 + i));
+            }
             if (!live) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) x[i] = 0.f;
+                for (int i = 0; i < 16; ++i) x[i] = 0.f;
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint4 q;
-                q.x = pack_bf16(x[c * 8], x[c * 8 + 1]); q.y = pack_bf16(x[c * 8 + 2], x[c * 8 + 3]);
-                q.z = pack_bf16(x[c * 8 + 4], x[c * 8 + 5]); q.w = pack_bf16(x[c * 8 + 6], x[c * 8 + 7]);
-                *reinterpret_cast<uint4*>(s_x + sw128_off(r, half * 4 + c)) = q;
-                if (layer == 4 && live) *reinterpret_cast<uint4*>(p.x_out + (row0 + r) * 64 + half * 32 + c * 8) = q;
+            for (int c = 0; c < 2; ++c) {
+                uint4 o;
+                o.x = pack_bf16(x[c * 8], x[c * 8 + 1]); o.y = pack_bf16(x[c * 8 + 2], x[c * 8 + 3]);
+                o.z = pack_bf16(x[c * 8 + 4], x[c * 8 + 5]); o.w = pack_bf16(x[c * 8 + 6], x[c * 8 + 7]);
+                *reinterpret_cast<uint4*>(s_x + sw128_off(r, q * 2 + c)) = o;
             }
-            fence_async_smem();
+            tc_fence_before();
+            fence_proxy_async_smem();
             __syncthreads();
         }
+        if (tid == 0) {                                // the tile's final node features leave by TMA (rows past the
+            tma_store_5d(&p.x_out, s_x, 0, static_cast<int>(row0), 0, 0, 0);   // end of the tensor are clipped)
+            tma_store_commit();
+        }
     }
+    if (tid == 0) tma_store_wait_read();
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// U rows of the extended GAT weight: the attention logits a_src . (W_h x) = (W_h^T a_src) . x come out of the
+// same MMA as H.  Rows 256+h: src (hi), 260+h: dst (hi), 264+h: src (lo), 268+h: dst (lo); hi + lo carries
+// ~16 mantissa bits of the fp32 fold, which is evaluated on the bf16-rounded W the MMA itself uses.
+__global__ void gat_fold_attention_kernel(__nv_bfloat16* __restrict__ wext, const float* __restrict__ att_src,
+                                          const float* __restrict__ att_dst) {
+    const int f = threadIdx.x & 63, h = (threadIdx.x >> 6) & 3, which = threadIdx.x >> 8;       // 512 threads
+    const float* a = which == 0 ? att_src : att_dst;
+    float u = 0.f;
+    for (int o = 0; o < kJointFeat; ++o)
+        u = fmaf(a[h * kJointFeat + o], __bfloat162float(wext[(h * kJointFeat + o) * kJointFeat + f]), u);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(u);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(u - __bfloat162float(hi));
+    wext[(256 + which * 4 + h) * kJointFeat + f] = hi;
+    wext[(264 + which * 4 + h) * kJointFeat + f] = lo;
 }
 
 }  // namespace
@@ -338,16 +422,24 @@ struct GnnFusedPlan {
 
 int make_weight_map(CUtensorMap* map, const void* w, long long n_rows, long long k, int box_rows);   // conv_gemm.cu
 
+int gat_fold_attention(__nv_bfloat16* wext, const float* att_src, const float* att_dst, cudaStream_t stream) {
+    gat_fold_attention_kernel<<<1, 512, 0, stream>>>(wext, att_src, att_dst);
+    a2m_count_launch();
+    A2M_LAUNCH_CHECK();
+    return A2M_OK;
+}
+
 int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_graphs, const __nv_bfloat16* x_in,
                    __nv_bfloat16* x_out, std::shared_ptr<GnnFusedPlan>* out) {
     A2M_ARG_CHECK(topo.n_nodes >= 1 && topo.n_nodes <= 48, "gnn: %d nodes per graph (max 48)", topo.n_nodes);
+    A2M_ARG_CHECK(n_graphs >= 1 && n_graphs * topo.n_nodes <= 0x7fffffffLL, "gnn: %lld graphs", n_graphs);
     auto plan = std::make_shared<GnnFusedPlan>();
     GnnParams& p = plan->p;
     memset(&p, 0, sizeof(p));
     for (int i = 0; i < 3; ++i) {
-        const int rc = make_weight_map(&p.w_gat[i], w.gat_w[i], 256, 64, 256);
+        const int rc = make_weight_map(&p.w_gat[i], w.gat_w[i], kGatRows, 64, 136);
         if (rc != A2M_OK) return rc;
-        p.att_src[i] = w.att_src[i]; p.att_dst[i] = w.att_dst[i]; p.gat_bias[i] = w.gat_bias[i];
+        p.gat_bias[i] = w.gat_bias[i];
     }
     for (int i = 0; i < 2; ++i) {
         const int rc = make_weight_map(&p.w_gc[i], w.gc_w[i], 64, 128, 64);
@@ -356,7 +448,12 @@ int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_graphs,
     }
     for (int i = 0; i < 5; ++i) { p.ln_w[i] = w.ln_w[i]; p.ln_b[i] = w.ln_b[i]; }
     p.nbr = topo.nbr; p.deg = topo.deg; p.J = topo.n_nodes; p.gpc = kRows / topo.n_nodes;
-    p.n_graphs = n_graphs; p.x_in = x_in; p.x_out = x_out;
+    p.n_graphs = n_graphs;
+    const int rows_per_tile = p.gpc * p.J;
+    int rc = make_weight_map(&p.x_in, x_in, n_graphs * p.J, 64, rows_per_tile);
+    if (rc != A2M_OK) return rc;
+    rc = make_weight_map(&p.x_out, x_out, n_graphs * p.J, 64, rows_per_tile);
+    if (rc != A2M_OK) return rc;
     const long long tiles = (n_graphs + p.gpc - 1) / p.gpc;
     const int sms = a2m_num_sms();
     plan->grid = static_cast<int>(tiles < sms ? tiles : sms);

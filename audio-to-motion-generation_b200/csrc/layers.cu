@@ -29,44 +29,60 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------ conv0
+// One CTA = kConv0Rows output rows of one clip: the 2R+2 input rows are staged (zero padded) in shared
+// memory; a warp owns one output column at a time (shared-memory reads are broadcasts) and its 32 lanes
+// own the 32 channel pairs, so every store instruction writes one whole 128-byte channel row.
+constexpr int kConv0Rows = 8;
 __global__ void __launch_bounds__(256)
 conv0_kernel(const float* __restrict__ mel, long long stride_b, long long stride_t, int T, int F,
              const float* __restrict__ w, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
-    extern __shared__ float s_rows[];                 // [4][F + 2], zero padded left/right
-    const int ho = blockIdx.x;
+    extern __shared__ float s_rows[];                 // [2R + 2][F + 2], zero padded left/right/top/bottom
+    const int ho0 = blockIdx.x * kConv0Rows;
     const long long b = blockIdx.y;
     const int Ho = T / 2, Wo = F / 2, stride = F + 2;
-    for (int i = threadIdx.x; i < 4 * stride; i += blockDim.x) {
+    const int n_in = 2 * kConv0Rows + 2;
+    for (int i = threadIdx.x; i < n_in * stride; i += blockDim.x) {
         const int r = i / stride, col = i - r * stride - 1;
-        const int h = 2 * ho + r - 1;
+        const int h = 2 * ho0 + r - 1;
         float v = 0.f;
-        if (h >= 0 && h < T && col >= 0 && col < F) v = mel[b * stride_b + h * stride_t + col];
+        if (h >= 0 && h < T && col >= 0 && col < F) v = __ldg(mel + b * stride_b + h * stride_t + col);
         s_rows[i] = v;
     }
-    const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;
-    float wr[16];
+    const int cp = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    float w0[16], w1[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) wr[i] = w[c * 16 + i];
-    const float bc = bias[c];
+    for (int i = 0; i < 16; ++i) { w0[i] = __ldg(w + (2 * cp) * 16 + i); w1[i] = __ldg(w + (2 * cp + 1) * 16 + i); }
+    const float b0 = __ldg(bias + 2 * cp), b1 = __ldg(bias + 2 * cp + 1);
     __syncthreads();
-    __nv_bfloat16* o = out + ((b * Ho + ho) * Wo) * 64 + c;
-    for (int wo = grp; wo < Wo; wo += 4) {
-        float acc = bc;
+    for (int r = 0; r < kConv0Rows; ++r) {
+        const int ho = ho0 + r;
+        if (ho >= Ho) break;
+        __nv_bfloat16* o = out + ((b * Ho + ho) * Wo) * 64 + 2 * cp;
+        for (int wo = grp; wo < Wo; wo += 8) {
+            float a0 = b0, a1 = b1;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc = fmaf(s_rows[i * stride + 2 * wo + j], wr[i * 4 + j], acc);
-        o[static_cast<long long>(wo) * 64] = __float2bfloat16_rn(leaky(acc));
+                for (int j = 0; j < 4; ++j) {
+                    const float x = s_rows[(2 * r + i) * stride + 2 * wo + j];
+                    a0 = fmaf(x, w0[i * 4 + j], a0);
+                    a1 = fmaf(x, w1[i * 4 + j], a1);
+                }
+            *reinterpret_cast<__nv_bfloat162*>(o + static_cast<long long>(wo) * 64) = __floats2bfloat162_rn(leaky(a0), leaky(a1));
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------ time interp
-__global__ void time_interp_kernel(const float* __restrict__ in, int Hc, int T, int C, long long total,
-                                   __nv_bfloat16* __restrict__ out) {
+// in: raw conv-4 sums (+ folded bias) fp32 [B, Hc, C]; LeakyReLU is applied here (the split-K GEMM
+// cannot), then the bilinear (T, 1) resize of model_layers.py:277; 8 channels per thread.
+__global__ void time_interp_kernel(const float* __restrict__ in, int n_planes, long long plane_stride, int Hc, int T,
+                                   int C, long long total8, __nv_bfloat16* __restrict__ out) {
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c = static_cast<int>(idx % C);
-    const long long bt = idx / C;
+    if (idx >= total8) return;
+    const int c8 = C / 8;
+    const int c = static_cast<int>(idx % c8) * 8;
+    const long long bt = idx / c8;
     const int t = static_cast<int>(bt % T);
     const long long b = bt / T;
     // torch upsample_bilinear2d, align_corners=False: src = scale * (dst + 0.5) - 0.5, clamped at 0
@@ -76,8 +92,18 @@ __global__ void time_interp_kernel(const float* __restrict__ in, int Hc, int T, 
     const int i0 = static_cast<int>(src);
     const int i1 = i0 + (i0 < Hc - 1 ? 1 : 0);
     const float l1 = src - static_cast<float>(i0), l0 = 1.f - l1;
-    const float* row = in + b * Hc * C + c;
-    out[idx] = __float2bfloat16_rn(l0 * row[static_cast<long long>(i0) * C] + l1 * row[static_cast<long long>(i1) * C]);
+    float x0[8] = {}, x1[8] = {};
+    for (int pl = 0; pl < n_planes; ++pl) {           // fixed summation order over the split-K planes
+        const float4* r0 = reinterpret_cast<const float4*>(in + pl * plane_stride + (b * Hc + i0) * C + c);
+        const float4* r1 = reinterpret_cast<const float4*>(in + pl * plane_stride + (b * Hc + i1) * C + c);
+        const float4 a0 = __ldg(r0), a1 = __ldg(r0 + 1), c0 = __ldg(r1), c1 = __ldg(r1 + 1);
+        x0[0] += a0.x; x0[1] += a0.y; x0[2] += a0.z; x0[3] += a0.w; x0[4] += a1.x; x0[5] += a1.y; x0[6] += a1.z; x0[7] += a1.w;
+        x1[0] += c0.x; x1[1] += c0.y; x1[2] += c0.z; x1[3] += c0.w; x1[4] += c1.x; x1[5] += c1.y; x1[6] += c1.z; x1[7] += c1.w;
+    }
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = l0 * leaky(x0[e]) + l1 * leaky(x1[e]);
+    *reinterpret_cast<uint4*>(out + (bt * C + c)) = float_to_bf16x8(f);
 }
 
 // -------------------------------------------------------------------------------------- attention
@@ -334,6 +360,10 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, long long n, __
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __float2bfloat16_rn(in[i]);
 }
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, long long n, float* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __bfloat162float(in[i]);
+}
 __global__ void ncw_to_btc_kernel(const float* __restrict__ in, int C, int T, __nv_bfloat16* __restrict__ out) {
     __shared__ float tile[32][33];
     const long long b = blockIdx.z;
@@ -373,14 +403,15 @@ __global__ void btc_to_ncw_kernel(const __nv_bfloat16* __restrict__ in, int C, i
 int launch_conv0(const float* mel, long long stride_b, long long stride_t, int B, int T, int F, const float* w_folded,
                  const float* bias_folded, __nv_bfloat16* out, cudaStream_t stream) {
     A2M_ARG_CHECK(T % 2 == 0 && F % 2 == 0 && B <= 65535, "conv0: T %d, F %d, B %d", T, F, B);
-    conv0_kernel<<<dim3(T / 2, B), 256, 4 * (F + 2) * sizeof(float), stream>>>(mel, stride_b, stride_t, T, F, w_folded,
-                                                                                 bias_folded, out);
+    conv0_kernel<<<dim3((T / 2 + kConv0Rows - 1) / kConv0Rows, B), 256, (2 * kConv0Rows + 2) * (F + 2) * sizeof(float), stream>>>(
+        mel, stride_b, stride_t, T, F, w_folded, bias_folded, out);
     A2M_AFTER_LAUNCH();
 }
 
-int launch_time_interp(const float* in, int B, int Hc, int T, int C, __nv_bfloat16* out, cudaStream_t stream) {
-    const long long total = static_cast<long long>(B) * T * C;
-    time_interp_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, Hc, T, C, total, out);
+int launch_time_interp(const float* in, int n_planes, int B, int Hc, int T, int C, __nv_bfloat16* out, cudaStream_t stream) {
+    A2M_ARG_CHECK(C % 8 == 0, "time_interp: C = %d", C);
+    const long long total = static_cast<long long>(B) * T * (C / 8);
+    time_interp_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, n_planes, static_cast<long long>(B) * Hc * C, Hc, T, C, total, out);
     A2M_AFTER_LAUNCH();
 }
 
@@ -449,6 +480,10 @@ int launch_pose_losses(const float* pose, const float* real_pose, int B, int T, 
 
 int launch_f32_to_bf16(const float* in, long long n, __nv_bfloat16* out, cudaStream_t stream) {
     f32_to_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, n, out);
+    A2M_AFTER_LAUNCH();
+}
+int launch_bf16_to_f32(const __nv_bfloat16* in, long long n, float* out, cudaStream_t stream) {
+    bf16_to_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, n, out);
     A2M_AFTER_LAUNCH();
 }
 int launch_ncw_to_btc(const float* in, int B, int C, int T, __nv_bfloat16* out, cudaStream_t stream) {

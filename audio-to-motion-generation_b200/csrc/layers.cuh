@@ -13,9 +13,10 @@ namespace a2m {
 int launch_conv0(const float* mel, long long stride_b, long long stride_t, int B, int T, int F, const float* w_folded,
                  const float* bias_folded, __nv_bfloat16* out, cudaStream_t stream);
 
-// F.interpolate(size=(T,1), mode='bilinear') + squeeze (model_layers.py:277-279) applied to the centre
-// column computed by the last encoder conv: in [B, Hc, C] fp32 -> out [B, T, C] bf16.
-int launch_time_interp(const float* in, int B, int Hc, int T, int C, __nv_bfloat16* out, cudaStream_t stream);
+// LeakyReLU(0.2) + F.interpolate(size=(T,1), mode='bilinear') + squeeze (model_layers.py:107,277-279) applied
+// to the centre column computed by the last encoder conv (pre-activation, split-K sums):
+// in [n_planes, B, Hc, C] fp32 (summed over the planes in order) -> out [B, T, C] bf16.
+int launch_time_interp(const float* in, int n_planes, int B, int Hc, int T, int C, __nv_bfloat16* out, cudaStream_t stream);
 
 // SelfAttention (model_layers.py:133-146) after the fused q|k|v 1x1-conv GEMM:
 //   qkv [B, T, 2*d + C] bf16 (q: d, k: d, v: C; d = C/8), x [B, T, C] bf16
@@ -44,13 +45,16 @@ constexpr int kGatHeads = 4;
 // Fused five-layer GNN stack (csrc/gnn_fused.cu): GAT, GraphConv, GAT, GraphConv, GAT, each followed by
 // LayerNorm(64) -> LeakyReLU(0.2) -> + residual, x_in/x_out [n_graphs * J, 64] bf16.
 struct GnnFusedWeights {
-    const __nv_bfloat16* gat_w[3];      // [256, 64] bf16 (lin.weight)
-    const float *att_src[3], *att_dst[3], *gat_bias[3];
+    const __nv_bfloat16* gat_w[3];      // [272, 64] bf16: lin.weight + 16 folded attention rows (gat_fold_attention)
+    const float* gat_bias[3];
     const __nv_bfloat16* gc_w[2];       // [64, 128] bf16 = [W_rel | W_root]
     const float* gc_bias[2];
     const float *ln_w[5], *ln_b[5];
 };
 struct GnnFusedPlan;
+// wext [272][64] bf16 with rows 0..255 = lin.weight already packed: fills rows 256..271 with W_h^T att_src / att_dst
+// (hi and lo bf16 parts) for the four heads.  att_src / att_dst: fp32 [4][64].
+int gat_fold_attention(__nv_bfloat16* wext, const float* att_src, const float* att_dst, cudaStream_t stream);
 int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_graphs, const __nv_bfloat16* x_in,
                    __nv_bfloat16* x_out, std::shared_ptr<GnnFusedPlan>* out);
 int gnn_fused_launch(const GnnFusedPlan& plan, int* err_flag, cudaStream_t stream);
@@ -62,6 +66,7 @@ int launch_pose_losses(const float* pose, const float* real_pose, int B, int T, 
                        int n_body, const int* parents, double* scratch, float* losses_out, cudaStream_t stream);
 
 int launch_f32_to_bf16(const float* in, long long n, __nv_bfloat16* out, cudaStream_t stream);
+int launch_bf16_to_f32(const __nv_bfloat16* in, long long n, float* out, cudaStream_t stream);
 // [B, C, T] fp32 (reference NCW layout) <-> [B, T, C] bf16 for the AudioEncoder / UNet1D drop-in surfaces
 int launch_ncw_to_btc(const float* in, int B, int C, int T, __nv_bfloat16* out, cudaStream_t stream);
 int launch_btc_to_ncw(const __nv_bfloat16* in, int B, int C, int T, float* out, cudaStream_t stream);

@@ -4,6 +4,7 @@
 // launches -- tcgen05 implicit-GEMM convolutions / linears (conv_gemm.cu) and the small fused kernels
 // of layers.cu -- and enqueues them on the caller's stream.  Decisions D1 (up_attention before the
 // skip concat) and D3 (eval semantics) of SURVEY.md section 8 apply.
+#include <algorithm>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -23,6 +24,7 @@ const int kParents[52] = {-1, 0, 1, 2, 0, 4, 5, 0, 7, 7, 6, 10, 11, 12, 13, 10, 
                           49, 50};
 constexpr int kBodyJoints = 10, kHandJoints = 42, kPoseFeats = 104, kBodyFeats = 20;
 constexpr float kBnEps = 1e-5f;
+constexpr int kConv4Splits = 8;           // split-K planes of the last encoder conv (K = 24 taps x 512)
 
 struct Param {
     const float* f32 = nullptr;
@@ -42,7 +44,7 @@ struct LayerW {                 // one packed GEMM layer
 
 struct AttnW { LayerW qkv; const float* gamma = nullptr; int C = 0; };
 struct ChanW { const float *w0, *b0, *w2, *b2; int C, hidden; };
-struct GatW { LayerW lin; const float *att_src, *att_dst, *bias; };
+struct GatW { LayerW lin; const float* bias; };
 struct LnW { const float *w, *b; };
 struct ResW { LayerW c1, c2; AttnW attn; };
 
@@ -237,9 +239,17 @@ struct Builder {
             for (const char* alt : {".lin_src.weight", ".lin_l.weight"})
                 if (find(p + alt, false)) { wname = p + alt; break; }
         }
-        linear(G.lin, wname, "", kJointFeat, kGatHeads * kJointFeat, kActNone);
-        G.att_src = keep(p + ".att_src", kGatHeads * kJointFeat);
-        G.att_dst = keep(p + ".att_dst", kGatHeads * kJointFeat);
+        // extended weight [272][64]: rows 0..255 = lin.weight (bf16), rows 256..271 = the attention vectors folded
+        // through W (a_src . (W_h x) = (W_h^T a_src) . x), so the logits come out of the same MMA as H
+        LayerW& L = G.lin;
+        L.taps = {tap(0, 0, 0, 0, kJointFeat, 0)};
+        L.N = kGatHeads * kJointFeat; L.act = kActNone;
+        L.w = alloc<__nv_bfloat16>(static_cast<size_t>(272) * kJointFeat);
+        const float* wsrc = f32(wname, static_cast<long long>(L.N) * kJointFeat);
+        const float *as = f32(p + ".att_src", kGatHeads * kJointFeat), *ad = f32(p + ".att_dst", kGatHeads * kJointFeat);
+        if (rc != A2M_OK) return;
+        check(pack_weights(wsrc, kJointFeat, 1, L.taps, L.N, nullptr, L.w, s));
+        check(gat_fold_attention(L.w, as, ad, s));
         G.bias = keep(p + ".bias", kJointFeat);
     }
     // GraphConv: lin_rel(sum_j x_j) + lin_root(x_i) = [agg | x] [W_rel | W_root]^T + b_rel  (two A sources)
@@ -425,14 +435,15 @@ struct Emit {
     std::string tag;                            // label of the ops emitted next (per-op profile)
 
     void gemm(const LayerW& L, std::vector<Tap> taps, const AView* views, int n_src, const int box[4], const int ext[4],
-              void* out, const long long ostride[4], long long obase, int out_type) {
+              void* out, const long long ostride[4], long long obase, int out_type, int act = -1, int split_k = 1,
+              long long split_stride = 0) {
         if (dry || rc != A2M_OK) return;
         ConvGemmDesc d;
         d.n_src = n_src;
         for (int s = 0; s < n_src; ++s) d.a[s] = views[s];
         for (int i = 0; i < 4; ++i) { d.box[i] = box[i]; d.m_extent[i] = ext[i]; d.out_stride[i] = ostride[i]; }
         d.taps = std::move(taps);
-        d.N = L.N; d.out_base = obase; d.act = L.act; d.out_type = out_type;
+        d.N = L.N; d.out_base = obase; d.act = act >= 0 ? act : L.act; d.out_type = out_type; d.split_k = split_k; d.split_stride = split_stride;
         auto plan = std::make_shared<ConvGemmPlan>();
         rc = conv_gemm_plan(d, L.w, L.bias, out, plan.get());
         if (rc != A2M_OK) return;
@@ -537,7 +548,7 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
         auto* a1 = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * H2 * W2 * 128);
         auto* a2 = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * H3 * W3 * 256);
         auto* a3 = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * H3 * W3 * 512);
-        auto* a4 = bufs.get<float>(static_cast<size_t>(B) * H3 * 256);
+        auto* a4 = bufs.get<float>(static_cast<size_t>(kConv4Splits) * B * H3 * 256);
         auto* e0 = bufs.get<__nv_bfloat16>(BT * 256);
         auto* s0 = bufs.get<__nv_bfloat16>(BT * 512);
         auto* u1 = bufs.get<__nv_bfloat16>(BT / 2 * 512);
@@ -598,10 +609,14 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
                 const int hb = std::min(128, pow2_at_least(H3));
                 const int box[4] = {1, hb, 128 / hb, 1}, ext[4] = {1, H3, B, 1};
                 const long long os[4] = {0, 256, 256LL * H3, 0};
-                E.gemm(m->enc[4], taps, &v, 1, box, ext, a4, os, 0, kOutF32);
+                // few M tiles (B*H3/128) but K = 12288: K is split over gridDim.z (a fixed count, so results do
+                // not depend on the batch size); each split writes its own fp32 plane and the interpolation
+                // kernel sums the planes in order, then applies LeakyReLU
+                E.gemm(m->enc[4], taps, &v, 1, box, ext, a4, os, 0, kOutF32, kActNone, kConv4Splits,
+                       static_cast<long long>(B) * H3 * 256);
             }
             E.tag = "enc.interp";
-            E.op([=](cudaStream_t s) { return launch_time_interp(a4, B, H3, T, 256, e0, s); });
+            E.op([=](cudaStream_t s) { return launch_time_interp(a4, kConv4Splits, B, H3, T, 256, e0, s); });
         }
         if (pass == 1) P->enc_end = static_cast<int>(P->ops.size());
 
@@ -666,8 +681,7 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
             if (!E.dry && E.rc == A2M_OK) {
                 GnnFusedWeights gw;
                 for (int i = 0; i < 3; ++i) {
-                    gw.gat_w[i] = D.gat[i].lin.w; gw.att_src[i] = D.gat[i].att_src; gw.att_dst[i] = D.gat[i].att_dst;
-                    gw.gat_bias[i] = D.gat[i].bias;
+                    gw.gat_w[i] = D.gat[i].lin.w; gw.gat_bias[i] = D.gat[i].bias;
                 }
                 for (int i = 0; i < 2; ++i) { gw.gc_w[i] = D.gconv[i].w; gw.gc_bias[i] = D.gconv[i].bias; }
                 for (int i = 0; i < 5; ++i) { gw.ln_w[i] = D.ln64[i].w; gw.ln_b[i] = D.ln64[i].b; }
@@ -837,6 +851,35 @@ extern "C" int a2m_model_unet_forward(a2m_model* m, const float* x_nct, int64_t 
     rc = run_ops(P, P->enc_end, P->unet_end, s);
     if (rc != A2M_OK) return rc;
     return launch_btc_to_ncw(P->unet_out, static_cast<int>(B), 256, T, out_nct, s);
+}
+
+// Unit-test / diagnostic surface of the fused graph stack: packs nothing (the handle's weights are used),
+// converts, launches and synchronises.
+extern "C" int a2m_model_gnn_forward(a2m_model* m, int part, const float* x, int64_t n_graphs, float* out, void* stream) {
+    A2M_ARG_CHECK(m != nullptr && x != nullptr && out != nullptr, "a2m_model_gnn_forward: NULL argument");
+    A2M_ARG_CHECK(m->has_decoders, "a2m_model_gnn_forward: no decoder tensors in the state_dict");
+    A2M_ARG_CHECK(part == 0 || part == 1, "a2m_model_gnn_forward: part %d (0 = body, 1 = hand)", part);
+    A2M_ARG_CHECK(n_graphs >= 1 && n_graphs <= (1 << 24), "a2m_model_gnn_forward: %lld graphs", (long long)n_graphs);
+    const DecoderW& D = m->dec[part];
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long n = n_graphs * D.joints * kJointFeat;
+    __nv_bfloat16* buf = nullptr;
+    A2M_CUDA_CHECK(cudaMalloc(&buf, static_cast<size_t>(2 * n) * sizeof(__nv_bfloat16) + 512));
+    GnnFusedWeights gw;
+    for (int i = 0; i < 3; ++i) { gw.gat_w[i] = D.gat[i].lin.w; gw.gat_bias[i] = D.gat[i].bias; }
+    for (int i = 0; i < 2; ++i) { gw.gc_w[i] = D.gconv[i].w; gw.gc_bias[i] = D.gconv[i].bias; }
+    for (int i = 0; i < 5; ++i) { gw.ln_w[i] = D.ln64[i].w; gw.ln_b[i] = D.ln64[i].b; }
+    __nv_bfloat16* xo = buf + ((n + 127) & ~127LL);
+    std::shared_ptr<GnnFusedPlan> gp;
+    int rc = launch_f32_to_bf16(x, n, buf, s);
+    if (rc == A2M_OK) rc = gnn_fused_plan(gw, GraphTopo{D.joints, D.nbr, D.deg}, n_graphs, buf, xo, &gp);
+    if (rc == A2M_OK) rc = gnn_fused_launch(*gp, m->err_flag, s);
+    if (rc == A2M_OK) rc = launch_bf16_to_f32(xo, n, out, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(buf);
+    if (rc != A2M_OK) return rc;
+    if (e != cudaSuccess) { a2m_set_error("a2m_model_gnn_forward: %s", cudaGetErrorString(e)); return (int)e; }
+    return a2m_model_status(m);
 }
 
 extern "C" int a2m_model_status(a2m_model* m) {

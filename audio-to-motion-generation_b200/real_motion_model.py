@@ -146,6 +146,22 @@ class SelfAttention_G(NativeModule):
                     state_dict.pop(base + dup, None)
         return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
+    def graph_stack(self, part, x):
+        """The five fused graph layers of one branch on their own (real_motion_model.py:172-201 / :224-253):
+        x [n_graphs, J, 64] fp32 -> same shape.  part: "body" (J = 10) or "hand" (J = 42).  Diagnostic / test
+        surface of csrc/gnn_fused.cu (a2m_model_gnn_forward)."""
+        self._require_eval()
+        h = self.native()
+        joints = {"body": 10, "hand": 42}[part]
+        x = torch.as_tensor(x).to(device=h.device, dtype=torch.float32).contiguous()
+        if x.dim() != 3 or x.shape[1] != joints or x.shape[2] != 64:
+            raise ValueError("graph_stack(%r) expects [n_graphs, %d, 64], got %s" % (part, joints, tuple(x.shape)))
+        out = torch.empty_like(x)
+        with torch.cuda.device(h.device):
+            _cabi.check(_cabi.lib().a2m_model_gnn_forward(h.ptr, 0 if part == "body" else 1, _cabi.ptr(x), x.shape[0],
+                                                          _cabi.ptr(out), _cabi.stream_ptr(h.device)))
+        return out
+
     def forward(self, audio, real_pose=None):
         """audio [B, T, F] (log-mel) -> (pose [B, T, 104] fp32, [angle_loss]) or
         (pose, [bone_loss, angle_loss]) when real_pose [B, T, 104] is given."""

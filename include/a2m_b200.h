@@ -177,6 +177,11 @@ int a2m_model_forward(a2m_model* model, const float* mel, int64_t mel_stride_b, 
 int a2m_model_encoder_forward(a2m_model* model, const float* mel, int64_t B, int T, int F, float* out_nct, void* stream);
 /* UNet1D.forward (model_layers.py:341-374, D1): [B, 256, T] fp32 -> [B, 256, T] fp32 */
 int a2m_model_unet_forward(a2m_model* model, const float* x_nct, int64_t B, int T, float* out_nct, void* stream);
+/* The fused five-layer graph stack of one decoder branch (real_motion_model.py:172-201 body / :224-253 hand:
+ * GATConv, GraphConv, GATConv, GraphConv, GATConv, each + LayerNorm(64) -> LeakyReLU(0.2) -> + residual) on its own:
+ * x, out fp32 [n_graphs, J, 64] (J = 10 body / 42 hand), converted to/from the kernel's bf16 node tiles.
+ * Unit-test / diagnostic surface: allocates scratch and synchronises. part: 0 = body, 1 = hand. */
+int a2m_model_gnn_forward(a2m_model* model, int part, const float* x, int64_t n_graphs, float* out, void* stream);
 /* Synchronises the device and reports whether any kernel's bounded barrier wait expired. */
 int a2m_model_status(a2m_model* model);
 /* Algorithmic FLOPs (2*M*N*K over valid rows) of the tensor-core GEMMs one forward of this shape launches. */

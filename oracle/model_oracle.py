@@ -129,6 +129,20 @@ def graph_conv(sd, p, x, adj):
         F.linear(x, sd[p + ".lin_root.weight"])
 
 
+def gnn_stack(sd, part, x):
+    """The five graph layers of one branch (real_motion_model.py:172-201 / :224-253): GAT, GraphConv, GAT,
+    GraphConv, GAT, each followed by LayerNorm(64) -> LeakyReLU(0.2) -> + residual.  x [G, J, 64] -> same."""
+    nj = x.shape[1]
+    adj = dense_adjacency(sd[f"{part}_edge_index_template"], nj)
+    for li in range(1, 6):
+        layer = gat if li % 2 == 1 else graph_conv
+        y = layer(sd, f"{part}_gcn{li}", x, adj)
+        y = F.layer_norm(y, (JOINT_FEAT,), sd[f"{part}_layer_norms.{li - 1}.weight"],
+                         sd[f"{part}_layer_norms.{li - 1}.bias"], LN_EPS)
+        x = F.leaky_relu(y, SLOPE) + x
+    return x
+
+
 def decoder(sd, part, feats):
     """One of the two branches of real_motion_model.py:160-262; feats [B,256,T] -> [B,n_feat,T]."""
     nj = N_BODY if part == "body" else N_HAND
@@ -142,13 +156,7 @@ def decoder(sd, part, feats):
     B, C, T = x.shape
     x = F.linear(x.permute(0, 2, 1), sd[f"{part}_proj_in.weight"], sd[f"{part}_proj_in.bias"])
     x = x.reshape(B * T, nj, JOINT_FEAT)
-    adj = dense_adjacency(sd[f"{part}_edge_index_template"], nj)
-    for li in range(1, 6):
-        layer = gat if li % 2 == 1 else graph_conv
-        y = layer(sd, f"{part}_gcn{li}", x, adj)
-        y = F.layer_norm(y, (JOINT_FEAT,), sd[f"{part}_layer_norms.{li - 1}.weight"],
-                         sd[f"{part}_layer_norms.{li - 1}.bias"], LN_EPS)
-        x = F.leaky_relu(y, SLOPE) + x
+    x = gnn_stack(sd, part, x)
     x = x.reshape(B, T, nj * JOINT_FEAT)
     x = F.linear(x, sd[f"{part}_proj_out.weight"], sd[f"{part}_proj_out.bias"])
     x = F.layer_norm(x, (C,), sd[f"{part}_norm.weight"], sd[f"{part}_norm.bias"], LN_EPS)
