@@ -41,7 +41,8 @@ constexpr int kOffP = kOffH + 4 * 16384;               // attention / adjacency 
 constexpr int kOffS = kOffP + 2 * 32768;               // s_src [128][4] fp32
 constexpr int kOffLn = kOffS + kRows * 4 * 4;          // LayerNorm partials [128][4][2] fp32
 constexpr int kOffTopo = kOffLn + kRows * 4 * 2 * 4;   // nbr [48][6], deg [48]
-constexpr int kOffBar = kOffTopo + 48 * kMaxDeg * 4 + 48 * 4;
+constexpr int kOffPar = kOffTopo + 48 * kMaxDeg * 4 + 48 * 4;   // per layer: bias[64], ln_w[64], ln_b[64] fp32
+constexpr int kOffBar = kOffPar + 5 * 192 * 4;
 constexpr int kSmemBytes = kOffBar + 64 + 1024;
 constexpr uint32_t kColS = 256, kColOut = 288;         // TMEM columns: H [0,256), S [256,272), OUT [288,352)
 static_assert(kOffX % 1024 == 0 && kOffH % 1024 == 0 && kOffP % 1024 == 0, "swizzled tiles need 1024 B alignment");
@@ -87,6 +88,7 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
     float* s_ln = reinterpret_cast<float*>(smem + kOffLn);
     int* s_nbr = reinterpret_cast<int*>(smem + kOffTopo);
     int* s_deg = s_nbr + 48 * kMaxDeg;
+    float* s_par = reinterpret_cast<float*>(smem + kOffPar);
     uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint64_t* mma_bar = w_bar + 1;
     uint64_t* x_bar = w_bar + 2;                       // [2]
@@ -129,6 +131,11 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
     if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     for (int i = tid; i < J * kMaxDeg; i += kThreads) s_nbr[i] = p.nbr[i];
     for (int i = tid; i < J; i += kThreads) s_deg[i] = p.deg[i];
+    for (int i = tid; i < 5 * 192; i += kThreads) {
+        const int layer = i / 192, j = i - layer * 192;
+        const float* src = j < 64 ? ((layer & 1) ? p.gc_bias[layer >> 1] : p.gat_bias[layer >> 1]) : j < 128 ? p.ln_w[layer] : p.ln_b[layer];
+        s_par[i] = src[j & 63];
+    }
     {   // zero the attention matrices (only the static neighbour positions are ever rewritten) and the rows of
         // the node tiles that TMA never writes (rows_per_tile .. 127): 0 x garbage must not become NaN
         uint4 z = make_uint4(0, 0, 0, 0);
@@ -192,7 +199,6 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
             w_parity ^= 1;
             if ((layer & 1) == 0) {
                 // ================= GATConv =================
-                const int gi = layer >> 1;
                 if (tid == 0) {
                     tc_fence_after();
 #pragma unroll
@@ -213,7 +219,9 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
                     uint32_t t[16];
                     tmem_ld_32x16(tmem_lane + kColS, t);
                     tmem_ld_wait();
-                    s_dst_q = __uint_as_float(t[4 + q]) + __uint_as_float(t[12 + q]);
+                    const uint32_t dh = q == 0 ? t[4] : q == 1 ? t[5] : q == 2 ? t[6] : t[7];
+                    const uint32_t dl = q == 0 ? t[12] : q == 1 ? t[13] : q == 2 ? t[14] : t[15];
+                    s_dst_q = __uint_as_float(dh) + __uint_as_float(dl);
                     if (q == 0) {
                         *reinterpret_cast<float4*>(s_src + r * 4) =
                             make_float4(__uint_as_float(t[0]) + __uint_as_float(t[8]), __uint_as_float(t[1]) + __uint_as_float(t[9]),
@@ -286,13 +294,11 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
                     uint32_t t[16];
                     tmem_ld_32x16(tmem_lane + kColOut + q * 16, t);
                     tmem_ld_wait();
-                    const float* gb = p.gat_bias[gi];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(t[i]) + __ldg(gb + q * 16 + i);
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(t[i]);
                 }
             } else {
                 // ================= GraphConv =================
-                const int ci = layer >> 1;
                 if (q == 0) {                              // adjacency (no self loops) into P buffer 0
                     const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
                     *reinterpret_cast<__nv_bfloat16*>(s_p + pofs[0]) = zero;
@@ -348,13 +354,18 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
                     uint32_t t[16];
                     tmem_ld_32x16(tmem_lane + q * 16, t);
                     tmem_ld_wait();
-                    const float* cb = p.gc_bias[ci];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(t[i]) + __ldg(cb + q * 16 + i);
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(t[i]);
                 }
             }
             // ---- LayerNorm(64) over the four 16-feature quarters of the node -> LeakyReLU -> + residual
             {
+                const float4* par = reinterpret_cast<const float4*>(s_par + layer * 192 + q * 16);   // warp-uniform: broadcasts
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const float4 b4 = par[i4];
+                    v[i4 * 4] += b4.x; v[i4 * 4 + 1] += b4.y; v[i4 * 4 + 2] += b4.z; v[i4 * 4 + 3] += b4.w;
+                }
                 float s = 0.f, sq = 0.f;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { s += v[i]; sq = fmaf(v[i], v[i], sq); }
@@ -364,11 +375,14 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
                 const float4 b = *reinterpret_cast<const float4*>(s_ln + r * 8 + 4);
                 const float mean = (a.x + a.z + b.x + b.z) * (1.f / 64.f);
                 const float rstd = rsqrtf(fmaxf((a.y + a.w + b.y + b.w) * (1.f / 64.f) - mean * mean, 0.f) + 1e-5f);
-                const float* lw = p.ln_w[layer];
-                const float* lb = p.ln_b[layer];
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    x[i] += leaky((v[i] - mean) * rstd * __ldg(lw + q * 16 + i) + __ldg(lb + q * 16 + i));
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const float4 w4 = par[16 + i4], b4 = par[32 + i4];
+                    x[i4 * 4] += leaky((v[i4 * 4] - mean) * rstd * w4.x + b4.x);
+                    x[i4 * 4 + 1] += leaky((v[i4 * 4 + 1] - mean) * rstd * w4.y + b4.y);
+                    x[i4 * 4 + 2] += leaky((v[i4 * 4 + 2] - mean) * rstd * w4.z + b4.z);
+                    x[i4 * 4 + 3] += leaky((v[i4 * 4 + 3] - mean) * rstd * w4.w + b4.w);
+                }
             }
             if (!live) {
 #pragma unroll

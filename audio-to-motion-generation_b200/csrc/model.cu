@@ -66,7 +66,8 @@ struct ForwardPlan {
     std::vector<int> op_is_gemm;                // parallel to ops
     std::vector<std::string> op_name;           // parallel to ops (measurement aid)
     std::vector<long long> op_flops;            // parallel to ops: 2*M*N*K for GEMMs, 0 otherwise
-    int enc_end = 0, unet_end = 0;              // op index ranges: [0,enc_end) encoder, [enc_end,unet_end) unet
+    int enc_end = 0, unet_end = 0;              // op index ranges: [0,enc_end) encoder, [enc_end,unet_end) unet,
+    int body_end = 0;                           // [unet_end,body_end) body decoder, [body_end,size) hand decoder
     float* mel_in = nullptr;                    // staging (fp32) used by the stage entry points
     __nv_bfloat16 *enc_out = nullptr, *unet_out = nullptr;
     float* pose_stage = nullptr;                // fp32 [B, T, 104] written by the two logits GEMMs
@@ -98,6 +99,9 @@ struct a2m_model {
     float* cur_pose = nullptr;
     std::map<std::string, std::unique_ptr<ForwardPlan>> plans;
     std::string build_error;
+    // the two decoder branches are independent: the body branch runs on a side stream, forked / joined with events
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -710,6 +714,7 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
             // logits: fp32 straight into pose[B, T, 104] at this branch's column block
             E.linear_rows(D.logits, last, nullptr, 256, static_cast<long long>(BT), pose_stage, kPoseFeats,
                           part == 0 ? 0 : kBodyFeats, kOutF32);
+            if (pass == 1 && part == 0) P->body_end = static_cast<int>(P->ops.size());
         }
         if (E.rc != A2M_OK) return E.rc;
     }
@@ -788,6 +793,9 @@ extern "C" int a2m_model_create(const a2m_tensor_desc* tensors, int n_tensors, i
         return b.rc;
     }
     m->params.clear();                       // the caller's tensors are not referenced after this point
+    A2M_CUDA_CHECK(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
+    A2M_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    A2M_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
     *out = m.release();
     return A2M_OK;
 }
@@ -795,8 +803,12 @@ extern "C" int a2m_model_create(const a2m_tensor_desc* tensors, int n_tensors, i
 extern "C" void a2m_model_destroy(a2m_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
     m->plans.clear();
     for (void* p : m->owned) cudaFree(p);
+    if (m->side_stream) cudaStreamDestroy(m->side_stream);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     delete m;
 }
 
@@ -812,8 +824,17 @@ extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t mel_str
     A2M_ARG_CHECK(mel_stride_t >= F && (B == 1 || mel_stride_b >= mel_stride_t), "a2m_model_forward: mel strides (%lld, %lld)",
                   (long long)mel_stride_b, (long long)mel_stride_t);
     m->cur_mel = mel; m->cur_stride_b = mel_stride_b; m->cur_stride_t = mel_stride_t;
-    rc = run_ops(P, 0, static_cast<int>(P->ops.size()), s);
+    // trunk on the caller's stream, then body decoder (side stream) || hand decoder (caller's stream)
+    rc = run_ops(P, 0, P->unet_end, s);
     if (rc != A2M_OK) return rc;
+    A2M_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
+    A2M_CUDA_CHECK(cudaStreamWaitEvent(m->side_stream, m->ev_fork, 0));
+    rc = run_ops(P, P->unet_end, P->body_end, m->side_stream);
+    if (rc != A2M_OK) return rc;
+    A2M_CUDA_CHECK(cudaEventRecord(m->ev_join, m->side_stream));
+    rc = run_ops(P, P->body_end, static_cast<int>(P->ops.size()), s);
+    if (rc != A2M_OK) return rc;
+    A2M_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join, 0));
     float* stage = P->pose_stage;
     A2M_CUDA_CHECK(cudaMemcpyAsync(pose, stage, static_cast<size_t>(B) * T * kPoseFeats * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (losses) {
