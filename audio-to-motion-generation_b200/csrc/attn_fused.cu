@@ -1,0 +1,333 @@
+// Fused SelfAttention block for the 256-channel decoder layers (model_layers.py:121-146):
+//     q | k | v = 1x1 convs of x (one GEMM, N = 32 + 32 + 256)      -> tcgen05, TMA-fed K pipeline
+//     S = q k^T  (no 1/sqrt(d): model_layers.py:140)                 -> tcgen05, all clips of the tile at once
+//     P = exp(S - rowmax) restricted to the row's own clip           -> CUDA cores, one thread per row
+//     O = P v                                                        -> tcgen05 (B = v read MN-major)
+//     out = gamma * O / rowsum + x (+ res2: the ResBlock skip, :190) -> bf16
+// One CTA owns 128 consecutive rows = 128 / T whole clips (T in {8, 16, 32, 64}); q, k, v, S and O never leave
+// the SM (TMEM accumulators, bf16 operand tiles in shared memory).  Replaces a GEMM launch + an attention
+// launch and the [B, T, 320] bf16 round trip through L2 between them.
+#include <cuda.h>
+#include <cstring>
+#include "conv_gemm.cuh"
+#include "layers.cuh"
+
+void a2m_count_launch();
+
+namespace a2m {
+
+int make_weight_map(CUtensorMap* map, const void* w, long long n_rows, long long k, int box_rows);   // conv_gemm.cu
+
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kC = 256, kD = 32, kNqkv = 2 * kD + kC;      // 320
+constexpr int kStages = 3;
+constexpr int kABytes = 128 * 64 * 2;                      // 16 KB
+constexpr int kBBytes = kNqkv * 64 * 2;                    // 40 KB
+constexpr int kStageBytes = kABytes + kBBytes;             // 56 KB
+// operand tiles that alias the (drained) pipeline ring
+constexpr int kOffQ = 0, kOffK = 16384, kOffP = 32768, kOffV = 65536;       // Q, K [128][64]; P [128][128]; V 4 x [128][64]
+constexpr int kOffSum = kStages * kStageBytes;             // row sums [128] fp32
+constexpr int kOffBar = kOffSum + 512;
+constexpr int kSmemBytes = kOffBar + 128 + 1024;
+constexpr uint32_t kColS = 320;                            // TMEM: QKV [0,320) (later O [0,256)), S [320,448)
+static_assert(kOffV + 65536 <= kStages * kStageBytes, "operand tiles must fit in the ring");
+
+struct AttnParams {
+    CUtensorMap x_map;        // [rows][256] bf16, box 64 x 128
+    CUtensorMap w_map;        // [320][256] bf16, box 64 x 160
+    const float* bias;        // [320]
+    const float* gamma;       // device scalar
+    const __nv_bfloat16* x;   // residual
+    const __nv_bfloat16* res2;
+    __nv_bfloat16* out;
+    long long n_rows;
+    int T;
+};
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ int sw128_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
+// MN-major SW128 descriptor with an explicit leading-dimension byte offset (stride between 64-element atoms along N)
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fused_kernel(const __grid_constant__ AttnParams p, int* __restrict__ err_flag) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    float* s_sum = reinterpret_cast<float*>(smem + kOffSum);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);      // [kStages]
+    uint64_t* free0_bar = full_bar + kStages;                              // stage 0 drained by the first K block
+    uint64_t* gemm_bar = free0_bar + 1;                                    // q | k | v accumulators complete
+    uint64_t* s_bar = gemm_bar + 1;                                        // S = q k^T complete
+    uint64_t* o_bar = s_bar + 1;                                           // O = P v complete
+    uint64_t* qk_bar = o_bar + 1;                                          // 128 arrivals: q | k staged
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qk_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid & 127, q = tid >> 7, quad = warp & 3;
+    const long long row0 = static_cast<long long>(blockIdx.x) * 128;
+    const int T = p.T;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&p.x_map);
+        tma_prefetch_desc(&p.w_map);
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        mbar_init(free0_bar, 1);
+        mbar_init(gemm_bar, 1);
+        mbar_init(s_bar, 1);
+        mbar_init(o_bar, 1);
+        mbar_init(qk_bar, 128);
+        mbar_fence_init();
+        for (int kb = 0; kb < kStages; ++kb) {           // the first kStages K blocks; the 4th reuses stage 0 below
+            unsigned char* st = smem + kb * kStageBytes;
+            mbar_expect_tx(&full_bar[kb], kStageBytes);
+            tma_load_5d(st, &p.x_map, &full_bar[kb], kb * 64, static_cast<int>(row0), 0, 0, 0);
+            tma_load_5d(st + kABytes, &p.w_map, &full_bar[kb], kb * 64, 0, 0, 0, 0);
+            tma_load_5d(st + kABytes + 160 * 128, &p.w_map, &full_bar[kb], kb * 64, 160, 0, 0, 0);
+        }
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t ring = smem_u32(smem);
+
+    // ---------------- q | k | v = x Wqkv^T : 4 K blocks through a 3-stage ring ----------------
+    if (tid == 0) {
+        const uint32_t id256 = umma_idesc_bf16(128, 256), id64 = umma_idesc_bf16(128, 64);
+        for (int kb = 0; kb < 4; ++kb) {
+            const int s = kb % kStages;
+            mbar_wait(&full_bar[s], (kb / kStages) & 1, err_flag, 21);
+            tc_fence_after();
+            const uint32_t a = ring + s * kStageBytes, b = a + kABytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                umma_bf16(tmem_base, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), id256, (kb | k) != 0);
+                umma_bf16(tmem_base + 256, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + 32768 + k * 32), id64, (kb | k) != 0);
+            }
+            if (kb == 0) {                                // stage 0 is free once these MMAs have read it: 4th K block
+                umma_commit(free0_bar);
+                mbar_wait(free0_bar, 0, err_flag, 22);
+                unsigned char* st = smem;
+                mbar_expect_tx(&full_bar[0], kStageBytes);
+                tma_load_5d(st, &p.x_map, &full_bar[0], 3 * 64, static_cast<int>(row0), 0, 0, 0);
+                tma_load_5d(st + kABytes, &p.w_map, &full_bar[0], 3 * 64, 0, 0, 0, 0);
+                tma_load_5d(st + kABytes + 160 * 128, &p.w_map, &full_bar[0], 3 * 64, 160, 0, 0, 0);
+            }
+        }
+        umma_commit(gemm_bar);
+    }
+    mbar_wait(gemm_bar, 0, err_flag, 23);
+    tc_fence_after();
+
+    // ---------------- stage q, k (quarter 0) and v (all quarters) as bf16 MMA operands ----------------
+    if (q == 0) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {                  // hf 0: q -> Qs, hf 1: k -> Ks; columns 32..63 of both are zero
+            uint32_t t[32];
+            tmem_ld_32x32(tmem_lane + hf * 32, t);
+            tmem_ld_wait();
+            unsigned char* dst = smem + (hf == 0 ? kOffQ : kOffK);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 o;
+                const float* bb = p.bias + hf * 32 + c * 8;
+                o.x = pack2(__uint_as_float(t[c * 8]) + __ldg(bb), __uint_as_float(t[c * 8 + 1]) + __ldg(bb + 1));
+                o.y = pack2(__uint_as_float(t[c * 8 + 2]) + __ldg(bb + 2), __uint_as_float(t[c * 8 + 3]) + __ldg(bb + 3));
+                o.z = pack2(__uint_as_float(t[c * 8 + 4]) + __ldg(bb + 4), __uint_as_float(t[c * 8 + 5]) + __ldg(bb + 5));
+                o.w = pack2(__uint_as_float(t[c * 8 + 6]) + __ldg(bb + 6), __uint_as_float(t[c * 8 + 7]) + __ldg(bb + 7));
+                *reinterpret_cast<uint4*>(dst + sw128_off(r, c)) = o;
+                *reinterpret_cast<uint4*>(dst + sw128_off(r, c + 4)) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(qk_bar);
+    }
+    if (tid == 128) {                                     // S = q k^T as soon as q | k are staged (v staging overlaps)
+        mbar_wait(qk_bar, 0, err_flag, 24);
+        tc_fence_after();
+        const uint32_t id128 = umma_idesc_bf16(128, 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + kColS, umma_desc_sw128(ring + kOffQ + k * 32), umma_desc_sw128(ring + kOffK + k * 32), id128, k != 0);
+        umma_commit(s_bar);
+    }
+    {   // v: this quarter's 64 channels -> Vs chunk q ([128 rows (time)][64 channels], read MN-major by the P.v MMA)
+        unsigned char* dst = smem + kOffV + q * 16384;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            uint32_t t[32];
+            tmem_ld_32x32(tmem_lane + 64 + q * 64 + hf * 32, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 o;
+                const float* bb = p.bias + 64 + q * 64 + hf * 32 + c * 8;
+                o.x = pack2(__uint_as_float(t[c * 8]) + __ldg(bb), __uint_as_float(t[c * 8 + 1]) + __ldg(bb + 1));
+                o.y = pack2(__uint_as_float(t[c * 8 + 2]) + __ldg(bb + 2), __uint_as_float(t[c * 8 + 3]) + __ldg(bb + 3));
+                o.z = pack2(__uint_as_float(t[c * 8 + 4]) + __ldg(bb + 4), __uint_as_float(t[c * 8 + 5]) + __ldg(bb + 5));
+                o.w = pack2(__uint_as_float(t[c * 8 + 6]) + __ldg(bb + 6), __uint_as_float(t[c * 8 + 7]) + __ldg(bb + 7));
+                *reinterpret_cast<uint4*>(dst + sw128_off(r, hf * 4 + c)) = o;
+            }
+        }
+    }
+    // zero P (quarters 1..3; the row threads then write their own clip's block)
+    if (q != 0) {
+        uint4* pz = reinterpret_cast<uint4*>(smem + kOffP);
+        for (int i = tid - 128; i < 32768 / 16; i += kThreads - 128) pz[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();                                      // P zeroed before the row threads write into it
+
+    // ---------------- softmax of each row over its own clip (quarter 0: one thread per row) ----------------
+    if (q == 0) {
+        mbar_wait(s_bar, 0, err_flag, 25);
+        tc_fence_after();
+        const int win = T < 32 ? 32 : T;                  // warp-uniform column window that covers the warp's clips
+        const int win0 = ((quad * 32) / win) * win;
+        const int c_lo = (r / T) * T - win0, c_hi = c_lo + T;    // my clip's columns inside the window
+        float e[64];
+        float m = -INFINITY;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            if (hf * 32 < win) {
+                uint32_t t[32];
+                tmem_ld_32x32(tmem_lane + kColS + win0 + hf * 32, t);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int c = hf * 32 + j;
+                    e[c] = (c >= c_lo && c < c_hi) ? __uint_as_float(t[j]) : -INFINITY;
+                    m = fmaxf(m, e[c]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) e[hf * 32 + j] = -INFINITY;
+            }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) { e[c] = __expf(e[c] - m); sum += e[c]; }       // exp(-inf) = 0 outside the clip
+        s_sum[r] = sum;
+        // P row: 8-column chunks of the window that intersect my clip (T is a multiple of 8, so whole chunks)
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+            const int c = ch * 8;
+            if (c >= c_lo && c < c_hi) {
+                uint4 o;
+                o.x = pack2(e[c], e[c + 1]); o.y = pack2(e[c + 2], e[c + 3]);
+                o.z = pack2(e[c + 4], e[c + 5]); o.w = pack2(e[c + 6], e[c + 7]);
+                const int col = win0 + c;                 // absolute column (time row of the tile)
+                *reinterpret_cast<uint4*>(smem + kOffP + (col >> 6) * 16384 + sw128_off(r, (col & 63) >> 3)) = o;
+            }
+        }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();                                      // v and P staged, all TMEM reads of q | k | v done
+
+    // ---------------- O = P v ----------------
+    if (tid == 0) {
+        tc_fence_after();
+        const uint32_t id_o = umma_idesc_bf16(128, 256) | (1u << 16);         // B (v) is MN-major
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+            umma_bf16(tmem_base, umma_desc_sw128(ring + kOffP + (kk >> 2) * 16384 + (kk & 3) * 32),
+                      umma_desc_mn(ring + kOffV + kk * 2048, 16384), id_o, kk != 0);
+        umma_commit(o_bar);
+    }
+    mbar_wait(o_bar, 0, err_flag, 26);
+    tc_fence_after();
+
+    // ---------------- out = gamma * O / rowsum + x (+ res2) ----------------
+    {
+        const float scale = __ldg(p.gamma) / s_sum[r];
+        const long long row = row0 + r;
+        const bool live = row < p.n_rows;
+        const long long base = row * kC + q * 64;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            uint32_t t[32];
+            tmem_ld_32x32(tmem_lane + q * 64 + hf * 32, t);
+            tmem_ld_wait();
+            if (live) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const long long o = base + hf * 32 + c * 8;
+                    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(p.x + o));
+                    uint4 rv = make_uint4(0, 0, 0, 0);
+                    if (p.res2) rv = __ldg(reinterpret_cast<const uint4*>(p.res2 + o));
+                    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, rs[4] = {rv.x, rv.y, rv.z, rv.w};
+                    uint32_t os[4];
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        const float a = scale * __uint_as_float(t[c * 8 + 2 * e2]) + __uint_as_float(xs[e2] << 16) +
+                                        __uint_as_float(rs[e2] << 16);
+                        const float b = scale * __uint_as_float(t[c * 8 + 2 * e2 + 1]) + __uint_as_float(xs[e2] & 0xffff0000u) +
+                                        __uint_as_float(rs[e2] & 0xffff0000u);
+                        os[e2] = pack2(a, b);
+                    }
+                    *reinterpret_cast<uint4*>(p.out + o) = make_uint4(os[0], os[1], os[2], os[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace
+
+struct AttnFusedPlan {
+    AttnParams p;
+    int grid;
+};
+
+bool attn_fused_supported(int T, int C) { return C == kC && T >= 8 && T <= 64 && (128 % T) == 0; }
+
+int attn_fused_plan(const __nv_bfloat16* w_qkv, const float* bias_qkv, const float* gamma, const __nv_bfloat16* x,
+                    const __nv_bfloat16* res2, int B, int T, int C, __nv_bfloat16* out, std::shared_ptr<AttnFusedPlan>* plan_out) {
+    A2M_ARG_CHECK(attn_fused_supported(T, C), "attn_fused: T = %d, C = %d not supported", T, C);
+    auto plan = std::make_shared<AttnFusedPlan>();
+    AttnParams& p = plan->p;
+    memset(&p, 0, sizeof(p));
+    const long long rows = static_cast<long long>(B) * T;
+    int rc = make_weight_map(&p.x_map, x, rows, kC, 128);
+    if (rc != A2M_OK) return rc;
+    rc = make_weight_map(&p.w_map, w_qkv, kNqkv, kC, 160);
+    if (rc != A2M_OK) return rc;
+    p.bias = bias_qkv; p.gamma = gamma; p.x = x; p.res2 = res2; p.out = out; p.n_rows = rows; p.T = T;
+    plan->grid = static_cast<int>((rows + 127) / 128);
+    *plan_out = plan;
+    return A2M_OK;
+}
+
+int attn_fused_launch(const AttnFusedPlan& plan, int* err_flag, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        configured = true;
+    }
+    attn_fused_kernel<<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.p, err_flag);
+    a2m_count_launch();
+    A2M_LAUNCH_CHECK();
+    return A2M_OK;
+}
+
+}  // namespace a2m

@@ -24,6 +24,14 @@ int launch_time_interp(const float* in, int n_planes, int B, int Hc, int T, int 
 int launch_attention(const __nv_bfloat16* qkv, const __nv_bfloat16* x, const __nv_bfloat16* res2, const float* gamma,
                      int B, int T, int C, __nv_bfloat16* out, cudaStream_t stream);
 
+// The same block fused with its q|k|v projection for the 256-channel decoder layers (csrc/attn_fused.cu):
+// w_qkv [320, 256] bf16 (q: 32, k: 32, v: 256 rows), bias_qkv [320]; T must divide 128.
+struct AttnFusedPlan;
+bool attn_fused_supported(int T, int C);
+int attn_fused_plan(const __nv_bfloat16* w_qkv, const float* bias_qkv, const float* gamma, const __nv_bfloat16* x,
+                    const __nv_bfloat16* res2, int B, int T, int C, __nv_bfloat16* out, std::shared_ptr<AttnFusedPlan>* plan);
+int attn_fused_launch(const AttnFusedPlan& plan, int* err_flag, cudaStream_t stream);
+
 // ChannelAttention (model_layers.py:167-174): x * (sigmoid(mlp(avg_T x)) + sigmoid(mlp(max_T x))), C = 256, hidden 32
 int launch_channel_attention(const __nv_bfloat16* x, int B, int T, int C, int hidden, const float* w0, const float* b0,
                              const float* w2, const float* b2, __nv_bfloat16* out, cudaStream_t stream);

@@ -509,8 +509,17 @@ struct Emit {
     void attention(const AttnW& A, const __nv_bfloat16* x, const __nv_bfloat16* res2, int len, int B, __nv_bfloat16* qkv,
                    __nv_bfloat16* out) {
         const int C = A.C, ld = 2 * (C / 8) + C;
-        linear_rows(A.qkv, x, nullptr, C, static_cast<long long>(B) * len, qkv, ld, 0, kOutBf16);
         const float* gamma = A.gamma;
+        if (attn_fused_supported(len, C)) {               // decoder blocks: projection + attention in one kernel
+            if (dry || rc != A2M_OK) return;
+            std::shared_ptr<AttnFusedPlan> ap;
+            rc = attn_fused_plan(A.qkv.w, A.qkv.bias, gamma, x, res2, B, len, C, out, &ap);
+            if (rc != A2M_OK) return;
+            int* flag = m->err_flag;
+            op([ap, flag](cudaStream_t s) { return attn_fused_launch(*ap, flag, s); });
+            return;
+        }
+        linear_rows(A.qkv, x, nullptr, C, static_cast<long long>(B) * len, qkv, ld, 0, kOutBf16);
         op([=](cudaStream_t s) { return launch_attention(qkv, x, res2, gamma, B, len, C, out, s); });
     }
     void channel(const ChanW& W, const __nv_bfloat16* x, int len, int B, __nv_bfloat16* out) {

@@ -12,6 +12,7 @@ build defines, written against the drop-in modules of this package:
 One process per GPU (torchrun); ranks own contiguous clip ranges; weights are replicated; the only
 collective is ``allreduce_metrics`` (NCCL over NVLink through liba2m_b200's run-time binding).
 """
+import copy
 import ctypes
 
 import torch
@@ -88,7 +89,10 @@ def allreduce_metrics(accum, comm=None):
 class AudioToPosePipeline:
     """mel -> generator -> evaluation on one GPU.  `model` is a SelfAttention_G drop-in in eval mode on `device`."""
 
-    def __init__(self, model, alpha=0.2, comm=None):
+    def __init__(self, model, alpha=0.2, comm=None, lanes=2):
+        """`lanes` > 1 runs consecutive batches on alternating CUDA streams, each lane with its own packed
+        weights and activation arena, so the latency-bound tail of one batch (graph decoders, small GEMMs)
+        overlaps the head of the next.  Results do not depend on the lane count."""
         self.model = model
         self.alpha = alpha
         self.comm = comm
@@ -97,20 +101,43 @@ class AudioToPosePipeline:
             raise RuntimeError("AudioToPosePipeline needs the model on a CUDA device; there is no CPU fallback")
         self.accum = motion_evaluation.new_metrics(self.device)
         self._copy_stream = torch.cuda.Stream(self.device)
+        self._lane_models = [model]
+        for _ in range(max(1, int(lanes)) - 1):
+            twin = copy.deepcopy(model).eval()
+            twin.repack()                       # its own native handle (weights + arena)
+            self._lane_models.append(twin)
+        self._lane_streams = [torch.cuda.Stream(self.device) for _ in self._lane_models]
+        self._turn = 0
 
     def reset(self):
+        self.sync_lanes()
         self.accum.zero_()
 
-    def generate(self, wav):
-        """wav [B, N] fp32 CUDA tensor -> pose [B, 64, 104] fp32."""
+    def sync_lanes(self):
+        """Make the caller's current stream wait for everything the lanes have been given so far."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self._lane_streams:
+            cur.wait_stream(st)
+
+    def generate(self, wav, model=None):
+        """wav [B, N] fp32 CUDA tensor -> pose [B, 64, 104] fp32 (on the current stream)."""
         logmel = audio_repr.log_mel_spectograms(wav)
-        pose, _ = self.model(adapter(logmel))
+        pose, _ = (model or self.model)(adapter(logmel))
         return pose
 
     def step(self, wav, gt_pose):
-        """One batch, inputs already on the device: accumulates the metric partials, returns the poses."""
-        pose = self.generate(wav)
-        motion_evaluation.evaluate_poses(pose, gt_pose, self.alpha, accum=self.accum)
+        """One batch, inputs already on the device: enqueues mel -> generator -> evaluation on the next lane and
+        accumulates the metric partials.  Returns the poses; they (and the metrics) are complete once
+        ``sync_lanes()`` / ``finish()`` has been called on the consuming stream."""
+        lane = self._turn % len(self._lane_models)
+        self._turn += 1
+        st = self._lane_streams[lane]
+        st.wait_stream(torch.cuda.current_stream(self.device))      # inputs were produced on the caller's stream
+        with torch.cuda.stream(st):
+            pose = self.generate(wav, self._lane_models[lane])
+            motion_evaluation.evaluate_poses(pose, gt_pose, self.alpha, accum=self.accum)
+        wav.record_stream(st)
+        gt_pose.record_stream(st)
         return pose
 
     def run_host_batches(self, batches):
@@ -145,6 +172,7 @@ class AudioToPosePipeline:
 
     def finish(self):
         """All-reduce (if sharded) and read the 64-byte result: {'pck', 'l1_pose', 'l1_motion', counts...}."""
+        self.sync_lanes()
         allreduce_metrics(self.accum, self.comm)
         m = motion_evaluation.read_metrics(self.accum)
         m.update(motion_evaluation.finalize_metrics(m))

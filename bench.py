@@ -130,6 +130,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--ref-clips", type=int, default=16)
+    ap.add_argument("--lanes", type=int, default=2, help="CUDA-stream lanes consecutive batches alternate over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -169,7 +170,7 @@ def main():
                 p.copy_(0.1 * torch.randn(p.shape, generator=g))
     model = model.to(device).eval()
     comm = pipeline.Communicator(rank, world, device) if world > 1 else None
-    pipe = pipeline.AudioToPosePipeline(model, comm=comm)
+    pipe = pipeline.AudioToPosePipeline(model, comm=comm, lanes=args.lanes)
 
     # ---- synthetic inputs: per-clip seeds make any sharding reproduce the same clips -----------------
     B = args.batch
@@ -288,6 +289,7 @@ def main():
                 "config": {"workload": "config2: PATS-shaped batch %d (68267 samples -> 425x64 log-mel -> 64x64 -> 64x104 poses), "
                                        "mel + SelfAttention_G forward + L1/PCK" % B,
                            "clips_per_step_per_gpu": B, "parallelism": "clip-sharded x%d" % world,
+                           "stream_lanes": args.lanes,
                            "l2": "inputs cycle through %d distinct batches (%.0f MB each) > L2" % (POOL, h2d / 1e6)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,

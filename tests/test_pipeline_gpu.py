@@ -1,0 +1,74 @@
+"""GPU test of the composed hot path (pipeline.AudioToPosePipeline: mel -> adapter D2 -> SelfAttention_G ->
+L1/PCK partials) against the oracle composition, and of the stream-lane pipelining (results must not depend on
+the number of lanes or on how clips are batched)."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import eval_oracle, mel_oracle, model_oracle, synth, weights
+
+pytestmark = pytest.mark.gpu
+PKG = "audio-to-motion-generation_b200"
+
+
+@pytest.fixture(scope="module")
+def setup(pkg):
+    mods = pkg.install_dropin()
+    pipeline = importlib.import_module(PKG + ".pipeline")
+    sd = weights.make_state_dict(0, "stress")
+    model = mods["real_motion_model"].SelfAttention_G().cuda().eval()
+    model.load_state_dict(sd)
+    return pipeline, model, sd
+
+
+def run(pipeline, model, lanes, batches):
+    pipe = pipeline.AudioToPosePipeline(model, lanes=lanes)
+    poses = [pipe.step(torch.from_numpy(w).cuda(), torch.from_numpy(g).cuda()) for w, g in batches]
+    out = pipe.finish()
+    return out, [p.cpu() for p in poses]
+
+
+def test_composed_path_matches_oracle(setup):
+    pipeline, model, sd = setup
+    wav, gt = synth.wav_batch(0, 3), synth.gt_pose_batch(0, 3)
+    out, poses = run(pipeline, model, 1, [(wav, gt)])
+    mel = mel_oracle.log_mel_batch(wav)
+    x = torch.from_numpy(synth.adapter(mel).astype(np.float32))
+    ref_pose, _ = model_oracle.generator_forward(sd, x)
+    rel = ((poses[0] - ref_pose).abs().sum() / ref_pose.abs().sum()).item()
+    assert rel <= 1e-2, rel
+    # the metrics of the GPU poses, evaluated by the oracle: hit counts bit-exact, sums to fp64 round-off
+    ref = eval_oracle.metric_partials(poses[0].numpy(), gt)
+    assert out["pck_hits"] == ref["pck_hits"] and out["n_keypoints"] == ref["n_keypoints"] == 3 * 64 * 52
+    np.testing.assert_allclose(out["abs_pose"], ref["abs_pose"], rtol=1e-9)
+    np.testing.assert_allclose(out["abs_motion"], ref["abs_motion"], rtol=1e-9)
+    fin = eval_oracle.finalize(ref)
+    np.testing.assert_allclose([out["pck"], out["l1_pose"], out["l1_motion"]],
+                               [fin["pck"], fin["l1_pose"], fin["l1_motion"]], rtol=1e-9)
+
+
+def test_lanes_and_batching_do_not_change_results(setup):
+    pipeline, model, _ = setup
+    wav, gt = synth.wav_batch(10, 8), synth.gt_pose_batch(10, 8)
+    whole, p1 = run(pipeline, model, 1, [(wav, gt)])
+    split = [(wav[i:i + 2], gt[i:i + 2]) for i in range(0, 8, 2)]
+    for lanes in (1, 2, 3):
+        out, poses = run(pipeline, model, lanes, split)
+        assert torch.equal(torch.cat(poses), p1[0])
+        assert out["pck_hits"] == whole["pck_hits"] and out["n_frames"] == whole["n_frames"] == 8 * 64
+        np.testing.assert_allclose(out["abs_pose"], whole["abs_pose"], rtol=1e-12)
+        np.testing.assert_allclose(out["abs_motion"], whole["abs_motion"], rtol=1e-12)
+
+
+def test_host_batches_end_to_end(setup):
+    pipeline, model, _ = setup
+    wav, gt = synth.wav_batch(20, 4), synth.gt_pose_batch(20, 4)
+    ref, _ = run(pipeline, model, 1, [(wav, gt)])
+    pipe = pipeline.AudioToPosePipeline(model, lanes=2)
+    host = [(torch.from_numpy(wav[i:i + 1]).pin_memory(), torch.from_numpy(gt[i:i + 1]).pin_memory()) for i in range(4)]
+    assert pipe.run_host_batches(host) == 4
+    out = pipe.finish()
+    assert out["pck_hits"] == ref["pck_hits"]
+    np.testing.assert_allclose(out["abs_pose"], ref["abs_pose"], rtol=1e-12)
