@@ -32,6 +32,24 @@ void a2m_set_error(const char* fmt, ...);
 
 int a2m_num_sms();   // cached SM count of the current device
 
+// Launch with programmatic dependent launch (PDL): the kernel may start while its predecessor in the stream is
+// still draining; it must execute pdl_wait() before it touches anything the predecessor wrote (or may still read).
+template <typename... KArgs, typename... Args>
+inline cudaError_t a2m_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // small device utilities
@@ -71,6 +89,12 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+
+// ------------------------------- programmatic dependent launch --------------------------------
+// launch_dependents: lets the next kernel of the stream begin its prologue; wait: blocks until the previous
+// kernel has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------- mbarrier ----------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

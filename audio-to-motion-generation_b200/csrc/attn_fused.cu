@@ -29,7 +29,8 @@ constexpr int kStageBytes = kABytes + kBBytes;             // 56 KB
 // operand tiles that alias the (drained) pipeline ring
 constexpr int kOffQ = 0, kOffK = 16384, kOffP = 32768, kOffV = 65536;       // Q, K [128][64]; P [128][128]; V 4 x [128][64]
 constexpr int kOffSum = kStages * kStageBytes;             // row sums [128] fp32
-constexpr int kOffBar = kOffSum + 512;
+constexpr int kOffBias = kOffSum + 512;                    // q | k | v bias [320] fp32
+constexpr int kOffBar = kOffBias + kNqkv * 4;
 constexpr int kSmemBytes = kOffBar + 128 + 1024;
 constexpr uint32_t kColS = 320;                            // TMEM: QKV [0,320) (later O [0,256)), S [320,448)
 static_assert(kOffV + 65536 <= kStages * kStageBytes, "operand tiles must fit in the ring");
@@ -68,6 +69,7 @@ attn_fused_kernel(const __grid_constant__ AttnParams p, int* __restrict__ err_fl
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     float* s_sum = reinterpret_cast<float*>(smem + kOffSum);
+    float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);      // [kStages]
     uint64_t* free0_bar = full_bar + kStages;                              // stage 0 drained by the first K block
     uint64_t* gemm_bar = free0_bar + 1;                                    // q | k | v accumulators complete
@@ -81,6 +83,7 @@ attn_fused_kernel(const __grid_constant__ AttnParams p, int* __restrict__ err_fl
     const long long row0 = static_cast<long long>(blockIdx.x) * 128;
     const int T = p.T;
 
+    pdl_launch_dependents();
     if (tid == 0) {
         tma_prefetch_desc(&p.x_map);
         tma_prefetch_desc(&p.w_map);
@@ -91,6 +94,17 @@ attn_fused_kernel(const __grid_constant__ AttnParams p, int* __restrict__ err_fl
         mbar_init(o_bar, 1);
         mbar_init(qk_bar, 128);
         mbar_fence_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if (tid < kNqkv) s_bias[tid] = __ldg(p.bias + tid);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t ring = smem_u32(smem);
+    pdl_wait();                                           // x (and res2) come from the previous kernels
+    if (tid == 0) {
         for (int kb = 0; kb < kStages; ++kb) {           // the first kStages K blocks; the 4th reuses stage 0 below
             unsigned char* st = smem + kb * kStageBytes;
             mbar_expect_tx(&full_bar[kb], kStageBytes);
@@ -99,13 +113,6 @@ attn_fused_kernel(const __grid_constant__ AttnParams p, int* __restrict__ err_fl
             tma_load_5d(st + kABytes + 160 * 128, &p.w_map, &full_bar[kb], kb * 64, 160, 0, 0, 0);
         }
     }
-    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const uint32_t ring = smem_u32(smem);
 
     // ---------------- q | k | v = x Wqkv^T : 4 K blocks through a 3-stage ring ----------------
     if (tid == 0) {
@@ -146,11 +153,12 @@ attn_fused_kernel(const __grid_constant__ AttnParams p, int* __restrict__ err_fl
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint4 o;
-                const float* bb = p.bias + hf * 32 + c * 8;
-                o.x = pack2(__uint_as_float(t[c * 8]) + __ldg(bb), __uint_as_float(t[c * 8 + 1]) + __ldg(bb + 1));
-                o.y = pack2(__uint_as_float(t[c * 8 + 2]) + __ldg(bb + 2), __uint_as_float(t[c * 8 + 3]) + __ldg(bb + 3));
-                o.z = pack2(__uint_as_float(t[c * 8 + 4]) + __ldg(bb + 4), __uint_as_float(t[c * 8 + 5]) + __ldg(bb + 5));
-                o.w = pack2(__uint_as_float(t[c * 8 + 6]) + __ldg(bb + 6), __uint_as_float(t[c * 8 + 7]) + __ldg(bb + 7));
+                const float4 b0 = *reinterpret_cast<const float4*>(s_bias + hf * 32 + c * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(s_bias + hf * 32 + c * 8 + 4);
+                o.x = pack2(__uint_as_float(t[c * 8]) + b0.x, __uint_as_float(t[c * 8 + 1]) + b0.y);
+                o.y = pack2(__uint_as_float(t[c * 8 + 2]) + b0.z, __uint_as_float(t[c * 8 + 3]) + b0.w);
+                o.z = pack2(__uint_as_float(t[c * 8 + 4]) + b1.x, __uint_as_float(t[c * 8 + 5]) + b1.y);
+                o.w = pack2(__uint_as_float(t[c * 8 + 6]) + b1.z, __uint_as_float(t[c * 8 + 7]) + b1.w);
                 *reinterpret_cast<uint4*>(dst + sw128_off(r, c)) = o;
                 *reinterpret_cast<uint4*>(dst + sw128_off(r, c + 4)) = make_uint4(0, 0, 0, 0);
             }
@@ -178,11 +186,12 @@ attn_fused_kernel(const __grid_constant__ AttnParams p, int* __restrict__ err_fl
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint4 o;
-                const float* bb = p.bias + 64 + q * 64 + hf * 32 + c * 8;
-                o.x = pack2(__uint_as_float(t[c * 8]) + __ldg(bb), __uint_as_float(t[c * 8 + 1]) + __ldg(bb + 1));
-                o.y = pack2(__uint_as_float(t[c * 8 + 2]) + __ldg(bb + 2), __uint_as_float(t[c * 8 + 3]) + __ldg(bb + 3));
-                o.z = pack2(__uint_as_float(t[c * 8 + 4]) + __ldg(bb + 4), __uint_as_float(t[c * 8 + 5]) + __ldg(bb + 5));
-                o.w = pack2(__uint_as_float(t[c * 8 + 6]) + __ldg(bb + 6), __uint_as_float(t[c * 8 + 7]) + __ldg(bb + 7));
+                const float4 b0 = *reinterpret_cast<const float4*>(s_bias + 64 + q * 64 + hf * 32 + c * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(s_bias + 64 + q * 64 + hf * 32 + c * 8 + 4);
+                o.x = pack2(__uint_as_float(t[c * 8]) + b0.x, __uint_as_float(t[c * 8 + 1]) + b0.y);
+                o.y = pack2(__uint_as_float(t[c * 8 + 2]) + b0.z, __uint_as_float(t[c * 8 + 3]) + b0.w);
+                o.z = pack2(__uint_as_float(t[c * 8 + 4]) + b1.x, __uint_as_float(t[c * 8 + 5]) + b1.y);
+                o.w = pack2(__uint_as_float(t[c * 8 + 6]) + b1.z, __uint_as_float(t[c * 8 + 7]) + b1.w);
                 *reinterpret_cast<uint4*>(dst + sw128_off(r, hf * 4 + c)) = o;
             }
         }
@@ -324,9 +333,8 @@ int attn_fused_launch(const AttnFusedPlan& plan, int* err_flag, cudaStream_t str
         A2M_CUDA_CHECK(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         configured = true;
     }
-    attn_fused_kernel<<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.p, err_flag);
+    A2M_CUDA_CHECK(a2m_launch_pdl(attn_fused_kernel, dim3(plan.grid), dim3(kThreads), kSmemBytes, stream, plan.p, err_flag));
     a2m_count_launch();
-    A2M_LAUNCH_CHECK();
     return A2M_OK;
 }
 

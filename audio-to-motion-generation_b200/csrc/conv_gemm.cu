@@ -30,7 +30,8 @@ struct Smem {
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = kStages * kStageBytes;
-    static constexpr int kTotal = kBarOffset + 128 + 1024;      // barriers + alignment slack
+    static constexpr int kBiasOffset = kBarOffset + 128;        // folded bias of this N tile, fp32 [BLOCK_N]
+    static constexpr int kTotal = kBiasOffset + BLOCK_N * 4 + 1024;      // + alignment slack
 };
 
 template <int BLOCK_N>
@@ -64,6 +65,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
     const int kb_lo = static_cast<int>(static_cast<long long>(blockIdx.z) * p.k_blocks / p.split_k);
     const int kb_hi = static_cast<int>(static_cast<long long>(blockIdx.z + 1) * p.k_blocks / p.split_k);
 
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.a_map[0]);
         tma_prefetch_desc(&p.a_map[1]);
@@ -80,6 +82,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                      // the prologue above overlapped the previous kernel's tail
 
     if (warp == 0) {
         if (lane == 0) {
@@ -123,6 +126,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
     } else {
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;
+        // the tile's bias goes to shared memory while the main loop runs (the epilogue then reads broadcasts)
+        float* s_bias = reinterpret_cast<float*>(smem + S::kBiasOffset);
+        for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128)
+            s_bias[i] = (bias != nullptr && n0 + i < p.N && blockIdx.z == 0) ? __ldg(bias + n0 + i) : 0.f;
+        named_barrier(2, 128);
         long long off = p.out_base;
         bool valid = true;
         {
@@ -153,14 +161,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0 + hf * 32, v);
                     tmem_ld_wait();
-                    const int nn = n + hf * 32;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         float f[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            float x = __uint_as_float(v[j + e]);
-                            if (bias != nullptr && nn + j + e < p.N) x += __ldg(bias + nn + j + e);
+                            float x = __uint_as_float(v[j + e]) + s_bias[c0 + hf * 32 + j + e];
                             if (p.act == kActLeaky) x = x > 0.f ? x : kLeakySlope * x;
                             else if (p.act == kActRelu) x = fmaxf(x, 0.f);
                             f[e] = x;
@@ -195,8 +201,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                float x = __uint_as_float(v[j]);
-                if (bias != nullptr && n + j < p.N && blockIdx.z == 0) x += __ldg(bias + n + j);
+                float x = __uint_as_float(v[j]) + s_bias[c0 + j];
                 if (p.act == kActLeaky) x = x > 0.f ? x : kLeakySlope * x;
                 else if (p.act == kActRelu) x = fmaxf(x, 0.f);
                 f[j] = x;
@@ -333,10 +338,9 @@ int launch_variant(const ConvGemmPlan& plan, int* err_flag, cudaStream_t stream)
                                             Smem<BLOCK_N>::kTotal));
         configured = true;
     }
-    conv_gemm_kernel<BLOCK_N><<<plan.grid, kThreads, Smem<BLOCK_N>::kTotal, stream>>>(
-        plan.p, plan.bias, plan.out, err_flag);
+    A2M_CUDA_CHECK(a2m_launch_pdl(conv_gemm_kernel<BLOCK_N>, plan.grid, dim3(kThreads), Smem<BLOCK_N>::kTotal, stream,
+                                  plan.p, plan.bias, plan.out, err_flag));
     a2m_count_launch();
-    A2M_LAUNCH_CHECK();
     return A2M_OK;
 }
 

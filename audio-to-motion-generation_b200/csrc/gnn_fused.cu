@@ -114,6 +114,7 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
         }
     };
 
+    pdl_launch_dependents();
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) tma_prefetch_desc(&p.w_gat[i]);
         for (int i = 0; i < 2; ++i) tma_prefetch_desc(&p.w_gc[i]);
@@ -124,9 +125,7 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
         mbar_init(&x_bar[0], 1);
         mbar_init(&x_bar[1], 1);
         mbar_fence_init();
-        load_weights(0);
-        mbar_expect_tx(&x_bar[0], tile_bytes);
-        tma_load_5d(smem + kOffX, &p.x_in, &x_bar[0], 0, static_cast<int>(blockIdx.x * static_cast<long long>(rows_per_tile)), 0, 0, 0);
+        load_weights(0);                               // weights are constants: no need to wait for the predecessor
     }
     if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     for (int i = tid; i < J * kMaxDeg; i += kThreads) s_nbr[i] = p.nbr[i];
@@ -151,6 +150,11 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    pdl_wait();                                        // node features come from the previous kernel (proj_in)
+    if (tid == 0) {
+        mbar_expect_tx(&x_bar[0], tile_bytes);
+        tma_load_5d(smem + kOffX, &p.x_in, &x_bar[0], 0, static_cast<int>(blockIdx.x * static_cast<long long>(rows_per_tile)), 0, 0, 0);
+    }
     const uint32_t idesc_h = umma_idesc_bf16(128, 256), idesc_s = umma_idesc_bf16(128, 16);
     const uint32_t idesc_agg = idesc_b_mn(128, 64), idesc_gc = umma_idesc_bf16(128, 64);
     const uint32_t w_addr = smem_u32(smem + kOffW), h_addr = smem_u32(s_h), p_addr = smem_u32(s_p);
@@ -481,9 +485,8 @@ int gnn_fused_launch(const GnnFusedPlan& plan, int* err_flag, cudaStream_t strea
         A2M_CUDA_CHECK(cudaFuncSetAttribute(gnn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         configured = true;
     }
-    gnn_fused_kernel<<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.p, err_flag);
+    A2M_CUDA_CHECK(a2m_launch_pdl(gnn_fused_kernel, dim3(plan.grid), dim3(kThreads), kSmemBytes, stream, plan.p, err_flag));
     a2m_count_launch();
-    A2M_LAUNCH_CHECK();
     return A2M_OK;
 }
 
