@@ -45,8 +45,8 @@ __device__ __forceinline__ bool pck_hit(float gx, float gy, float px, float py, 
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-eval_l1_pck_kernel(const float* __restrict__ pred, const float* __restrict__ gt, long long n_clips, int T, float alpha,
-                   double* __restrict__ pck_per_frame, float* __restrict__ radius_per_frame,
+eval_l1_pck_kernel(const float* __restrict__ pred, const float* __restrict__ gt, long long n_clips, int T, int seg_frames,
+                   int segs, float alpha, double* __restrict__ pck_per_frame, float* __restrict__ radius_per_frame,
                    a2m_metrics* __restrict__ accum) {
     __shared__ double s_pose[kWarpsPerBlock], s_motion[kWarpsPerBlock];
     __shared__ unsigned long long s_hits[kWarpsPerBlock];
@@ -55,14 +55,21 @@ eval_l1_pck_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
     double abs_pose = 0.0, abs_motion = 0.0;
     unsigned long long hits = 0;
 
-    for (long long clip = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp; clip < n_clips;
-         clip += static_cast<long long>(gridDim.x) * kWarpsPerBlock) {
+    // work item = (clip, time segment): small batches still fill the machine; a segment that does not start the clip
+    // loads the frame before it for the motion difference
+    const long long n_items = n_clips * segs;
+    for (long long item = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp; item < n_items;
+         item += static_cast<long long>(gridDim.x) * kWarpsPerBlock) {
+        const long long clip = item / segs;
+        const int t_begin = static_cast<int>(item - clip * segs) * seg_frames;
+        const int t_end = min(T, t_begin + seg_frames);
         const float* p = pred + clip * T * kFeat;
         const float* g = gt + clip * T * kFeat;
-        FrameRegs cur = load_frame(p, g, lane, has_b), prev = cur;
-        for (int t = 0; t < T; ++t) {
+        FrameRegs cur = load_frame(p + t_begin * kFeat, g + t_begin * kFeat, lane, has_b), prev = cur;
+        if (t_begin > 0) prev = load_frame(p + (t_begin - 1) * kFeat, g + (t_begin - 1) * kFeat, lane, has_b);
+        for (int t = t_begin; t < t_end; ++t) {
             FrameRegs nxt = cur;
-            if (t + 1 < T) nxt = load_frame(p + (t + 1) * kFeat, g + (t + 1) * kFeat, lane, has_b);   // prefetch
+            if (t + 1 < t_end) nxt = load_frame(p + (t + 1) * kFeat, g + (t + 1) * kFeat, lane, has_b);   // prefetch
             // bounding box of the ground truth (lanes without a second keypoint contribute neutral values)
             float mnx = has_b ? fminf(cur.gxa, cur.gxb) : cur.gxa, mxx = has_b ? fmaxf(cur.gxa, cur.gxb) : cur.gxa;
             float mny = has_b ? fminf(cur.gya, cur.gyb) : cur.gya, mxy = has_b ? fmaxf(cur.gya, cur.gyb) : cur.gya;
@@ -130,11 +137,19 @@ extern "C" int a2m_eval_l1_pck_f32(const float* pred, const float* gt, int64_t n
     A2M_ARG_CHECK(accum != nullptr, "a2m_eval_l1_pck_f32: accum is NULL");
     if (n_clips == 0 || frames_per_clip == 0) return A2M_OK;
     A2M_ARG_CHECK(pred != nullptr && gt != nullptr, "a2m_eval_l1_pck_f32: NULL pose buffer");
-    long long blocks = (n_clips + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    // split clips into time segments until there are ~8 warps of work per SM sub-partition (never below 4 frames)
+    const long long want = 32LL * a2m_num_sms();
+    int segs = static_cast<int>((want + n_clips - 1) / n_clips);
+    segs = segs < 1 ? 1 : segs;
+    int seg_frames = (frames_per_clip + segs - 1) / segs;
+    if (seg_frames < 4) seg_frames = frames_per_clip < 4 ? frames_per_clip : 4;
+    segs = (frames_per_clip + seg_frames - 1) / seg_frames;
+    const long long n_items = static_cast<long long>(n_clips) * segs;
+    long long blocks = (n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const long long cap = 32LL * a2m_num_sms();
     if (blocks > cap) blocks = cap;
     eval_l1_pck_kernel<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        pred, gt, n_clips, frames_per_clip, alpha, pck_per_frame, radius_per_frame, accum);
+        pred, gt, n_clips, frames_per_clip, seg_frames, segs, alpha, pck_per_frame, radius_per_frame, accum);
     a2m_count_launch();
     A2M_LAUNCH_CHECK();
     return A2M_OK;

@@ -199,8 +199,9 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
         for (int layer = 0; layer < 5; ++layer) {
             float v[16];
             const bool more_weights = !(layer == 4 && it + 1 == my_tiles);
-            mbar_wait(w_bar, w_parity, err_flag, 11);
-            w_parity ^= 1;
+            // only the MMA-issuing thread consumes the weights (through the tensor core), so only it waits for them;
+            // the other threads never see w_bar and cannot fall a phase behind it
+            if (tid == 0) { mbar_wait(w_bar, w_parity, err_flag, 11); w_parity ^= 1; }
             if ((layer & 1) == 0) {
                 // ================= GATConv =================
                 if (tid == 0) {

@@ -30,16 +30,18 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
 
 // ------------------------------------------------------------------------------------------ conv0
 // One CTA = kConv0Rows output rows of one clip: the 2R+2 input rows are staged (zero padded) in shared
-// memory; a warp owns one output column at a time (shared-memory reads are broadcasts) and its 32 lanes
-// own the 32 channel pairs, so every store instruction writes one whole 128-byte channel row.
+// memory.  A warp computes four adjacent output columns of one output row at a time: its 32 lanes own the
+// 32 channel pairs (so every store instruction writes one whole 128-byte channel row) and all lanes read the
+// same 4 x 10 input window as broadcast vector loads (12 loads for 8 x 16 FMAs per lane).
 constexpr int kConv0Rows = 8;
 __global__ void __launch_bounds__(256)
 conv0_kernel(const float* __restrict__ mel, long long stride_b, long long stride_t, int T, int F,
              const float* __restrict__ w, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
-    extern __shared__ float s_rows[];                 // [2R + 2][F + 2], zero padded left/right/top/bottom
+    extern __shared__ __align__(16) float s_rows[];   // [2R + 2][stride]: column c of the input at index c + 1
     const int ho0 = blockIdx.x * kConv0Rows;
     const long long b = blockIdx.y;
-    const int Ho = T / 2, Wo = F / 2, stride = F + 2;
+    const int Ho = T / 2, Wo = F / 2;
+    const int stride = ((F + 2 + 3) / 4) * 4 + 4;     // multiple of 4 floats, room for the 10-wide window of the last group
     const int n_in = 2 * kConv0Rows + 2;
     for (int i = threadIdx.x; i < n_in * stride; i += blockDim.x) {
         const int r = i / stride, col = i - r * stride - 1;
@@ -48,62 +50,102 @@ conv0_kernel(const float* __restrict__ mel, long long stride_b, long long stride
         if (h >= 0 && h < T && col >= 0 && col < F) v = __ldg(mel + b * stride_b + h * stride_t + col);
         s_rows[i] = v;
     }
-    const int cp = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int cp = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float w0[16], w1[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { w0[i] = __ldg(w + (2 * cp) * 16 + i); w1[i] = __ldg(w + (2 * cp + 1) * 16 + i); }
+    for (int i = 0; i < 16; ++i) {                    // w is tap-major [16][64]: one coalesced 256-byte row per tap
+        const float2 ww = __ldg(reinterpret_cast<const float2*>(w + i * 64) + cp);
+        w0[i] = ww.x; w1[i] = ww.y;
+    }
     const float b0 = __ldg(bias + 2 * cp), b1 = __ldg(bias + 2 * cp + 1);
     __syncthreads();
-    for (int r = 0; r < kConv0Rows; ++r) {
+    const int groups = (Wo + 3) / 4;
+    for (int item = warp; item < kConv0Rows * groups; item += 8) {
+        const int r = item / groups, wo0 = (item - r * groups) * 4;
         const int ho = ho0 + r;
         if (ho >= Ho) break;
-        __nv_bfloat16* o = out + ((b * Ho + ho) * Wo) * 64 + 2 * cp;
-        for (int wo = grp; wo < Wo; wo += 8) {
-            float a0 = b0, a1 = b1;
+        float a0[4] = {b0, b0, b0, b0}, a1[4] = {b1, b1, b1, b1};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i) {
+            const float* row = s_rows + (2 * r + i) * stride + 2 * wo0;       // 16-byte aligned: stride and 2*wo0 are multiples of 4
+            const float4 x0 = *reinterpret_cast<const float4*>(row);
+            const float4 x1 = *reinterpret_cast<const float4*>(row + 4);
+            const float2 x2 = *reinterpret_cast<const float2*>(row + 8);
+            const float xs[10] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float x = s_rows[(2 * r + i) * stride + 2 * wo + j];
-                    a0 = fmaf(x, w0[i * 4 + j], a0);
-                    a1 = fmaf(x, w1[i * 4 + j], a1);
+                    a0[u] = fmaf(xs[2 * u + j], w0[i * 4 + j], a0[u]);
+                    a1[u] = fmaf(xs[2 * u + j], w1[i * 4 + j], a1[u]);
                 }
-            *reinterpret_cast<__nv_bfloat162*>(o + static_cast<long long>(wo) * 64) = __floats2bfloat162_rn(leaky(a0), leaky(a1));
         }
+        __nv_bfloat16* o = out + ((b * Ho + ho) * Wo + wo0) * 64 + 2 * cp;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (wo0 + u < Wo)
+                *reinterpret_cast<__nv_bfloat162*>(o + u * 64) = __floats2bfloat162_rn(leaky(a0[u]), leaky(a1[u]));
     }
 }
 
 // ------------------------------------------------------------------------------------ time interp
-// in: raw conv-4 sums (+ folded bias) fp32 [B, Hc, C]; LeakyReLU is applied here (the split-K GEMM
-// cannot), then the bilinear (T, 1) resize of model_layers.py:277; 8 channels per thread.
-__global__ void time_interp_kernel(const float* __restrict__ in, int n_planes, long long plane_stride, int Hc, int T,
-                                   int C, long long total8, __nv_bfloat16* __restrict__ out) {
+// in: raw conv-4 sums (+ folded bias) as n_planes split-K planes of fp32 [B, Hc, C].  One thread owns 8 channels
+// of one source row g of one clip and emits the T / Hc output rows that interpolate around it: it sums the planes
+// of rows g-1, g, g+1 in a fixed order (deterministic), applies LeakyReLU (the split-K GEMM cannot), then the
+// bilinear (T, 1) resize of model_layers.py:277 (align_corners=False: src = (t + 0.5) * Hc / T - 0.5, clamped at 0).
+constexpr int kMaxPlanes = 8;
+__global__ void __launch_bounds__(256)
+time_interp_kernel(const float* __restrict__ in, int n_planes, long long plane_stride, int Hc, int T, int C,
+                   long long total, __nv_bfloat16* __restrict__ out) {
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= total8) return;
+    if (idx >= total) return;
     const int c8 = C / 8;
     const int c = static_cast<int>(idx % c8) * 8;
-    const long long bt = idx / c8;
-    const int t = static_cast<int>(bt % T);
-    const long long b = bt / T;
-    // torch upsample_bilinear2d, align_corners=False: src = scale * (dst + 0.5) - 0.5, clamped at 0
-    const float scale = static_cast<float>(Hc) / static_cast<float>(T);
-    float src = scale * (static_cast<float>(t) + 0.5f) - 0.5f;
-    if (src < 0.f) src = 0.f;
-    const int i0 = static_cast<int>(src);
-    const int i1 = i0 + (i0 < Hc - 1 ? 1 : 0);
-    const float l1 = src - static_cast<float>(i0), l0 = 1.f - l1;
-    float x0[8] = {}, x1[8] = {};
-    for (int pl = 0; pl < n_planes; ++pl) {           // fixed summation order over the split-K planes
-        const float4* r0 = reinterpret_cast<const float4*>(in + pl * plane_stride + (b * Hc + i0) * C + c);
-        const float4* r1 = reinterpret_cast<const float4*>(in + pl * plane_stride + (b * Hc + i1) * C + c);
-        const float4 a0 = __ldg(r0), a1 = __ldg(r0 + 1), c0 = __ldg(r1), c1 = __ldg(r1 + 1);
-        x0[0] += a0.x; x0[1] += a0.y; x0[2] += a0.z; x0[3] += a0.w; x0[4] += a1.x; x0[5] += a1.y; x0[6] += a1.z; x0[7] += a1.w;
-        x1[0] += c0.x; x1[1] += c0.y; x1[2] += c0.z; x1[3] += c0.w; x1[4] += c1.x; x1[5] += c1.y; x1[6] += c1.z; x1[7] += c1.w;
-    }
-    float f[8];
+    const long long bg = idx / c8;
+    const int g = static_cast<int>(bg % Hc);
+    const long long b = bg / Hc;
+    const int rows[3] = {g > 0 ? g - 1 : 0, g, g < Hc - 1 ? g + 1 : Hc - 1};
+    float v[3][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = l0 * leaky(x0[e]) + l1 * leaky(x1[e]);
-    *reinterpret_cast<uint4*>(out + (bt * C + c)) = float_to_bf16x8(f);
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[r][e] = 0.f;
+#pragma unroll
+    for (int pl = 0; pl < kMaxPlanes; ++pl) {             // fixed summation order over the split-K planes
+        if (pl < n_planes) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float4* src = reinterpret_cast<const float4*>(in + pl * plane_stride + (b * Hc + rows[r]) * C + c);
+                const float4 a0 = __ldg(src), a1 = __ldg(src + 1);
+                v[r][0] += a0.x; v[r][1] += a0.y; v[r][2] += a0.z; v[r][3] += a0.w;
+                v[r][4] += a1.x; v[r][5] += a1.y; v[r][6] += a1.z; v[r][7] += a1.w;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[r][e] = leaky(v[r][e]);
+    const int rep = T / Hc;
+    const float scale = static_cast<float>(Hc) / static_cast<float>(T);
+    for (int u = 0; u < rep; ++u) {
+        const int t = g * rep + u;
+        float src = scale * (static_cast<float>(t) + 0.5f) - 0.5f;
+        if (src < 0.f) src = 0.f;
+        const int i0 = static_cast<int>(src);
+        const int i1 = i0 + (i0 < Hc - 1 ? 1 : 0);
+        const float l1 = src - static_cast<float>(i0), l0 = 1.f - l1;
+        // i0, i1 are in {g-1, g, g+1} (clamped): pick the staged rows
+        const int s0 = i0 < g ? 0 : (i0 == g ? 1 : 2), s1 = i1 < g ? 0 : (i1 == g ? 1 : 2);
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float a = s0 == 0 ? v[0][e] : (s0 == 1 ? v[1][e] : v[2][e]);
+            const float d = s1 == 0 ? v[0][e] : (s1 == 1 ? v[1][e] : v[2][e]);
+            f[e] = l0 * a + l1 * d;
+        }
+        *reinterpret_cast<uint4*>(out + (b * T + t) * C + c) = float_to_bf16x8(f);
+    }
 }
 
 // -------------------------------------------------------------------------------------- attention
@@ -221,47 +263,76 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __r
 }
 
 // ------------------------------------------------------------------------------ channel attention
-__global__ void __launch_bounds__(1024)
+// One CTA (256 threads = 8 warps) per clip.  Pooling and the final scaling move 8 channels per thread as 16-byte
+// vectors, warp w taking the time steps w, w + 8, ...; the per-warp partial sums / maxima meet in shared memory.
+__global__ void __launch_bounds__(256)
 channel_attention_kernel(const __nv_bfloat16* __restrict__ x, int T, int C, int hidden, const float* __restrict__ w0,
                          const float* __restrict__ b0, const float* __restrict__ w2, const float* __restrict__ b2,
                          __nv_bfloat16* __restrict__ out) {
-    extern __shared__ float s_ca[];
-    float* s_avg = s_ca;                 // [C]
+    extern __shared__ __align__(16) float s_ca[];
+    float* s_psum = s_ca;                // [8][C]
+    float* s_pmax = s_psum + 8 * C;      // [8][C]
+    float* s_avg = s_pmax + 8 * C;       // [C]
     float* s_max = s_avg + C;            // [C]
-    float* s_h = s_max + C;              // [2][hidden]
+    float* s_scale = s_max + C;          // [C]
+    float* s_h = s_scale + C;            // [2][hidden]
     const long long b = blockIdx.x;
-    const int c = threadIdx.x;           // blockDim.x == C
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const __nv_bfloat16* xb = x + b * T * C;
-    float sum = 0.f, mx = -INFINITY;
-    for (int t = 0; t < T; ++t) {
-        const float v = __bfloat162float(xb[static_cast<long long>(t) * C + c]);
-        sum += v;
-        mx = fmaxf(mx, v);
+    const int groups = C / 8;
+    for (int cg = lane; cg < groups; cg += 32) {
+        float sum[8], mx[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sum[e] = 0.f; mx[e] = -INFINITY; }
+        for (int t = warp; t < T; t += 8) {
+            float f[8];
+            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(t) * C + cg * 8)), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { sum[e] += f[e]; mx[e] = fmaxf(mx[e], f[e]); }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s_psum[warp * C + cg * 8 + e] = sum[e]; s_pmax[warp * C + cg * 8 + e] = mx[e]; }
     }
-    s_avg[c] = sum / static_cast<float>(T);
-    s_max[c] = mx;
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-    for (int u = warp; u < 2 * hidden; u += n_warps) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float sum = 0.f, mx = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { sum += s_psum[w * C + c]; mx = fmaxf(mx, s_pmax[w * C + c]); }
+        s_avg[c] = sum / static_cast<float>(T);
+        s_max[c] = mx;
+    }
+    __syncthreads();
+    for (int u = warp; u < 2 * hidden; u += 8) {
         const int unit = u % hidden;
         const float* src = u < hidden ? s_avg : s_max;
         float acc = 0.f;
-        for (int k = lane; k < C; k += 32) acc = fmaf(w0[unit * C + k], src[k], acc);
+        for (int k = lane; k < C; k += 32) acc = fmaf(__ldg(w0 + unit * C + k), src[k], acc);
         acc = warp_sum(acc);
-        if (lane == 0) s_h[u] = fmaxf(acc + b0[unit], 0.f);
+        if (lane == 0) s_h[u] = fmaxf(acc + __ldg(b0 + unit), 0.f);
     }
     __syncthreads();
-    float za = b2[c], zm = b2[c];
-    for (int u = 0; u < hidden; ++u) {
-        const float w = w2[c * hidden + u];
-        za = fmaf(w, s_h[u], za);
-        zm = fmaf(w, s_h[hidden + u], zm);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float za = __ldg(b2 + c), zm = za;
+        for (int u = 0; u < hidden; ++u) {
+            const float w = __ldg(w2 + u * C + c);           // w2 is stored transposed [hidden][C]
+            za = fmaf(w, s_h[u], za);
+            zm = fmaf(w, s_h[hidden + u], zm);
+        }
+        s_scale[c] = 1.f / (1.f + __expf(-za)) + 1.f / (1.f + __expf(-zm));      // sigmoid each, then add
     }
-    const float scale = 1.f / (1.f + __expf(-za)) + 1.f / (1.f + __expf(-zm));      // sigmoid each, then add
+    __syncthreads();
     __nv_bfloat16* ob = out + b * T * C;
-    for (int t = 0; t < T; ++t) {
-        const long long o = static_cast<long long>(t) * C + c;
-        ob[o] = __float2bfloat16_rn(__bfloat162float(xb[o]) * scale);
+    for (int cg = lane; cg < groups; cg += 32) {
+        const float4 s0 = *reinterpret_cast<const float4*>(s_scale + cg * 8), s1 = *reinterpret_cast<const float4*>(s_scale + cg * 8 + 4);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        for (int t = warp; t < T; t += 8) {
+            const long long o = static_cast<long long>(t) * C + cg * 8;
+            float f[8];
+            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(xb + o)), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] *= sc[e];
+            *reinterpret_cast<uint4*>(ob + o) = float_to_bf16x8(f);
+        }
     }
 }
 
@@ -291,21 +362,25 @@ layernorm256_kernel(const __nv_bfloat16* __restrict__ x, long long rows, const f
 __global__ void __launch_bounds__(256)
 angle_loss_kernel(const float* __restrict__ pose, long long n_frames, const int* __restrict__ triples, int n_hand,
                   int n_body, double* __restrict__ scratch) {
+    // one thread per (frame, triple): 35 triples x B*T frames of independent atan2 work
     __shared__ float s_hand[8], s_body[8];
-    const long long f = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int n_tri = n_hand + n_body;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     float hand = 0.f, body = 0.f;
-    if (f < n_frames) {
+    if (idx < n_frames * n_tri) {
+        const long long f = idx / n_tri;
+        const int t = static_cast<int>(idx - f * n_tri);
         const float* p = pose + f * 104;                 // interleaved (x, y) per joint: view(B,T,52,2)
         const float pi = 3.14159265358979323846f;
-        for (int t = 0; t < n_hand + n_body; ++t) {
-            const int jp = triples[3 * t], jj = triples[3 * t + 1], jc = triples[3 * t + 2];
-            const float ax = p[2 * jj] - p[2 * jp], ay = p[2 * jj + 1] - p[2 * jp + 1];
-            const float bx = p[2 * jc] - p[2 * jj], by = p[2 * jc + 1] - p[2 * jj + 1];
-            const float th = atan2f(ax * by - ay * bx, ax * bx + ay * by);
-            const float lo = t < n_hand ? 0.f : -0.5f * pi;
-            const float pen = fmaxf(lo - th, 0.f) + fmaxf(th - pi, 0.f);
-            if (t < n_hand) hand += pen; else body += pen;
-        }
+        const int jp = __ldg(triples + 3 * t), jj = __ldg(triples + 3 * t + 1), jc = __ldg(triples + 3 * t + 2);
+        const float2 pp = __ldg(reinterpret_cast<const float2*>(p) + jp), pj = __ldg(reinterpret_cast<const float2*>(p) + jj),
+                     pc = __ldg(reinterpret_cast<const float2*>(p) + jc);
+        const float ax = pj.x - pp.x, ay = pj.y - pp.y;
+        const float bx = pc.x - pj.x, by = pc.y - pj.y;
+        const float th = atan2f(ax * by - ay * bx, ax * bx + ay * by);
+        const float lo = t < n_hand ? 0.f : -0.5f * pi;
+        const float pen = fmaxf(lo - th, 0.f) + fmaxf(th - pi, 0.f);
+        if (t < n_hand) hand = pen; else body = pen;
     }
     hand = warp_sum(hand);
     body = warp_sum(body);
@@ -403,14 +478,16 @@ __global__ void btc_to_ncw_kernel(const __nv_bfloat16* __restrict__ in, int C, i
 int launch_conv0(const float* mel, long long stride_b, long long stride_t, int B, int T, int F, const float* w_folded,
                  const float* bias_folded, __nv_bfloat16* out, cudaStream_t stream) {
     A2M_ARG_CHECK(T % 2 == 0 && F % 2 == 0 && B <= 65535, "conv0: T %d, F %d, B %d", T, F, B);
-    conv0_kernel<<<dim3((T / 2 + kConv0Rows - 1) / kConv0Rows, B), 256, (2 * kConv0Rows + 2) * (F + 2) * sizeof(float), stream>>>(
+    const int stride = ((F + 2 + 3) / 4) * 4 + 4;
+    conv0_kernel<<<dim3((T / 2 + kConv0Rows - 1) / kConv0Rows, B), 256, (2 * kConv0Rows + 2) * stride * sizeof(float), stream>>>(
         mel, stride_b, stride_t, T, F, w_folded, bias_folded, out);
     A2M_AFTER_LAUNCH();
 }
 
 int launch_time_interp(const float* in, int n_planes, int B, int Hc, int T, int C, __nv_bfloat16* out, cudaStream_t stream) {
-    A2M_ARG_CHECK(C % 8 == 0, "time_interp: C = %d", C);
-    const long long total = static_cast<long long>(B) * T * (C / 8);
+    A2M_ARG_CHECK(C % 8 == 0 && Hc >= 1 && T % Hc == 0 && n_planes >= 1 && n_planes <= kMaxPlanes,
+                  "time_interp: C = %d, Hc = %d, T = %d, planes = %d", C, Hc, T, n_planes);
+    const long long total = static_cast<long long>(B) * Hc * (C / 8);
     time_interp_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, n_planes, static_cast<long long>(B) * Hc * C, Hc, T, C, total, out);
     A2M_AFTER_LAUNCH();
 }
@@ -450,8 +527,8 @@ int launch_attention(const __nv_bfloat16* qkv, const __nv_bfloat16* x, const __n
 
 int launch_channel_attention(const __nv_bfloat16* x, int B, int T, int C, int hidden, const float* w0, const float* b0,
                              const float* w2, const float* b2, __nv_bfloat16* out, cudaStream_t stream) {
-    A2M_ARG_CHECK(C % 32 == 0 && C <= 1024 && hidden >= 1, "channel attention: C = %d hidden = %d", C, hidden);
-    channel_attention_kernel<<<B, C, (2 * C + 2 * hidden) * sizeof(float), stream>>>(x, T, C, hidden, w0, b0, w2, b2, out);
+    A2M_ARG_CHECK(C % 8 == 0 && C <= 1024 && hidden >= 1 && hidden <= 256, "channel attention: C = %d hidden = %d", C, hidden);
+    channel_attention_kernel<<<B, 256, (19 * C + 2 * hidden) * sizeof(float), stream>>>(x, T, C, hidden, w0, b0, w2, b2, out);
     A2M_AFTER_LAUNCH();
 }
 
@@ -466,7 +543,8 @@ int launch_pose_losses(const float* pose, const float* real_pose, int B, int T, 
                        int n_body, const int* parents, double* scratch, float* losses_out, cudaStream_t stream) {
     const long long frames = static_cast<long long>(B) * T;
     A2M_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), stream));
-    angle_loss_kernel<<<static_cast<unsigned>((frames + 255) / 256), 256, 0, stream>>>(pose, frames, triples, n_hand, n_body, scratch);
+    const long long items = frames * (n_hand + n_body);
+    angle_loss_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, stream>>>(pose, frames, triples, n_hand, n_body, scratch);
     a2m_count_launch();
     A2M_LAUNCH_CHECK();
     if (real_pose) {

@@ -9,7 +9,7 @@ namespace a2m {
 
 // AudioEncoder conv 0: Conv2d(1 -> 64, k4, s2, p1) + BatchNorm(eval) + LeakyReLU(0.2)  (model_layers.py:252)
 //   mel [B, T, F] fp32 (element strides stride_b, stride_t, 1: the D2 adapter slice is read in place)
-//   -> out [B, T/2, F/2, 64] bf16.  w_folded [64][16] fp32 (BN scale folded), bias_folded [64].
+//   -> out [B, T/2, F/2, 64] bf16.  w_folded [16 taps][64 channels] fp32 (BN scale folded), bias_folded [64].
 int launch_conv0(const float* mel, long long stride_b, long long stride_t, int B, int T, int F, const float* w_folded,
                  const float* bias_folded, __nv_bfloat16* out, cudaStream_t stream);
 
@@ -32,7 +32,8 @@ int attn_fused_plan(const __nv_bfloat16* w_qkv, const float* bias_qkv, const flo
                     const __nv_bfloat16* res2, int B, int T, int C, __nv_bfloat16* out, std::shared_ptr<AttnFusedPlan>* plan);
 int attn_fused_launch(const AttnFusedPlan& plan, int* err_flag, cudaStream_t stream);
 
-// ChannelAttention (model_layers.py:167-174): x * (sigmoid(mlp(avg_T x)) + sigmoid(mlp(max_T x))), C = 256, hidden 32
+// ChannelAttention (model_layers.py:167-174): x * (sigmoid(mlp(avg_T x)) + sigmoid(mlp(max_T x))), C = 256, hidden 32;
+// w0 = fc.0.weight [hidden, C], w2 = fc.2.weight TRANSPOSED to [hidden, C]
 int launch_channel_attention(const __nv_bfloat16* x, int B, int T, int C, int hidden, const float* w0, const float* b0,
                              const float* w2, const float* b2, __nv_bfloat16* out, cudaStream_t stream);
 

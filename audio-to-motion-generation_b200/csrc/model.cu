@@ -229,7 +229,18 @@ struct Builder {
     void channel(ChanW& Cw, const std::string& p, int C) {
         Cw.C = C; Cw.hidden = C / 8;
         Cw.w0 = keep(p + ".fc.0.weight", static_cast<long long>(Cw.hidden) * C); Cw.b0 = keep(p + ".fc.0.bias", Cw.hidden);
-        Cw.w2 = keep(p + ".fc.2.weight", static_cast<long long>(C) * Cw.hidden); Cw.b2 = keep(p + ".fc.2.bias", C);
+        Cw.b2 = keep(p + ".fc.2.bias", C);
+        // fc.2.weight [C, hidden] is kept transposed ([hidden, C]) so that channel-per-thread reads coalesce
+        const float* w2 = f32(p + ".fc.2.weight", static_cast<long long>(C) * Cw.hidden);
+        float* w2t = alloc<float>(static_cast<size_t>(C) * Cw.hidden);
+        if (rc != A2M_OK) return;
+        std::vector<float> h(static_cast<size_t>(C) * Cw.hidden), ht(h.size());
+        cudaError_t e = cudaMemcpy(h.data(), w2, h.size() * sizeof(float), cudaMemcpyDeviceToHost);
+        for (int c = 0; c < C; ++c)
+            for (int u = 0; u < Cw.hidden; ++u) ht[static_cast<size_t>(u) * C + c] = h[static_cast<size_t>(c) * Cw.hidden + u];
+        if (e == cudaSuccess) e = cudaMemcpy(w2t, ht.data(), ht.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { a2m_set_error("model: transposing '%s.fc.2.weight': %s", p.c_str(), cudaGetErrorString(e)); rc = (int)e; return; }
+        Cw.w2 = w2t;
     }
     void resblock(ResW& R, const std::string& p, int C) {
         conv1d_k3(R.c1, p + ".conv1", C, 0, C);
@@ -318,7 +329,7 @@ struct Builder {
         topology(D, part + "_edge_index_template", J);
     }
     void encoder() {
-        // conv 0 (1 -> 64, k4 s2 p1): tiny, folded on the host into fp32 [64][16] + bias[64]
+        // conv 0 (1 -> 64, k4 s2 p1): tiny, folded on the host into fp32 [16 taps][64 channels] + bias[64]
         const std::string p = "audio_encoder.conv.0";
         const float *w = f32(p + ".conv.weight", 64 * 16), *cb = f32(p + ".conv.bias", 64), *g = f32(p + ".norm.weight", 64),
                     *b = f32(p + ".norm.bias", 64), *mu = f32(p + ".norm.running_mean", 64), *var = f32(p + ".norm.running_var", 64);
@@ -327,12 +338,13 @@ struct Builder {
         cudaMemcpy(hw.data(), w, hw.size() * 4, cudaMemcpyDeviceToHost); cudaMemcpy(hcb.data(), cb, 256, cudaMemcpyDeviceToHost);
         cudaMemcpy(hg.data(), g, 256, cudaMemcpyDeviceToHost); cudaMemcpy(hb.data(), b, 256, cudaMemcpyDeviceToHost);
         cudaMemcpy(hmu.data(), mu, 256, cudaMemcpyDeviceToHost); cudaMemcpy(hvar.data(), var, 256, cudaMemcpyDeviceToHost);
-        std::vector<float> fb(64);
+        std::vector<float> fb(64), wt(16 * 64);          // wt: tap-major [16][64] so a warp's weight loads coalesce
         for (int c = 0; c < 64; ++c) {
             const float sc = hg[c] / sqrtf(hvar[c] + kBnEps);
-            for (int i = 0; i < 16; ++i) hw[c * 16 + i] *= sc;
+            for (int i = 0; i < 16; ++i) wt[i * 64 + c] = hw[c * 16 + i] * sc;
             fb[c] = (hcb[c] - hmu[c]) * sc + hb[c];
         }
+        hw = wt;
         m->conv0_w = alloc<float>(64 * 16); m->conv0_b = alloc<float>(64);
         if (rc != A2M_OK) return;
         cudaMemcpy(m->conv0_w, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice);

@@ -30,6 +30,19 @@ CLIP_SAMPLES = 68267
 POOL = 6                     # distinct input batches cycled through: 6 x 77 MB > 126 MB of L2
 
 
+def ncu_traffic():
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel class, summed over its
+    launches in one step, from the committed ncu capture (profiles/r1_traffic.json; ncu serialises launches and
+    starts each one cold, so this is an upper bound for the pipelined run).  None if the file is absent."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        return json.load(open(path))
+    except (OSError, ValueError):
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -248,7 +261,9 @@ def main():
         achieved = flops / (out_ms[1] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, %d launches/step)" % n_gemm.value,
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                "peak_kind": pk["src"] + " sustained (kernel timed inside a long step)", "traffic": None,
+                "peak_kind": pk["src"] + " sustained (kernel timed inside a long step)",
+                "traffic": (ncu_traffic() or {}).get("conv_gemm_bytes_per_step"),
+                "traffic_note": (ncu_traffic() or {}).get("note"),
                 "gemm_ms_per_step": out_ms[1], "other_ms_per_step": out_ms[2], "algorithmic_gflop_per_step": flops / 1e9}
 
         def ev_time(fn, n=10):
@@ -276,7 +291,7 @@ def main():
         threads = os.cpu_count() or 1
         cpu_reference_run(2, threads)
         n, spent, runs = args.ref_clips, 0.0, 0
-        while spent < 10.0 and runs < 8:
+        while spent < 12.0 and runs < 200:
             spent += cpu_reference_run(n, threads)
             runs += 1
         cpu = {"value": n * runs / spent, "unit": UNIT, "cores": threads, "kind": "port",
