@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <cstdlib>
 
 #include "../../include/a2m_b200.h"
 
@@ -45,8 +46,9 @@ inline cudaError_t a2m_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr.val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("A2M_DEBUG_NO_PDL") != nullptr;       // debugging aid: plain stream order
     cfg.attrs = &attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = no_pdl ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

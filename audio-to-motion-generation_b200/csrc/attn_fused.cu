@@ -278,9 +278,12 @@ attn_fused_kernel(const __grid_constant__ AttnParams p, int* __restrict__ err_fl
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const long long o = base + hf * 32 + c * 8;
-                    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(p.x + o));
+                    // x / res2 were written by earlier kernels of the stream that this (programmatically launched)
+                    // kernel overlapped with: read them through L2 (ld.global.cg), never through the
+                    // non-coherent path, whose L1 lines may predate those writes
+                    const uint4 xv = __ldcg(reinterpret_cast<const uint4*>(p.x + o));
                     uint4 rv = make_uint4(0, 0, 0, 0);
-                    if (p.res2) rv = __ldg(reinterpret_cast<const uint4*>(p.res2 + o));
+                    if (p.res2) rv = __ldcg(reinterpret_cast<const uint4*>(p.res2 + o));
                     const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, rs[4] = {rv.x, rv.y, rv.z, rv.w};
                     uint32_t os[4];
 #pragma unroll

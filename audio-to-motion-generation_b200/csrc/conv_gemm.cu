@@ -346,6 +346,12 @@ int launch_variant(const ConvGemmPlan& plan, int* err_flag, cudaStream_t stream)
 
 }  // namespace
 
+// generic bf16 view (<= 5-D, dim 0 = unit-stride channels) as a 128B-swizzled TMA map
+int make_map_bf16(CUtensorMap* map, const void* ptr, int rank, const long long* dims, const long long* strides,
+                  const int* box, const char* what) {
+    return make_map(map, ptr, rank, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what);
+}
+
 // 2-D bf16 weight matrix [n_rows, k] (K-major) as a 128B-swizzled TMA map with box (64, box_rows)
 int make_weight_map(CUtensorMap* map, const void* w, long long n_rows, long long k, int box_rows) {
     long long wd[2] = {k, n_rows}, ws[2] = {1, k};

@@ -51,7 +51,7 @@ static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 struct GnnParams {
     CUtensorMap w_gat[3];                // [272][64] bf16, box 64 x 136
     CUtensorMap w_gc[2];                 // [64][128] bf16, box 64 x 64
-    CUtensorMap x_in, x_out;             // [rows][64] bf16, box 64 x rows_per_tile
+    CUtensorMap x_in, x_out;             // [groups][group_rows][64] bf16, box 64 x rows_per_tile x 1
     const float* gat_bias[3];
     const float* gc_bias[2];
     const float* ln_w[5];
@@ -59,7 +59,8 @@ struct GnnParams {
     const int* nbr;
     const int* deg;
     int J, gpc;
-    long long n_graphs;
+    long long n_groups;                  // graphs are tiled per group (= clip), so a graph's slot in its tile -- and with
+    int group_graphs, tiles_per_group;   // it the MMA accumulation order -- never depends on how clips are batched
 };
 
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeakySlope * x; }
@@ -97,8 +98,8 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
     const int tid = threadIdx.x, warp = tid >> 5;
     const int r = tid & 127, q = tid >> 7, quad = warp & 3;
     const int J = p.J, rows_per_tile = p.gpc * J;
-    const long long n_rows = p.n_graphs * J;
-    const long long n_tiles = (p.n_graphs + p.gpc - 1) / p.gpc;
+    const int group_rows = p.group_graphs * J;
+    const long long n_tiles = p.n_groups * p.tiles_per_group;
     const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;    // >= 1 by construction of the grid
     const uint32_t tile_bytes = static_cast<uint32_t>(rows_per_tile) * 128u;
 
@@ -153,7 +154,8 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
     pdl_wait();                                        // node features come from the previous kernel (proj_in)
     if (tid == 0) {
         mbar_expect_tx(&x_bar[0], tile_bytes);
-        tma_load_5d(smem + kOffX, &p.x_in, &x_bar[0], 0, static_cast<int>(blockIdx.x * static_cast<long long>(rows_per_tile)), 0, 0, 0);
+        tma_load_5d(smem + kOffX, &p.x_in, &x_bar[0], 0, static_cast<int>(blockIdx.x % p.tiles_per_group) * rows_per_tile,
+                    static_cast<int>(blockIdx.x / p.tiles_per_group), 0, 0);
     }
     const uint32_t idesc_h = umma_idesc_bf16(128, 256), idesc_s = umma_idesc_bf16(128, 16);
     const uint32_t idesc_agg = idesc_b_mn(128, 64), idesc_gc = umma_idesc_bf16(128, 64);
@@ -173,16 +175,18 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
     uint32_t mma_parity = 0, w_parity = 0;
     for (long long it = 0; it < my_tiles; ++it) {
         const long long tile = blockIdx.x + it * gridDim.x;
-        const long long row0 = tile * rows_per_tile;
+        const int group = static_cast<int>(tile / p.tiles_per_group);
+        const int row0 = static_cast<int>(tile - static_cast<long long>(group) * p.tiles_per_group) * rows_per_tile;   // within the group
         const int buf = static_cast<int>(it & 1);
         unsigned char* s_x = smem + kOffX + buf * 16384;
         const uint32_t x_addr = smem_u32(s_x);
-        const bool live = valid_row && row0 + r < n_rows;
+        const bool live = valid_row && row0 + r < group_rows;      // rows past the group are zero-filled on load, clipped on store
         if (tid == 0 && it + 1 < my_tiles) {           // prefetch the next tile into the other buffer
             tma_store_wait_read();                     // ... once the store that last read it has drained
             mbar_expect_tx(&x_bar[buf ^ 1], tile_bytes);
+            const long long nt = tile + gridDim.x;
             tma_load_5d(smem + kOffX + (buf ^ 1) * 16384, &p.x_in, &x_bar[buf ^ 1], 0,
-                        static_cast<int>((tile + gridDim.x) * rows_per_tile), 0, 0, 0);
+                        static_cast<int>(nt % p.tiles_per_group) * rows_per_tile, static_cast<int>(nt / p.tiles_per_group), 0, 0);
         }
         mbar_wait(&x_bar[buf], static_cast<uint32_t>((it >> 1) & 1), err_flag, 10);
         // residual stream: this thread's 16 features in fp32 registers
@@ -405,7 +409,7 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
             __syncthreads();
         }
         if (tid == 0) {                                // the tile's final node features leave by TMA (rows past the
-            tma_store_5d(&p.x_out, s_x, 0, static_cast<int>(row0), 0, 0, 0);   // end of the tensor are clipped)
+            tma_store_5d(&p.x_out, s_x, 0, row0, group, 0, 0);                 // end of the group are clipped)
             tma_store_commit();
         }
     }
@@ -448,10 +452,15 @@ int gat_fold_attention(__nv_bfloat16* wext, const float* att_src, const float* a
     return A2M_OK;
 }
 
-int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_graphs, const __nv_bfloat16* x_in,
+int make_map_bf16(CUtensorMap* map, const void* ptr, int rank, const long long* dims, const long long* strides,
+                  const int* box, const char* what);                                                   // conv_gemm.cu
+
+int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_groups, int group_graphs, const __nv_bfloat16* x_in,
                    __nv_bfloat16* x_out, std::shared_ptr<GnnFusedPlan>* out) {
     A2M_ARG_CHECK(topo.n_nodes >= 1 && topo.n_nodes <= 48, "gnn: %d nodes per graph (max 48)", topo.n_nodes);
-    A2M_ARG_CHECK(n_graphs >= 1 && n_graphs * topo.n_nodes <= 0x7fffffffLL, "gnn: %lld graphs", n_graphs);
+    A2M_ARG_CHECK(n_groups >= 1 && group_graphs >= 1 && n_groups * group_graphs * topo.n_nodes <= 0x7fffffffLL &&
+                  static_cast<long long>(group_graphs) * topo.n_nodes <= 0x7fffffffLL && n_groups <= 0x7fffffffLL,
+                  "gnn: %lld groups of %d graphs", n_groups, group_graphs);
     auto plan = std::make_shared<GnnFusedPlan>();
     GnnParams& p = plan->p;
     memset(&p, 0, sizeof(p));
@@ -467,13 +476,17 @@ int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_graphs,
     }
     for (int i = 0; i < 5; ++i) { p.ln_w[i] = w.ln_w[i]; p.ln_b[i] = w.ln_b[i]; }
     p.nbr = topo.nbr; p.deg = topo.deg; p.J = topo.n_nodes; p.gpc = kRows / topo.n_nodes;
-    p.n_graphs = n_graphs;
+    p.n_groups = n_groups; p.group_graphs = group_graphs;
+    p.tiles_per_group = (group_graphs + p.gpc - 1) / p.gpc;
     const int rows_per_tile = p.gpc * p.J;
-    int rc = make_weight_map(&p.x_in, x_in, n_graphs * p.J, 64, rows_per_tile);
+    const long long group_rows = static_cast<long long>(group_graphs) * p.J;
+    const long long dims[3] = {64, group_rows, n_groups}, strides[3] = {1, 64, group_rows * 64};
+    const int box[5] = {64, rows_per_tile, 1, 1, 1};
+    int rc = make_map_bf16(&p.x_in, x_in, 3, dims, strides, box, "gnn node features (in)");
     if (rc != A2M_OK) return rc;
-    rc = make_weight_map(&p.x_out, x_out, n_graphs * p.J, 64, rows_per_tile);
+    rc = make_map_bf16(&p.x_out, x_out, 3, dims, strides, box, "gnn node features (out)");
     if (rc != A2M_OK) return rc;
-    const long long tiles = (n_graphs + p.gpc - 1) / p.gpc;
+    const long long tiles = n_groups * p.tiles_per_group;
     const int sms = a2m_num_sms();
     plan->grid = static_cast<int>(tiles < sms ? tiles : sms);
     *out = plan;

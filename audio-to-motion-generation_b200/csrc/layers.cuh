@@ -64,7 +64,9 @@ struct GnnFusedPlan;
 // wext [272][64] bf16 with rows 0..255 = lin.weight already packed: fills rows 256..271 with W_h^T att_src / att_dst
 // (hi and lo bf16 parts) for the four heads.  att_src / att_dst: fp32 [4][64].
 int gat_fold_attention(__nv_bfloat16* wext, const float* att_src, const float* att_dst, cudaStream_t stream);
-int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_graphs, const __nv_bfloat16* x_in,
+// Graphs are tiled per group of `group_graphs` consecutive graphs (a clip's T frames): a graph's position inside
+// its 128-row tile -- and with it the tensor-core accumulation order -- never depends on how clips are batched.
+int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_groups, int group_graphs, const __nv_bfloat16* x_in,
                    __nv_bfloat16* x_out, std::shared_ptr<GnnFusedPlan>* out);
 int gnn_fused_launch(const GnnFusedPlan& plan, int* err_flag, cudaStream_t stream);
 

@@ -6,10 +6,11 @@
 // element written once; everything in between lives in registers / shared memory.
 //
 // Mapping: 16 threads own one frame (two register-resident radix-16 passes of a 256-point complex
-// FFT of the even/odd-packed frame, one padded shared-memory exchange in between, partner bins of
-// the real-input untangle fetched with warp shuffles).  A 256-thread CTA works on 16 frames at a
-// time and walks over tiles of <= 32 consecutive frames of one clip; samples of a tile are staged
-// once in shared memory, results are staged and written back as whole 256-byte rows.
+// FFT of the even/odd-packed frame, one padded shared-memory exchange in between; the spectrum Z is
+// dumped to shared memory so the partner bin of the real-input untangle is one conflict-free load).
+// A 256-thread CTA works on a tile of 16 consecutive frames of one clip; a tile's samples are staged
+// in shared memory with cp.async into one of two buffers while the previous tile is transformed, and
+// results are staged and written back as whole 256-byte rows.
 #include <cmath>
 #include <vector>
 #include <cstring>
@@ -21,83 +22,98 @@ using a2m_fft::cpx;
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kSlots = kThreads / 16;         // frames in flight per CTA
-constexpr int kMaxTileFrames = 32;
-constexpr int kSpanFloats = 5632;             // staged samples per tile (22 KB)
+constexpr int kSlots = kThreads / 16;         // frames in flight per CTA = frames per tile
+constexpr int kSpanFloats = 2816;             // staged samples per tile buffer (15 * 160 + 416), two buffers
 constexpr int kXchgStride = 18;               // float2 units; 144 B rows keep LDS.128 conflict-free
+constexpr int kSlotZ = 16 * kXchgStride;      // float2 per slot: exchange rows, later Z[0..255]
+constexpr int kSlotMag = 260;                 // floats per slot: |X[k]|, k = 0..256
 constexpr int kMaxMel = 128;
 constexpr int kNfft = 512;
 constexpr int kBins = kNfft / 2 + 1;
 
 struct MelTables {                // device-resident constants of a plan
-    const float* window;          // [window]
-    const float2* w256;           // [256]  exp(-2 pi i e / 256)
+    const float* window;          // [512]  periodic Hann, zero padded past the window length
+    const float2* tw;             // [16][16] exp(-2 pi i m2 k1 / 256) at [k1][m2]
     const float2* untangle;       // [256]  (-sin, -cos)(2 pi k / 512)
-    const int* col_start;         // [n_mel] first spectrogram bin with a non-zero weight
-    const int* col_count;         // [n_mel]
-    const int* col_ptr;           // [n_mel] offset into weights
+    const int4* col_meta;         // [n_mel] {first bin, bin count, offset into weights, 0}
     const float* weights;         // [nnz]
 };
 
 struct MelGeom {
     int window, hop, n_mel, nnz;
-    int tile_frames;              // frames per tile
+    int tile_frames;              // frames per tile (<= kSlots)
     int max_bin;                  // highest spectrogram bin with a non-zero mel weight
     float log_offset;
 };
 
 struct SmemLayout {
-    int samples, xchg, out, window, w256, untangle, col_start, col_count, col_ptr, weights, total;
+    int samples, slot_z, slot_mag, out, window, tw, untangle, col_meta, weights, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(int n_mel, int nnz, bool mag_only) {
     SmemLayout L;
     int off = 0;
-    L.samples = off;   off += kSpanFloats * 4;
-    L.xchg = off;      off += kSlots * 16 * kXchgStride * 8;
-    L.out = off;       off += mag_only ? 0 : kMaxTileFrames * n_mel * 4;
+    L.samples = off;   off += 2 * kSpanFloats * 4;
+    L.slot_z = off;    off += kSlots * kSlotZ * 8;
+    L.slot_mag = off;  off += kSlots * kSlotMag * 4;
+    L.out = off;       off += mag_only ? 0 : kSlots * n_mel * 4;
     L.window = off;    off += kNfft * 4;
-    L.w256 = off;      off += 256 * 8;
+    L.tw = off;        off += 256 * 8;
     L.untangle = off;  off += 256 * 8;
-    L.col_start = off; off += kMaxMel * 4;
-    L.col_count = off; off += kMaxMel * 4;
-    L.col_ptr = off;   off += kMaxMel * 4;
+    L.col_meta = off;  off += kMaxMel * 16;
     L.weights = off;   off += ((nnz + 3) / 4) * 16;
     L.total = off;
     return L;
 }
 
-// One frame by 16 lanes.  `lane16` = position in the 16-lane group, `frame_smp` = first sample of
-// the frame in the staged span.  On return mag[] (the group's exchange slot, reused) holds |X[k]|
-// for k < 16 * n_k2 (and k = 256 at index 256 when kMagOnly).
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a2m::smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// One frame by 16 lanes.  `lane16` = position in the 16-lane group, s = first sample of the frame in the staged
+// span.  On return mag[k] = |X[k]| for k < 16 * n_k2 (and k = 256 when kMagOnly).
+//   pass 1: lane m2 holds z[16 m1 + m2] = (x[32 m1 + 2 m2], x[.. + 1]) * hann, DFT16 over m1, * W256^(m2 k1)
+//   exchange through shared memory ([k1][m2], padded rows)
+//   pass 2: lane k1, DFT16 over m2 -> Z[k1 + 16 k2]
+//   untangle: Z is dumped to shared memory so that the partner bin Z[(256 - k) & 255] is one conflict-free load
 template <bool kMagOnly>
-__device__ __forceinline__ void frame_spectrum(const float* __restrict__ s_samples, int frame_smp, int window,
-                                               const float* __restrict__ s_window,
-                                               const float2* __restrict__ s_w256,
-                                               const float2* __restrict__ s_unt, float2* __restrict__ slot,
-                                               int lane16, int n_k2) {
+__device__ __forceinline__ void frame_spectrum(const float* __restrict__ s, int window, bool even_hop,
+                                               const float* __restrict__ s_window, const float2* __restrict__ s_tw,
+                                               const float2* __restrict__ s_unt, float2* __restrict__ zs,
+                                               float* __restrict__ mag, int lane16, int n_k2) {
     cpx v[16];
-    // ---- pass 1: thread m2 = lane16 loads z[16 m1 + m2] = (x[32 m1 + 2 m2], x[.. + 1]) * hann
+    const int n_m1 = (window + 31) >> 5;                    // rows of the 16 x 16 input that are not all padding
 #pragma unroll
     for (int m1 = 0; m1 < 16; ++m1) {
-        const int n = 32 * m1 + 2 * lane16;
-        float a = 0.f, b = 0.f;
-        if (n < window) a = s_samples[frame_smp + n] * s_window[n];
-        if (n + 1 < window) b = s_samples[frame_smp + n + 1] * s_window[n + 1];
-        v[m1] = a2m_fft::make(a, b);
+        if (m1 < n_m1) {                                    // uniform
+            const int n = 32 * m1 + 2 * lane16;
+            const float2 w = *reinterpret_cast<const float2*>(s_window + n);          // zero past the window
+            float2 x;
+            if (even_hop) x = *reinterpret_cast<const float2*>(s + n);
+            else x = make_float2(s[n], s[n + 1]);
+            v[m1] = a2m_fft::make(x.x * w.x, x.y * w.y);
+        } else {
+            v[m1] = a2m_fft::make(0.f, 0.f);
+        }
     }
     a2m_fft::dft16(v);                                      // Y[m2][k1], k1 = register index
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) {                       // * W256^(m2 k1)
-        const float2 w = s_w256[lane16 * k1];
+        const float2 w = s_tw[k1 * 16 + lane16];
         v[k1] = a2m_fft::mul(v[k1], a2m_fft::make(w.x, w.y));
     }
-    // ---- exchange: slot[k1 * stride + m2]  (writes: 16 lanes contiguous; reads: one 144 B row each)
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) slot[k1 * kXchgStride + lane16] = make_float2(v[k1].x, v[k1].y);
+    for (int k1 = 0; k1 < 16; ++k1) zs[k1 * kXchgStride + lane16] = make_float2(v[k1].x, v[k1].y);
     __syncwarp();
     {
-        const float4* row = reinterpret_cast<const float4*>(slot + lane16 * kXchgStride);
+        const float4* row = reinterpret_cast<const float4*>(zs + lane16 * kXchgStride);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 q = row[j];
@@ -105,26 +121,20 @@ __device__ __forceinline__ void frame_spectrum(const float* __restrict__ s_sampl
             v[2 * j + 1] = a2m_fft::make(q.z, q.w);
         }
     }
-    __syncwarp();                                           // slot is reused for magnitudes below
-    // ---- pass 2: thread k1 = lane16, DFT over m2 -> Z[k1 + 16 k2] in v[k2]
-    a2m_fft::dft16(v);
-    // ---- untangle: partner bin 256-k lives in lane (16-k1)&15 at register 15-k2 (k1 != 0)
-    float* mag = reinterpret_cast<float*>(slot);
-    const int src = (threadIdx.x & 16) | ((16 - lane16) & 15);
+    __syncwarp();                                           // the exchange rows are overwritten by Z below
+    a2m_fft::dft16(v);                                      // v[k2] = Z[lane16 + 16 k2]
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) zs[lane16 + 16 * k2] = make_float2(v[k2].x, v[k2].y);
+    __syncwarp();
     if (kMagOnly && lane16 == 0) mag[256] = fabsf(v[0].x - v[0].y);      // X[256] = Re Z0 - Im Z0
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) {
-        float px = __shfl_sync(0xffffffffu, v[15 - k2].x, src);
-        float py = __shfl_sync(0xffffffffu, v[15 - k2].y, src);
-        if (lane16 == 0) {                                  // k1 == 0: partner is own bin 16*((16-k2)&15)
-            px = v[(16 - k2) & 15].x;
-            py = v[(16 - k2) & 15].y;
-        }
-        if (k2 < n_k2) {
+        if (k2 < n_k2) {                                    // uniform
             const int k = lane16 + 16 * k2;
+            const float2 pz = zs[(256 - k) & 255];          // k = 0 pairs with itself
             const float2 t = s_unt[k];
-            const cpx x2 = a2m_fft::untangle2(v[k2], a2m_fft::make(px, py), a2m_fft::make(t.x, t.y));
-            mag[k] = a2m_fft::half_magnitude(x2);
+            const cpx x2 = a2m_fft::untangle2(v[k2], a2m_fft::make(pz.x, pz.y), a2m_fft::make(t.x, t.y));
+            mag[k] = 0.5f * fast_sqrt(x2.x * x2.x + x2.y * x2.y);
         }
     }
     __syncwarp();
@@ -138,65 +148,76 @@ logmel_kernel(const float* __restrict__ wav, long long n_clips, long long n_samp
     extern __shared__ __align__(16) unsigned char smem[];
     const SmemLayout L = smem_layout(g.n_mel, g.nnz, kMagOnly);
     float* s_samples = reinterpret_cast<float*>(smem + L.samples);
-    float2* s_xchg = reinterpret_cast<float2*>(smem + L.xchg);
     float* s_out = reinterpret_cast<float*>(smem + L.out);
     float* s_window = reinterpret_cast<float*>(smem + L.window);
-    float2* s_w256 = reinterpret_cast<float2*>(smem + L.w256);
+    float2* s_tw = reinterpret_cast<float2*>(smem + L.tw);
     float2* s_unt = reinterpret_cast<float2*>(smem + L.untangle);
-    int* s_col_start = reinterpret_cast<int*>(smem + L.col_start);
-    int* s_col_count = reinterpret_cast<int*>(smem + L.col_count);
-    int* s_col_ptr = reinterpret_cast<int*>(smem + L.col_ptr);
+    int4* s_meta = reinterpret_cast<int4*>(smem + L.col_meta);
     float* s_weights = reinterpret_cast<float*>(smem + L.weights);
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < g.window; i += kThreads) s_window[i] = tab.window[i];
-    for (int i = tid; i < 256; i += kThreads) { s_w256[i] = tab.w256[i]; s_unt[i] = tab.untangle[i]; }
+    for (int i = tid; i < kNfft; i += kThreads) s_window[i] = tab.window[i];
+    for (int i = tid; i < 256; i += kThreads) { s_tw[i] = tab.tw[i]; s_unt[i] = tab.untangle[i]; }
     if (!kMagOnly) {
-        for (int i = tid; i < g.n_mel; i += kThreads) {
-            s_col_start[i] = tab.col_start[i]; s_col_count[i] = tab.col_count[i]; s_col_ptr[i] = tab.col_ptr[i];
-        }
+        for (int i = tid; i < g.n_mel; i += kThreads) s_meta[i] = tab.col_meta[i];
         for (int i = tid; i < g.nnz; i += kThreads) s_weights[i] = tab.weights[i];
     }
+    // samples read past a tile's span are multiplied by the zero padding of the window: keep them finite
+    for (int i = tid; i < 2 * kSpanFloats; i += kThreads) s_samples[i] = 0.f;
 
     const int lane16 = tid & 15;
     const int slot_id = tid >> 4;
-    float2* slot = s_xchg + slot_id * 16 * kXchgStride;
+    float2* zs = reinterpret_cast<float2*>(smem + L.slot_z) + slot_id * kSlotZ;
+    float* mag = reinterpret_cast<float*>(smem + L.slot_mag) + slot_id * kSlotMag;
     const int n_k2 = kMagOnly ? 16 : (g.max_bin >> 4) + 1;
     const int out_width = kMagOnly ? kBins : g.n_mel;
+    const bool even_hop = (g.hop & 1) == 0;
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    auto stage = [&](long long tile, int buf) {             // asynchronous copy of one tile's samples
         const long long clip = tile / tiles_per_clip;
         const int f0 = static_cast<int>(tile - clip * tiles_per_clip) * g.tile_frames;
         const int nf = static_cast<int>(min(static_cast<long long>(g.tile_frames), frames_per_clip - f0));
         const int span = (nf - 1) * g.hop + g.window;
         const float* src = wav + clip * wav_stride + static_cast<long long>(f0) * g.hop;
-        __syncthreads();                                      // previous tile fully consumed / tables visible
-        for (int i = tid; i < span; i += kThreads) s_samples[i] = __ldg(src + i);
-        __syncthreads();
+        float* dst = s_samples + buf * kSpanFloats;
+        for (int i = tid; i < span; i += kThreads) cp_async4(dst + i, src + i);
+        cp_async_commit();
+    };
+
+    __syncthreads();                                        // tables and the zero fill are in place
+    long long tile = blockIdx.x;
+    if (tile < n_tiles) stage(tile, 0);
+    int buf = 0;
+    for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        const long long clip = tile / tiles_per_clip;
+        const int f0 = static_cast<int>(tile - clip * tiles_per_clip) * g.tile_frames;
+        const int nf = static_cast<int>(min(static_cast<long long>(g.tile_frames), frames_per_clip - f0));
+        cp_async_wait_all();
+        __syncthreads();                                    // this tile's samples landed; the other buffer and s_out are free
+        if (tile + gridDim.x < n_tiles) stage(tile + gridDim.x, buf ^ 1);      // overlaps the FFTs below
         float* out_tile = out + (clip * frames_per_clip + f0) * out_width;
-        for (int fb = 0; fb < nf; fb += kSlots) {
-            const int f = fb + slot_id;
-            // the shuffles inside frame_spectrum use the full mask: an idle 16-lane group (ragged tile
-            // end) still runs the FFT on frame 0 of the span and discards the result
-            const bool active = f < nf;
-            const int fs = active ? f * g.hop : 0;
-            frame_spectrum<kMagOnly>(s_samples, fs, g.window, s_window, s_w256, s_unt, slot, lane16, n_k2);
-            const float* mag = reinterpret_cast<const float*>(slot);
-            if (kMagOnly) {
-                if (active)
-                    for (int k = lane16; k < kBins; k += 16) out_tile[static_cast<long long>(f) * kBins + k] = mag[k];
-            } else if (active) {
+        // the warp-level syncs inside frame_spectrum need every lane: an idle 16-lane group (ragged tile end)
+        // runs the FFT on frame 0 of the span and discards the result
+        const bool active = slot_id < nf;
+        const int fs = active ? slot_id * g.hop : 0;
+        frame_spectrum<kMagOnly>(s_samples + buf * kSpanFloats + fs, g.window, even_hop, s_window, s_tw, s_unt, zs, mag,
+                                 lane16, n_k2);
+        if (kMagOnly) {
+            if (active)
+                for (int k = lane16; k < kBins; k += 16) out_tile[static_cast<long long>(slot_id) * kBins + k] = mag[k];
+        } else {
+            if (active) {
                 for (int c = lane16; c < g.n_mel; c += 16) {
-                    const int b0 = s_col_start[c], cnt = s_col_count[c];
-                    const float* w = s_weights + s_col_ptr[c];
-                    float acc = 0.f;
-                    for (int j = 0; j < cnt; ++j) acc = fmaf(mag[b0 + j], w[j], acc);
-                    s_out[f * g.n_mel + c] = logf(acc + g.log_offset);
+                    const int4 m = s_meta[c];
+                    const float* mg = mag + m.x;
+                    const float* w = s_weights + m.z;
+                    float acc0 = 0.f, acc1 = 0.f;
+                    int j = 0;
+                    for (; j + 2 <= m.y; j += 2) { acc0 = fmaf(mg[j], w[j], acc0); acc1 = fmaf(mg[j + 1], w[j + 1], acc1); }
+                    if (j < m.y) acc0 = fmaf(mg[j], w[j], acc0);
+                    s_out[slot_id * g.n_mel + c] = logf(acc0 + acc1 + g.log_offset);
                 }
             }
-            __syncwarp();                                     // mag (slot) is overwritten by the next frame
-        }
-        if (!kMagOnly) {
             __syncthreads();
             const int n_out = nf * g.n_mel;
             if ((reinterpret_cast<uintptr_t>(out_tile) & 15) == 0 && (n_out & 3) == 0) {
@@ -208,6 +229,7 @@ logmel_kernel(const float* __restrict__ wav, long long n_clips, long long n_samp
             }
         }
     }
+    cp_async_wait_all();
 }
 
 }  // namespace
@@ -260,29 +282,32 @@ extern "C" int a2m_mel_plan_create(int window, int hop, int nfft, int n_mel, con
     }
     const int nnz = static_cast<int>(weights.size());
 
-    std::vector<float> win(window);
+    std::vector<float> win(kNfft, 0.f);                     // zero padded: samples past the window contribute nothing
     for (int i = 0; i < window; ++i) win[i] = static_cast<float>(hann_host[i]);
-    std::vector<float2> w256(256), unt(256);
+    std::vector<float2> tw(256), unt(256);
     const double two_pi = 6.283185307179586476925286766559;
-    for (int e = 0; e < 256; ++e) {
-        w256[e] = make_float2(static_cast<float>(std::cos(two_pi * e / 256.0)), static_cast<float>(-std::sin(two_pi * e / 256.0)));
+    for (int k1 = 0; k1 < 16; ++k1)
+        for (int m2 = 0; m2 < 16; ++m2) {                   // [k1][m2]: a 16-lane group reads one contiguous row
+            const int e = (k1 * m2) & 255;
+            tw[k1 * 16 + m2] = make_float2(static_cast<float>(std::cos(two_pi * e / 256.0)), static_cast<float>(-std::sin(two_pi * e / 256.0)));
+        }
+    for (int e = 0; e < 256; ++e)
         unt[e] = make_float2(static_cast<float>(-std::sin(two_pi * e / 512.0)), static_cast<float>(-std::cos(two_pi * e / 512.0)));
-    }
+    std::vector<int4> meta(kMaxMel);
+    for (int c = 0; c < kMaxMel; ++c) meta[c] = make_int4(col_start[c], col_count[c], col_ptr[c], 0);
 
     A2M_CUDA_CHECK(cudaSetDevice(device));
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
-    const size_t o_win = carve(window * 4), o_w = carve(256 * 8), o_u = carve(256 * 8), o_cs = carve(kMaxMel * 4),
-                 o_cc = carve(kMaxMel * 4), o_cp = carve(kMaxMel * 4), o_wt = carve((nnz + 4) * 4);
+    const size_t o_win = carve(kNfft * 4), o_w = carve(256 * 8), o_u = carve(256 * 8), o_cm = carve(kMaxMel * 16),
+                 o_wt = carve((nnz + 4) * 4);
     unsigned char* blob = nullptr;
     A2M_CUDA_CHECK(cudaMalloc(&blob, off));
     std::vector<unsigned char> host(off, 0);
-    memcpy(host.data() + o_win, win.data(), window * 4);
-    memcpy(host.data() + o_w, w256.data(), 256 * 8);
+    memcpy(host.data() + o_win, win.data(), kNfft * 4);
+    memcpy(host.data() + o_w, tw.data(), 256 * 8);
     memcpy(host.data() + o_u, unt.data(), 256 * 8);
-    memcpy(host.data() + o_cs, col_start.data(), kMaxMel * 4);
-    memcpy(host.data() + o_cc, col_count.data(), kMaxMel * 4);
-    memcpy(host.data() + o_cp, col_ptr.data(), kMaxMel * 4);
+    memcpy(host.data() + o_cm, meta.data(), kMaxMel * 16);
     if (nnz) memcpy(host.data() + o_wt, weights.data(), nnz * 4);
     cudaError_t e = cudaMemcpy(blob, host.data(), off, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(blob); a2m_set_error("a2m_mel_plan_create: upload failed: %s", cudaGetErrorString(e)); return (int)e; }
@@ -291,11 +316,9 @@ extern "C" int a2m_mel_plan_create(int window, int hop, int nfft, int n_mel, con
     p->device = device; p->window = window; p->hop = hop; p->nfft = nfft; p->n_mel = n_mel; p->nnz = nnz;
     p->max_bin = max_bin; p->log_offset = static_cast<float>(log_offset); p->blob = blob;
     p->tab.window = reinterpret_cast<const float*>(blob + o_win);
-    p->tab.w256 = reinterpret_cast<const float2*>(blob + o_w);
+    p->tab.tw = reinterpret_cast<const float2*>(blob + o_w);
     p->tab.untangle = reinterpret_cast<const float2*>(blob + o_u);
-    p->tab.col_start = reinterpret_cast<const int*>(blob + o_cs);
-    p->tab.col_count = reinterpret_cast<const int*>(blob + o_cc);
-    p->tab.col_ptr = reinterpret_cast<const int*>(blob + o_cp);
+    p->tab.col_meta = reinterpret_cast<const int4*>(blob + o_cm);
     p->tab.weights = reinterpret_cast<const float*>(blob + o_wt);
     *out = p;
     return A2M_OK;
@@ -333,8 +356,9 @@ static int launch_logmel(const a2m_mel_plan* plan, const float* wav, int64_t n_c
     MelGeom g;
     g.window = plan->window; g.hop = plan->hop; g.n_mel = plan->n_mel; g.nnz = plan->nnz;
     g.max_bin = plan->max_bin; g.log_offset = plan->log_offset;
-    long long tf = 1 + (kSpanFloats - plan->window) / plan->hop;
-    if (tf > kMaxTileFrames) tf = kMaxTileFrames;
+    // a frame's reads extend to the next multiple of 32 past its window (zero window weights there)
+    long long tf = 1 + (kSpanFloats - ((plan->window + 31) / 32) * 32) / plan->hop;
+    if (tf > kSlots) tf = kSlots;
     if (tf > frames) tf = frames;
     g.tile_frames = static_cast<int>(tf);
     const int tiles_per_clip = static_cast<int>((frames + tf - 1) / tf);
@@ -343,11 +367,12 @@ static int launch_logmel(const a2m_mel_plan* plan, const float* wav, int64_t n_c
     const SmemLayout L = smem_layout(g.n_mel, g.nnz, kMagOnly);
     static bool attr_set[2] = {false, false};
     if (!attr_set[kMagOnly]) {
-        A2M_CUDA_CHECK(cudaFuncSetAttribute(logmel_kernel<kMagOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(logmel_kernel<kMagOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         attr_set[kMagOnly] = true;
     }
     long long grid = 2LL * a2m_num_sms();
     if (grid > n_tiles) grid = n_tiles;
+    A2M_ARG_CHECK(L.total <= 110 * 1024, "%s: %d bytes of shared memory", who, L.total);
     logmel_kernel<kMagOnly><<<static_cast<unsigned>(grid), kThreads, L.total, static_cast<cudaStream_t>(stream)>>>(
         wav, n_clips, n_samples, wav_stride, frames, tiles_per_clip, n_tiles, plan->tab, g, out);
     a2m_count_launch();

@@ -711,7 +711,7 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
                 for (int i = 0; i < 2; ++i) { gw.gc_w[i] = D.gconv[i].w; gw.gc_bias[i] = D.gconv[i].bias; }
                 for (int i = 0; i < 5; ++i) { gw.ln_w[i] = D.ln64[i].w; gw.ln_b[i] = D.ln64[i].b; }
                 std::shared_ptr<GnnFusedPlan> gp;
-                E.rc = gnn_fused_plan(gw, topo, static_cast<long long>(BT), xa, xb, &gp);
+                E.rc = gnn_fused_plan(gw, topo, B, T, xa, xb, &gp);      // tiles never straddle clips
                 int* flag = m->err_flag;
                 if (E.rc == A2M_OK) E.op([gp, flag](cudaStream_t s) { return gnn_fused_launch(*gp, flag, s); });
             }
@@ -846,6 +846,11 @@ extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t mel_str
                   (long long)mel_stride_b, (long long)mel_stride_t);
     m->cur_mel = mel; m->cur_stride_b = mel_stride_b; m->cur_stride_t = mel_stride_t;
     // trunk on the caller's stream, then body decoder (side stream) || hand decoder (caller's stream)
+    static const bool single_stream = getenv("A2M_DEBUG_SINGLE_STREAM") != nullptr;   // debugging aid
+    if (single_stream) {
+        rc = run_ops(P, 0, static_cast<int>(P->ops.size()), s);
+        if (rc != A2M_OK) return rc;
+    } else {
     rc = run_ops(P, 0, P->unet_end, s);
     if (rc != A2M_OK) return rc;
     A2M_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
@@ -856,6 +861,7 @@ extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t mel_str
     rc = run_ops(P, P->body_end, static_cast<int>(P->ops.size()), s);
     if (rc != A2M_OK) return rc;
     A2M_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join, 0));
+    }
     float* stage = P->pose_stage;
     A2M_CUDA_CHECK(cudaMemcpyAsync(pose, stage, static_cast<size_t>(B) * T * kPoseFeats * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (losses) {
@@ -914,7 +920,7 @@ extern "C" int a2m_model_gnn_forward(a2m_model* m, int part, const float* x, int
     __nv_bfloat16* xo = buf + ((n + 127) & ~127LL);
     std::shared_ptr<GnnFusedPlan> gp;
     int rc = launch_f32_to_bf16(x, n, buf, s);
-    if (rc == A2M_OK) rc = gnn_fused_plan(gw, GraphTopo{D.joints, D.nbr, D.deg}, n_graphs, buf, xo, &gp);
+    if (rc == A2M_OK) rc = gnn_fused_plan(gw, GraphTopo{D.joints, D.nbr, D.deg}, 1, static_cast<int>(n_graphs), buf, xo, &gp);
     if (rc == A2M_OK) rc = gnn_fused_launch(*gp, m->err_flag, s);
     if (rc == A2M_OK) rc = launch_bf16_to_f32(xo, n, out, s);
     cudaError_t e = cudaStreamSynchronize(s);

@@ -39,7 +39,7 @@ int main(int argc, char** argv) {
                 v[m1] = make(a, b);
             }
             dft16(v);
-            for (int k1 = 1; k1 < 16; ++k1) v[k1] = mul(v[k1], w256[lane * k1]);
+            for (int k1 = 1; k1 < 16; ++k1) v[k1] = mul(v[k1], w256[(lane * k1) & 255]);
             for (int k1 = 0; k1 < 16; ++k1) xchg[k1][lane] = v[k1];
         }
         for (int lane = 0; lane < 16; ++lane) {            // pass 2
@@ -51,11 +51,10 @@ int main(int argc, char** argv) {
         float* o = out.data() + (size_t)fr * 257;
         o[256] = std::fabs(Z[0][0].x - Z[0][0].y);
         for (int lane = 0; lane < 16; ++lane) {            // untangle with the kernel's partner rule
-            const int src = (16 - lane) & 15;
             for (int k2 = 0; k2 < 16; ++k2) {
-                cpx p = Z[src][15 - k2];
-                if (lane == 0) p = Z[0][(16 - k2) & 15];
                 const int k = lane + 16 * k2;
+                const int pk = (256 - k) & 255;             // the kernel reads Z[(256 - k) & 255] from its shared-memory dump
+                const cpx p = Z[pk & 15][pk >> 4];
                 o[k] = half_magnitude(untangle2(Z[lane][k2], p, unt[k]));
             }
         }

@@ -40,12 +40,15 @@ def test_graph_stack_matches_oracle(model_and_sd, part, joints, n_graphs):
 
 
 def test_graph_stack_is_per_graph(model_and_sd):
-    """Graphs never mix: the result for a graph does not depend on its tile neighbours or its position."""
+    """Graphs never mix: the result for a graph does not depend on its tile neighbours.  A graph in the same slot
+    of its tile gives bit-identical results; in another slot only the tensor-core accumulation order changes
+    (rare bf16 rounding flips), so that comparison carries a tolerance."""
     m, _ = model_and_sd
     g = torch.Generator().manual_seed(3)
     x = torch.randn(7, 42, 64, generator=g).cuda()
     full = m.graph_stack("hand", x)
-    for i in (0, 3, 6):
+    for i in (0, 3, 6):                                  # 3 hand graphs per tile: these start a tile in both runs
         assert torch.equal(m.graph_stack("hand", x[i:i + 1]), full[i:i + 1])
-    rev = m.graph_stack("hand", x.flip(0))
-    assert torch.equal(rev.flip(0), full)
+    rev = m.graph_stack("hand", x.flip(0)).flip(0)
+    assert rel_l1(rev, full.cpu()) <= 1e-3
+    assert torch.equal(rev[[0, 3, 6]], full[[0, 3, 6]])  # slots 0 <-> 0 under the reversal of 7 graphs
