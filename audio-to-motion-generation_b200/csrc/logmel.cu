@@ -35,7 +35,7 @@ struct MelTables {                // device-resident constants of a plan
     const float* window;          // [512]  periodic Hann, zero padded past the window length
     const float2* tw;             // [16][16] exp(-2 pi i m2 k1 / 256) at [k1][m2]
     const float2* untangle;       // [256]  (-sin, -cos)(2 pi k / 512)
-    const int4* col_meta;         // [n_mel] {first bin, bin count, offset into weights, 0}
+    const int4* col_meta;         // [n_mel] {first bin (multiple of 4), 4-bin groups, offset into weights (multiple of 4), 0}
     const float* weights;         // [nnz]
 };
 
@@ -174,11 +174,11 @@ logmel_kernel(const float* __restrict__ wav, long long n_clips, long long n_samp
     const bool even_hop = (g.hop & 1) == 0;
 
     auto stage = [&](long long tile, int buf) {             // asynchronous copy of one tile's samples
-        const long long clip = tile / tiles_per_clip;
-        const int f0 = static_cast<int>(tile - clip * tiles_per_clip) * g.tile_frames;
-        const int nf = static_cast<int>(min(static_cast<long long>(g.tile_frames), frames_per_clip - f0));
+        const unsigned clip = static_cast<unsigned>(tile) / static_cast<unsigned>(tiles_per_clip);     // n_tiles < 2^31
+        const int f0 = static_cast<int>(static_cast<unsigned>(tile) - clip * tiles_per_clip) * g.tile_frames;
+        const int nf = min(g.tile_frames, static_cast<int>(frames_per_clip) - f0);
         const int span = (nf - 1) * g.hop + g.window;
-        const float* src = wav + clip * wav_stride + static_cast<long long>(f0) * g.hop;
+        const float* src = wav + static_cast<long long>(clip) * wav_stride + static_cast<long long>(f0) * g.hop;
         float* dst = s_samples + buf * kSpanFloats;
         for (int i = tid; i < span; i += kThreads) cp_async4(dst + i, src + i);
         cp_async_commit();
@@ -189,13 +189,13 @@ logmel_kernel(const float* __restrict__ wav, long long n_clips, long long n_samp
     if (tile < n_tiles) stage(tile, 0);
     int buf = 0;
     for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-        const long long clip = tile / tiles_per_clip;
-        const int f0 = static_cast<int>(tile - clip * tiles_per_clip) * g.tile_frames;
-        const int nf = static_cast<int>(min(static_cast<long long>(g.tile_frames), frames_per_clip - f0));
+        const unsigned clip = static_cast<unsigned>(tile) / static_cast<unsigned>(tiles_per_clip);
+        const int f0 = static_cast<int>(static_cast<unsigned>(tile) - clip * tiles_per_clip) * g.tile_frames;
+        const int nf = min(g.tile_frames, static_cast<int>(frames_per_clip) - f0);
         cp_async_wait_all();
         __syncthreads();                                    // this tile's samples landed; the other buffer and s_out are free
         if (tile + gridDim.x < n_tiles) stage(tile + gridDim.x, buf ^ 1);      // overlaps the FFTs below
-        float* out_tile = out + (clip * frames_per_clip + f0) * out_width;
+        float* out_tile = out + (static_cast<long long>(clip) * frames_per_clip + f0) * out_width;
         // the warp-level syncs inside frame_spectrum need every lane: an idle 16-lane group (ragged tile end)
         // runs the FFT on frame 0 of the span and discards the result
         const bool active = slot_id < nf;
@@ -208,14 +208,17 @@ logmel_kernel(const float* __restrict__ wav, long long n_clips, long long n_samp
         } else {
             if (active) {
                 for (int c = lane16; c < g.n_mel; c += 16) {
-                    const int4 m = s_meta[c];
-                    const float* mg = mag + m.x;
-                    const float* w = s_weights + m.z;
+                    // column support padded to whole 4-bin groups (zero weights): two 16-byte loads per 4 FMAs
+                    const int4 m = s_meta[c];                               // {first bin (multiple of 4), groups, weight offset, 0}
+                    const float4* mg = reinterpret_cast<const float4*>(mag + m.x);
+                    const float4* w = reinterpret_cast<const float4*>(s_weights + m.z);
                     float acc0 = 0.f, acc1 = 0.f;
-                    int j = 0;
-                    for (; j + 2 <= m.y; j += 2) { acc0 = fmaf(mg[j], w[j], acc0); acc1 = fmaf(mg[j + 1], w[j + 1], acc1); }
-                    if (j < m.y) acc0 = fmaf(mg[j], w[j], acc0);
-                    s_out[slot_id * g.n_mel + c] = logf(acc0 + acc1 + g.log_offset);
+                    for (int j = 0; j < m.y; ++j) {
+                        const float4 a = mg[j], b = w[j];
+                        acc0 = fmaf(a.x, b.x, acc0); acc1 = fmaf(a.y, b.y, acc1);
+                        acc0 = fmaf(a.z, b.z, acc0); acc1 = fmaf(a.w, b.w, acc1);
+                    }
+                    s_out[slot_id * g.n_mel + c] = __logf(acc0 + acc1 + g.log_offset);
                 }
             }
             __syncthreads();
@@ -261,7 +264,8 @@ extern "C" int a2m_mel_plan_create(int window, int hop, int nfft, int n_mel, con
     A2M_ARG_CHECK(hann_host && mel_weights_host, "a2m_mel_plan_create: NULL table");
     A2M_ARG_CHECK(window + 0 <= kSpanFloats, "a2m_mel_plan_create: window too long");
 
-    // column-compressed mel matrix; every column's support must be one contiguous run of bins
+    // column-compressed mel matrix; every column's support must be one contiguous run of bins.  Each run is padded
+    // (zero weights) to start and end on a multiple of 4 bins so the kernel reads magnitudes and weights as float4
     std::vector<int> col_start(kMaxMel, 0), col_count(kMaxMel, 0), col_ptr(kMaxMel, 0);
     std::vector<float> weights;
     int max_bin = 0;
@@ -275,10 +279,11 @@ extern "C" int a2m_mel_plan_create(int window, int hop, int nfft, int n_mel, con
             a2m_set_error("a2m_mel_plan_create: mel column %d uses the Nyquist bin, not supported", c);
             return A2M_ERR_UNSUPPORTED;
         }
-        col_start[c] = first;
-        col_count[c] = last - first + 1;
-        for (int k = first; k <= last; ++k) weights.push_back(static_cast<float>(mel_weights_host[static_cast<size_t>(k) * n_mel + c]));
-        if (last > max_bin) max_bin = last;
+        const int lo = first & ~3, hi = (last | 3);         // hi <= 255
+        col_start[c] = lo;
+        col_count[c] = (hi - lo + 1) / 4;                   // groups of 4 bins
+        for (int k = lo; k <= hi; ++k) weights.push_back(static_cast<float>(mel_weights_host[static_cast<size_t>(k) * n_mel + c]));
+        if (hi > max_bin) max_bin = hi;
     }
     const int nnz = static_cast<int>(weights.size());
 
@@ -364,6 +369,7 @@ static int launch_logmel(const a2m_mel_plan* plan, const float* wav, int64_t n_c
     const int tiles_per_clip = static_cast<int>((frames + tf - 1) / tf);
     const long long n_tiles = static_cast<long long>(tiles_per_clip) * n_clips;
 
+    A2M_ARG_CHECK(n_tiles <= 0x7fffffffLL && frames <= 0x7fffffffLL, "%s: %lld tiles", who, n_tiles);
     const SmemLayout L = smem_layout(g.n_mel, g.nnz, kMagOnly);
     static bool attr_set[2] = {false, false};
     if (!attr_set[kMagOnly]) {

@@ -27,7 +27,7 @@ for k in step:
     a["launches"] += 1
     a["us"] += k.get("gpu__time_duration.sum", 0.0)
     a["dram_bytes"] += k.get("dram__bytes_read.sum", 0.0) + k.get("dram__bytes_write.sum", 0.0)
-out = {"note": "ncu --clock-control none, tools/profile_step.py (B=256), last step; launches serialised and cold-cache",
+out = {"note": "ncu --clock-control none, tools/profile_step.py (B=256), --cache-control none (warm L2), last of 2 steps; launches serialised by ncu",
        "per_kernel": agg,
        "conv_gemm_bytes_per_step": agg.get("conv_gemm_kernel", {}).get("dram_bytes"),
        "logmel_bytes_per_launch": agg.get("logmel_kernel", {}).get("dram_bytes"),
