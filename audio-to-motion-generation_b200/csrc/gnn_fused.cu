@@ -21,6 +21,7 @@
 // buffered, prefetched one tile ahead) and leave by TMA store; per-layer weights stream through one 34 KB
 // shared-memory buffer by TMA, prefetched as soon as the MMA that reads the previous layer's has completed.
 #include <cuda.h>
+#include <cstdlib>
 #include <cstring>
 #include "conv_gemm.cuh"
 #include "layers.cuh"
@@ -419,6 +420,390 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// =====================================================================================================
+// v3: the same layer math, restructured so that TWO CTAs fit on one SM (<= 111 KB shared memory and 256 TMEM
+// columns each) and hide each other's MMA / barrier latency -- the v2 kernel above is bound by the serial
+// chain  MMA -> stage -> softmax -> MMA -> epilogue  of a single tile (issue slots ~30 % used).
+//   * 256 threads = 2 per node row (32 features each);
+//   * GAT heads are processed one at a time: H^h = X W_h^T lands in one of two 64-column TMEM buffers, is staged
+//     as bf16 into one of two 16 KB shared-memory tiles, and P^h (single 32 KB buffer) multiplies it into OUT;
+//     the per-head 8 KB weight slices stream through a two-slot ring, always two slices ahead;
+//   * the attention logits (S = X U^T) and everything else are as in v2.
+// =====================================================================================================
+namespace v3 {
+
+constexpr int kThreads3 = 256;
+constexpr int kOffW3 = 0;                               // 2 x 8 KB weight slots (GAT head slices / GraphConv W_rel, W_root)
+constexpr int kOffU3 = 16384;                           // GAT attention rows [16][64] bf16
+constexpr int kOffX3 = 18432;                           // node tile, bf16 [128][64] SW128
+constexpr int kOffH3 = kOffX3 + 16384;                  // 2 x 16 KB: H^h tiles (GraphConv: AGG tile in slot 0)
+constexpr int kOffP3 = kOffH3 + 2 * 16384;              // attention / adjacency matrix [128][128] bf16
+constexpr int kOffS3 = kOffP3 + 32768;                  // s_src [128][4] fp32
+constexpr int kOffLn3 = kOffS3 + kRows * 4 * 4;         // LayerNorm partials [128][2][2] fp32
+constexpr int kOffTopo3 = kOffLn3 + kRows * 2 * 2 * 4;  // nbr [48][6], deg [48]
+constexpr int kOffPar3 = kOffTopo3 + 48 * kMaxDeg * 4 + 48 * 4;
+constexpr int kOffBar3 = kOffPar3 + 5 * 192 * 4;
+constexpr int kSmemBytes3 = kOffBar3 + 64 + 1024;
+constexpr uint32_t kColHB = 0, kColS3 = 128, kColOut3 = 160;        // TMEM: HB0 [0,64) HB1 [64,128) S [128,144) OUT [160,224)
+static_assert(kOffX3 % 1024 == 0 && kOffH3 % 1024 == 0 && kOffP3 % 1024 == 0, "swizzled tiles need 1024 B alignment");
+static_assert(2 * (kSmemBytes3 + 1024) <= 228 * 1024, "two CTAs per SM");
+
+struct Gnn3Params {
+    CUtensorMap w_head[3];               // GAT [272][64] bf16, box 64 x 64 (head slices)
+    CUtensorMap w_att[3];                // same tensor, box 64 x 16 (rows 256..271)
+    CUtensorMap w_gc[2];                 // [64][128] bf16, box 64 x 64
+    CUtensorMap x_in, x_out;
+    const float* gat_bias[3];
+    const float* gc_bias[2];
+    const float* ln_w[5];
+    const float* ln_b[5];
+    const int* nbr;
+    const int* deg;
+    int J, gpc;
+    long long n_groups;
+    int group_graphs, tiles_per_group;
+};
+
+__global__ void __launch_bounds__(kThreads3, 2)
+gnn3_kernel(const __grid_constant__ Gnn3Params p, int* __restrict__ err_flag) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    unsigned char* s_x = smem + kOffX3;
+    unsigned char* s_h = smem + kOffH3;
+    unsigned char* s_p = smem + kOffP3;
+    float* s_src = reinterpret_cast<float*>(smem + kOffS3);
+    float* s_ln = reinterpret_cast<float*>(smem + kOffLn3);
+    int* s_nbr = reinterpret_cast<int*>(smem + kOffTopo3);
+    int* s_deg = s_nbr + 48 * kMaxDeg;
+    float* s_par = reinterpret_cast<float*>(smem + kOffPar3);
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + kOffBar3);    // [2] weight slots (waited on by thread 0 only)
+    uint64_t* h_bar = w_bar + 2;                                       // [2] H buffer b holds a finished MMA
+    uint64_t* o_bar = w_bar + 4;                                       // OUT updated / P and H tile consumed
+    uint64_t* x_bar = w_bar + 5;                                       // node tile landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 6);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid & 127, half = tid >> 7, quad = warp & 3;
+    const int J = p.J, rows_per_tile = p.gpc * J;
+    const int group_rows = p.group_graphs * J;
+    const long long n_tiles = p.n_groups * p.tiles_per_group;
+    const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const uint32_t tile_bytes = static_cast<uint32_t>(rows_per_tile) * 128u;
+    const long long n_items = my_tiles * 16;            // weight slices this CTA consumes, 16 per tile
+
+    // weight slice `item` (0..15 within a tile: GAT heads 0-3 | GC rel, root | GAT | GC | GAT) into slot item & 1
+    auto load_item = [&](long long item) {             // thread 0 only
+        if (item >= n_items) return;
+        const int i = static_cast<int>(item & 15), slot = i & 1;
+        const int layer = i < 4 ? 0 : i < 6 ? 1 : i < 10 ? 2 : i < 12 ? 3 : 4;
+        unsigned char* dst = smem + kOffW3 + slot * 8192;
+        if ((layer & 1) == 0) {
+            const int h = i - (layer == 0 ? 0 : layer == 2 ? 6 : 12);
+            mbar_expect_tx(&w_bar[slot], h == 0 ? 8192 + 2048 : 8192);
+            tma_load_5d(dst, &p.w_head[layer >> 1], &w_bar[slot], 0, h * 64, 0, 0, 0);
+            if (h == 0) tma_load_5d(smem + kOffU3, &p.w_att[layer >> 1], &w_bar[slot], 0, 256, 0, 0, 0);
+        } else {
+            mbar_expect_tx(&w_bar[slot], 8192);
+            tma_load_5d(dst, &p.w_gc[layer >> 1], &w_bar[slot], slot * 64, 0, 0, 0, 0);   // slot 0: W_rel (k 0..63), slot 1: W_root
+        }
+    };
+
+    pdl_launch_dependents();
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) { tma_prefetch_desc(&p.w_head[i]); tma_prefetch_desc(&p.w_att[i]); }
+        for (int i = 0; i < 2; ++i) tma_prefetch_desc(&p.w_gc[i]);
+        tma_prefetch_desc(&p.x_in);
+        tma_prefetch_desc(&p.x_out);
+        for (int i = 0; i < 6; ++i) mbar_init(&w_bar[i], 1);
+        mbar_fence_init();
+        load_item(0);                                  // weights are constants: no need to wait for the predecessor
+        load_item(1);
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+    for (int i = tid; i < J * kMaxDeg; i += kThreads3) s_nbr[i] = p.nbr[i];
+    for (int i = tid; i < J; i += kThreads3) s_deg[i] = p.deg[i];
+    for (int i = tid; i < 5 * 192; i += kThreads3) {
+        const int layer = i / 192, j = i - layer * 192;
+        const float* src = j < 64 ? ((layer & 1) ? p.gc_bias[layer >> 1] : p.gat_bias[layer >> 1]) : j < 128 ? p.ln_w[layer] : p.ln_b[layer];
+        s_par[i] = src[j & 63];
+    }
+    {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < 32768 / 16; i += kThreads3) reinterpret_cast<uint4*>(s_p)[i] = z;
+        for (int i = tid; i < 16384 / 16; i += kThreads3)
+            if ((i >> 3) >= rows_per_tile) reinterpret_cast<uint4*>(s_x)[i] = z;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    pdl_wait();                                        // node features come from the previous kernel (proj_in)
+    auto load_tile = [&](long long tile) {             // thread 0 only
+        const int group = static_cast<int>(tile / p.tiles_per_group);
+        const int row0 = static_cast<int>(tile - static_cast<long long>(group) * p.tiles_per_group) * rows_per_tile;
+        mbar_expect_tx(x_bar, tile_bytes);
+        tma_load_5d(s_x, &p.x_in, x_bar, 0, row0, group, 0, 0);
+    };
+    if (tid == 0) load_tile(blockIdx.x);
+    const uint32_t idesc_h = umma_idesc_bf16(128, 64), idesc_s = umma_idesc_bf16(128, 16);
+    const uint32_t idesc_agg = idesc_b_mn(128, 64);
+    const uint32_t w_addr = smem_u32(smem + kOffW3), u_addr = smem_u32(smem + kOffU3), x_addr = smem_u32(s_x),
+                   h_addr = smem_u32(s_h), p_addr = smem_u32(s_p);
+
+    const bool valid_row = r < rows_per_tile;
+    const int jloc = r % J, g0 = r - jloc;
+    const int dg = valid_row ? s_deg[jloc] : 0;
+    int idx[kMaxDeg + 1];
+    idx[0] = r;
+#pragma unroll
+    for (int k = 0; k < kMaxDeg; ++k) idx[k + 1] = k < dg ? g0 + s_nbr[jloc * kMaxDeg + k] : r;
+
+    uint32_t wpar[2] = {0, 0}, hpar[2] = {0, 0}, opar = 0;     // wpar is used by thread 0 only
+    long long item = 0;                                // first weight slice of the current layer (thread 0's view)
+    for (long long it = 0; it < my_tiles; ++it) {
+        const long long tile = blockIdx.x + it * gridDim.x;
+        const int group = static_cast<int>(tile / p.tiles_per_group);
+        const int row0 = static_cast<int>(tile - static_cast<long long>(group) * p.tiles_per_group) * rows_per_tile;
+        const bool live = valid_row && row0 + r < group_rows;
+        mbar_wait(x_bar, static_cast<uint32_t>(it & 1), err_flag, 30);
+        float x[32];                                   // residual stream: this thread's 32 features in fp32
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint4 u = *reinterpret_cast<const uint4*>(s_x + sw128_off(r, half * 4 + c));
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { x[c * 8 + 2 * e] = bf_lo(w4[e]); x[c * 8 + 2 * e + 1] = bf_hi(w4[e]); }
+        }
+
+#pragma unroll 1
+        for (int layer = 0; layer < 5; ++layer) {
+            float v[32];
+            if ((layer & 1) == 0) {
+                // ================= GATConv, one head at a time =================
+                if (tid == 0) {
+                    tc_fence_after();
+                    mbar_wait(&w_bar[0], wpar[0], err_flag, 31); wpar[0] ^= 1;          // head 0 slice + attention rows
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        umma_bf16(tmem_base + kColS3, umma_desc_sw128(x_addr + k * 32), umma_desc_sw128(u_addr + k * 32), idesc_s, k != 0);
+                        umma_bf16(tmem_base + kColHB, umma_desc_sw128(x_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc_h, k != 0);
+                    }
+                    umma_commit(&h_bar[0]);
+                    mbar_wait(&w_bar[1], wpar[1], err_flag, 31); wpar[1] ^= 1;          // head 1 slice
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + kColHB + 64, umma_desc_sw128(x_addr + k * 32), umma_desc_sw128(w_addr + 8192 + k * 32), idesc_h, k != 0);
+                    umma_commit(&h_bar[1]);
+                }
+                float s_dst2[2] = {0.f, 0.f};           // attention logit (destination part) of my two heads: half, half + 2
+#pragma unroll 1
+                for (int h = 0; h < 4; ++h) {
+                    const int b = h & 1;
+                    mbar_wait(&h_bar[b], hpar[b], err_flag, 32);
+                    hpar[b] ^= 1;
+                    tc_fence_after();
+                    if (tid == 0) load_item(item + h + 2);             // slot b is free: MMA1_h has read it
+                    if (h == 0) {
+                        uint32_t t[16];
+                        tmem_ld_32x16(tmem_lane + kColS3, t);
+                        tmem_ld_wait();
+                        s_dst2[0] = half == 0 ? __uint_as_float(t[4]) + __uint_as_float(t[12]) : __uint_as_float(t[5]) + __uint_as_float(t[13]);
+                        s_dst2[1] = half == 0 ? __uint_as_float(t[6]) + __uint_as_float(t[14]) : __uint_as_float(t[7]) + __uint_as_float(t[15]);
+                        if (half == 0) {
+                            *reinterpret_cast<float4*>(s_src + r * 4) =
+                                make_float4(__uint_as_float(t[0]) + __uint_as_float(t[8]), __uint_as_float(t[1]) + __uint_as_float(t[9]),
+                                            __uint_as_float(t[2]) + __uint_as_float(t[10]), __uint_as_float(t[3]) + __uint_as_float(t[11]));
+                        }
+                    }
+                    {   // stage my half of H^h (32 features) as bf16 into tile b
+                        uint32_t t[32];
+                        tmem_ld_32x32(tmem_lane + kColHB + b * 64 + half * 32, t);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint4 o;
+                            o.x = pack_bf16(__uint_as_float(t[c * 8]), __uint_as_float(t[c * 8 + 1]));
+                            o.y = pack_bf16(__uint_as_float(t[c * 8 + 2]), __uint_as_float(t[c * 8 + 3]));
+                            o.z = pack_bf16(__uint_as_float(t[c * 8 + 4]), __uint_as_float(t[c * 8 + 5]));
+                            o.w = pack_bf16(__uint_as_float(t[c * 8 + 6]), __uint_as_float(t[c * 8 + 7]));
+                            *reinterpret_cast<uint4*>(s_h + b * 16384 + sw128_off(r, half * 4 + c)) = o;
+                        }
+                    }
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    __syncthreads();                    // H^h staged (and, for h = 0, s_src visible); TMEM buffer b is free
+                    // P^h is written by the threads of half (h & 1); it needs the previous head's MMA to have drained P
+                    if (h > 0) { mbar_wait(o_bar, opar, err_flag, 33); opar ^= 1; }
+                    if (half == b) {
+                        const float sd = (h >> 1) ? s_dst2[1] : s_dst2[0];
+                        float alpha[kMaxDeg + 1];
+                        float m = -INFINITY;
+#pragma unroll
+                        for (int k = 0; k <= kMaxDeg; ++k) {
+                            alpha[k] = k <= dg ? leaky(s_src[idx[k] * 4 + h] + sd) : -INFINITY;
+                            m = fmaxf(m, alpha[k]);
+                        }
+                        float den = 0.f;
+#pragma unroll
+                        for (int k = 0; k <= kMaxDeg; ++k) { alpha[k] = k <= dg ? __expf(alpha[k] - m) : 0.f; den += alpha[k]; }
+                        const float inv = 0.25f / den;                  // softmax normaliser and the head mean
+#pragma unroll
+                        for (int k = 0; k <= kMaxDeg; ++k)
+                            if (k <= dg) *reinterpret_cast<__nv_bfloat16*>(s_p + p_off(r, idx[k])) = __float2bfloat16_rn(alpha[k] * inv);
+                    }
+                    fence_proxy_async_smem();
+                    __syncthreads();
+                    if (tid == 0) {
+                        tc_fence_after();
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk)
+                            umma_bf16(tmem_base + kColOut3, umma_desc_sw128(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32),
+                                      umma_desc_sw128(h_addr + b * 16384 + kk * 2048), idesc_agg, (h | kk) != 0);
+                        umma_commit(o_bar);
+                        if (h + 2 < 4) {                // H^{h+2} into the TMEM buffer drained at the barrier above; its weight
+                            mbar_wait(&w_bar[b], wpar[b], err_flag, 31); wpar[b] ^= 1;      // slice had this whole round to land
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(tmem_base + kColHB + b * 64, umma_desc_sw128(x_addr + k * 32),
+                                          umma_desc_sw128(w_addr + b * 8192 + k * 32), idesc_h, k != 0);
+                            umma_commit(&h_bar[b]);
+                        }
+                    }
+                }
+                mbar_wait(o_bar, opar, err_flag, 34);
+                opar ^= 1;
+                tc_fence_after();
+                if (tid == 0) item += 4;
+                {
+                    uint32_t t[32];
+                    tmem_ld_32x32(tmem_lane + kColOut3 + half * 32, t);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(t[i]);
+                }
+            } else {
+                // ================= GraphConv =================
+                if (half == 0) {                           // adjacency (no self loops) into P
+                    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+                    *reinterpret_cast<__nv_bfloat16*>(s_p + p_off(r, idx[0])) = zero;
+#pragma unroll
+                    for (int k = 1; k <= kMaxDeg; ++k)
+                        if (k <= dg) *reinterpret_cast<__nv_bfloat16*>(s_p + p_off(r, idx[k])) = one;
+                }
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)       // AGG = Adj . X (exact: 0/1 weights, fp32 accumulation)
+                        umma_bf16(tmem_base + kColOut3, umma_desc_sw128(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32),
+                                  umma_desc_sw128(x_addr + kk * 2048), idesc_agg, kk != 0);
+                    umma_commit(o_bar);
+                }
+                mbar_wait(o_bar, opar, err_flag, 35);
+                opar ^= 1;
+                tc_fence_after();
+                {
+                    uint32_t t[32];
+                    tmem_ld_32x32(tmem_lane + kColOut3 + half * 32, t);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(t[c * 8]), __uint_as_float(t[c * 8 + 1]));
+                        o.y = pack_bf16(__uint_as_float(t[c * 8 + 2]), __uint_as_float(t[c * 8 + 3]));
+                        o.z = pack_bf16(__uint_as_float(t[c * 8 + 4]), __uint_as_float(t[c * 8 + 5]));
+                        o.w = pack_bf16(__uint_as_float(t[c * 8 + 6]), __uint_as_float(t[c * 8 + 7]));
+                        *reinterpret_cast<uint4*>(s_h + sw128_off(r, half * 4 + c)) = o;
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    mbar_wait(&w_bar[0], wpar[0], err_flag, 31); wpar[0] ^= 1;
+                    mbar_wait(&w_bar[1], wpar[1], err_flag, 31); wpar[1] ^= 1;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)           // W_rel . agg
+                        umma_bf16(tmem_base + kColHB, umma_desc_sw128(h_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc_h, k != 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)           // + W_root . x
+                        umma_bf16(tmem_base + kColHB, umma_desc_sw128(x_addr + k * 32), umma_desc_sw128(w_addr + 8192 + k * 32), idesc_h, 1);
+                    umma_commit(&h_bar[0]);
+                }
+                mbar_wait(&h_bar[0], hpar[0], err_flag, 36);
+                hpar[0] ^= 1;
+                tc_fence_after();
+                if (tid == 0) { load_item(item + 2); load_item(item + 3); item += 2; }
+                {
+                    uint32_t t[32];
+                    tmem_ld_32x32(tmem_lane + kColHB + half * 32, t);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(t[i]);
+                }
+            }
+            // ---- + bias, LayerNorm(64) over the two 32-feature halves of the node -> LeakyReLU -> + residual
+            {
+                const float4* par = reinterpret_cast<const float4*>(s_par + layer * 192 + half * 32);
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 b4 = par[i4];
+                    v[i4 * 4] += b4.x; v[i4 * 4 + 1] += b4.y; v[i4 * 4 + 2] += b4.z; v[i4 * 4 + 3] += b4.w;
+                }
+                float s = 0.f, sq = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { s += v[i]; sq = fmaf(v[i], v[i], sq); }
+                *reinterpret_cast<float2*>(s_ln + (r * 2 + half) * 2) = make_float2(s, sq);
+                __syncthreads();
+                const float4 a = *reinterpret_cast<const float4*>(s_ln + r * 4);
+                const float mean = (a.x + a.z) * (1.f / 64.f);
+                const float rstd = rsqrtf(fmaxf((a.y + a.w) * (1.f / 64.f) - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 w4 = par[16 + i4], b4 = par[32 + i4];
+                    x[i4 * 4] += leaky((v[i4 * 4] - mean) * rstd * w4.x + b4.x);
+                    x[i4 * 4 + 1] += leaky((v[i4 * 4 + 1] - mean) * rstd * w4.y + b4.y);
+                    x[i4 * 4 + 2] += leaky((v[i4 * 4 + 2] - mean) * rstd * w4.z + b4.z);
+                    x[i4 * 4 + 3] += leaky((v[i4 * 4 + 3] - mean) * rstd * w4.w + b4.w);
+                }
+            }
+            if (!live) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x[i] = 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 o;
+                o.x = pack_bf16(x[c * 8], x[c * 8 + 1]); o.y = pack_bf16(x[c * 8 + 2], x[c * 8 + 3]);
+                o.z = pack_bf16(x[c * 8 + 4], x[c * 8 + 5]); o.w = pack_bf16(x[c * 8 + 6], x[c * 8 + 7]);
+                *reinterpret_cast<uint4*>(s_x + sw128_off(r, half * 4 + c)) = o;
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncthreads();
+        }
+        if (tid == 0) {                                // store this tile, then (same buffer) fetch the next one
+            tma_store_5d(&p.x_out, s_x, 0, row0, group, 0, 0);
+            tma_store_commit();
+            if (it + 1 < my_tiles) {
+                tma_store_wait_read();
+                load_tile(tile + gridDim.x);
+            }
+        }
+    }
+    if (tid == 0) tma_store_wait_read();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+}  // namespace v3
+
 // U rows of the extended GAT weight: the attention logits a_src . (W_h x) = (W_h^T a_src) . x come out of the
 // same MMA as H.  Rows 256+h: src (hi), 260+h: dst (hi), 264+h: src (lo), 268+h: dst (lo); hi + lo carries
 // ~16 mantissa bits of the fp32 fold, which is evaluated on the bf16-rounded W the MMA itself uses.
@@ -439,7 +824,9 @@ __global__ void gat_fold_attention_kernel(__nv_bfloat16* __restrict__ wext, cons
 
 // Host side ---------------------------------------------------------------------------------------
 struct GnnFusedPlan {
-    GnnParams p;
+    GnnParams p;                 // v2 (one CTA per SM)
+    v3::Gnn3Params p3;           // v3 (two CTAs per SM, per-head pipeline): the default
+    bool use_v3;
     int grid;
 };
 
@@ -488,7 +875,27 @@ int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_groups,
     if (rc != A2M_OK) return rc;
     const long long tiles = n_groups * p.tiles_per_group;
     const int sms = a2m_num_sms();
-    plan->grid = static_cast<int>(tiles < sms ? tiles : sms);
+    static const bool force_v2 = getenv("A2M_GNN_V2") != nullptr;            // A/B aid
+    plan->use_v3 = !force_v2;
+    if (plan->use_v3) {
+        v3::Gnn3Params& q = plan->p3;
+        memset(&q, 0, sizeof(q));
+        for (int i = 0; i < 3; ++i) {
+            rc = make_weight_map(&q.w_head[i], w.gat_w[i], kGatRows, 64, 64);
+            if (rc != A2M_OK) return rc;
+            rc = make_weight_map(&q.w_att[i], w.gat_w[i], kGatRows, 64, 16);
+            if (rc != A2M_OK) return rc;
+            q.gat_bias[i] = w.gat_bias[i];
+        }
+        for (int i = 0; i < 2; ++i) { q.w_gc[i] = p.w_gc[i]; q.gc_bias[i] = w.gc_bias[i]; }
+        for (int i = 0; i < 5; ++i) { q.ln_w[i] = w.ln_w[i]; q.ln_b[i] = w.ln_b[i]; }
+        q.x_in = p.x_in; q.x_out = p.x_out;
+        q.nbr = p.nbr; q.deg = p.deg; q.J = p.J; q.gpc = p.gpc;
+        q.n_groups = p.n_groups; q.group_graphs = p.group_graphs; q.tiles_per_group = p.tiles_per_group;
+        plan->grid = static_cast<int>(tiles < 2LL * sms ? tiles : 2LL * sms);
+    } else {
+        plan->grid = static_cast<int>(tiles < sms ? tiles : sms);
+    }
     *out = plan;
     return A2M_OK;
 }
@@ -497,7 +904,13 @@ int gnn_fused_launch(const GnnFusedPlan& plan, int* err_flag, cudaStream_t strea
     static bool configured = false;
     if (!configured) {
         A2M_CUDA_CHECK(cudaFuncSetAttribute(gnn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(v3::gnn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::kSmemBytes3));
         configured = true;
+    }
+    if (plan.use_v3) {
+        A2M_CUDA_CHECK(a2m_launch_pdl(v3::gnn3_kernel, dim3(plan.grid), dim3(v3::kThreads3), v3::kSmemBytes3, stream, plan.p3, err_flag));
+        a2m_count_launch();
+        return A2M_OK;
     }
     A2M_CUDA_CHECK(a2m_launch_pdl(gnn_fused_kernel, dim3(plan.grid), dim3(kThreads), kSmemBytes, stream, plan.p, err_flag));
     a2m_count_launch();

@@ -57,12 +57,17 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """Samples taken before this call are warm-up samples; they are only used if the timed region was too short
+        for nvidia-smi to report during it."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -80,7 +85,8 @@ class ClockSampler:
         self.proc.terminate()
         self.thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows[self.first:] if len(self.rows) - self.first >= 2 else self.rows[max(0, self.first - 3):]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -206,15 +212,17 @@ def main():
         return ms
 
     # ---- device-resident arm -------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                          # nvidia-smi needs ~0.1 s to produce its first line: start it before the warm-up
     for i in range(args.warmup):
         pipe.step(wav_dev[i % POOL], gt_dev[i % POOL])
     pipe.finish()
     model.check_device_status()
     pipe.reset()
-    sampler = ClockSampler(local)
     barrier()
     if rank == 0:
-        sampler.start()
+        sampler.mark()                           # samples from here on are "under load"
     lib.a2m_launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
