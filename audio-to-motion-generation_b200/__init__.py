@@ -23,6 +23,7 @@ _DROPIN = {
     "pose_video.mel_features": ".pose_video.mel_features",
     "pose_video.audio_repr": ".pose_video.audio_repr",
     "motion_evaluation": ".motion_evaluation",
+    "normalization_tools": ".normalization_tools",
     "model_layers": ".model_layers",
     "real_motion_model": ".real_motion_model",
 }

@@ -32,6 +32,28 @@ def shard_range(n_items, rank, world):
     return lo, min(n_items, lo + per)
 
 
+WINDOW_HOP = 5              # version5_model_train.py:205 (window_hop): consecutive windows start 5 * fs_ratio frames apart
+
+
+def window_starts(n_frames, frames=POSE_FRAMES, stride=ADAPTER_STRIDE, window_hop=WINDOW_HOP):
+    """First log-mel frame of every sliding window, the reference's index arithmetic (MiniData.update_idx_list,
+    dataUtils.py:585-620): window = frames * stride feature rows, starts = range(0, len - window, window_hop * stride)."""
+    return list(range(0, n_frames - frames * stride, window_hop * stride))
+
+
+def sliding_windows(logmel_clip, frames=POSE_FRAMES, stride=ADAPTER_STRIDE, window_hop=WINDOW_HOP):
+    """One clip's log-mel [n_frames, F] -> all its model inputs [n_windows, frames, F] as a strided VIEW
+    (window w, step t = row w * window_hop * stride + t * stride): nothing is gathered or copied, the first
+    encoder kernel reads the overlapping windows in place."""
+    n, f = logmel_clip.shape
+    n_win = len(window_starts(n, frames, stride, window_hop))
+    if n_win == 0:
+        return logmel_clip.new_empty((0, frames, f))
+    s0 = logmel_clip.stride(0)
+    return logmel_clip.as_strided((n_win, frames, f), (window_hop * stride * s0, stride * s0, 1),
+                                  logmel_clip.storage_offset())
+
+
 def adapter(logmel, frames=POSE_FRAMES, stride=ADAPTER_STRIDE):
     """D2: [B, >=frames*stride, F] -> strided view [B, frames, F] (no copy)."""
     span = frames * stride
@@ -124,6 +146,21 @@ class AudioToPosePipeline:
         logmel = audio_repr.log_mel_spectograms(wav)
         pose, _ = (model or self.model)(adapter(logmel))
         return pose
+
+    def generate_long(self, wav, window_hop=WINDOW_HOP, model=None):
+        """Long-form audio (BASELINE config 4): wav [B, N] (e.g. 60 s = 960 000 samples) -> poses
+        [B, n_windows, 64, 104].  The log-mel of every stream is computed once; each clip's overlapping windows
+        (384-frame span, stride 6, hop window_hop * 6 frames -- the reference's window arithmetic) are fed to the
+        generator as one strided view per clip, so no window is ever materialised."""
+        logmel = audio_repr.log_mel_spectograms(wav)                       # [B, frames, 64]
+        net = model or self.model
+        out = []
+        for b in range(logmel.shape[0]):
+            x = sliding_windows(logmel[b], window_hop=window_hop)
+            if x.shape[0] == 0:
+                raise ValueError("the audio is shorter than one window (%d log-mel frames)" % logmel.shape[1])
+            out.append(net(x)[0])
+        return torch.stack(out)
 
     def step(self, wav, gt_pose):
         """One batch, inputs already on the device: enqueues mel -> generator -> evaluation on the next lane and

@@ -88,6 +88,21 @@ int a2m_eval_l1_pck_f32(const float* pred, const float* gt, int64_t n_clips, int
                         a2m_metrics* accum /* device */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * pose (de)normalisation on either side of the generator: replaces the element-wise
+ * steps of version5_model_train.py:300-307 / generate_motion_video.py:247-255 (view [.., 2, 52], subtract the
+ * neck = joint 0 of the x block and of the y block, then (x - mean) / std), generate_motion_video.py:259-260
+ * (x * std + mean) and the accumulation of normalization_tools.py:24-45 get_mean_std_necksub.
+ * pose, out: [n_frames, 104] fp32; mean, std: [104] fp32 (device).  Single IEEE operations in the reference's
+ * order, so results equal torch's CPU results bit for bit.
+ * a2m_pose_stats_f64 ADDS to accum (device double[209]): [0,104) sum, [104,208) sum of fp32 squares of the
+ * neck-subtracted poses, [208] frame count.
+ * ---------------------------------------------------------------------------------------------- */
+int a2m_pose_normalize_f32(const float* pose, const float* mean, const float* std, int64_t n_frames, float* out, void* stream);
+int a2m_pose_denormalize_f32(const float* pose, const float* mean, const float* std, int64_t n_frames, float* out,
+                             void* stream);
+int a2m_pose_stats_f64(const float* pose, int64_t n_frames, double* accum, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * the one collective of the path: sum the 64-byte partials over the ranks.
  * NCCL is bound at run time (dlopen of the libnccl.so.2 already loaded by torch); the unique id is
  * distributed by the caller (torch.distributed store).

@@ -72,3 +72,36 @@ def test_host_batches_end_to_end(setup):
     out = pipe.finish()
     assert out["pck_hits"] == ref["pck_hits"]
     np.testing.assert_allclose(out["abs_pose"], ref["abs_pose"], rtol=1e-12)
+
+
+def test_long_form_sliding_windows(setup):
+    """BASELINE config 4 (streaming mel + sliding-window generation) at a reduced length: the windows are strided
+    views of one log-mel per clip; results must equal the oracle composition window by window."""
+    pipeline, model, sd = setup
+    n = 16000 * 6 + 123                                     # 6 s -> 598 frames -> 8 windows (hop 30 frames)
+    wav = np.stack([synth.wav_clip(40 + i, n) for i in range(2)])
+    pipe = pipeline.AudioToPosePipeline(model, lanes=1)
+    poses = pipe.generate_long(torch.from_numpy(wav).cuda()).cpu()
+    mel = mel_oracle.log_mel_batch(wav)
+    starts = pipeline.window_starts(mel.shape[1])
+    assert starts == list(range(0, mel.shape[1] - 384, 30)) and poses.shape == (2, len(starts), 64, 104)
+    for b in range(2):
+        x = np.stack([mel[b, s:s + 384:6] for s in starts]).astype(np.float32)
+        ref, _ = model_oracle.generator_forward(sd, torch.from_numpy(x))
+        rel = ((poses[b] - ref).abs().sum() / ref.abs().sum()).item()
+        assert rel <= 1e-2, rel
+    # the strided view must give exactly what a gathered copy gives
+    lm = pipeline.audio_repr.log_mel_spectograms(torch.from_numpy(wav[:1]).cuda())[0]
+    view = pipeline.sliding_windows(lm)
+    gathered = torch.stack([lm[s:s + 384:6] for s in starts]).contiguous()
+    assert torch.equal(view, gathered)
+    assert torch.equal(model(view)[0], model(gathered)[0])
+
+
+def test_long_form_full_size_shape(setup):
+    """60 s streams: 960 000 samples -> 5 998 frames -> 188 windows per clip."""
+    pipeline, model, _ = setup
+    assert len(pipeline.window_starts(5998)) == 188
+    wav = 0.1 * torch.randn(2, 960000, device="cuda")
+    poses = pipeline.AudioToPosePipeline(model, lanes=1).generate_long(wav)
+    assert poses.shape == (2, 188, 64, 104) and torch.isfinite(poses).all()
