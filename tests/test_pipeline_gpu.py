@@ -23,9 +23,14 @@ def setup(pkg):
     return pipeline, model, sd
 
 
-def run(pipeline, model, lanes, batches):
-    pipe = pipeline.AudioToPosePipeline(model, lanes=lanes)
-    poses = [pipe.step(torch.from_numpy(w).cuda(), torch.from_numpy(g).cuda()) for w, g in batches]
+def run(pipeline, model, lanes, batches, graphs=False):
+    pipe = pipeline.AudioToPosePipeline(model, lanes=lanes, graphs=graphs)
+    poses = []
+    for w, g in batches:
+        p = pipe.step(torch.from_numpy(w).cuda(), torch.from_numpy(g).cuda())
+        if graphs:
+            pipe.sync_lanes()                   # graph lanes hand back their static output buffer: copy it out now
+        poses.append(p.clone() if graphs else p)
     out = pipe.finish()
     return out, [p.cpu() for p in poses]
 
@@ -60,6 +65,18 @@ def test_lanes_and_batching_do_not_change_results(setup):
         assert out["pck_hits"] == whole["pck_hits"] and out["n_frames"] == whole["n_frames"] == 8 * 64
         np.testing.assert_allclose(out["abs_pose"], whole["abs_pose"], rtol=1e-12)
         np.testing.assert_allclose(out["abs_motion"], whole["abs_motion"], rtol=1e-12)
+
+
+def test_cuda_graph_replay_equals_eager(setup):
+    pipeline, model, _ = setup
+    wav, gt = synth.wav_batch(30, 8), synth.gt_pose_batch(30, 8)
+    split = [(wav[i:i + 2], gt[i:i + 2]) for i in range(0, 8, 2)]
+    eager, p_eager = run(pipeline, model, 1, split)
+    for lanes in (1, 2):
+        out, poses = run(pipeline, model, lanes, split, graphs=True)
+        assert torch.equal(torch.cat(poses), torch.cat(p_eager))
+        assert out["pck_hits"] == eager["pck_hits"] and out["n_frames"] == eager["n_frames"]
+        np.testing.assert_allclose(out["abs_pose"], eager["abs_pose"], rtol=1e-12)
 
 
 def test_host_batches_end_to_end(setup):
