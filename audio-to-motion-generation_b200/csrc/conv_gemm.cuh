@@ -49,6 +49,7 @@ struct ConvGemmDesc {
     long long out_base;
     int act;
     int out_type;
+    int block_n_hint = 0;       // 256: use 128 x 256 tiles if the layer allows it (N % 256 == 0, bf16 output)
     int split_k = 1;            // > 1: K blocks split over gridDim.z; split z writes its fp32 partial sums at
     long long split_stride = 0; // out + z * split_stride (act must be none; bias added by split 0); the consumer
                                 // sums the planes in a fixed order (deterministic, batch-invariant)

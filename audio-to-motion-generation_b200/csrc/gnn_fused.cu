@@ -892,7 +892,9 @@ int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_groups,
         q.x_in = p.x_in; q.x_out = p.x_out;
         q.nbr = p.nbr; q.deg = p.deg; q.J = p.J; q.gpc = p.gpc;
         q.n_groups = p.n_groups; q.group_graphs = p.group_graphs; q.tiles_per_group = p.tiles_per_group;
-        plan->grid = static_cast<int>(tiles < 2LL * sms ? tiles : 2LL * sms);
+        static const char* per_sm_env = getenv("A2M_GNN_CTAS_PER_SM");      // experiment knob: 1 leaves half of each SM to other streams
+        const long long per_sm = per_sm_env ? atoi(per_sm_env) : 2;
+        plan->grid = static_cast<int>(tiles < per_sm * sms ? tiles : per_sm * sms);
     } else {
         plan->grid = static_cast<int>(tiles < sms ? tiles : sms);
     }

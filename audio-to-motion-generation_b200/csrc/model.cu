@@ -5,6 +5,7 @@
 // of layers.cu -- and enqueues them on the caller's stream.  Decisions D1 (up_attention before the
 // skip concat) and D3 (eval semantics) of SURVEY.md section 8 apply.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -460,6 +461,13 @@ struct Emit {
         for (int i = 0; i < 4; ++i) { d.box[i] = box[i]; d.m_extent[i] = ext[i]; d.out_stride[i] = ostride[i]; }
         d.taps = std::move(taps);
         d.N = L.N; d.out_base = obase; d.act = act >= 0 ? act : L.act; d.out_type = out_type; d.split_k = split_k; d.split_stride = split_stride;
+        {   // wide layers with enough tiles to fill the SMs run 128 x 256 tiles (one CTA per SM, fewer operand bytes per FLOP)
+            static const char* env = getenv("A2M_GEMM_BN256");
+            const int mode = env ? atoi(env) : 1;
+            long long m_tiles = 1;
+            for (int i = 0; i < 4; ++i) m_tiles *= (ext[i] + box[i] - 1) / box[i];
+            if (mode && L.N % 256 == 0 && L.N >= 512 && m_tiles * (L.N / 256) >= 120) d.block_n_hint = 256;
+        }
         auto plan = std::make_shared<ConvGemmPlan>();
         rc = conv_gemm_plan(d, L.w, L.bias, out, plan.get());
         if (rc != A2M_OK) return;
