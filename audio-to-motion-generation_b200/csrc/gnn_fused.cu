@@ -429,6 +429,9 @@ gnn_fused_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag
 //     as bf16 into one of two 16 KB shared-memory tiles, and P^h (single 32 KB buffer) multiplies it into OUT;
 //     the per-head 8 KB weight slices stream through a two-slot ring, always two slices ahead;
 //   * the attention logits (S = X U^T) and everything else are as in v2.
+// Tried and dropped: a ninth, dedicated issuer warp with mbarrier hand-offs instead of __syncthreads.  Nine warps per
+// CTA put three warps of each CTA on one SM sub-partition, whose 16 K registers then hold only one CTA's worth at
+// 112 registers per thread: occupancy fell to one CTA per SM and the kernel was 37 % slower (profiles/).
 // =====================================================================================================
 namespace v3 {
 
