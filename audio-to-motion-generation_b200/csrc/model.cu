@@ -466,7 +466,7 @@ struct Emit {
             const int mode = env ? atoi(env) : 1;
             long long m_tiles = 1;
             for (int i = 0; i < 4; ++i) m_tiles *= (ext[i] + box[i] - 1) / box[i];
-            if (mode && L.N % 256 == 0 && L.N >= 512 && m_tiles * (L.N / 256) >= 120) d.block_n_hint = 256;
+            if (mode && L.N % 256 == 0 && L.N >= (mode == 2 ? 256 : 512) && m_tiles * (L.N / 256) >= 120) d.block_n_hint = 256;
         }
         auto plan = std::make_shared<ConvGemmPlan>();
         rc = conv_gemm_plan(d, L.w, L.bias, out, plan.get());
