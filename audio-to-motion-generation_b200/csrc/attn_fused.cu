@@ -260,15 +260,29 @@ attn_fused_kernel(const __grid_constant__ AttnParams p, int* __restrict__ err_fl
                       umma_desc_mn(ring + kOffV + kk * 2048, 16384), id_o, kk != 0);
         umma_commit(o_bar);
     }
+    // the residual rows are fetched while the P.v MMA runs (16 independent 16-byte loads per thread in flight).
+    // x / res2 were written by earlier kernels of the stream that this (programmatically launched) kernel
+    // overlapped with: read them through L2 (ld.global.cg), never through the non-coherent path, whose L1
+    // lines may predate those writes
+    const long long row = row0 + r;
+    const bool live = row < p.n_rows;
+    const long long base = row * kC + q * 64;
+    uint4 xv[8], rv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        xv[i] = make_uint4(0, 0, 0, 0);
+        rv[i] = make_uint4(0, 0, 0, 0);
+        if (live) {
+            xv[i] = __ldcg(reinterpret_cast<const uint4*>(p.x + base + i * 8));
+            if (p.res2) rv[i] = __ldcg(reinterpret_cast<const uint4*>(p.res2 + base + i * 8));
+        }
+    }
     mbar_wait(o_bar, 0, err_flag, 26);
     tc_fence_after();
 
     // ---------------- out = gamma * O / rowsum + x (+ res2) ----------------
     {
         const float scale = __ldg(p.gamma) / s_sum[r];
-        const long long row = row0 + r;
-        const bool live = row < p.n_rows;
-        const long long base = row * kC + q * 64;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
             uint32_t t[32];
@@ -277,14 +291,8 @@ attn_fused_kernel(const __grid_constant__ AttnParams p, int* __restrict__ err_fl
             if (live) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const long long o = base + hf * 32 + c * 8;
-                    // x / res2 were written by earlier kernels of the stream that this (programmatically launched)
-                    // kernel overlapped with: read them through L2 (ld.global.cg), never through the
-                    // non-coherent path, whose L1 lines may predate those writes
-                    const uint4 xv = __ldcg(reinterpret_cast<const uint4*>(p.x + o));
-                    uint4 rv = make_uint4(0, 0, 0, 0);
-                    if (p.res2) rv = __ldcg(reinterpret_cast<const uint4*>(p.res2 + o));
-                    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, rs[4] = {rv.x, rv.y, rv.z, rv.w};
+                    const uint4 xq = xv[hf * 4 + c], rq = rv[hf * 4 + c];
+                    const uint32_t xs[4] = {xq.x, xq.y, xq.z, xq.w}, rs[4] = {rq.x, rq.y, rq.z, rq.w};
                     uint32_t os[4];
 #pragma unroll
                     for (int e2 = 0; e2 < 4; ++e2) {
@@ -294,7 +302,7 @@ attn_fused_kernel(const __grid_constant__ AttnParams p, int* __restrict__ err_fl
                                         __uint_as_float(rs[e2] & 0xffff0000u);
                         os[e2] = pack2(a, b);
                     }
-                    *reinterpret_cast<uint4*>(p.out + o) = make_uint4(os[0], os[1], os[2], os[3]);
+                    *reinterpret_cast<uint4*>(p.out + base + hf * 32 + c * 8) = make_uint4(os[0], os[1], os[2], os[3]);
                 }
             }
         }
