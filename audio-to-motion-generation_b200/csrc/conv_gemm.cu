@@ -11,6 +11,7 @@
 //               + folded bias, LeakyReLU(0.2) / ReLU, bf16 (or fp32) vector stores, strided so
 //               ConvTranspose parities and the [B,T,104] pose layout are written in place
 // Two CTAs fit per SM (3 stages x 32 KB), so one CTA's epilogue overlaps the other's main loop.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include "conv_gemm.cuh"
@@ -27,9 +28,9 @@ constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB
 // 128 x 128 tiles: 3 stages x 32 KB, two CTAs per SM (one CTA's epilogue overlaps the other's main loop).
 // 128 x 256 tiles (wide layers): 4 stages x 48 KB, one CTA per SM -- 33 % fewer operand bytes per FLOP from L2
 // (85 instead of 64 FLOP/B), which is what bounds the large-K UNet layers.
-template <int BLOCK_N>
+template <int BLOCK_N, int STAGES>
 struct Smem {
-    static constexpr int kStages = BLOCK_N > 128 ? 4 : 3;
+    static constexpr int kStages = STAGES;
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = kStages * kStageBytes;
@@ -37,11 +38,11 @@ struct Smem {
     static constexpr int kTotal = kBiasOffset + BLOCK_N * 4 + 1024;      // + alignment slack
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kThreads)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restrict__ bias, void* __restrict__ out,
                  int* __restrict__ err_flag) {
-    using S = Smem<BLOCK_N>;
+    using S = Smem<BLOCK_N, STAGES>;
     constexpr int kStages = S::kStages;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -336,15 +337,15 @@ int make_map(CUtensorMap* map, const void* ptr, int rank, const long long* dims,
     return A2M_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int STAGES>
 int launch_variant(const ConvGemmPlan& plan, int* err_flag, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        A2M_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            Smem<BLOCK_N>::kTotal));
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Smem<BLOCK_N, STAGES>::kTotal));
         configured = true;
     }
-    A2M_CUDA_CHECK(a2m_launch_pdl(conv_gemm_kernel<BLOCK_N>, plan.grid, dim3(kThreads), Smem<BLOCK_N>::kTotal, stream,
+    A2M_CUDA_CHECK(a2m_launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES>, plan.grid, dim3(kThreads), Smem<BLOCK_N, STAGES>::kTotal, stream,
                                   plan.p, plan.bias, plan.out, err_flag));
     a2m_count_launch();
     return A2M_OK;
@@ -487,6 +488,12 @@ int conv_gemm_plan(const ConvGemmDesc& d, const void* w_packed, const float* bia
     plan->bias = bias;
     plan->out = out;
     plan->block_n = block_n;
+    {   // short K loops (decoder layers): two 32 KB stages let a third CTA -- typically the next layer's, launched
+        // programmatically -- become resident while this layer's CTAs drain
+        static const char* env = getenv("A2M_GEMM_STAGES2");
+        const int mode = env ? atoi(env) : 1;
+        plan->stages = (mode && block_n == 128 && kb <= 16) ? 2 : 3;
+    }
     plan->grid = dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>((d.N + block_n - 1) / block_n),
                       static_cast<unsigned>(d.split_k));
     plan->flops = 2 * m_valid * d.N * K;
@@ -495,10 +502,10 @@ int conv_gemm_plan(const ConvGemmDesc& d, const void* w_packed, const float* bia
 
 int conv_gemm_launch(const ConvGemmPlan& plan, int* err_flag, cudaStream_t stream) {
     switch (plan.block_n) {
-        case 32: return launch_variant<32>(plan, err_flag, stream);
-        case 64: return launch_variant<64>(plan, err_flag, stream);
-        case 128: return launch_variant<128>(plan, err_flag, stream);
-        case 256: return launch_variant<256>(plan, err_flag, stream);
+        case 32: return launch_variant<32, 3>(plan, err_flag, stream);
+        case 64: return launch_variant<64, 3>(plan, err_flag, stream);
+        case 128: return plan.stages == 2 ? launch_variant<128, 2>(plan, err_flag, stream) : launch_variant<128, 3>(plan, err_flag, stream);
+        case 256: return launch_variant<256, 4>(plan, err_flag, stream);
         default: a2m_set_error("conv_gemm_launch: block_n %d", plan.block_n); return A2M_ERR_STATE;
     }
 }

@@ -84,6 +84,7 @@ struct ConvGemmPlan {
     const float* bias;          // fp32 [N] (folded), may be null
     void* out;
     int block_n;
+    int stages;                 // shared-memory ring depth of the 128 x 128 variant (2 or 3)
     dim3 grid;
     long long flops;            // 2 * M * N * K of the valid output rows
 };

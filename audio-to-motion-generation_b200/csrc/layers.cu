@@ -235,29 +235,63 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __r
     __syncthreads();
     const float gamma = *gamma_p;
     const __nv_bfloat16* vbase = base + 2 * d;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float acc[T];
+    if constexpr (T <= 32) {
+        // each thread owns two adjacent channels (4-byte loads / stores, two independent accumulator sets)
+        for (int c = 2 * threadIdx.x; c < C; c += 2 * blockDim.x) {
+            float acc0[T], acc1[T];
 #pragma unroll
-        for (int t = 0; t < T; ++t) acc[t] = 0.f;
+            for (int t = 0; t < T; ++t) { acc0[t] = 0.f; acc1[t] = 0.f; }
 #pragma unroll 4
-        for (int j = 0; j < T; ++j) {
-            const float v = __bfloat162float(vbase[static_cast<long long>(j) * ld + c]);
-            const float4* pt = reinterpret_cast<const float4*>(s_p + j * T);
+            for (int j = 0; j < T; ++j) {
+                const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vbase + static_cast<long long>(j) * ld + c));
+                const float4* pt = reinterpret_cast<const float4*>(s_p + j * T);
 #pragma unroll
-            for (int t4 = 0; t4 < T / 4; ++t4) {
-                const float4 p4 = pt[t4];
-                acc[4 * t4] = fmaf(p4.x, v, acc[4 * t4]);
-                acc[4 * t4 + 1] = fmaf(p4.y, v, acc[4 * t4 + 1]);
-                acc[4 * t4 + 2] = fmaf(p4.z, v, acc[4 * t4 + 2]);
-                acc[4 * t4 + 3] = fmaf(p4.w, v, acc[4 * t4 + 3]);
+                for (int t4 = 0; t4 < T / 4; ++t4) {
+                    const float4 p4 = pt[t4];
+                    acc0[4 * t4] = fmaf(p4.x, v.x, acc0[4 * t4]);         acc1[4 * t4] = fmaf(p4.x, v.y, acc1[4 * t4]);
+                    acc0[4 * t4 + 1] = fmaf(p4.y, v.x, acc0[4 * t4 + 1]); acc1[4 * t4 + 1] = fmaf(p4.y, v.y, acc1[4 * t4 + 1]);
+                    acc0[4 * t4 + 2] = fmaf(p4.z, v.x, acc0[4 * t4 + 2]); acc1[4 * t4 + 2] = fmaf(p4.z, v.y, acc1[4 * t4 + 2]);
+                    acc0[4 * t4 + 3] = fmaf(p4.w, v.x, acc0[4 * t4 + 3]); acc1[4 * t4 + 3] = fmaf(p4.w, v.y, acc1[4 * t4 + 3]);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const long long o = (b * T + t) * C + c;
+                const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + o));
+                float r0 = gamma * acc0[t] + xv.x, r1 = gamma * acc1[t] + xv.y;
+                if (res2) {
+                    const float2 rv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(res2 + o));
+                    r0 += rv.x; r1 += rv.y;
+                }
+                *reinterpret_cast<__nv_bfloat162*>(out + o) = __floats2bfloat162_rn(r0, r1);
             }
         }
+    } else {
+        // long sequences: one channel per thread keeps the T accumulators in registers
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float acc[T];
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const long long o = (b * T + t) * C + c;
-            float r = gamma * acc[t] + __bfloat162float(x[o]);
-            if (res2) r += __bfloat162float(res2[o]);
-            out[o] = __float2bfloat16_rn(r);
+            for (int t = 0; t < T; ++t) acc[t] = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < T; ++j) {
+                const float v = __bfloat162float(vbase[static_cast<long long>(j) * ld + c]);
+                const float4* pt = reinterpret_cast<const float4*>(s_p + j * T);
+#pragma unroll
+                for (int t4 = 0; t4 < T / 4; ++t4) {
+                    const float4 p4 = pt[t4];
+                    acc[4 * t4] = fmaf(p4.x, v, acc[4 * t4]);
+                    acc[4 * t4 + 1] = fmaf(p4.y, v, acc[4 * t4 + 1]);
+                    acc[4 * t4 + 2] = fmaf(p4.z, v, acc[4 * t4 + 2]);
+                    acc[4 * t4 + 3] = fmaf(p4.w, v, acc[4 * t4 + 3]);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const long long o = (b * T + t) * C + c;
+                float r = gamma * acc[t] + __bfloat162float(x[o]);
+                if (res2) r += __bfloat162float(res2[o]);
+                out[o] = __float2bfloat16_rn(r);
+            }
         }
     }
 }
