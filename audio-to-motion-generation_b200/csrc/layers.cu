@@ -296,6 +296,50 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __r
     }
 }
 
+// Any sequence length up to 64 (the UNet attentions run at T/4 and T/2 of the clip length, e.g. 2, 6, 14): plain
+// loops, one CTA per clip; only the odd sizes the tiled kernel above does not cover come here.
+__global__ void __launch_bounds__(256)
+attention_generic_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ x,
+                         const __nv_bfloat16* __restrict__ res2, const float* __restrict__ gamma_p, int T, int C,
+                         __nv_bfloat16* __restrict__ out) {
+    __shared__ float s_p[64 * 64];
+    const int d = C / 8, ld = 2 * d + C;
+    const long long b = blockIdx.x;
+    const __nv_bfloat16* base = qkv + b * T * ld;
+    for (int idx = threadIdx.x; idx < T * T; idx += blockDim.x) {
+        const int i = idx / T, j = idx - i * T;
+        const __nv_bfloat16* qi = base + static_cast<long long>(i) * ld;
+        const __nv_bfloat16* kj = base + static_cast<long long>(j) * ld + d;
+        float acc = 0.f;
+        for (int c = 0; c < d; ++c) acc = fmaf(__bfloat162float(qi[c]), __bfloat162float(kj[c]), acc);
+        s_p[idx] = acc;                                   // no 1/sqrt(d): model_layers.py:140
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < T; i += 8) {
+        float v0 = lane < T ? s_p[i * T + lane] : -INFINITY, v1 = lane + 32 < T ? s_p[i * T + lane + 32] : -INFINITY;
+        const float m = warp_max(fmaxf(v0, v1));
+        v0 = lane < T ? __expf(v0 - m) : 0.f;
+        v1 = lane + 32 < T ? __expf(v1 - m) : 0.f;
+        const float inv = 1.f / warp_sum(v0 + v1);
+        if (lane < T) s_p[i * T + lane] = v0 * inv;
+        if (lane + 32 < T) s_p[i * T + lane + 32] = v1 * inv;
+    }
+    __syncthreads();
+    const float gamma = *gamma_p;
+    const __nv_bfloat16* vbase = base + 2 * d;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        for (int t = 0; t < T; ++t) {
+            float acc = 0.f;
+            for (int j = 0; j < T; ++j) acc = fmaf(s_p[t * T + j], __bfloat162float(vbase[static_cast<long long>(j) * ld + c]), acc);
+            const long long o = (b * T + t) * C + c;
+            float r = gamma * acc + __bfloat162float(x[o]);
+            if (res2) r += __bfloat162float(res2[o]);
+            out[o] = __float2bfloat16_rn(r);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ channel attention
 // One CTA (256 threads = 8 warps) per clip.  Pooling and the final scaling move 8 channels per thread as 16-byte
 // vectors, warp w taking the time steps w, w + 8, ...; the per-warp partial sums / maxima meet in shared memory.
@@ -554,8 +598,9 @@ int launch_attention(const __nv_bfloat16* qkv, const __nv_bfloat16* x, const __n
         case 56: return launch_attention_t<56>(qkv, x, res2, gamma, B, C, out, stream);
         case 64: return launch_attention_t<64>(qkv, x, res2, gamma, B, C, out, stream);
         default:
-            a2m_set_error("attention: T = %d; this build implements T in {8, 16, ..., 64}", T);
-            return A2M_ERR_UNSUPPORTED;
+            A2M_ARG_CHECK(T >= 1 && T <= 64, "attention: T = %d; this build implements T <= 64", T);
+            attention_generic_kernel<<<B, 256, 0, stream>>>(qkv, x, res2, gamma, T, C, out);
+            A2M_AFTER_LAUNCH();
     }
 }
 

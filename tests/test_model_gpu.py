@@ -79,6 +79,19 @@ def test_generator_vs_oracle_other_seed(mods):
     assert rel_l1(pose, ref) <= REL_L1
 
 
+@pytest.mark.parametrize("T,F,B", [(8, 64, 3), (16, 64, 2), (24, 64, 2), (48, 32, 1), (56, 64, 1), (64, 128, 1)])
+def test_other_sequence_lengths_vs_oracle(stress_model, T, F, B):
+    """Every T the native path accepts (multiples of 8 up to 64): 8 / 16 / 32 / 64 run the fused decoder attention,
+    24 / 40 / 48 / 56 the GEMM + attention-kernel path; partial 128-row tiles everywhere for small B * T."""
+    sd = weights.make_state_dict(0, "stress")
+    x = model_input(20 + T, B, T, F)
+    pose, _ = stress_model(x.cuda())
+    stress_model.check_device_status()
+    ref, _ = model_oracle.generator_forward(sd, x)
+    assert pose.shape == (B, T, 104)
+    assert rel_l1(pose, ref) <= REL_L1
+
+
 def test_batch_invariance_and_config2_size(stress_model):
     """BASELINE config 2 (B = 256, T = 64, F = 64): each clip's pose is independent of the batch it is in."""
     x = model_input(11, 8, 64, 64).cuda().repeat(32, 1, 1)
