@@ -44,9 +44,10 @@ void a2m_launch_count_reset(void);
  * The plan carries the constants the reference recomputes on every call: the periodic Hann window
  * and the mel matrix, both computed by the caller on the host in fp64 with the reference formulas
  * (the Python drop-in does that) and rounded to fp32 here.
- *   window <= nfft, nfft in {256, 512, 1024}, hop >= 1, 1 <= n_mel <= 128,
- *   mel_weights: host fp64 [nfft/2+1, n_mel] row-major with at most two (adjacent-column) non-zeros
- *   per row -- true of every matrix spectrogram_to_mel_matrix can produce.
+ *   nfft == 512 (the hot path's 25 ms window at 16 kHz; other lengths return A2M_ERR_UNSUPPORTED),
+ *   1 <= window <= nfft, hop >= 1, 1 <= n_mel <= 128,
+ *   mel_weights: host fp64 [nfft/2+1, n_mel] row-major; every column's non-zeros must form one contiguous run of
+ *   bins below the Nyquist bin -- true of every matrix spectrogram_to_mel_matrix can produce.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct a2m_mel_plan a2m_mel_plan;
 int a2m_mel_plan_create(int window, int hop, int nfft, int n_mel, const double* hann_host,
