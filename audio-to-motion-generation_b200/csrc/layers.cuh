@@ -32,6 +32,14 @@ int attn_fused_plan(const __nv_bfloat16* w_qkv, const float* bias_qkv, const flo
                     const __nv_bfloat16* res2, int B, int T, int C, __nv_bfloat16* out, std::shared_ptr<AttnFusedPlan>* plan);
 int attn_fused_launch(const AttnFusedPlan& plan, int* err_flag, cudaStream_t stream);
 
+// Tensor-core attention core for the wide UNet attentions (csrc/attn_core.cu), after the q|k|v GEMM: T must divide
+// 128, C a multiple of 256 with C / 8 in {64, 128, 192, 256}.
+struct AttnCorePlan;
+bool attn_core_supported(int T, int C);
+int attn_core_plan(const __nv_bfloat16* qkv, const float* gamma, const __nv_bfloat16* x, const __nv_bfloat16* res2, int B, int T,
+                   int C, __nv_bfloat16* out, std::shared_ptr<AttnCorePlan>* plan);
+int attn_core_launch(const AttnCorePlan& plan, int* err_flag, cudaStream_t stream);
+
 // ChannelAttention (model_layers.py:167-174): x * (sigmoid(mlp(avg_T x)) + sigmoid(mlp(max_T x))), C = 256, hidden 32;
 // w0 = fc.0.weight [hidden, C], w2 = fc.2.weight TRANSPOSED to [hidden, C]
 int launch_channel_attention(const __nv_bfloat16* x, int B, int T, int C, int hidden, const float* w0, const float* b0,

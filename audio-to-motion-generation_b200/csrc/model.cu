@@ -540,6 +540,16 @@ struct Emit {
             return;
         }
         linear_rows(A.qkv, x, nullptr, C, static_cast<long long>(B) * len, qkv, ld, 0, kOutBf16);
+        static const bool no_core = getenv("A2M_ATTN_CUDA_CORES") != nullptr;     // A/B aid
+        if (attn_core_supported(len, C) && !no_core) {    // wide UNet attentions: S, P.v on the tensor cores
+            if (dry || rc != A2M_OK) return;
+            std::shared_ptr<AttnCorePlan> cp;
+            rc = attn_core_plan(qkv, gamma, x, res2, B, len, C, out, &cp);
+            if (rc != A2M_OK) return;
+            int* flag = m->err_flag;
+            op([cp, flag](cudaStream_t s) { return attn_core_launch(*cp, flag, s); });
+            return;
+        }
         op([=](cudaStream_t s) { return launch_attention(qkv, x, res2, gamma, B, len, C, out, s); });
     }
     void channel(const ChanW& W, const __nv_bfloat16* x, int len, int B, __nv_bfloat16* out) {
