@@ -807,6 +807,395 @@ gnn3_kernel(const __grid_constant__ Gnn3Params p, int* __restrict__ err_flag) {
 
 }  // namespace v3
 
+// =====================================================================================================
+// v4: aggregate first, A operand from tensor memory.  out_i = sum_h W_h (sum_j alpha^h_ij / 4 x_j) + b, so per GAT layer
+//   S   = X U^T                      (attention logits straight from the node tile: all four softmaxes start at once)
+//   Z^h = P^h X                      (B = the node tile itself, MN-major; two heads per round, two P buffers)
+//   OUT = sum_h bf16(Z^h) W_h^T      (A = Z^h written back to TENSOR MEMORY as packed bf16 by the row threads)
+// No H staging through shared memory, no per-head barrier chain: six CTA barriers and four MMA round trips per GAT
+// layer (v3: ten and ~six).  GraphConv: AGG = Adj X -> bf16 in TMEM -> OUT = AGG W_rel^T + X W_root^T.
+// TMEM (256 columns, two CTAs per SM): OUT [0,64)  Zf [64,192) (two heads, fp32)  Zb [192,256) (two heads, bf16 A
+// operand; the 16 logit columns S alias its start -- S is dead before the first Zb store).
+// Weight slices (8 KB: one head / W_rel / W_root) stream through a three-slot ring, three ahead.
+// =====================================================================================================
+namespace v4 {
+
+constexpr int kThreads4 = 256;
+constexpr int kOffW4 = 0;                               // 3 x 8 KB weight slots
+constexpr int kOffU4 = 24576;                           // GAT attention rows [16][64] bf16
+constexpr int kOffX4 = 26624;                           // node tile, bf16 [128][64] SW128
+constexpr int kOffP4 = kOffX4 + 16384;                  // 2 x attention / adjacency matrix [128][128] bf16
+constexpr int kOffS4 = kOffP4 + 2 * 32768;              // s_src [128][4] fp32; LayerNorm partials [128][2][2] alias it
+constexpr int kOffTopo4 = kOffS4 + kRows * 4 * 4;       // nbr [48][6], deg [48]
+constexpr int kOffPar4 = kOffTopo4 + 48 * kMaxDeg * 4 + 48 * 4;   // this layer's bias[64], ln_w[64], ln_b[64]
+constexpr int kOffBar4 = kOffPar4 + 192 * 4;
+constexpr int kSmemBytes4 = kOffBar4 + 128 + 1024;
+constexpr uint32_t kColOut4 = 0, kColZf = 64, kColZb = 192, kColS4 = 192;
+static_assert(kOffX4 % 1024 == 0 && kOffP4 % 1024 == 0 && kOffU4 % 1024 == 0, "swizzled tiles need 1024 B alignment");
+static_assert(2 * (kSmemBytes4 + 1024) <= 228 * 1024, "two CTAs per SM");
+
+using v3::Gnn3Params;
+
+__device__ __forceinline__ uint64_t desc_add(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
+
+__global__ void __launch_bounds__(kThreads4, 2)
+gnn4_kernel(const __grid_constant__ Gnn3Params p, int* __restrict__ err_flag) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    unsigned char* s_x = smem + kOffX4;
+    unsigned char* s_p = smem + kOffP4;
+    float* s_src = reinterpret_cast<float*>(smem + kOffS4);
+    float* s_ln = s_src;
+    int* s_nbr = reinterpret_cast<int*>(smem + kOffTopo4);
+    int* s_deg = s_nbr + 48 * kMaxDeg;
+    float* s_par = reinterpret_cast<float*>(smem + kOffPar4);
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + kOffBar4);    // [3] weight slots (thread 0 only)
+    uint64_t* u_bar = w_bar + 3;                                       // attention rows landed (thread 0 only)
+    uint64_t* s_bar = w_bar + 4;                                       // logits MMA done
+    uint64_t* z_bar = w_bar + 5;                                       // aggregation MMAs done (P buffers free, Zf valid)
+    uint64_t* o_bar = w_bar + 6;                                       // OUT complete
+    uint64_t* x_bar = w_bar + 7;                                       // node tile landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid & 127, half = tid >> 7, quad = warp & 3;
+    const int J = p.J, rows_per_tile = p.gpc * J;
+    const int group_rows = p.group_graphs * J;
+    const long long n_tiles = p.n_groups * p.tiles_per_group;
+    const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const uint32_t tile_bytes = static_cast<uint32_t>(rows_per_tile) * 128u;
+    const long long n_items = my_tiles * 16;            // weight slices this CTA consumes, 16 per tile
+
+    // weight slice `item` (within a tile: GAT heads 0-3 | GC rel, root | GAT | GC | GAT) into slot item % 3
+    auto load_item = [&](long long item) {             // thread 0 only
+        if (item >= n_items) return;
+        const int i = static_cast<int>(item & 15), slot = static_cast<int>(item % 3);
+        const int layer = i < 4 ? 0 : i < 6 ? 1 : i < 10 ? 2 : i < 12 ? 3 : 4;
+        unsigned char* dst = smem + kOffW4 + slot * 8192;
+        mbar_expect_tx(&w_bar[slot], 8192);
+        if ((layer & 1) == 0) {
+            const int h = i - (layer == 0 ? 0 : layer == 2 ? 6 : 12);
+            tma_load_5d(dst, &p.w_head[layer >> 1], &w_bar[slot], 0, h * 64, 0, 0, 0);
+        } else {
+            tma_load_5d(dst, &p.w_gc[layer >> 1], &w_bar[slot], (i & 1) * 64, 0, 0, 0, 0);   // even item: W_rel (k 0..63), odd: W_root
+        }
+    };
+    auto load_u = [&](int gat) {                       // thread 0 only
+        mbar_expect_tx(u_bar, 2048);
+        tma_load_5d(smem + kOffU4, &p.w_att[gat], u_bar, 0, 256, 0, 0, 0);
+    };
+
+    pdl_launch_dependents();
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) { tma_prefetch_desc(&p.w_head[i]); tma_prefetch_desc(&p.w_att[i]); }
+        for (int i = 0; i < 2; ++i) tma_prefetch_desc(&p.w_gc[i]);
+        tma_prefetch_desc(&p.x_in);
+        tma_prefetch_desc(&p.x_out);
+        for (int i = 0; i < 8; ++i) mbar_init(&w_bar[i], 1);
+        mbar_fence_init();
+        load_u(0);                                     // weights are constants: no need to wait for the predecessor
+        load_item(0);
+        load_item(1);
+        load_item(2);
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+    for (int i = tid; i < J * kMaxDeg; i += kThreads4) s_nbr[i] = p.nbr[i];
+    for (int i = tid; i < J; i += kThreads4) s_deg[i] = p.deg[i];
+    {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < 2 * 32768 / 16; i += kThreads4) reinterpret_cast<uint4*>(s_p)[i] = z;
+        for (int i = tid; i < 16384 / 16; i += kThreads4)
+            if ((i >> 3) >= rows_per_tile) reinterpret_cast<uint4*>(s_x)[i] = z;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    pdl_wait();                                        // node features come from the previous kernel (proj_in)
+    auto load_tile = [&](long long tile) {             // thread 0 only
+        const int group = static_cast<int>(tile / p.tiles_per_group);
+        const int row0 = static_cast<int>(tile - static_cast<long long>(group) * p.tiles_per_group) * rows_per_tile;
+        mbar_expect_tx(x_bar, tile_bytes);
+        tma_load_5d(s_x, &p.x_in, x_bar, 0, row0, group, 0, 0);
+    };
+    if (tid == 0) load_tile(blockIdx.x);
+    const uint32_t idesc_h = umma_idesc_bf16(128, 64), idesc_s = umma_idesc_bf16(128, 16);
+    const uint32_t idesc_agg = idesc_b_mn(128, 64);
+    const uint64_t w_desc = umma_desc_sw128(smem_u32(smem + kOffW4)), u_desc = umma_desc_sw128(smem_u32(smem + kOffU4)),
+                   x_desc = umma_desc_sw128(smem_u32(s_x)), p_desc = umma_desc_sw128(smem_u32(s_p));
+
+    const bool valid_row = r < rows_per_tile;
+    const int jloc = r % J, g0 = r - jloc;
+    const int dg = valid_row ? s_deg[jloc] : 0;
+    int idx[kMaxDeg + 1], pofs[kMaxDeg + 1];
+    idx[0] = r;
+#pragma unroll
+    for (int k = 0; k < kMaxDeg; ++k) idx[k + 1] = k < dg ? g0 + s_nbr[jloc * kMaxDeg + k] : r;
+#pragma unroll
+    for (int k = 0; k <= kMaxDeg; ++k) pofs[k] = half * 32768 + p_off(r, idx[k]);     // my P buffer is buffer `half`
+
+    // softmax over {self} + neighbours for head h (the head mean 1/4 folded in) -> my P buffer
+    auto write_p = [&](int h, float sd) {
+        float alpha[kMaxDeg + 1];
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k <= kMaxDeg; ++k) {
+            alpha[k] = k <= dg ? leaky(s_src[idx[k] * 4 + h] + sd) : -INFINITY;
+            m = fmaxf(m, alpha[k]);
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int k = 0; k <= kMaxDeg; ++k) { alpha[k] = k <= dg ? __expf(alpha[k] - m) : 0.f; den += alpha[k]; }
+        const float inv = 0.25f / den;
+#pragma unroll
+        for (int k = 0; k <= kMaxDeg; ++k)
+            if (k <= dg) *reinterpret_cast<__nv_bfloat16*>(s_p + pofs[k]) = __float2bfloat16_rn(alpha[k] * inv);
+    };
+    // my 32 fp32 columns of Zf (starting at column c0 of the Zf region) -> packed bf16 -> 16 columns of Zb at cb
+    auto convert = [&](uint32_t c0, uint32_t cb) {
+        uint32_t t[32], o[16];
+        tmem_ld_32x32(tmem_lane + kColZf + c0, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = pack_bf16(__uint_as_float(t[2 * i]), __uint_as_float(t[2 * i + 1]));
+        tmem_st_32x16(tmem_lane + kColZb + cb, o);
+    };
+
+    uint32_t wpar[3] = {0, 0, 0}, upar = 0;             // thread 0 only
+    uint32_t spar = 0, zpar = 0, opar = 0;
+    long long item = 0;                                // first weight slice of the current layer (thread 0's view)
+    auto wait_item = [&](long long it_) {              // thread 0 only
+        const int slot = static_cast<int>(it_ % 3);
+        mbar_wait(&w_bar[slot], wpar[slot], err_flag, 41);
+        wpar[slot] ^= 1;
+        return desc_add(w_desc, static_cast<uint32_t>(slot) * 8192u);
+    };
+
+    for (long long it = 0; it < my_tiles; ++it) {
+        const long long tile = blockIdx.x + it * gridDim.x;
+        const int group = static_cast<int>(tile / p.tiles_per_group);
+        const int row0 = static_cast<int>(tile - static_cast<long long>(group) * p.tiles_per_group) * rows_per_tile;
+        const bool live = valid_row && row0 + r < group_rows;
+        mbar_wait(x_bar, static_cast<uint32_t>(it & 1), err_flag, 40);
+        float x[32];                                   // residual stream: this thread's 32 features in fp32
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint4 u = *reinterpret_cast<const uint4*>(s_x + sw128_off(r, half * 4 + c));
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { x[c * 8 + 2 * e] = bf_lo(w4[e]); x[c * 8 + 2 * e + 1] = bf_hi(w4[e]); }
+        }
+
+#pragma unroll 1
+        for (int layer = 0; layer < 5; ++layer) {
+            float v[32];
+            if (tid < 192) {                            // this layer's bias | ln_w | ln_b (read after several barriers)
+                const float* src = tid < 64 ? ((layer & 1) ? p.gc_bias[layer >> 1] : p.gat_bias[layer >> 1])
+                                            : tid < 128 ? p.ln_w[layer] : p.ln_b[layer];
+                s_par[tid] = __ldg(src + (tid & 63));
+            }
+            if ((layer & 1) == 0) {
+                // ================= GATConv =================
+                if (tid == 0) {
+                    tc_fence_after();
+                    mbar_wait(u_bar, upar, err_flag, 42); upar ^= 1;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + kColS4, desc_add(x_desc, k * 32), desc_add(u_desc, k * 32), idesc_s, k != 0);
+                    umma_commit(s_bar);
+                }
+                mbar_wait(s_bar, spar, err_flag, 43);
+                spar ^= 1;
+                tc_fence_after();
+                if (tid == 0 && !(layer == 4 && it + 1 == my_tiles)) load_u(layer == 4 ? 0 : (layer >> 1) + 1);
+                float sd0, sd1;                          // destination logits of my heads: half, half + 2
+                {
+                    uint32_t t[16];
+                    tmem_ld_32x16(tmem_lane + kColS4, t);
+                    tmem_ld_wait();
+                    sd0 = half == 0 ? __uint_as_float(t[4]) + __uint_as_float(t[12]) : __uint_as_float(t[5]) + __uint_as_float(t[13]);
+                    sd1 = half == 0 ? __uint_as_float(t[6]) + __uint_as_float(t[14]) : __uint_as_float(t[7]) + __uint_as_float(t[15]);
+                    if (half == 0) {
+                        *reinterpret_cast<float4*>(s_src + r * 4) =
+                            make_float4(__uint_as_float(t[0]) + __uint_as_float(t[8]), __uint_as_float(t[1]) + __uint_as_float(t[9]),
+                                        __uint_as_float(t[2]) + __uint_as_float(t[10]), __uint_as_float(t[3]) + __uint_as_float(t[11]));
+                    }
+                }
+                tc_fence_before();
+                __syncthreads();                        // s_src visible
+                write_p(half, sd0);                     // round 1: heads 0 (buffer 0) and 1 (buffer 1)
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk)
+                            umma_bf16(tmem_base + kColZf + b * 64, desc_add(p_desc, b * 32768 + (kk >> 2) * 16384 + (kk & 3) * 32),
+                                      desc_add(x_desc, kk * 2048), idesc_agg, kk != 0);
+                    umma_commit(z_bar);
+                }
+                mbar_wait(z_bar, zpar, err_flag, 44);
+                zpar ^= 1;
+                tc_fence_after();
+                write_p(half + 2, sd1);                 // round 2: heads 2 and 3 (the MMAs that read round 1 are done)
+                convert(half * 64, half * 32);
+                convert(half * 64 + 32, half * 32 + 16);
+                tmem_st_wait();
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {       // OUT = Z^0 W_0^T + Z^1 W_1^T
+                        const uint64_t wd = wait_item(item + b);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ts(tmem_base + kColOut4, tmem_base + kColZb + b * 32 + k * 8, desc_add(wd, k * 32), idesc_h, (b | k) != 0);
+                    }
+#pragma unroll
+                    for (int b = 0; b < 2; ++b)
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk)
+                            umma_bf16(tmem_base + kColZf + b * 64, desc_add(p_desc, b * 32768 + (kk >> 2) * 16384 + (kk & 3) * 32),
+                                      desc_add(x_desc, kk * 2048), idesc_agg, kk != 0);
+                    umma_commit(z_bar);
+                }
+                mbar_wait(z_bar, zpar, err_flag, 45);
+                zpar ^= 1;
+                tc_fence_after();
+                if (tid == 0) { load_item(item + 3); load_item(item + 4); }     // slices 0, 1 are consumed
+                convert(half * 64, half * 32);
+                convert(half * 64 + 32, half * 32 + 16);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {       // OUT += Z^2 W_2^T + Z^3 W_3^T
+                        const uint64_t wd = wait_item(item + 2 + b);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ts(tmem_base + kColOut4, tmem_base + kColZb + b * 32 + k * 8, desc_add(wd, k * 32), idesc_h, 1);
+                    }
+                    umma_commit(o_bar);
+                }
+                mbar_wait(o_bar, opar, err_flag, 46);
+                opar ^= 1;
+                tc_fence_after();
+                if (tid == 0) { load_item(item + 5); load_item(item + 6); item += 4; }
+            } else {
+                // ================= GraphConv =================
+                if (half == 0) {                           // adjacency (no self loops) into P buffer 0
+                    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+                    *reinterpret_cast<__nv_bfloat16*>(s_p + pofs[0]) = zero;
+#pragma unroll
+                    for (int k = 1; k <= kMaxDeg; ++k)
+                        if (k <= dg) *reinterpret_cast<__nv_bfloat16*>(s_p + pofs[k]) = one;
+                }
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)       // AGG = Adj . X (exact: 0/1 weights, fp32 accumulation)
+                        umma_bf16(tmem_base + kColZf, desc_add(p_desc, (kk >> 2) * 16384 + (kk & 3) * 32),
+                                  desc_add(x_desc, kk * 2048), idesc_agg, kk != 0);
+                    umma_commit(z_bar);
+                }
+                mbar_wait(z_bar, zpar, err_flag, 47);
+                zpar ^= 1;
+                tc_fence_after();
+                convert(half * 32, half * 16);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    const uint64_t wrel = wait_item(item), wroot = wait_item(item + 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)           // W_rel . agg
+                        umma_bf16_ts(tmem_base + kColOut4, tmem_base + kColZb + k * 8, desc_add(wrel, k * 32), idesc_h, k != 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)           // + W_root . x
+                        umma_bf16(tmem_base + kColOut4, desc_add(x_desc, k * 32), desc_add(wroot, k * 32), idesc_h, 1);
+                    umma_commit(o_bar);
+                }
+                mbar_wait(o_bar, opar, err_flag, 48);
+                opar ^= 1;
+                tc_fence_after();
+                if (tid == 0) { load_item(item + 3); load_item(item + 4); item += 2; }
+            }
+            {
+                uint32_t t[32];
+                tmem_ld_32x32(tmem_lane + kColOut4 + half * 32, t);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(t[i]);
+            }
+            // ---- + bias, LayerNorm(64) over the two 32-feature halves of the node -> LeakyReLU -> + residual
+            {
+                const float4* par = reinterpret_cast<const float4*>(s_par + half * 32);
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 b4 = par[i4];
+                    v[i4 * 4] += b4.x; v[i4 * 4 + 1] += b4.y; v[i4 * 4 + 2] += b4.z; v[i4 * 4 + 3] += b4.w;
+                }
+                float s = 0.f, sq = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { s += v[i]; sq = fmaf(v[i], v[i], sq); }
+                *reinterpret_cast<float2*>(s_ln + (r * 2 + half) * 2) = make_float2(s, sq);
+                __syncthreads();
+                const float4 a = *reinterpret_cast<const float4*>(s_ln + r * 4);
+                const float mean = (a.x + a.z) * (1.f / 64.f);
+                const float rstd = rsqrtf(fmaxf((a.y + a.w) * (1.f / 64.f) - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 w4 = par[16 + i4], b4 = par[32 + i4];
+                    x[i4 * 4] += leaky((v[i4 * 4] - mean) * rstd * w4.x + b4.x);
+                    x[i4 * 4 + 1] += leaky((v[i4 * 4 + 1] - mean) * rstd * w4.y + b4.y);
+                    x[i4 * 4 + 2] += leaky((v[i4 * 4 + 2] - mean) * rstd * w4.z + b4.z);
+                    x[i4 * 4 + 3] += leaky((v[i4 * 4 + 3] - mean) * rstd * w4.w + b4.w);
+                }
+            }
+            if (!live) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x[i] = 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 o;
+                o.x = pack_bf16(x[c * 8], x[c * 8 + 1]); o.y = pack_bf16(x[c * 8 + 2], x[c * 8 + 3]);
+                o.z = pack_bf16(x[c * 8 + 4], x[c * 8 + 5]); o.w = pack_bf16(x[c * 8 + 6], x[c * 8 + 7]);
+                *reinterpret_cast<uint4*>(s_x + sw128_off(r, half * 4 + c)) = o;
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncthreads();
+        }
+        if (tid == 0) {                                // store this tile, then (same buffer) fetch the next one
+            tma_store_5d(&p.x_out, s_x, 0, row0, group, 0, 0);
+            tma_store_commit();
+            if (it + 1 < my_tiles) {
+                tma_store_wait_read();
+                load_tile(tile + gridDim.x);
+            }
+        }
+    }
+    if (tid == 0) tma_store_wait_read();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+}  // namespace v4
+
 // U rows of the extended GAT weight: the attention logits a_src . (W_h x) = (W_h^T a_src) . x come out of the
 // same MMA as H.  Rows 256+h: src (hi), 260+h: dst (hi), 264+h: src (lo), 268+h: dst (lo); hi + lo carries
 // ~16 mantissa bits of the fp32 fold, which is evaluated on the bf16-rounded W the MMA itself uses.
@@ -830,6 +1219,7 @@ struct GnnFusedPlan {
     GnnParams p;                 // v2 (one CTA per SM)
     v3::Gnn3Params p3;           // v3 (two CTAs per SM, per-head pipeline): the default
     bool use_v3;
+    bool use_v4;                 // v4 (aggregate first, A operand from tensor memory) shares v3's parameter block
     int grid;
 };
 
@@ -879,7 +1269,9 @@ int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_groups,
     const long long tiles = n_groups * p.tiles_per_group;
     const int sms = a2m_num_sms();
     static const bool force_v2 = getenv("A2M_GNN_V2") != nullptr;            // A/B aid
+    static const bool force_v3 = getenv("A2M_GNN_V3") != nullptr;            // A/B aid
     plan->use_v3 = !force_v2;
+    plan->use_v4 = !force_v2 && !force_v3;
     if (plan->use_v3) {
         v3::Gnn3Params& q = plan->p3;
         memset(&q, 0, sizeof(q));
@@ -910,7 +1302,13 @@ int gnn_fused_launch(const GnnFusedPlan& plan, int* err_flag, cudaStream_t strea
     if (!configured) {
         A2M_CUDA_CHECK(cudaFuncSetAttribute(gnn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         A2M_CUDA_CHECK(cudaFuncSetAttribute(v3::gnn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::kSmemBytes3));
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(v4::gnn4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v4::kSmemBytes4));
         configured = true;
+    }
+    if (plan.use_v4) {
+        A2M_CUDA_CHECK(a2m_launch_pdl(v4::gnn4_kernel, dim3(plan.grid), dim3(v4::kThreads4), v4::kSmemBytes4, stream, plan.p3, err_flag));
+        a2m_count_launch();
+        return A2M_OK;
     }
     if (plan.use_v3) {
         A2M_CUDA_CHECK(a2m_launch_pdl(v3::gnn3_kernel, dim3(plan.grid), dim3(v3::kThreads3), v3::kSmemBytes3, stream, plan.p3, err_flag));
