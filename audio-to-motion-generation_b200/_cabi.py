@@ -55,12 +55,14 @@ SIGNATURES = {
     "a2m_stft_magnitude_f32": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
     "a2m_eval_l1_pck_f32": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
+    "a2m_motion_smoothness_f32": (c_int, [c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "a2m_pose_normalize_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "a2m_pose_denormalize_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "a2m_pose_stats_f64": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
     "a2m_comm_unique_id": (c_int, [c_void_p]),
     "a2m_comm_init": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
     "a2m_allreduce_metrics": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "a2m_allreduce_smoothness": (c_int, [c_void_p, c_void_p, c_void_p]),
     "a2m_comm_destroy": (None, [c_void_p]),
     "a2m_model_create": (c_int, [ctypes.POINTER(TensorDesc), c_int, c_int, ctypes.POINTER(c_void_p)]),
     "a2m_model_destroy": (None, [c_void_p]),

@@ -156,6 +156,117 @@ extern "C" int a2m_eval_l1_pck_f32(const float* pred, const float* gt, int64_t n
 }
 
 // ---------------------------------------------------------------------------------------------
+// temporal smoothness / jerk of a motion sequence (version5_model_train.py:216-248): mean over (clip, t) of the L2 norm
+// over the features of the second / third difference.  One warp per (clip, time segment); lane l owns features
+// l, l + 32, l + 64, l + 96; differences are single fp32 subtractions in the reference's order, the squared norm is an
+// fp32 lane sum + warp shuffle tree, the sum over frames is fp64.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kSmoothMaxPerLane = 4;       // features <= 128
+
+struct FeatRegs { float v[kSmoothMaxPerLane]; };
+
+__device__ __forceinline__ FeatRegs load_feats(const float* __restrict__ row, int lane, int feat) {
+    FeatRegs r;
+#pragma unroll
+    for (int i = 0; i < kSmoothMaxPerLane; ++i) r.v[i] = lane + 32 * i < feat ? __ldg(row + lane + 32 * i) : 0.f;
+    return r;
+}
+__device__ __forceinline__ FeatRegs feat_sub(const FeatRegs& a, const FeatRegs& b) {
+    FeatRegs r;
+#pragma unroll
+    for (int i = 0; i < kSmoothMaxPerLane; ++i) r.v[i] = __fsub_rn(a.v[i], b.v[i]);
+    return r;
+}
+__device__ __forceinline__ float feat_norm(const FeatRegs& a) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSmoothMaxPerLane; ++i) s = fmaf(a.v[i], a.v[i], s);
+    return sqrtf(a2m::warp_sum(s));
+}
+
+// seq [n_clips, L, feat]; from_pose: the motion is the first difference of seq (L poses -> L - 1 velocities)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+motion_smoothness_kernel(const float* __restrict__ seq, long long n_clips, int L, int feat, int from_pose, int seg_frames,
+                         int segs, a2m_smooth_metrics* __restrict__ accum) {
+    __shared__ double s_acc[kWarpsPerBlock], s_jerk[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int M = from_pose ? L - 1 : L;          // velocities per clip
+    const int n_acc = M - 1, n_jerk = M - 2;      // accelerations a[t] = m[t+1] - m[t], jerks j[t] = a[t+1] - a[t]
+    double sum_acc = 0.0, sum_jerk = 0.0;
+    const long long n_items = n_clips * segs;
+    for (long long item = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp; item < n_items;
+         item += static_cast<long long>(gridDim.x) * kWarpsPerBlock) {
+        const long long clip = item / segs;
+        const int t0 = static_cast<int>(item - clip * segs) * seg_frames;
+        const int t1 = min(n_acc, t0 + seg_frames);
+        const float* base = seq + clip * L * feat;
+        auto velocity = [&](int i) {               // m[i]
+            if (from_pose) return feat_sub(load_feats(base + static_cast<long long>(i + 1) * feat, lane, feat),
+                                           load_feats(base + static_cast<long long>(i) * feat, lane, feat));
+            return load_feats(base + static_cast<long long>(i) * feat, lane, feat);
+        };
+        if (t0 >= t1) continue;
+        FeatRegs m1 = velocity(t0 + 1);
+        FeatRegs a0 = feat_sub(m1, velocity(t0));  // a[t0]
+        for (int t = t0; t < t1; ++t) {
+            sum_acc += feat_norm(a0);
+            if (t < n_jerk) {
+                const FeatRegs m2 = velocity(t + 2);
+                const FeatRegs a1 = feat_sub(m2, m1);
+                sum_jerk += feat_norm(feat_sub(a1, a0));
+                a0 = a1;
+                m1 = m2;
+            }
+        }
+    }
+    if (lane == 0) { s_acc[warp] = sum_acc; s_jerk[warp] = sum_jerk; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0.0, sj = 0.0;
+        for (int w = 0; w < kWarpsPerBlock; ++w) { sa += s_acc[w]; sj += s_jerk[w]; }
+        atomicAdd(&accum->sum_accel_norm, sa);
+        atomicAdd(&accum->sum_jerk_norm, sj);
+        if (blockIdx.x == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(&accum->n_accel),
+                      static_cast<unsigned long long>(n_clips) * (n_acc > 0 ? n_acc : 0));
+            atomicAdd(reinterpret_cast<unsigned long long*>(&accum->n_jerk),
+                      static_cast<unsigned long long>(n_clips) * (n_jerk > 0 ? n_jerk : 0));
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int a2m_motion_smoothness_f32(const float* seq, int64_t n_clips, int frames_per_clip, int n_features, int from_pose,
+                                         a2m_smooth_metrics* accum, void* stream) {
+    A2M_ARG_CHECK(n_clips >= 0 && frames_per_clip >= 0, "a2m_motion_smoothness_f32: negative size");
+    A2M_ARG_CHECK(n_features >= 1 && n_features <= 32 * kSmoothMaxPerLane, "a2m_motion_smoothness_f32: %d features (1..%d)",
+                  n_features, 32 * kSmoothMaxPerLane);
+    A2M_ARG_CHECK(accum != nullptr, "a2m_motion_smoothness_f32: accum is NULL");
+    const int M = from_pose ? frames_per_clip - 1 : frames_per_clip;
+    if (n_clips == 0 || M < 2) return A2M_OK;             // no acceleration: the reference's mean of an empty tensor is NaN
+    A2M_ARG_CHECK(seq != nullptr, "a2m_motion_smoothness_f32: NULL sequence");
+    const int n_acc = M - 1;
+    const long long want = 32LL * a2m_num_sms();
+    int segs = static_cast<int>((want + n_clips - 1) / n_clips);
+    segs = segs < 1 ? 1 : segs;
+    int seg_frames = (n_acc + segs - 1) / segs;
+    if (seg_frames < 8) seg_frames = n_acc < 8 ? n_acc : 8;
+    segs = (n_acc + seg_frames - 1) / seg_frames;
+    const long long n_items = static_cast<long long>(n_clips) * segs;
+    long long blocks = (n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const long long cap = 32LL * a2m_num_sms();
+    if (blocks > cap) blocks = cap;
+    motion_smoothness_kernel<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        seq, n_clips, frames_per_clip, n_features, from_pose ? 1 : 0, seg_frames, segs, accum);
+    a2m_count_launch();
+    A2M_LAUNCH_CHECK();
+    return A2M_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // NCCL, bound at run time so the library has no link-time dependency on a particular libnccl
 // ---------------------------------------------------------------------------------------------
 namespace {
@@ -239,6 +350,18 @@ extern "C" int a2m_allreduce_metrics(a2m_comm* comm, a2m_metrics* inout, void* s
     A2M_NCCL_CHECK(api, api->GroupStart());
     A2M_NCCL_CHECK(api, api->AllReduce(&inout->pck_hits, &inout->pck_hits, 5, kNcclInt64, kNcclSum, comm->comm, s));
     A2M_NCCL_CHECK(api, api->AllReduce(&inout->abs_pose, &inout->abs_pose, 2, kNcclFloat64, kNcclSum, comm->comm, s));
+    A2M_NCCL_CHECK(api, api->GroupEnd());
+    return A2M_OK;
+}
+
+extern "C" int a2m_allreduce_smoothness(a2m_comm* comm, a2m_smooth_metrics* inout, void* stream) {
+    A2M_ARG_CHECK(comm != nullptr && inout != nullptr, "a2m_allreduce_smoothness: NULL");
+    NcclApi* api = nccl_api();
+    if (!api) return A2M_ERR_STATE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    A2M_NCCL_CHECK(api, api->GroupStart());
+    A2M_NCCL_CHECK(api, api->AllReduce(&inout->sum_accel_norm, &inout->sum_accel_norm, 2, kNcclFloat64, kNcclSum, comm->comm, s));
+    A2M_NCCL_CHECK(api, api->AllReduce(&inout->n_accel, &inout->n_accel, 2, kNcclInt64, kNcclSum, comm->comm, s));
     A2M_NCCL_CHECK(api, api->GroupEnd());
     return A2M_OK;
 }

@@ -67,6 +67,67 @@ def evaluate_poses(pred, gt, alpha=0.2, accum=None, pck_per_frame=None, radius_p
     return accum
 
 
+SMOOTH_FIELDS = ("sum_accel_norm", "sum_jerk_norm", "n_accel", "n_jerk")
+
+
+def new_smoothness(device="cuda"):
+    """Zeroed 32-byte accumulator (a2m_smooth_metrics) as an int64[4] CUDA tensor (two fp64 sums, two counts)."""
+    return torch.zeros(4, dtype=torch.int64, device=device)
+
+
+def evaluate_smoothness(seq, accum=None, from_pose=False):
+    """Accumulate the smoothness / jerk partial sums of a batch [B, L, F] (fp32 CUDA): ``seq`` is the motion
+    (velocities) the reference functions take, or poses when ``from_pose`` (their first difference is taken on
+    the fly, pos_to_motion)."""
+    _cabi.require_cuda("evaluate_smoothness")
+    if seq.dim() != 3:
+        raise ValueError("motion sequence must be [B, L, F], got %s" % (tuple(seq.shape),))
+    seq = seq.to(device="cuda", dtype=torch.float32).contiguous()
+    if accum is None:
+        accum = new_smoothness(seq.device)
+    with torch.cuda.device(seq.device):
+        _cabi.check(_cabi.lib().a2m_motion_smoothness_f32(
+            _cabi.ptr(seq), seq.shape[0], seq.shape[1], seq.shape[2], int(bool(from_pose)), _cabi.ptr(accum),
+            _cabi.stream_ptr(seq.device)))
+    return accum
+
+
+def read_smoothness(buf):
+    """Device accumulator -> {'smoothness', 'jerk', sums, counts} (one 32-byte D2H copy); an empty mean is NaN as
+    in the reference (torch.mean of an empty tensor)."""
+    host = buf.cpu()
+    sums = host[0:2].view(torch.float64)
+    out = {"sum_accel_norm": float(sums[0]), "sum_jerk_norm": float(sums[1]), "n_accel": int(host[2]), "n_jerk": int(host[3])}
+    out["smoothness"] = out["sum_accel_norm"] / out["n_accel"] if out["n_accel"] else float("nan")
+    out["jerk"] = out["sum_jerk_norm"] / out["n_jerk"] if out["n_jerk"] else float("nan")
+    return out
+
+
+def pos_to_motion(pose_batch):
+    """First difference along time (version5_model_train.py:208-213); a torch op on the caller's device -- the fused
+    kernels take poses directly (``evaluate_poses``, ``evaluate_smoothness(from_pose=True)``)."""
+    return torch.diff(pose_batch, n=1, dim=1)
+
+
+def _smooth_scalar(motion_seq, key):
+    was_numpy = not isinstance(motion_seq, torch.Tensor)
+    t = torch.as_tensor(np.asarray(motion_seq)) if was_numpy else motion_seq
+    val = read_smoothness(evaluate_smoothness(t))[key]
+    return np.float32(val) if was_numpy else torch.tensor(val, dtype=torch.float32, device=t.device)
+
+
+def compute_temporal_smoothness_loss(motion_seq):
+    """mean_{b,t} ||motion[b,t+1] - motion[b,t]||_2 (version5_model_train.py:216-230), a 0-dim fp32 tensor."""
+    _cabi.require_cuda("compute_temporal_smoothness_loss")
+    return _smooth_scalar(motion_seq, "smoothness")
+
+
+def compute_jerk_loss(motion_seq):
+    """mean_{b,t} ||accel[b,t+1] - accel[b,t]||_2 (version5_model_train.py:233-248), a 0-dim fp32 tensor."""
+    _cabi.require_cuda("compute_jerk_loss")
+    return _smooth_scalar(motion_seq, "jerk")
+
+
 def _per_frame(pred, gt, alpha, want):
     p, was_numpy = _frames_on_device(pred, "pred")
     g, _ = _frames_on_device(gt, "gt")

@@ -83,6 +83,10 @@ class Communicator:
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().a2m_allreduce_metrics(self.ptr, _cabi.ptr(accum), _cabi.stream_ptr(self.device)))
 
+    def allreduce_smoothness(self, accum):
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().a2m_allreduce_smoothness(self.ptr, _cabi.ptr(accum), _cabi.stream_ptr(self.device)))
+
     def close(self):
         if self.ptr:
             _cabi.lib().a2m_comm_destroy(self.ptr)
@@ -108,15 +112,35 @@ def allreduce_metrics(accum, comm=None):
     return accum
 
 
+def allreduce_smoothness(accum, comm=None):
+    """The same for the 32-byte smoothness / jerk partials (two fp64 sums, two int64 counts)."""
+    if comm is not None and accum.is_cuda:
+        comm.allreduce_smoothness(accum)
+        return accum
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if accum.is_cuda:
+            raise RuntimeError("CUDA accumulator without a Communicator: create one with Communicator(rank, world, device)")
+        sums = accum[0:2].view(torch.float64).clone()
+        counts = accum[2:4].clone()
+        dist.all_reduce(sums)
+        dist.all_reduce(counts)
+        accum[0:2] = sums.view(torch.int64)
+        accum[2:4] = counts
+    return accum
+
+
 class AudioToPosePipeline:
     """mel -> generator -> evaluation on one GPU.  `model` is a SelfAttention_G drop-in in eval mode on `device`."""
 
-    def __init__(self, model, alpha=0.2, comm=None, lanes=2, graphs=False):
+    def __init__(self, model, alpha=0.2, comm=None, lanes=2, graphs=False, smoothness=False):
         """`lanes` > 1 runs consecutive batches on alternating CUDA streams, each lane with its own packed
         weights and activation arena, so the latency-bound tail of one batch (graph decoders, small GEMMs)
         overlaps the head of the next.  `graphs=True` captures each lane's whole step (about 60 launches, the
         two-stream decoder fork and the programmatic-dependent-launch edges included) into a CUDA graph per input
-        shape and replays it; inputs are copied into the graph's static buffers.  Results depend on neither."""
+        shape and replays it; inputs are copied into the graph's static buffers.  Results depend on neither.
+        `smoothness=True` also accumulates the validation loop's temporal-smoothness and jerk metrics of the generated
+        poses (version5_model_train.py:456-459), one more small kernel per step."""
         self.model = model
         self.alpha = alpha
         self.comm = comm
@@ -124,6 +148,7 @@ class AudioToPosePipeline:
         if self.device.type != "cuda":
             raise RuntimeError("AudioToPosePipeline needs the model on a CUDA device; there is no CPU fallback")
         self.accum = motion_evaluation.new_metrics(self.device)
+        self.smooth = motion_evaluation.new_smoothness(self.device) if smoothness else None
         self._copy_stream = torch.cuda.Stream(self.device)
         self._lane_models = [model]
         for _ in range(max(1, int(lanes)) - 1):
@@ -139,6 +164,8 @@ class AudioToPosePipeline:
     def reset(self):
         self.sync_lanes()
         self.accum.zero_()
+        if self.smooth is not None:
+            self.smooth.zero_()
 
     def sync_lanes(self):
         """Make the caller's current stream wait for everything the lanes have been given so far."""
@@ -181,6 +208,8 @@ class AudioToPosePipeline:
             else:
                 pose = self.generate(wav, self._lane_models[lane])
                 motion_evaluation.evaluate_poses(pose, gt_pose, self.alpha, accum=self.accum)
+            if self.smooth is not None:
+                motion_evaluation.evaluate_smoothness(pose, accum=self.smooth, from_pose=True)
         wav.record_stream(st)
         gt_pose.record_stream(st)
         return pose
@@ -251,4 +280,7 @@ class AudioToPosePipeline:
         allreduce_metrics(self.accum, self.comm)
         m = motion_evaluation.read_metrics(self.accum)
         m.update(motion_evaluation.finalize_metrics(m))
+        if self.smooth is not None:
+            allreduce_smoothness(self.smooth, self.comm)
+            m.update(motion_evaluation.read_smoothness(self.smooth))
         return m

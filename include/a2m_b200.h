@@ -89,6 +89,27 @@ int a2m_eval_l1_pck_f32(const float* pred, const float* gt, int64_t n_clips, int
                         a2m_metrics* accum /* device */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * temporal smoothness / jerk metrics of the validation loop: replaces
+ * version5_model_train.py:216-230 compute_temporal_smoothness_loss() and :233-248 compute_jerk_loss():
+ *   accel = m[:, 1:] - m[:, :-1];  smoothness = mean over (clip, t) of ||accel||_2 over the features
+ *   jerk  = accel[:, 1:] - accel[:, :-1];  jerk loss = mean of ||jerk||_2
+ * seq: [n_clips, frames_per_clip, n_features] fp32 (n_features <= 128).  from_pose = 0: seq is the motion
+ * (velocities) the reference functions take; from_pose = 1: seq holds poses and the motion is their first
+ * difference (pos_to_motion, :208-213), taken on the fly.  Differences are single fp32 subtractions in the
+ * reference's order; norms are fp32, the sums over frames fp64.  Partial sums are ADDED to *accum (zero it
+ * first): mean = sum / n; n_accel = n_clips * (M - 1), n_jerk = n_clips * (M - 2), M velocities per clip.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct a2m_smooth_metrics {
+    double sum_accel_norm;
+    double sum_jerk_norm;
+    int64_t n_accel;
+    int64_t n_jerk;
+} a2m_smooth_metrics;      /* 32 bytes */
+
+int a2m_motion_smoothness_f32(const float* seq, int64_t n_clips, int frames_per_clip, int n_features, int from_pose,
+                              a2m_smooth_metrics* accum /* device */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * pose (de)normalisation on either side of the generator: replaces the element-wise
  * steps of version5_model_train.py:300-307 / generate_motion_video.py:247-255 (view [.., 2, 52], subtract the
  * neck = joint 0 of the x block and of the y block, then (x - mean) / std), generate_motion_video.py:259-260
@@ -112,6 +133,7 @@ typedef struct a2m_comm a2m_comm;
 int a2m_comm_unique_id(void* out128_host);
 int a2m_comm_init(const void* id128_host, int rank, int world, int device, a2m_comm** out);
 int a2m_allreduce_metrics(a2m_comm* comm, a2m_metrics* inout /* device */, void* stream);
+int a2m_allreduce_smoothness(a2m_comm* comm, a2m_smooth_metrics* inout /* device */, void* stream);
 void a2m_comm_destroy(a2m_comm* comm);
 
 /* ------------------------------------------------------------------------------------------------

@@ -80,3 +80,19 @@ def finalize(partials):
         l1_pose=partials["abs_pose"] / max(partials["n_pose"], 1),
         l1_motion=partials["abs_motion"] / max(partials["n_motion"], 1),
     )
+
+
+def smoothness(motion_seq):
+    """compute_temporal_smoothness_loss (version5_model_train.py:216-230): mean over (b, t) of the L2 norm over the
+    features of the second difference; fp32 differences, fp64 norm accumulation here."""
+    m = np.asarray(motion_seq, dtype=np.float32)
+    acc = m[:, 1:] - m[:, :-1]
+    return float(np.mean(np.sqrt(np.sum(acc.astype(np.float64) ** 2, axis=-1))))
+
+
+def jerk(motion_seq):
+    """compute_jerk_loss (version5_model_train.py:233-248): the same on the third difference."""
+    m = np.asarray(motion_seq, dtype=np.float32)
+    acc = m[:, 1:] - m[:, :-1]
+    j = acc[:, 1:] - acc[:, :-1]
+    return float(np.mean(np.sqrt(np.sum(j.astype(np.float64) ** 2, axis=-1))))

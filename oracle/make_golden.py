@@ -47,7 +47,47 @@ def real_pose_input(case_seed, B, T):
     return torch.randn(B, T, synth.POSE_FEATS, generator=g, dtype=torch.float32)
 
 
+def reference_functions(path, names):
+    """The UNMODIFIED source of top-level functions of a reference script that cannot be imported (it starts data
+    loaders and training at import time): parsed with ast, compiled from the original text, nothing rewritten."""
+    import ast
+    src = open(path, encoding="utf-8").read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "np": np}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    missing = [n for n in names if n not in ns]
+    assert not missing, missing
+    return {n: ns[n] for n in names}
+
+
+def smoothness_golden():
+    """tests/golden/smooth_reference.npz: compute_temporal_smoothness_loss / compute_jerk_loss / pos_to_motion of
+    version5_model_train.py on seeded pose batches."""
+    fns = reference_functions(os.path.join(ref_shim.REFERENCE_ROOT, "version5_model_train.py"),
+                              ["pos_to_motion", "compute_temporal_smoothness_loss", "compute_jerk_loss"])
+    out = {}
+    for name, first, n in SMOOTH_CASES:
+        pose = torch.from_numpy(synth.noisy_pred_batch(first, n))
+        motion = fns["pos_to_motion"](pose)
+        out[name + "_smoothness"] = np.array(fns["compute_temporal_smoothness_loss"](motion).item())
+        out[name + "_jerk"] = np.array(fns["compute_jerk_loss"](motion).item())
+    short = torch.from_numpy(synth.noisy_pred_batch(9, 2)[:, :4])           # 4 poses -> 3 velocities -> 2 accel -> 1 jerk
+    m = fns["pos_to_motion"](short)
+    out["short_smoothness"] = np.array(fns["compute_temporal_smoothness_loss"](m).item())
+    out["short_jerk"] = np.array(fns["compute_jerk_loss"](m).item())
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "smooth_reference.npz"), **out)
+    print("smoothness goldens:", {k: float(v) for k, v in out.items()})
+
+
+SMOOTH_CASES = [("b4", 0, 4), ("b1", 7, 1), ("b16", 20, 16)]     # (name, first clip, clips)
+
+
 def main():
+    if "--smoothness-only" in sys.argv:
+        os.makedirs(GOLDEN_DIR, exist_ok=True)
+        return smoothness_golden()
     ref = ref_shim.import_reference()
     mf, me, rm = ref["mel_features"], ref["motion_evaluation"], ref["real_motion_model"]
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -113,6 +153,7 @@ def main():
             mo[name + "_unet"] = captured["unet"].numpy()
         print(name, pose.shape, mo[name + "_losses"], float(pose.abs().mean()))
     np.savez_compressed(os.path.join(GOLDEN_DIR, "model_reference.npz"), **mo)
+    smoothness_golden()
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
 

@@ -84,3 +84,53 @@ def test_full_size_properties(ev):
     assert ident["pck"] == 1.0 and ident["l1_pose"] == 0.0 and ident["l1_motion"] == 0.0
     ref = eval_oracle.metric_partials(pred[:64].cpu().numpy(), gt[:64].cpu().numpy())
     assert ev.read_metrics(ev.evaluate_poses(pred[:64], gt[:64]))["pck_hits"] == ref["pck_hits"]
+
+
+def test_smoothness_and_jerk_match_reference_golden(ev, golden):
+    """version5_model_train.py:216-248 through the drop-in names; fp32 norms, fp64 sums: rtol 1e-6 (written here)."""
+    from oracle.make_golden import SMOOTH_CASES
+    g = golden["smooth"]
+    for name, first, n in SMOOTH_CASES:
+        pose = torch.from_numpy(synth.noisy_pred_batch(first, n)).cuda()
+        motion = ev.pos_to_motion(pose)
+        s, j = ev.compute_temporal_smoothness_loss(motion), ev.compute_jerk_loss(motion)
+        assert isinstance(s, torch.Tensor) and s.dim() == 0 and s.dtype == torch.float32 and s.is_cuda
+        np.testing.assert_allclose(s.item(), g[name + "_smoothness"], rtol=1e-6)
+        np.testing.assert_allclose(j.item(), g[name + "_jerk"], rtol=1e-6)
+        fused = ev.read_smoothness(ev.evaluate_smoothness(pose, from_pose=True))     # poses in, motion on the fly
+        np.testing.assert_allclose(fused["smoothness"], g[name + "_smoothness"], rtol=1e-6)
+        np.testing.assert_allclose(fused["jerk"], g[name + "_jerk"], rtol=1e-6)
+        assert fused["n_accel"] == n * 62 and fused["n_jerk"] == n * 61
+    short = synth.noisy_pred_batch(9, 2)[:, :4]
+    got = ev.compute_jerk_loss(np.diff(short, axis=1))                                # numpy in -> numpy scalar out
+    assert isinstance(got, np.floating)
+    np.testing.assert_allclose(got, g["short_jerk"], rtol=1e-6)
+
+
+def test_smoothness_shapes_and_accumulation(ev):
+    """Partial sums add up over shards; odd lengths / feature counts; too-short sequences give the reference's NaN."""
+    pose = synth.noisy_pred_batch(3, 37, 29)
+    m = eval_oracle.motion(pose)
+    whole = ev.read_smoothness(ev.evaluate_smoothness(torch.from_numpy(m).cuda()))
+    np.testing.assert_allclose(whole["smoothness"], eval_oracle.smoothness(m), rtol=1e-6)
+    np.testing.assert_allclose(whole["jerk"], eval_oracle.jerk(m), rtol=1e-6)
+    acc = ev.new_smoothness()
+    for lo, hi in ((0, 5), (5, 6), (6, 37)):
+        ev.evaluate_smoothness(torch.from_numpy(m[lo:hi]).cuda(), accum=acc)
+    parts = ev.read_smoothness(acc)
+    assert parts["n_accel"] == whole["n_accel"] and parts["n_jerk"] == whole["n_jerk"]
+    np.testing.assert_allclose(parts["sum_accel_norm"], whole["sum_accel_norm"], rtol=1e-12)
+    np.testing.assert_allclose(parts["sum_jerk_norm"], whole["sum_jerk_norm"], rtol=1e-12)
+    g = torch.Generator().manual_seed(5)
+    odd = torch.randn(3, 11, 7, generator=g)
+    got = ev.read_smoothness(ev.evaluate_smoothness(odd.cuda()))
+    np.testing.assert_allclose(got["smoothness"], eval_oracle.smoothness(odd.numpy()), rtol=1e-6)
+    np.testing.assert_allclose(got["jerk"], eval_oracle.jerk(odd.numpy()), rtol=1e-6)
+    two = ev.read_smoothness(ev.evaluate_smoothness(odd[:, :2].cuda()))             # 2 velocities: 1 accel, no jerk
+    assert two["n_accel"] == 3 and two["n_jerk"] == 0 and np.isnan(two["jerk"])
+    one = ev.read_smoothness(ev.evaluate_smoothness(odd[:, :1].cuda()))
+    assert one["n_accel"] == 0 and np.isnan(one["smoothness"])
+    with pytest.raises(ValueError):
+        ev.evaluate_smoothness(torch.zeros(4, 5).cuda())
+    with pytest.raises(Exception):
+        ev.evaluate_smoothness(torch.zeros(2, 5, 200).cuda())

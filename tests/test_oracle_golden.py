@@ -67,6 +67,19 @@ def test_eval_oracle_matches_reference(golden):
     np.testing.assert_allclose(fin["l1_motion"], g["l1_motion"], rtol=1e-5)
 
 
+def test_smoothness_oracle_matches_reference(golden):
+    """compute_temporal_smoothness_loss / compute_jerk_loss of the unmodified version5_model_train.py."""
+    from oracle.make_golden import SMOOTH_CASES
+    g = golden["smooth"]
+    for name, first, n in SMOOTH_CASES:
+        m = eval_oracle.motion(synth.noisy_pred_batch(first, n))
+        np.testing.assert_allclose(eval_oracle.smoothness(m), g[name + "_smoothness"], rtol=1e-6)
+        np.testing.assert_allclose(eval_oracle.jerk(m), g[name + "_jerk"], rtol=1e-6)
+    m = eval_oracle.motion(synth.noisy_pred_batch(9, 2)[:, :4])
+    np.testing.assert_allclose(eval_oracle.smoothness(m), g["short_smoothness"], rtol=1e-6)
+    np.testing.assert_allclose(eval_oracle.jerk(m), g["short_jerk"], rtol=1e-6)
+
+
 def test_weight_contract():
     con = weights.contract()
     sd = weights.make_state_dict(0, "stress")

@@ -122,3 +122,19 @@ def test_long_form_full_size_shape(setup):
     wav = 0.1 * torch.randn(2, 960000, device="cuda")
     poses = pipeline.AudioToPosePipeline(model, lanes=1).generate_long(wav)
     assert poses.shape == (2, 188, 64, 104) and torch.isfinite(poses).all()
+
+
+def test_pipeline_smoothness_metrics(setup):
+    """Optional validation-loop metrics (version5_model_train.py:456-459) of the generated poses, accumulated over
+    batches and lanes: equal to the oracle's smoothness / jerk of the same GPU poses."""
+    pipeline, model, _ = setup
+    wav, gt = synth.wav_batch(30, 6), synth.gt_pose_batch(30, 6)
+    pipe = pipeline.AudioToPosePipeline(model, lanes=2, smoothness=True)
+    poses = [pipe.step(torch.from_numpy(wav[i:i + 2]).cuda(), torch.from_numpy(gt[i:i + 2]).cuda()) for i in (0, 2, 4)]
+    out = pipe.finish()
+    m = eval_oracle.motion(torch.cat(poses).cpu().numpy())
+    assert out["n_accel"] == 6 * 62 and out["n_jerk"] == 6 * 61
+    np.testing.assert_allclose(out["smoothness"], eval_oracle.smoothness(m), rtol=1e-6)
+    np.testing.assert_allclose(out["jerk"], eval_oracle.jerk(m), rtol=1e-6)
+    pipe.reset()
+    assert int(pipe.smooth.abs().sum()) == 0
