@@ -92,6 +92,8 @@ struct a2m_model {
     int* triples = nullptr; int n_hand_triples = 0, n_body_triples = 0;
     int* parents = nullptr;
     double* loss_scratch = nullptr;
+    float* denorm = nullptr;                    // [2][104] mean | std of the optional output de-normalisation
+    bool denorm_on = false;
     int* err_flag = nullptr;
     bool has_encoder = false, has_unet = false, has_decoders = false;
     // per-forward mutable slots read by the op closures
@@ -881,12 +883,33 @@ extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t mel_str
     A2M_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join, 0));
     }
     float* stage = P->pose_stage;
-    A2M_CUDA_CHECK(cudaMemcpyAsync(pose, stage, static_cast<size_t>(B) * T * kPoseFeats * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (m->denorm_on) {     // x * std + mean (generate_motion_video.py:259-260) instead of the plain copy out of the arena
+        rc = a2m_pose_denormalize_f32(stage, m->denorm, m->denorm + kPoseFeats, static_cast<int64_t>(B) * T, pose, stream);
+        if (rc != A2M_OK) return rc;
+    } else {
+        A2M_CUDA_CHECK(cudaMemcpyAsync(pose, stage, static_cast<size_t>(B) * T * kPoseFeats * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
     if (losses) {
         rc = launch_pose_losses(stage, real_pose, static_cast<int>(B), T, m->triples, m->n_hand_triples, m->n_body_triples,
                                 m->parents, m->loss_scratch, losses, s);
         if (rc != A2M_OK) return rc;
     }
+    return A2M_OK;
+}
+
+extern "C" int a2m_model_set_output_denorm(a2m_model* m, const float* mean, const float* stdv, void* stream) {
+    A2M_ARG_CHECK(m != nullptr, "a2m_model_set_output_denorm: NULL model");
+    A2M_ARG_CHECK((mean == nullptr) == (stdv == nullptr), "a2m_model_set_output_denorm: give both mean and std, or neither");
+    if (mean == nullptr) { m->denorm_on = false; return A2M_OK; }
+    A2M_CUDA_CHECK(cudaSetDevice(m->device));
+    if (!m->denorm) {
+        A2M_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&m->denorm), 2 * kPoseFeats * sizeof(float)));
+        m->owned.push_back(m->denorm);
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    A2M_CUDA_CHECK(cudaMemcpyAsync(m->denorm, mean, kPoseFeats * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    A2M_CUDA_CHECK(cudaMemcpyAsync(m->denorm + kPoseFeats, stdv, kPoseFeats * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    m->denorm_on = true;
     return A2M_OK;
 }
 

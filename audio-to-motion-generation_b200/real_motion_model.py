@@ -162,11 +162,45 @@ class SelfAttention_G(NativeModule):
                                                           _cabi.ptr(out), _cabi.stream_ptr(h.device)))
         return out
 
+    def set_output_denorm(self, pose_mean=None, pose_std=None):
+        """Fuse the de-normalisation that follows the generator in real use (generate_motion_video.py:259-260,
+        ``pose * std + mean``) into the forward's output pass; ``set_output_denorm()`` switches it off.  The
+        returned poses then equal ``normalization_tools.denormalize_pose(forward(x)[0], mean, std)`` bit for bit;
+        the internal losses are still those of the normalised output."""
+        if (pose_mean is None) != (pose_std is None):
+            raise ValueError("give both pose_mean and pose_std, or neither")
+        if pose_mean is None:
+            self.__dict__["_denorm"] = None
+        else:
+            mean = torch.as_tensor(pose_mean).detach().to(dtype=torch.float32).reshape(-1).clone()
+            std = torch.as_tensor(pose_std).detach().to(dtype=torch.float32).reshape(-1).clone()
+            if mean.numel() != 104 or std.numel() != 104:
+                raise ValueError("pose_mean and pose_std must have 104 elements")
+            self.__dict__["_denorm"] = (mean, std)
+        self.__dict__["_denorm_token"] = object()     # a handle carries the token of the setting it was given
+
+    def _sync_denorm(self, h):
+        token = self.__dict__.get("_denorm_token")
+        if token is None or getattr(h, "denorm_token", None) is token:
+            return
+        d = self.__dict__["_denorm"]
+        with torch.cuda.device(h.device):
+            if d is None:
+                _cabi.check(_cabi.lib().a2m_model_set_output_denorm(h.ptr, None, None, _cabi.stream_ptr(h.device)))
+            else:
+                mean, std = d[0].to(h.device), d[1].to(h.device)
+                _cabi.check(_cabi.lib().a2m_model_set_output_denorm(h.ptr, _cabi.ptr(mean), _cabi.ptr(std),
+                                                                    _cabi.stream_ptr(h.device)))
+                mean.record_stream(torch.cuda.current_stream(h.device))
+                std.record_stream(torch.cuda.current_stream(h.device))
+        h.denorm_token = token
+
     def forward(self, audio, real_pose=None):
         """audio [B, T, F] (log-mel) -> (pose [B, T, 104] fp32, [angle_loss]) or
         (pose, [bone_loss, angle_loss]) when real_pose [B, T, 104] is given."""
         self._require_eval()
         h = self.native()
+        self._sync_denorm(h)
         x = as_input(audio, h.device, "SelfAttention_G expects audio [B, T, F], got %s", keep_strides=True)
         B, T, F = x.shape
         if T % 4 != 0:

@@ -212,6 +212,12 @@ int a2m_model_forward(a2m_model* model, const float* mel, int64_t mel_stride_b, 
                       int F, float* pose, float* losses, const float* real_pose /* nullable [B, T, 104] */,
                       void* stream);
 /* AudioEncoder.forward (model_layers.py:267-280): mel [B, T, F] -> [B, 256, T] fp32 (reference NCW layout) */
+/* Optional fused output de-normalisation (generate_motion_video.py:259-260): when
+ * set, a2m_model_forward writes pose * std + mean (single fp32 multiply then add, equal to
+ * a2m_pose_denormalize_f32 bit for bit) in the pass that copies the poses out of the arena; the internal
+ * losses are still computed on the network's (normalised) output as in the reference.  mean, std: device
+ * float[104], copied into the handle on `stream`; NULL, NULL switches it off. */
+int a2m_model_set_output_denorm(a2m_model* model, const float* mean, const float* std, void* stream);
 int a2m_model_encoder_forward(a2m_model* model, const float* mel, int64_t B, int T, int F, float* out_nct, void* stream);
 /* UNet1D.forward (model_layers.py:341-374, D1): [B, 256, T] fp32 -> [B, 256, T] fp32 */
 int a2m_model_unet_forward(a2m_model* model, const float* x_nct, int64_t B, int T, float* out_nct, void* stream);

@@ -41,3 +41,30 @@ def test_streaming_statistics_match_reference(nt):
     np.testing.assert_allclose(mean.numpy(), ref_mean.numpy(), rtol=1e-5, atol=1e-4)
     np.testing.assert_allclose(std.numpy(), ref_std.numpy(), rtol=1e-5, atol=1e-4)
     assert std[0] == 1.0 and std[52] == 1.0
+
+
+def test_fused_output_denorm_equals_separate_pass(pkg, nt):
+    """SelfAttention_G.set_output_denorm: the forward's output pass applies pose * std + mean; bit-equal to the
+    separate kernel (and to the oracle's torch restatement) on the same normalised poses; losses unchanged;
+    survives a repack; off again with set_output_denorm()."""
+    from oracle import weights
+    mods = pkg.install_dropin()
+    model = mods["real_motion_model"].SelfAttention_G().cuda().eval()
+    model.load_state_dict(weights.make_state_dict(3, "stress"))
+    g = torch.Generator().manual_seed(11)
+    x = (-1.5 + 1.5 * torch.randn(3, 64, 64, generator=g)).cuda()
+    mean, std = torch.randn(104, generator=g) * 40 + 300, 5 + 20 * torch.rand(104, generator=g)
+    plain, losses0 = model(x)
+    model.set_output_denorm(mean, std)
+    fused, losses1 = model(x)
+    assert torch.equal(fused, nt.denormalize_pose(plain, mean, std))
+    assert torch.equal(fused.cpu(), norm_oracle.denormalize(plain.cpu(), mean, std))
+    assert torch.equal(losses0[0], losses1[0])
+    model.repack()                                      # a new native handle must receive the setting again
+    assert torch.equal(model(x)[0], fused)
+    model.set_output_denorm()
+    assert torch.equal(model(x)[0], plain)
+    with pytest.raises(ValueError):
+        model.set_output_denorm(mean, None)
+    with pytest.raises(ValueError):
+        model.set_output_denorm(mean[:50], std[:50])
