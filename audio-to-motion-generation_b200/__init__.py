@@ -29,11 +29,20 @@ _DROPIN = {
 }
 
 
+# registered only when asked for by name: "pats" is a large package of the reference (data loaders, skeleton, ...) of
+# which only the audio feature extraction has a B200 implementation -- shadowing it wholesale would hide the rest
+_DROPIN_ON_REQUEST = {
+    "pats.data_loading.audio": ".pats_audio",
+}
+
+
 def install_dropin(names=None):
     """Register this package's modules under the reference's top-level module names, so code written
     against the reference (``from pose_video.mel_features import ...``) runs on the B200 path."""
     installed = {}
-    for public, relative in _DROPIN.items():
+    table = dict(_DROPIN)
+    table.update({k: v for k, v in _DROPIN_ON_REQUEST.items() if names is not None and k in names})
+    for public, relative in table.items():
         if names is not None and public not in names:
             continue
         try:

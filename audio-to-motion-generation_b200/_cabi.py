@@ -49,6 +49,8 @@ SIGNATURES = {
     "a2m_launch_count_reset": (None, []),
     "a2m_mel_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_double, c_int,
                                     ctypes.POINTER(c_void_p)]),
+    "a2m_mel_plan_create_ex": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_double, c_int, c_int,
+                                       ctypes.POINTER(c_void_p)]),
     "a2m_mel_plan_destroy": (None, [c_void_p]),
     "a2m_mel_num_frames": (c_i64, [c_void_p, c_i64]),
     "a2m_logmel_f32": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p]),

@@ -44,6 +44,7 @@ struct MelGeom {
     int tile_frames;              // frames per tile (<= kSlots)
     int max_bin;                  // highest spectrogram bin with a non-zero mel weight
     float log_offset;
+    int log_mode;                 // 0: log(x + offset) (mel_features.py:223); 1: log(x == 0 ? offset : x) (pats/data_loading/audio.py:117-119)
 };
 
 struct SmemLayout {
@@ -218,7 +219,8 @@ logmel_kernel(const float* __restrict__ wav, long long n_clips, long long n_samp
                         acc0 = fmaf(a.x, b.x, acc0); acc1 = fmaf(a.y, b.y, acc1);
                         acc0 = fmaf(a.z, b.z, acc0); acc1 = fmaf(a.w, b.w, acc1);
                     }
-                    s_out[slot_id * g.n_mel + c] = __logf(acc0 + acc1 + g.log_offset);
+                    const float e = acc0 + acc1;
+                    s_out[slot_id * g.n_mel + c] = __logf(g.log_mode ? (e == 0.f ? g.log_offset : e) : e + g.log_offset);
                 }
             }
             __syncthreads();
@@ -244,6 +246,7 @@ struct a2m_mel_plan {
     int device;
     int window, hop, nfft, n_mel, nnz, max_bin;
     float log_offset;
+    int log_mode;
     void* blob;           // one device allocation holding all tables
     MelTables tab;
 };
@@ -251,8 +254,16 @@ struct a2m_mel_plan {
 extern "C" int a2m_mel_plan_create(int window, int hop, int nfft, int n_mel, const double* hann_host,
                                    const double* mel_weights_host, double log_offset, int device,
                                    a2m_mel_plan** out) {
+    return a2m_mel_plan_create_ex(window, hop, nfft, n_mel, hann_host, mel_weights_host, log_offset, A2M_LOG_ADD_OFFSET,
+                                  device, out);
+}
+
+extern "C" int a2m_mel_plan_create_ex(int window, int hop, int nfft, int n_mel, const double* hann_host,
+                                      const double* mel_weights_host, double log_offset, int log_mode, int device,
+                                      a2m_mel_plan** out) {
     A2M_ARG_CHECK(out != nullptr, "a2m_mel_plan_create: out is NULL");
     *out = nullptr;
+    A2M_ARG_CHECK(log_mode == A2M_LOG_ADD_OFFSET || log_mode == A2M_LOG_FLOOR_ZEROS, "a2m_mel_plan_create: log_mode %d", log_mode);
     if (nfft != kNfft) {
         a2m_set_error("a2m_mel_plan_create: fft length %d not supported (this build implements nfft = %d, "
                       "i.e. 257 spectrogram bins)", nfft, kNfft);
@@ -319,7 +330,7 @@ extern "C" int a2m_mel_plan_create(int window, int hop, int nfft, int n_mel, con
 
     a2m_mel_plan* p = new a2m_mel_plan();
     p->device = device; p->window = window; p->hop = hop; p->nfft = nfft; p->n_mel = n_mel; p->nnz = nnz;
-    p->max_bin = max_bin; p->log_offset = static_cast<float>(log_offset); p->blob = blob;
+    p->max_bin = max_bin; p->log_offset = static_cast<float>(log_offset); p->log_mode = log_mode; p->blob = blob;
     p->tab.window = reinterpret_cast<const float*>(blob + o_win);
     p->tab.tw = reinterpret_cast<const float2*>(blob + o_w);
     p->tab.untangle = reinterpret_cast<const float2*>(blob + o_u);
@@ -360,7 +371,7 @@ static int launch_logmel(const a2m_mel_plan* plan, const float* wav, int64_t n_c
 
     MelGeom g;
     g.window = plan->window; g.hop = plan->hop; g.n_mel = plan->n_mel; g.nnz = plan->nnz;
-    g.max_bin = plan->max_bin; g.log_offset = plan->log_offset;
+    g.max_bin = plan->max_bin; g.log_offset = plan->log_offset; g.log_mode = plan->log_mode;
     // a frame's reads extend to the next multiple of 32 past its window (zero window weights there)
     long long tf = 1 + (kSpanFloats - ((plan->window + 31) / 32) * 32) / plan->hop;
     if (tf > kSlots) tf = kSlots;

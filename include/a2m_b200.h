@@ -52,6 +52,15 @@ void a2m_launch_count_reset(void);
 typedef struct a2m_mel_plan a2m_mel_plan;
 int a2m_mel_plan_create(int window, int hop, int nfft, int n_mel, const double* hann_host,
                         const double* mel_weights_host, double log_offset, int device, a2m_mel_plan** out);
+/* The same with the log variant chosen: A2M_LOG_ADD_OFFSET log(x + log_offset) (mel_features.py:223), or
+ * A2M_LOG_FLOOR_ZEROS log(x == 0 ? log_offset : x), the masking of the PATS front ends
+ * (pats/data_loading/audio.py:117-119 log_mel_400, :70-79 log_mel_512).  The window table may carry leading zeros
+ * (librosa centres a short window inside the fft frame: window = nfft, pats/data_loading/audio.py:98-104). */
+#define A2M_LOG_ADD_OFFSET 0
+#define A2M_LOG_FLOOR_ZEROS 1
+int a2m_mel_plan_create_ex(int window, int hop, int nfft, int n_mel, const double* hann_host,
+                           const double* mel_weights_host, double log_offset, int log_mode, int device,
+                           a2m_mel_plan** out);
 void a2m_mel_plan_destroy(a2m_mel_plan* plan);
 /* 1 + floor((n_samples - window) / hop), mel_features.py:41-42; negative when the reference would raise */
 int64_t a2m_mel_num_frames(const a2m_mel_plan* plan, int64_t n_samples);

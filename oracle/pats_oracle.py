@@ -1,0 +1,61 @@
+"""Oracle (test infrastructure): numpy restatement of the PATS-native audio front ends of the reference,
+``/root/reference/pats/data_loading/audio.py`` ``log_mel_400`` :86-120 (and the filterbank / framing pieces
+``log_mel_512`` :58-79 shares).
+
+PARITY UNPINNED: the arithmetic lives in librosa (``librosa.core.stft``, ``librosa.feature.melspectrogram``,
+``librosa.filters.mel``), a third-party dependency that is absent here and unpinned in the reference (no
+requirements file; the code's ``np.float`` dates it to numpy < 1.24 / librosa 0.8-0.9).  This file restates
+librosa's published algorithm -- Slaney mel scale (linear to 1 kHz, then log with step ln(6.4)/27), triangular
+filters in Hz, ``center=False`` framing of n_fft samples with the win_length window zero-padded to n_fft on both
+sides, periodic Hann -- and is anchored only by its own known answers (tests/test_pats_audio_cpu.py).  fp64 throughout.
+"""
+import numpy as np
+
+
+def slaney_mel(hz):
+    hz = np.asarray(hz, dtype=np.float64)
+    lin = 3.0 * hz / 200.0
+    log_region = 15.0 + 27.0 * np.log(np.maximum(hz, 1.0) / 1000.0) / np.log(6.4)
+    return np.where(hz >= 1000.0, log_region, lin)
+
+
+def slaney_hz(mel):
+    mel = np.asarray(mel, dtype=np.float64)
+    return np.where(mel >= 15.0, 1000.0 * 6.4 ** ((mel - 15.0) / 27.0), 200.0 * mel / 3.0)
+
+
+def filterbank(sr, n_fft, n_mels, fmin, fmax, area_norm):
+    """[n_mels, n_fft//2+1]: filter i rises from centre i-1... over centres c[i], c[i+1], c[i+2] (Hz)."""
+    bins = np.arange(n_fft // 2 + 1) * (sr / n_fft)
+    c = slaney_hz(np.linspace(slaney_mel(fmin), slaney_mel(fmax), n_mels + 2))
+    w = np.zeros((n_mels, bins.size))
+    for i in range(n_mels):
+        rise = (bins - c[i]) / (c[i + 1] - c[i])
+        fall = (c[i + 2] - bins) / (c[i + 2] - c[i + 1])
+        w[i] = np.clip(np.minimum(rise, fall), 0.0, None)
+        if area_norm:
+            w[i] *= 2.0 / (c[i + 2] - c[i])
+    return w.astype(np.float32).astype(np.float64)          # librosa stores the basis as float32
+
+
+def stft_mag_uncentred(y, n_fft, hop, win_length):
+    """|STFT| with center=False: frames y[t*hop : t*hop + n_fft] times the padded periodic Hann -> [frames, bins]."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    n = np.arange(win_length)
+    hann = 0.5 - 0.5 * np.cos(2.0 * np.pi * n / win_length)
+    left = (n_fft - win_length) // 2
+    win = np.zeros(n_fft)
+    win[left:left + win_length] = hann
+    n_frames = 1 + (y.size - n_fft) // hop
+    if n_frames < 1:
+        raise ValueError("too short for one frame")
+    frames = np.stack([y[t * hop:t * hop + n_fft] for t in range(n_frames)])
+    return np.abs(np.fft.rfft(frames * win, axis=1))
+
+
+def log_mel_400(y, eps=1e-6):
+    """audio.py:86-120 for 16 kHz input: [frames, 64]."""
+    mag = stft_mag_uncentred(y, 512, 160, 400)
+    spec = mag @ filterbank(16000, 512, 64, 125.0, 7500.0, area_norm=False).T
+    spec = np.where(spec == 0, eps, spec)
+    return np.log(spec)
