@@ -9,8 +9,14 @@ It runs on the same fused CUDA kernel (csrc/logmel.cu) through ``a2m_mel_plan_cr
 window table and ``A2M_LOG_FLOOR_ZEROS``; the window and the filterbank are evaluated on the host in fp64 from
 librosa's published formulas (librosa itself is not a dependency of this package).
 
-Not implemented on the GPU (raises NotImplementedError, never a CPU fallback): ``log_mel_512`` (2048-point FFT) and
-resampling (``sr`` must already be 16 kHz for ``log_mel_400``).
+``log_mel_512`` (the representation the shipped training configuration reads, ``audio/log_mel_512``) is librosa's
+default mel spectrogram: 2048-point centred frames at hop 512, periodic Hann, POWER spectrum, 128 Slaney bands 0..sr/2
+with area normalisation, zeros floored to ``eps``, log.  It runs on its own kernel (csrc/melspec_wide.cu, radix-4
+Stockham FFT in shared memory).  librosa's padding default changed from 'reflect' (< 0.10, the reference's era) to
+'constant' (>= 0.10): ``pad_mode`` selects, default 'reflect'.
+
+Not implemented on the GPU (raises NotImplementedError, never a CPU fallback): resampling (``sr`` must already be
+16 kHz for ``log_mel_400``).
 """
 import ctypes
 
@@ -110,10 +116,46 @@ def log_mel_400(y, sr=16000, eps=1e-6):
     return out.cpu().numpy() if was_numpy else out
 
 
-def log_mel_512(y, sr, eps=1e-10):
-    """pats/data_loading/audio.py:58-79 (n_fft 2048, hop 512, 128 Slaney mel bands, power 2): no CUDA kernel yet."""
-    raise NotImplementedError("log_mel_512 needs a 2048-point FFT; the B200 log-mel kernel implements fft_length 512 "
-                              "(there is no CPU fallback)")
+_PAD_MODES = {None: 0, "none": 0, "reflect": 1, "constant": 2, "zeros": 2}
+
+
+class _WidePlan:
+    def __init__(self, handle, n_mel):
+        self.handle, self.n_mel = handle, n_mel
+
+
+def _plan_512(device_index, sr, eps, pad_mode):
+    key = (device_index, "log_mel_512", float(sr), float(eps), pad_mode)
+    plan = _plans.get(key)
+    if plan is None:
+        window = np.ascontiguousarray(centred_window(2048, 2048), dtype=np.float64)
+        weights = np.ascontiguousarray(mel_filterbank(sr, 2048, n_mels=128).T, dtype=np.float64)      # [1025, 128]
+        out = ctypes.c_void_p()
+        _cabi.check(_cabi.lib().a2m_melspec_plan_create(
+            2048, 512, 128, 2, _PAD_MODES[pad_mode], window.ctypes.data_as(ctypes.c_void_p),
+            weights.ctypes.data_as(ctypes.c_void_p), float(eps), 1, device_index, ctypes.byref(out)))
+        plan = _plans[key] = _WidePlan(out, 128)
+    return plan
+
+
+def log_mel_512(y, sr, eps=1e-10, pad_mode="reflect"):
+    """pats/data_loading/audio.py:58-79 on the GPU: waveform [N] (or batch [B, N]) at ``sr`` Hz ->
+    log-mel [1 + N // 512, 128]."""
+    _cabi.require_cuda("log_mel_512")
+    if pad_mode not in ("reflect", "constant", "zeros"):
+        raise ValueError("log_mel_512: pad_mode must be 'reflect' or 'constant', got %r" % (pad_mode,))
+    wav, batched, was_numpy = mel_features._to_device(y)
+    if pad_mode == "reflect" and wav.shape[1] <= 1024:
+        raise ValueError("log_mel_512: reflect padding needs more than 1024 samples, got %d" % wav.shape[1])
+    plan = _plan_512(wav.device.index, float(sr), eps, pad_mode)
+    frames = int(_cabi.lib().a2m_melspec_num_frames(plan.handle, wav.shape[1]))
+    out = torch.empty((wav.shape[0], frames, 128), dtype=torch.float32, device=wav.device)
+    with torch.cuda.device(wav.device):
+        _cabi.check(_cabi.lib().a2m_melspec_f32(plan.handle, _cabi.ptr(wav), wav.shape[0], wav.shape[1], wav.stride(0),
+                                                _cabi.ptr(out), _cabi.stream_ptr(wav.device)))
+    if not batched:
+        out = out[0]
+    return out.cpu().numpy() if was_numpy else out
 
 
 class Audio:
@@ -127,8 +169,8 @@ class Audio:
     def log_mel_400(self, y, sr, eps=1e-6):
         return log_mel_400(y, sr, eps)
 
-    def log_mel_512(self, y, sr, eps=1e-10):
-        return log_mel_512(y, sr, eps)
+    def log_mel_512(self, y, sr, eps=1e-10, pad_mode="reflect"):
+        return log_mel_512(y, sr, eps, pad_mode)
 
     @property
     def fs_map(self):

@@ -73,6 +73,28 @@ int a2m_stft_magnitude_f32(const a2m_mel_plan* plan, const float* wav, int64_t n
                            int64_t wav_stride, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * long-FFT mel spectrogram: replaces pats/data_loading/audio.py:58-79 log_mel_512 =
+ * log(floor-zeros(librosa.feature.melspectrogram(y, sr, n_fft=2048, hop_length=512))) transposed to [frames, n_mel].
+ *   nfft == 2048; window_host: fp64 [nfft] (librosa pads a shorter window to nfft on both sides);
+ *   power: 1 = |X|, 2 = |X|^2;  pad_mode: A2M_PAD_NONE (center=False, 1 + (n - nfft) / hop frames), A2M_PAD_REFLECT
+ *   (center=True with np.pad 'reflect', librosa < 0.10 default) or A2M_PAD_ZEROS (librosa >= 0.10 default), both
+ *   1 + n / hop frames;  mel_weights_host: fp64 [nfft/2+1, n_mel] row-major, every column one contiguous run of bins.
+ * wav: [n_clips] rows of n_samples fp32, row stride wav_stride; out: [n_clips, frames, n_mel] fp32 contiguous.
+ * ---------------------------------------------------------------------------------------------- */
+#define A2M_PAD_NONE 0
+#define A2M_PAD_REFLECT 1
+#define A2M_PAD_ZEROS 2
+typedef struct a2m_melspec_plan a2m_melspec_plan;
+int a2m_melspec_plan_create(int nfft, int hop, int n_mel, int power, int pad_mode, const double* window_host,
+                            const double* mel_weights_host, double log_offset, int log_mode, int device,
+                            a2m_melspec_plan** out);
+void a2m_melspec_plan_destroy(a2m_melspec_plan* plan);
+int64_t a2m_melspec_num_frames(const a2m_melspec_plan* plan, int64_t n_samples);   /* negative: too short */
+int a2m_melspec_f32(const a2m_melspec_plan* plan, const float* wav, int64_t n_clips, int64_t n_samples,
+                    int64_t wav_stride, float* out, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
  * evaluation: replaces motion_evaluation.py:4-23 compute_pck()/compute_pck_radius() and the
  * nn.L1Loss() metric of version5_model_train.py:264,367,467 (on poses and on pos_to_motion :208-213).
  *

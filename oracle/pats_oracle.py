@@ -59,3 +59,23 @@ def log_mel_400(y, eps=1e-6):
     spec = mag @ filterbank(16000, 512, 64, 125.0, 7500.0, area_norm=False).T
     spec = np.where(spec == 0, eps, spec)
     return np.log(spec)
+
+
+def stft_power_centred(y, n_fft, hop, pad_mode="reflect"):
+    """|STFT|^2 with center=True: y padded by n_fft // 2 on both sides ('reflect' without edge repeat, or zeros),
+    full-length periodic Hann -> [1 + N // hop, bins]."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    yp = np.pad(y, n_fft // 2, mode="reflect" if pad_mode == "reflect" else "constant")
+    n = np.arange(n_fft)
+    hann = 0.5 - 0.5 * np.cos(2.0 * np.pi * n / n_fft)
+    n_frames = 1 + (yp.size - n_fft) // hop
+    frames = np.stack([yp[t * hop:t * hop + n_fft] for t in range(n_frames)])
+    return np.abs(np.fft.rfft(frames * hann, axis=1)) ** 2
+
+
+def log_mel_512(y, sr, eps=1e-10, pad_mode="reflect"):
+    """audio.py:58-79: librosa.feature.melspectrogram(y, sr, n_fft=2048, hop_length=512) defaults (power 2, 128 bands
+    0..sr/2, Slaney area normalisation) -> zeros to eps -> log -> [frames, 128]."""
+    spec = stft_power_centred(y, 2048, 512, pad_mode) @ filterbank(sr, 2048, 128, 0.0, sr / 2.0, area_norm=True).T
+    spec = np.where(spec == 0, eps, spec)
+    return np.log(spec)

@@ -65,6 +65,25 @@ def test_no_cpu_fallback_and_unsupported(pa):
         pytest.skip("CPU-only check")
     with pytest.raises(RuntimeError):
         pa.log_mel_400(np.zeros(2000, np.float32), 16000)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):
         pa.log_mel_512(np.zeros(4096, np.float32), 44100)
     assert pa.Audio().fs("audio/log_mel_400") == 103 and pa.Audio().fs_map["log_mel_512"] == 89
+
+
+def test_log_mel_512_oracle_known_answers():
+    """Frame count 1 + N // 512; reflect padding makes frame 0 symmetric about sample 0; silence -> log(eps); a pure
+    tone lands in the band whose centre is nearest."""
+    sr = 44100
+    y = synth.wav_clip(11, 6000)
+    ref = pats_oracle.log_mel_512(y, sr)
+    assert ref.shape == (1 + 6000 // 512, 128)
+    assert np.all(pats_oracle.log_mel_512(np.zeros(3000), sr) == np.log(1e-10))
+    t = np.arange(20000) / sr
+    tone = np.sin(2 * np.pi * 2000.0 * t)
+    band = pats_oracle.log_mel_512(tone, sr)[10].argmax()
+    centres = pats_oracle.slaney_hz(np.linspace(0, pats_oracle.slaney_mel(sr / 2), 130))[1:-1]
+    assert abs(centres[band] - 2000.0) == np.abs(centres - 2000.0).min()
+    zc = pats_oracle.stft_power_centred(y, 2048, 512, "constant")
+    zr = pats_oracle.stft_power_centred(y, 2048, 512, "reflect")
+    np.testing.assert_allclose(zc[3:-3], zr[3:-3], rtol=1e-12)          # interior frames never see the padding
+    assert not np.allclose(zc[0], zr[0])

@@ -55,3 +55,31 @@ def test_zeros_floor_and_batches(pa):
         pa.log_mel_400(wav[0], 44100)
     with pytest.raises(ValueError):
         pa.log_mel_400(np.zeros(511, np.float32), 16000)
+
+
+@pytest.mark.parametrize("kind,n,idx,sr,pad", [("noise", 30000, 21, 44100, "reflect"), ("noise", 30000, 21, 44100, "constant"),
+                                                ("int16", 9000, 22, 16000, "reflect"), ("noise", 1025, 23, 44100, "reflect"),
+                                                ("noise", 2047, 24, 22050, "reflect"), ("tone", 20000, 25, 44100, "reflect")])
+def test_log_mel_512_matches_oracle(pa, kind, n, idx, sr, pad):
+    """audio.py:58-79 (2048-point centred frames, power spectrum, 128 area-normalised Slaney bands).  Power doubles the
+    dynamic range in dB, so the tone + 1e-4 noise clip (no additive offset, fp32 FFT) carries max|a-b| <= 1e-2 (measured
+    6.6e-3; numpy's fp32 pocketfft is off by 2.2e-3 on the same clip); its sum|a-b| / sum|b| still meets 1e-4."""
+    y = synth.wav_clip(idx, n, kind)
+    got = pa.log_mel_512(y, sr, pad_mode=pad)
+    ref = pats_oracle.log_mel_512(y, sr, pad_mode=pad)
+    assert isinstance(got, np.ndarray) and got.shape == ref.shape == (1 + n // 512, 128)
+    close(got, ref, 1e-2 if kind == "tone" else None)
+
+
+def test_log_mel_512_zeros_batches_and_errors(pa):
+    z = pa.log_mel_512(np.zeros(3000, np.float32), 44100)
+    assert z.shape == (6, 128) and np.allclose(z, np.log(1e-10), rtol=0, atol=1e-4)
+    wav = synth.wav_batch(60, 4)
+    got = pa.Audio().log_mel_512(torch.from_numpy(wav).cuda(), 16000)
+    assert got.is_cuda and got.shape == (4, 1 + wav.shape[1] // 512, 128)
+    close(got[3].cpu().numpy(), pats_oracle.log_mel_512(wav[3], 16000))
+    assert torch.equal(got[1], pa.log_mel_512(torch.from_numpy(wav[1]).cuda(), 16000))
+    with pytest.raises(ValueError):
+        pa.log_mel_512(np.zeros(1024, np.float32), 44100)               # reflect needs > 1024 samples
+    with pytest.raises(ValueError):
+        pa.log_mel_512(wav[0], 44100, pad_mode="edge")
