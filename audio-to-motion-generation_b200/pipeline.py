@@ -150,6 +150,7 @@ class AudioToPosePipeline:
         self.accum = motion_evaluation.new_metrics(self.device)
         self.smooth = motion_evaluation.new_smoothness(self.device) if smoothness else None
         self._copy_stream = torch.cuda.Stream(self.device)
+        self._staging = {}                      # (wav shape, gt shape, depth) -> ring of [wav_dev, gt_dev, last-use event]
         self._lane_models = [model]
         for _ in range(max(1, int(lanes)) - 1):
             twin = copy.deepcopy(model).eval()
@@ -194,7 +195,7 @@ class AudioToPosePipeline:
             out.append(net(x)[0])
         return torch.stack(out)
 
-    def step(self, wav, gt_pose):
+    def step(self, wav, gt_pose, done_event=None):
         """One batch, inputs already on the device: enqueues mel -> generator -> evaluation on the next lane and
         accumulates the metric partials.  Returns the poses; they (and the metrics) are complete once
         ``sync_lanes()`` / ``finish()`` has been called on the consuming stream."""
@@ -210,6 +211,8 @@ class AudioToPosePipeline:
                 motion_evaluation.evaluate_poses(pose, gt_pose, self.alpha, accum=self.accum)
             if self.smooth is not None:
                 motion_evaluation.evaluate_smoothness(pose, accum=self.smooth, from_pose=True)
+            if done_event is not None:
+                done_event.record(st)                               # the lane no longer reads wav / gt_pose after this
         wav.record_stream(st)
         gt_pose.record_stream(st)
         return pose
@@ -244,34 +247,46 @@ class AudioToPosePipeline:
         self.replayed_launches += n_kernels
         return s_pose
 
-    def run_host_batches(self, batches):
-        """End-to-end over HOST batches [(wav_pinned [B,N], gt_pinned [B,64,104]), ...]: the H2D copy of batch
-        i+1 (side stream) overlaps the kernels of batch i; returns the number of clips processed."""
+    def run_host_batches(self, batches, depth=3):
+        """End-to-end over HOST batches [(wav_pinned [B,N], gt_pinned [B,64,104]), ...]: batch i+1 is copied to the
+        device on a side stream while the kernels of batch i run.  The copies land in a ring of `depth` preallocated
+        device buffers per input shape (no allocation inside the loop); a slot is rewritten only after the lane that
+        consumed it has finished with it.  Returns the number of clips processed."""
         main = torch.cuda.current_stream(self.device)
         clips = 0
-        staged = None
         it = iter(batches)
+        turn = 0
 
         def stage(pair):
+            nonlocal turn
+            key = (tuple(pair[0].shape), tuple(pair[1].shape), depth)
+            ring = self._staging.get(key)
+            if ring is None:
+                ring = self._staging[key] = [
+                    [torch.empty(pair[0].shape, dtype=torch.float32, device=self.device),
+                     torch.empty(pair[1].shape, dtype=torch.float32, device=self.device), None] for _ in range(depth)]
+            slot = ring[turn % depth]
+            turn += 1
             with torch.cuda.stream(self._copy_stream):
-                w = pair[0].to(self.device, non_blocking=True)
-                g = pair[1].to(self.device, non_blocking=True)
+                if slot[2] is not None:
+                    self._copy_stream.wait_event(slot[2])           # the step that last read this slot is done
+                slot[0].copy_(pair[0], non_blocking=True)
+                slot[1].copy_(pair[1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
-            return w, g, ev
+            return slot, ev
 
         nxt = next(it, None)
-        if nxt is not None:
-            staged = stage(nxt)
+        staged = stage(nxt) if nxt is not None else None
         while staged is not None:
-            w, g, ev = staged
+            slot, ev = staged
             nxt = next(it, None)
             staged = stage(nxt) if nxt is not None else None
             main.wait_event(ev)
-            self.step(w, g)
-            w.record_stream(main)
-            g.record_stream(main)
-            clips += w.shape[0]
+            done = torch.cuda.Event()
+            self.step(slot[0], slot[1], done_event=done)
+            slot[2] = done
+            clips += slot[0].shape[0]
         return clips
 
     def finish(self):

@@ -117,7 +117,7 @@ def cpu_reference_run(n_clips, threads):
     return time.perf_counter() - t0
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out=sys.stdout):
     """--impl reference: the reference algorithm on the host cores (oracle port; the reference itself is
     pure Python and not importable as shipped)."""
     if rank != 0:
@@ -138,7 +138,16 @@ def run_reference(args, rank, world):
                              "sample": "%d clips per step x %d steps (oracle port of the reference CPU path)" % (sample, args.steps)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
+
+
+def _claim_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1: point fd 1 at stderr for the run and return a file on
+    the real stdout, which then carries exactly one line -- the JSON result."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -154,11 +163,12 @@ def main():
                     "over two eager stream lanes, which already hide the launch gaps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    out = _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, rank, world, out)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -325,7 +335,7 @@ def main():
                 "result": {k: result[k] for k in ("pck", "l1_pose", "l1_motion", "n_frames")},
                 "result_e2e": {k: result_e2e[k] for k in ("pck", "n_frames")}}
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if comm is not None:
         comm.close()
     if world > 1:
