@@ -17,7 +17,7 @@ import ctypes
 
 import torch
 
-from . import _cabi, motion_evaluation
+from . import _cabi, motion_evaluation, pats_audio
 from .pose_video import audio_repr
 
 ADAPTER_STRIDE = 6          # dataUtils.py:654 strided slice, fs_ratio = 6 (audio.py:177)
@@ -133,14 +133,25 @@ def allreduce_smoothness(accum, comm=None):
 class AudioToPosePipeline:
     """mel -> generator -> evaluation on one GPU.  `model` is a SelfAttention_G drop-in in eval mode on `device`."""
 
-    def __init__(self, model, alpha=0.2, comm=None, lanes=2, graphs=False, smoothness=False):
+    FRONT_ENDS = ("vggish", "log_mel_400", "log_mel_512")
+
+    def __init__(self, model, alpha=0.2, comm=None, lanes=2, graphs=False, smoothness=False, front_end="vggish",
+                 sample_rate=None):
         """`lanes` > 1 runs consecutive batches on alternating CUDA streams, each lane with its own packed
         weights and activation arena, so the latency-bound tail of one batch (graph decoders, small GEMMs)
         overlaps the head of the next.  `graphs=True` captures each lane's whole step (about 60 launches, the
         two-stream decoder fork and the programmatic-dependent-launch edges included) into a CUDA graph per input
         shape and replays it; inputs are copied into the graph's static buffers.  Results depend on neither.
+        `front_end` selects the audio features: "vggish" (pose_video/audio_repr.py, 64 bands -- the path BASELINE's
+        configs name), or the PATS-native "log_mel_400" (64 bands) / "log_mel_512" (128 bands at `sample_rate`, the
+        representation the shipped training configuration reads; pats/data_loading/audio.py).  All are fed to the
+        generator through the same stride-6 adapter.
         `smoothness=True` also accumulates the validation loop's temporal-smoothness and jerk metrics of the generated
         poses (version5_model_train.py:456-459), one more small kernel per step."""
+        if front_end not in self.FRONT_ENDS:
+            raise ValueError("front_end must be one of %s, got %r" % (self.FRONT_ENDS, front_end))
+        self.front_end = front_end
+        self.sample_rate = sample_rate if sample_rate is not None else (44100 if front_end == "log_mel_512" else 16000)
         self.model = model
         self.alpha = alpha
         self.comm = comm
@@ -174,9 +185,17 @@ class AudioToPosePipeline:
         for st in self._lane_streams:
             cur.wait_stream(st)
 
+    def features(self, wav):
+        """wav [B, N] -> the front end's log-mel [B, frames, 64 | 128]."""
+        if self.front_end == "log_mel_512":
+            return pats_audio.log_mel_512(wav, self.sample_rate)
+        if self.front_end == "log_mel_400":
+            return pats_audio.log_mel_400(wav, self.sample_rate)
+        return audio_repr.log_mel_spectograms(wav, audio_sample_rate=self.sample_rate)
+
     def generate(self, wav, model=None):
         """wav [B, N] fp32 CUDA tensor -> pose [B, 64, 104] fp32 (on the current stream)."""
-        logmel = audio_repr.log_mel_spectograms(wav)
+        logmel = self.features(wav)
         pose, _ = (model or self.model)(adapter(logmel))
         return pose
 
@@ -185,7 +204,7 @@ class AudioToPosePipeline:
         [B, n_windows, 64, 104].  The log-mel of every stream is computed once; each clip's overlapping windows
         (384-frame span, stride 6, hop window_hop * 6 frames -- the reference's window arithmetic) are fed to the
         generator as one strided view per clip, so no window is ever materialised."""
-        logmel = audio_repr.log_mel_spectograms(wav)                       # [B, frames, 64]
+        logmel = self.features(wav)                                        # [B, frames, 64 | 128]
         net = model or self.model
         out = []
         for b in range(logmel.shape[0]):

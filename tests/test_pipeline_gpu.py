@@ -138,3 +138,27 @@ def test_pipeline_smoothness_metrics(setup):
     np.testing.assert_allclose(out["jerk"], eval_oracle.jerk(m), rtol=1e-6)
     pipe.reset()
     assert int(pipe.smooth.abs().sum()) == 0
+
+
+def test_pats_front_end_f128_matches_oracle_composition(setup):
+    """The shipped configuration's features: log_mel_512 (128 bands, pats/data_loading/audio.py:58-79) -> stride-6
+    adapter -> SelfAttention_G with F = 128.  Poses within the bf16 bar of the oracle composition."""
+    from oracle import pats_oracle
+    pipeline, model, sd = setup
+    n = 380 * 512                                                        # 381 frames >= the adapter's 379
+    wav = np.stack([synth.wav_clip(70 + i, n) for i in range(2)])
+    gt = synth.gt_pose_batch(70, 2)
+    pipe = pipeline.AudioToPosePipeline(model, lanes=1, front_end="log_mel_512", sample_rate=44100)
+    pose = pipe.step(torch.from_numpy(wav).cuda(), torch.from_numpy(gt).cuda())
+    out = pipe.finish()
+    mel = np.stack([pats_oracle.log_mel_512(w, 44100) for w in wav])
+    assert mel.shape == (2, 381, 128)
+    x = torch.from_numpy(synth.adapter(mel).astype(np.float32))
+    assert x.shape == (2, 64, 128)
+    ref_pose, _ = model_oracle.generator_forward(sd, x)
+    rel = ((pose.cpu() - ref_pose).abs().sum() / ref_pose.abs().sum()).item()
+    assert rel <= 1e-2, rel
+    ref = eval_oracle.metric_partials(pose.cpu().numpy(), gt)
+    assert out["pck_hits"] == ref["pck_hits"] and out["n_frames"] == 128
+    with pytest.raises(ValueError):
+        pipeline.AudioToPosePipeline(model, front_end="mfcc")
