@@ -1070,10 +1070,18 @@ gnn4_kernel(const __grid_constant__ Gnn3Params p, int* __restrict__ err_flag) {
                 zpar ^= 1;
                 tc_fence_after();
                 if (tid == 0) { load_item(item + 3); load_item(item + 4); }     // slices 0, 1 are consumed
+                if (layer < 4 && half == 0) {              // P buffer 0 is drained: the adjacency (no self loops) of the
+                    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);    // GraphConv layer that follows
+                    *reinterpret_cast<__nv_bfloat16*>(s_p + pofs[0]) = zero;
+#pragma unroll
+                    for (int k = 1; k <= kMaxDeg; ++k)
+                        if (k <= dg) *reinterpret_cast<__nv_bfloat16*>(s_p + pofs[k]) = one;
+                }
                 convert(half * 64, half * 32);
                 convert(half * 64 + 32, half * 32 + 16);
                 tmem_st_wait();
                 tc_fence_before();
+                fence_proxy_async_smem();
                 __syncthreads();
                 if (tid == 0) {
                     tc_fence_after();
@@ -1092,15 +1100,7 @@ gnn4_kernel(const __grid_constant__ Gnn3Params p, int* __restrict__ err_flag) {
                 if (tid == 0) { load_item(item + 5); load_item(item + 6); item += 4; }
             } else {
                 // ================= GraphConv =================
-                if (half == 0) {                           // adjacency (no self loops) into P buffer 0
-                    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
-                    *reinterpret_cast<__nv_bfloat16*>(s_p + pofs[0]) = zero;
-#pragma unroll
-                    for (int k = 1; k <= kMaxDeg; ++k)
-                        if (k <= dg) *reinterpret_cast<__nv_bfloat16*>(s_p + pofs[k]) = one;
-                }
-                fence_proxy_async_smem();
-                __syncthreads();
+                // P buffer 0 already holds the adjacency: the preceding GAT layer wrote it once its own aggregation was done
                 if (tid == 0) {
                     tc_fence_after();
 #pragma unroll
@@ -1151,7 +1151,12 @@ gnn4_kernel(const __grid_constant__ Gnn3Params p, int* __restrict__ err_flag) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) { s += v[i]; sq = fmaf(v[i], v[i], sq); }
                 *reinterpret_cast<float2*>(s_ln + (r * 2 + half) * 2) = make_float2(s, sq);
-                __syncthreads();
+                switch (quad) {                            // only the two warps that share these 32 rows (warp, warp + 4);
+                    case 0: named_barrier(1, 64); break;   // literal ids keep the kernel at five hardware barriers
+                    case 1: named_barrier(2, 64); break;
+                    case 2: named_barrier(3, 64); break;
+                    default: named_barrier(4, 64); break;
+                }
                 const float4 a = *reinterpret_cast<const float4*>(s_ln + r * 4);
                 const float mean = (a.x + a.z) * (1.f / 64.f);
                 const float rstd = rsqrtf(fmaxf((a.y + a.w) * (1.f / 64.f) - mean * mean, 0.f) + 1e-5f);
