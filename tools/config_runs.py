@@ -51,7 +51,25 @@ acc = ev.new_metrics()
 ms = timeit(lambda: ev.evaluate_poses(pr, gt, accum=acc))
 out["config3_eval_100k"] = {"clips": n, "ms": ms, "clips_per_s": n / ms * 1e3, "gbs": n * 64 * 104 * 8 / ms / 1e6,
                             "frac_of_hbm": n * 64 * 104 * 8 / ms / 1e6 / PEAK}
+sm = ev.new_smoothness()
+ms = timeit(lambda: ev.evaluate_smoothness(pr, accum=sm, from_pose=True))
+out["smoothness_jerk_100k"] = {"clips": n, "ms": ms, "clips_per_s": n / ms * 1e3, "gbs": n * 64 * 104 * 4 / ms / 1e6,
+                               "frac_of_hbm": n * 64 * 104 * 4 / ms / 1e6 / PEAK}
 del gt, pr
+
+# PATS-native front ends: 4.27 s clips, log_mel_400 at 16 kHz and log_mel_512 at 44.1 kHz
+pa = importlib.import_module("audio-to-motion-generation_b200.pats_audio")
+pats = []
+for name, sr, fn in (("log_mel_400", 16000, lambda w: pa.log_mel_400(w, 16000)), ("log_mel_512", 44100, lambda w: pa.log_mel_512(w, 44100))):
+    for B in (256, 4096):
+        wav = 0.1 * torch.randn(B, int(round(sr * 64 / 15)), device="cuda")
+        y = fn(wav)
+        ms = timeit(lambda: fn(wav), iters=5)
+        byt = wav.numel() * 4 + y.numel() * 4
+        pats.append({"front_end": name, "clips": B, "samples": wav.shape[1], "frames": y.shape[1], "ms": ms,
+                     "clips_per_s": B / ms * 1e3, "gbs": byt / ms / 1e6, "frac_of_hbm": byt / ms / 1e6 / PEAK})
+        del wav, y
+out["pats_front_ends"] = pats
 
 torch.manual_seed(0)
 model = mods["real_motion_model"].SelfAttention_G().cuda().eval()
