@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <cstdlib>
+#include <atomic>
 
 #include "../../include/a2m_b200.h"
 
@@ -32,6 +33,18 @@ void a2m_set_error(const char* fmt, ...);
 #define A2M_LAUNCH_CHECK() A2M_CUDA_CHECK(cudaGetLastError())
 
 int a2m_num_sms();   // cached SM count of the current device
+
+// cudaFuncSetAttribute (opt-in dynamic shared memory) is per device: remembers, per device ordinal, whether the calling
+// launch site has configured its kernel there.  `if (flag.first()) { cudaFuncSetAttribute(...); }`
+struct A2mPerDeviceOnce {
+    std::atomic<unsigned long long> mask[2];
+    bool first() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long bit = 1ull << (d & 63);
+        return (mask[(d >> 6) & 1].fetch_or(bit) & bit) == 0;
+    }
+};
 
 // Launch with programmatic dependent launch (PDL): the kernel may start while its predecessor in the stream is
 // still draining; it must execute pdl_wait() before it touches anything the predecessor wrote (or may still read).

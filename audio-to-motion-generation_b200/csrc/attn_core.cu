@@ -249,10 +249,9 @@ int attn_core_plan(const __nv_bfloat16* qkv, const float* gamma, const __nv_bflo
 }
 
 int attn_core_launch(const AttnCorePlan& plan, int* err_flag, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static A2mPerDeviceOnce configured;
+    if (configured.first()) {
         A2M_CUDA_CHECK(cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        configured = true;
     }
     A2M_CUDA_CHECK(a2m_launch_pdl(attn_core_kernel, plan.grid, dim3(kThreads), kSmemBytes, stream, plan.p, err_flag));
     a2m_count_launch();

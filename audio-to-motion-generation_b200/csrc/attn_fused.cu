@@ -339,10 +339,9 @@ int attn_fused_plan(const __nv_bfloat16* w_qkv, const float* bias_qkv, const flo
 }
 
 int attn_fused_launch(const AttnFusedPlan& plan, int* err_flag, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static A2mPerDeviceOnce configured;
+    if (configured.first()) {
         A2M_CUDA_CHECK(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        configured = true;
     }
     A2M_CUDA_CHECK(a2m_launch_pdl(attn_fused_kernel, dim3(plan.grid), dim3(kThreads), kSmemBytes, stream, plan.p, err_flag));
     a2m_count_launch();

@@ -354,11 +354,10 @@ int make_map(CUtensorMap* map, const void* ptr, int rank, const long long* dims,
 
 template <int BLOCK_N, int STAGES, int CLUSTER>
 int launch_variant(const ConvGemmPlan& plan, int* err_flag, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static A2mPerDeviceOnce configured;
+    if (configured.first()) {
         A2M_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Smem<BLOCK_N, STAGES>::kTotal));
-        configured = true;
     }
     A2M_CUDA_CHECK(a2m_launch_pdl_cluster(conv_gemm_kernel<BLOCK_N, STAGES, CLUSTER>, plan.grid, dim3(kThreads),
                                           Smem<BLOCK_N, STAGES>::kTotal, stream, CLUSTER, plan.p, plan.bias, plan.out, err_flag));

@@ -7,19 +7,24 @@
 //     j in N(i) + {i}, alpha = softmax_j(e_ij), out_i = mean_heads(sum_j alpha_ij h_j) + bias
 //   GraphConv(64, 64), aggr = add:        out_i = W_rel (sum_{j in N(i)} x_j) + b_rel + W_root x_i
 //
+// Three generations of the kernel live in this file; the last one runs, the others are A/B aids (A2M_GNN_V3 / A2M_GNN_V2):
+//   v4 (namespace v4, default): aggregate first -- Z^h = P^h X, the fp32 Z^h converted and written back to TENSOR MEMORY
+//      as the bf16 A operand, OUT = sum_h Z^h W_h^T; 2 CTAs per SM; see the comment above namespace v4
+//   v3: linear first per head (H^h = X W_h^T staged through shared memory as the B operand of OUT += P^h H^h), 2 CTAs per SM
+//   v2: the same with all heads at once, one 512-thread CTA per SM
 // Everything that is a contraction runs on the tensor cores, including the neighbourhood aggregation:
-// a tile is 128 node rows = whole graphs (3 hand graphs or 12 body graphs), and per layer
+// a tile is 128 node rows = whole graphs (3 hand graphs or 12 body graphs); the description below is v2's layer math,
+// which v3 / v4 re-order but do not change:
 //   GAT:   [H | S] = X [W | U]^T           (tcgen05, N = 256 + 16; U = W^T a_src / W^T a_dst folded at load, so the
-//                                           attention logits s_src, s_dst come out of the same MMA, hi + lo split)
+//                                           attention logits s_src, s_dst come out of the same MMA as H, hi + lo split)
 //          P^h     = softmax rows (fp32, CUDA cores; <= 7 entries per row) scattered as bf16 into a dense
 //                    block-diagonal [128 x 128] matrix in shared memory (zeros elsewhere, written once)
 //          OUT     = sum_h P^h H^h          (tcgen05, A = P^h K-major, B = H^h staged as bf16 in shared memory and
 //                                           read MN-major; the head mean is folded into P)
 //   GraphConv: AGG = Adj X (tcgen05, B = the node tile itself read MN-major), OUT = AGG W_rel^T + X W_root^T
-// The epilogue threads (4 per node row, 16 features each, residual stream in fp32 registers) do the softmax,
-// bias, LayerNorm, LeakyReLU and residual.  One persistent CTA per SM; node tiles arrive by TMA (double
-// buffered, prefetched one tile ahead) and leave by TMA store; per-layer weights stream through one 34 KB
-// shared-memory buffer by TMA, prefetched as soon as the MMA that reads the previous layer's has completed.
+// The row threads (residual stream in fp32 registers) do the softmax, bias, LayerNorm, LeakyReLU and residual.  Persistent
+// CTAs; node tiles arrive by TMA and leave by TMA store; per-layer weights stream through shared memory by TMA,
+// prefetched as soon as the MMA that reads the previous slice has completed.
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
@@ -1303,12 +1308,11 @@ int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_groups,
 }
 
 int gnn_fused_launch(const GnnFusedPlan& plan, int* err_flag, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static A2mPerDeviceOnce configured;
+    if (configured.first()) {
         A2M_CUDA_CHECK(cudaFuncSetAttribute(gnn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         A2M_CUDA_CHECK(cudaFuncSetAttribute(v3::gnn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::kSmemBytes3));
         A2M_CUDA_CHECK(cudaFuncSetAttribute(v4::gnn4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v4::kSmemBytes4));
-        configured = true;
     }
     if (plan.use_v4) {
         A2M_CUDA_CHECK(a2m_launch_pdl(v4::gnn4_kernel, dim3(plan.grid), dim3(v4::kThreads4), v4::kSmemBytes4, stream, plan.p3, err_flag));

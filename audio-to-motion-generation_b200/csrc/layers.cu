@@ -575,10 +575,9 @@ static int launch_attention_t(const __nv_bfloat16* qkv, const __nv_bfloat16* x, 
                               const float* gamma, int B, int C, __nv_bfloat16* out, cudaStream_t stream) {
     const int d = C / 8;
     const size_t smem = (2 * static_cast<size_t>(T) * (d + 4) + static_cast<size_t>(T) * (T + 1)) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static A2mPerDeviceOnce configured;
+    if (configured.first()) {
         A2M_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured = true;
     }
     A2M_ARG_CHECK(smem <= 100 * 1024, "attention: T %d x C %d needs %zu B of shared memory", T, C, smem);
     attention_kernel<T><<<B, 256, smem, stream>>>(qkv, x, res2, gamma, C, out);

@@ -382,10 +382,9 @@ static int launch_logmel(const a2m_mel_plan* plan, const float* wav, int64_t n_c
 
     A2M_ARG_CHECK(n_tiles <= 0x7fffffffLL && frames <= 0x7fffffffLL, "%s: %lld tiles", who, n_tiles);
     const SmemLayout L = smem_layout(g.n_mel, g.nnz, kMagOnly);
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[kMagOnly]) {
+    static A2mPerDeviceOnce attr_set;                       // one instance per template instantiation
+    if (attr_set.first()) {
         A2M_CUDA_CHECK(cudaFuncSetAttribute(logmel_kernel<kMagOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        attr_set[kMagOnly] = true;
     }
     long long grid = 2LL * a2m_num_sms();
     if (grid > n_tiles) grid = n_tiles;

@@ -300,11 +300,9 @@ extern "C" int a2m_melspec_f32(const a2m_melspec_plan* plan, const float* wav, i
     g.n_items = static_cast<long long>(g.chunks_per_clip) * n_clips;
     const int smem = kSmemFixedWide + 4 * ((plan->nnz + 3) & ~3);
     A2M_ARG_CHECK(smem <= 100 * 1024, "a2m_melspec_f32: %d bytes of shared memory", smem);
-    static int attr_bytes = 0;
-    if (smem > attr_bytes) {
-        A2M_CUDA_CHECK(cudaFuncSetAttribute(melspec_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_bytes = smem;
-    }
+    static A2mPerDeviceOnce attr_set;
+    if (attr_set.first())                                  // the cap of the argument check above: covers every plan
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(melspec_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     long long grid = 4LL * a2m_num_sms();
     if (grid > g.n_items) grid = g.n_items;
     melspec_wide_kernel<<<static_cast<unsigned>(grid), kThreadsW, smem, static_cast<cudaStream_t>(stream)>>>(
