@@ -136,7 +136,7 @@ class AudioToPosePipeline:
     FRONT_ENDS = ("vggish", "log_mel_400", "log_mel_512")
 
     def __init__(self, model, alpha=0.2, comm=None, lanes=2, graphs=False, smoothness=False, front_end="vggish",
-                 sample_rate=None):
+                 sample_rate=None, adapter_frames_only=False):
         """`lanes` > 1 runs consecutive batches on alternating CUDA streams, each lane with its own packed
         weights and activation arena, so the latency-bound tail of one batch (graph decoders, small GEMMs)
         overlaps the head of the next.  `graphs=True` captures each lane's whole step (about 60 launches, the
@@ -146,11 +146,17 @@ class AudioToPosePipeline:
         configs name), or the PATS-native "log_mel_400" (64 bands) / "log_mel_512" (128 bands at `sample_rate`, the
         representation the shipped training configuration reads; pats/data_loading/audio.py).  All are fed to the
         generator through the same stride-6 adapter.
+        `adapter_frames_only=True` ("vggish" front end) computes only the log-mel frames the stride-6 adapter feeds to the
+        generator (hop 60 ms = 6 x 10 ms: frame t of that transform is frame 6 t of the full one, bit for bit) instead of
+        all 425 -- an end-to-end shortcut; off by default, and never used by bench.py's headline.
         `smoothness=True` also accumulates the validation loop's temporal-smoothness and jerk metrics of the generated
         poses (version5_model_train.py:456-459), one more small kernel per step."""
         if front_end not in self.FRONT_ENDS:
             raise ValueError("front_end must be one of %s, got %r" % (self.FRONT_ENDS, front_end))
         self.front_end = front_end
+        if adapter_frames_only and front_end != "vggish":
+            raise ValueError("adapter_frames_only is implemented for the 'vggish' front end")
+        self.adapter_frames_only = bool(adapter_frames_only)
         self.sample_rate = sample_rate if sample_rate is not None else (44100 if front_end == "log_mel_512" else 16000)
         self.model = model
         self.alpha = alpha
@@ -195,8 +201,16 @@ class AudioToPosePipeline:
 
     def generate(self, wav, model=None):
         """wav [B, N] fp32 CUDA tensor -> pose [B, 64, 104] fp32 (on the current stream)."""
-        logmel = self.features(wav)
-        pose, _ = (model or self.model)(adapter(logmel))
+        if self.adapter_frames_only:
+            # frames 0, 6, 12, ... only: same window, hop = ADAPTER_STRIDE x 10 ms
+            logmel = audio_repr.log_mel_spectograms(wav, audio_sample_rate=self.sample_rate,
+                                                    hop_length_secs=0.010 * ADAPTER_STRIDE)
+            if logmel.shape[1] < POSE_FRAMES:
+                raise ValueError("the audio gives %d adapter frames, the generator needs %d" % (logmel.shape[1], POSE_FRAMES))
+            x = logmel[:, :POSE_FRAMES, :]
+        else:
+            x = adapter(self.features(wav))
+        pose, _ = (model or self.model)(x)
         return pose
 
     def generate_long(self, wav, window_hop=WINDOW_HOP, model=None):

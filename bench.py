@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=2, help="CUDA-stream lanes consecutive batches alternate over")
     ap.add_argument("--graphs", type=int, default=0, help="1: replay each lane's step as a CUDA graph (measured: no gain "
                     "over two eager stream lanes, which already hide the launch gaps)")
+    ap.add_argument("--adapter-frames-only", type=int, default=0, help="1: compute only the 64 log-mel frames the adapter "
+                    "feeds to the generator (an end-to-end shortcut; NOT the headline configuration, which produces all 425)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     out = _claim_stdout()
@@ -201,7 +203,8 @@ def main():
                 p.copy_(0.1 * torch.randn(p.shape, generator=g))
     model = model.to(device).eval()
     comm = pipeline.Communicator(rank, world, device) if world > 1 else None
-    pipe = pipeline.AudioToPosePipeline(model, comm=comm, lanes=args.lanes, graphs=bool(args.graphs))
+    pipe = pipeline.AudioToPosePipeline(model, comm=comm, lanes=args.lanes, graphs=bool(args.graphs),
+                                        adapter_frames_only=bool(args.adapter_frames_only))
 
     # ---- synthetic inputs: per-clip seeds make any sharding reproduce the same clips -----------------
     B = args.batch
@@ -326,6 +329,7 @@ def main():
                                        "mel + SelfAttention_G forward + L1/PCK" % B,
                            "clips_per_step_per_gpu": B, "parallelism": "clip-sharded x%d" % world,
                            "stream_lanes": args.lanes, "cuda_graphs": bool(args.graphs),
+                           "mel_frames": "64 adapter frames only (shortcut)" if args.adapter_frames_only else "all 425 per clip",
                            "l2": "inputs cycle through %d distinct batches (%.0f MB each) > L2" % (POOL, h2d / 1e6)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,

@@ -162,3 +162,22 @@ def test_pats_front_end_f128_matches_oracle_composition(setup):
     assert out["pck_hits"] == ref["pck_hits"] and out["n_frames"] == 128
     with pytest.raises(ValueError):
         pipeline.AudioToPosePipeline(model, front_end="mfcc")
+
+
+def test_adapter_frames_only_is_bit_identical(setup):
+    """Computing only the 64 log-mel frames the adapter picks (hop 960 samples) gives the same frames, poses and
+    metrics as computing all 425 and slicing."""
+    pipeline, model, _ = setup
+    wav, gt = synth.wav_batch(80, 4), synth.gt_pose_batch(80, 4)
+    mods = importlib.import_module(PKG).install_dropin()
+    lm = mods["pose_video.audio_repr"].log_mel_spectograms
+    w = torch.from_numpy(wav).cuda()
+    dense = lm(w)[:, 0:384:6, :]
+    sparse = lm(w, hop_length_secs=0.06)[:, :64, :]
+    assert torch.equal(dense, sparse)
+    full, p_full = run(pipeline, model, 1, [(wav, gt)])
+    pipe = pipeline.AudioToPosePipeline(model, lanes=1, adapter_frames_only=True)
+    p_sparse = pipe.step(w, torch.from_numpy(gt).cuda())
+    out = pipe.finish()
+    assert torch.equal(p_sparse.cpu(), p_full[0])
+    assert out["pck_hits"] == full["pck_hits"] and out["abs_pose"] == full["abs_pose"]
