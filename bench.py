@@ -171,7 +171,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world, out)
-    args.warmup = max(args.warmup, 3)
+    args.warmup = max(args.warmup, 3, args.lanes)      # every lane builds its launch program on its first step
 
     import torch
     import torch.distributed as dist
