@@ -4,6 +4,9 @@
 //     P = exp(S - rowmax) restricted to the row's own clip           -> CUDA cores, one thread per row
 //     O = P v                                                        -> tcgen05 (B = v read MN-major)
 //     out = gamma * O / rowsum + x (+ res2: the ResBlock skip, :190) -> bf16
+// Optionally the ChannelAttention that follows the block in the hand decoder (model_layers.py:167-174) is applied in
+// the epilogue: the CTA holds whole clips, so the per-clip average / maximum over time, the 256 -> 32 -> 256 MLP and the
+// per-channel rescale need nothing from outside the tile (one launch and one [B, T, 256] round trip less).
 // One CTA owns 128 consecutive rows = 128 / T whole clips (T in {8, 16, 32, 64}); q, k, v, S and O never leave
 // the SM (TMEM accumulators, bf16 operand tiles in shared memory).  Replaces a GEMM launch + an attention
 // launch and the [B, T, 320] bf16 round trip through L2 between them.
@@ -45,6 +48,12 @@ struct AttnParams {
     __nv_bfloat16* out;
     long long n_rows;
     int T;
+    // optional ChannelAttention applied to the block's output (model_layers.py:167-174), hand decoder order
+    // SelfAttention -> ChannelAttention: out * (sigmoid(mlp(avg_T out)) + sigmoid(mlp(max_T out))); hidden = 32
+    const float* ca_w0;       // fc.0.weight [32][256]; NULL = no channel attention
+    const float* ca_b0;       // [32]
+    const float* ca_w2;       // fc.2.weight transposed [32][256]
+    const float* ca_b2;       // [256]
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -281,6 +290,11 @@ attn_fused_kernel(const __grid_constant__ AttnParams p, int* __restrict__ err_fl
     tc_fence_after();
 
     // ---------------- out = gamma * O / rowsum + x (+ res2) ----------------
+    const bool chan = p.ca_w0 != nullptr;                 // kernel-uniform
+    // with channel attention the bf16 output tile goes to the (drained) operand ring first, rows padded to 528 B so that
+    // both the row-wise 16-byte stores and the column walks of the pooling are conflict-free
+    constexpr int kRowB = 2 * kC + 16;
+    unsigned char* s_o = smem;
     {
         const float scale = __ldg(p.gamma) / s_sum[r];
 #pragma unroll
@@ -288,22 +302,82 @@ attn_fused_kernel(const __grid_constant__ AttnParams p, int* __restrict__ err_fl
             uint32_t t[32];
             tmem_ld_32x32(tmem_lane + q * 64 + hf * 32, t);
             tmem_ld_wait();
-            if (live) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint4 xq = xv[hf * 4 + c], rq = rv[hf * 4 + c];
-                    const uint32_t xs[4] = {xq.x, xq.y, xq.z, xq.w}, rs[4] = {rq.x, rq.y, rq.z, rq.w};
-                    uint32_t os[4];
+            for (int c = 0; c < 4; ++c) {
+                const uint4 xq = xv[hf * 4 + c], rq = rv[hf * 4 + c];
+                const uint32_t xs[4] = {xq.x, xq.y, xq.z, xq.w}, rs[4] = {rq.x, rq.y, rq.z, rq.w};
+                uint32_t os[4];
 #pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                        const float a = scale * __uint_as_float(t[c * 8 + 2 * e2]) + __uint_as_float(xs[e2] << 16) +
-                                        __uint_as_float(rs[e2] << 16);
-                        const float b = scale * __uint_as_float(t[c * 8 + 2 * e2 + 1]) + __uint_as_float(xs[e2] & 0xffff0000u) +
-                                        __uint_as_float(rs[e2] & 0xffff0000u);
-                        os[e2] = pack2(a, b);
-                    }
-                    *reinterpret_cast<uint4*>(p.out + base + hf * 32 + c * 8) = make_uint4(os[0], os[1], os[2], os[3]);
+                for (int e2 = 0; e2 < 4; ++e2) {
+                    const float a = scale * __uint_as_float(t[c * 8 + 2 * e2]) + __uint_as_float(xs[e2] << 16) +
+                                    __uint_as_float(rs[e2] << 16);
+                    const float b = scale * __uint_as_float(t[c * 8 + 2 * e2 + 1]) + __uint_as_float(xs[e2] & 0xffff0000u) +
+                                    __uint_as_float(rs[e2] & 0xffff0000u);
+                    os[e2] = pack2(a, b);
                 }
+                const uint4 o4 = make_uint4(os[0], os[1], os[2], os[3]);
+                if (chan) *reinterpret_cast<uint4*>(s_o + r * kRowB + (q * 64 + hf * 32 + c * 8) * 2) = o4;
+                else if (live) *reinterpret_cast<uint4*>(p.out + base + hf * 32 + c * 8) = o4;
+            }
+        }
+    }
+    if (chan) {
+        float* s_avg = reinterpret_cast<float*>(smem + 128 * kRowB);       // [clips][256]
+        const int clips = 128 / T;
+        float* s_max = s_avg + clips * kC;                                 // [clips][256]
+        float* s_scale = s_max + clips * kC;                               // [clips][256]
+        float* s_hid = s_scale + clips * kC;                               // [clips][2][32]
+        __syncthreads();
+        for (int item = tid; item < clips * kC; item += kThreads) {         // per clip and channel: mean and max over time
+            const int clip = item >> 8, c = item & (kC - 1);
+            const unsigned char* col = s_o + (clip * T) * kRowB + c * 2;
+            float sum = 0.f, mx = -INFINITY;
+            for (int t = 0; t < T; ++t) {
+                const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(col + t * kRowB));
+                sum += v;
+                mx = fmaxf(mx, v);
+            }
+            s_avg[item] = sum / static_cast<float>(T);
+            s_max[item] = mx;
+        }
+        __syncthreads();
+        for (int u = warp; u < clips * 64; u += kThreads / 32) {            // hidden units: relu(w0 . pooled + b0), 32 per branch
+            const int clip = u >> 6, which = (u >> 5) & 1, unit = u & 31;
+            const float* src = (which ? s_max : s_avg) + clip * kC;
+            const int lane = tid & 31;
+            float acc = 0.f;
+            for (int k = lane; k < kC; k += 32) acc = fmaf(__ldg(p.ca_w0 + unit * kC + k), src[k], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) s_hid[u] = fmaxf(acc + __ldg(p.ca_b0 + unit), 0.f);
+        }
+        __syncthreads();
+        for (int item = tid; item < clips * kC; item += kThreads) {
+            const int clip = item >> 8, c = item & (kC - 1);
+            const float* h = s_hid + clip * 64;
+            float za = __ldg(p.ca_b2 + c), zm = za;
+#pragma unroll 8
+            for (int u = 0; u < 32; ++u) {
+                const float w = __ldg(p.ca_w2 + u * kC + c);
+                za = fmaf(w, h[u], za);
+                zm = fmaf(w, h[32 + u], zm);
+            }
+            s_scale[item] = 1.f / (1.f + __expf(-za)) + 1.f / (1.f + __expf(-zm));       // sigmoid each, then add
+        }
+        __syncthreads();
+        if (live) {
+            const float* sc = s_scale + (r / T) * kC + q * 64;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 mine = *reinterpret_cast<const uint4*>(s_o + r * kRowB + (q * 64 + i * 8) * 2);
+                const uint32_t ov[4] = {mine.x, mine.y, mine.z, mine.w};
+                uint32_t o4[4];
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                    const uint32_t v = ov[e2];
+                    const int c = i * 8 + e2 * 2;
+                    o4[e2] = pack2(__uint_as_float(v << 16) * sc[c], __uint_as_float(v & 0xffff0000u) * sc[c + 1]);
+                }
+                *reinterpret_cast<uint4*>(p.out + base + i * 8) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
             }
         }
     }
@@ -322,7 +396,8 @@ struct AttnFusedPlan {
 bool attn_fused_supported(int T, int C) { return C == kC && T >= 8 && T <= 64 && (128 % T) == 0; }
 
 int attn_fused_plan(const __nv_bfloat16* w_qkv, const float* bias_qkv, const float* gamma, const __nv_bfloat16* x,
-                    const __nv_bfloat16* res2, int B, int T, int C, __nv_bfloat16* out, std::shared_ptr<AttnFusedPlan>* plan_out) {
+                    const __nv_bfloat16* res2, int B, int T, int C, __nv_bfloat16* out, std::shared_ptr<AttnFusedPlan>* plan_out,
+                    const float* ca_w0, const float* ca_b0, const float* ca_w2, const float* ca_b2) {
     A2M_ARG_CHECK(attn_fused_supported(T, C), "attn_fused: T = %d, C = %d not supported", T, C);
     auto plan = std::make_shared<AttnFusedPlan>();
     AttnParams& p = plan->p;
@@ -333,6 +408,7 @@ int attn_fused_plan(const __nv_bfloat16* w_qkv, const float* bias_qkv, const flo
     rc = make_weight_map(&p.w_map, w_qkv, kNqkv, kC, 160);
     if (rc != A2M_OK) return rc;
     p.bias = bias_qkv; p.gamma = gamma; p.x = x; p.res2 = res2; p.out = out; p.n_rows = rows; p.T = T;
+    p.ca_w0 = ca_w0; p.ca_b0 = ca_b0; p.ca_w2 = ca_w2; p.ca_b2 = ca_b2;
     plan->grid = static_cast<int>((rows + 127) / 128);
     *plan_out = plan;
     return A2M_OK;

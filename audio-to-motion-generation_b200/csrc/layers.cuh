@@ -29,7 +29,9 @@ int launch_attention(const __nv_bfloat16* qkv, const __nv_bfloat16* x, const __n
 struct AttnFusedPlan;
 bool attn_fused_supported(int T, int C);
 int attn_fused_plan(const __nv_bfloat16* w_qkv, const float* bias_qkv, const float* gamma, const __nv_bfloat16* x,
-                    const __nv_bfloat16* res2, int B, int T, int C, __nv_bfloat16* out, std::shared_ptr<AttnFusedPlan>* plan);
+                    const __nv_bfloat16* res2, int B, int T, int C, __nv_bfloat16* out, std::shared_ptr<AttnFusedPlan>* plan,
+                    const float* ca_w0 = nullptr, const float* ca_b0 = nullptr, const float* ca_w2 = nullptr,
+                    const float* ca_b2 = nullptr);      // ca_*: optional ChannelAttention (hidden 32) fused into the epilogue
 int attn_fused_launch(const AttnFusedPlan& plan, int* err_flag, cudaStream_t stream);
 
 // Tensor-core attention core for the wide UNet attentions (csrc/attn_core.cu), after the q|k|v GEMM: T must divide

@@ -528,14 +528,22 @@ struct Emit {
         }
     }
 
+    // SelfAttention followed by ChannelAttention (the hand decoder's order): one kernel when the fused block applies
+    bool attention_then_channel(const AttnW& A, const ChanW& W, const __nv_bfloat16* x, int len, int B, __nv_bfloat16* out) {
+        static const bool unfused = getenv("A2M_NO_CHAN_FUSION") != nullptr;       // A/B aid
+        if (unfused || !attn_fused_supported(len, A.C) || W.C != A.C || W.hidden != 32) return false;
+        attention(A, x, nullptr, len, B, nullptr, out, &W);
+        return true;
+    }
     void attention(const AttnW& A, const __nv_bfloat16* x, const __nv_bfloat16* res2, int len, int B, __nv_bfloat16* qkv,
-                   __nv_bfloat16* out) {
+                   __nv_bfloat16* out, const ChanW* chan = nullptr) {
         const int C = A.C, ld = 2 * (C / 8) + C;
         const float* gamma = A.gamma;
         if (attn_fused_supported(len, C)) {               // decoder blocks: projection + attention in one kernel
             if (dry || rc != A2M_OK) return;
             std::shared_ptr<AttnFusedPlan> ap;
-            rc = attn_fused_plan(A.qkv.w, A.qkv.bias, gamma, x, res2, B, len, C, out, &ap);
+            rc = chan ? attn_fused_plan(A.qkv.w, A.qkv.bias, gamma, x, res2, B, len, C, out, &ap, chan->w0, chan->b0, chan->w2, chan->b2)
+                      : attn_fused_plan(A.qkv.w, A.qkv.bias, gamma, x, res2, B, len, C, out, &ap);
             if (rc != A2M_OK) return;
             int* flag = m->err_flag;
             op([ap, flag](cudaStream_t s) { return attn_fused_launch(*ap, flag, s); });
@@ -716,8 +724,10 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
                 E.channel(D.pre_chan, t1, T, B, t2);
                 E.attention(D.pre_attn, t2, nullptr, T, B, qkv, t3);
             } else {
-                E.attention(D.pre_attn, t1, nullptr, T, B, qkv, t2);
-                E.channel(D.pre_chan, t2, T, B, t3);
+                if (!E.attention_then_channel(D.pre_attn, D.pre_chan, t1, T, B, t3)) {
+                    E.attention(D.pre_attn, t1, nullptr, T, B, qkv, t2);
+                    E.channel(D.pre_chan, t2, T, B, t3);
+                }
             }
             E.tag = dn + ".proj_in";
             E.linear_rows(D.proj_in, t3, nullptr, 256, static_cast<long long>(BT), xa, static_cast<long long>(J) * 64, 0, kOutBf16);
@@ -748,9 +758,13 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
             E.tag = dn + ".post_conv";
             E.conv_k3(D.post_conv, t4, 256, nullptr, 0, T, B, t1);
             E.tag = dn + ".post_attn";
-            E.attention(D.post_attn, t1, nullptr, T, B, qkv, t2);
             const __nv_bfloat16* last = t2;
-            if (D.has_post_chan) { E.channel(D.post_chan, t2, T, B, t3); last = t3; }
+            if (D.has_post_chan && E.attention_then_channel(D.post_attn, D.post_chan, t1, T, B, t3)) {
+                last = t3;
+            } else {
+                E.attention(D.post_attn, t1, nullptr, T, B, qkv, t2);
+                if (D.has_post_chan) { E.channel(D.post_chan, t2, T, B, t3); last = t3; }
+            }
             E.tag = dn + ".logits";
             // logits: fp32 straight into pose[B, T, 104] at this branch's column block
             E.linear_rows(D.logits, last, nullptr, 256, static_cast<long long>(BT), pose_stage, kPoseFeats,
