@@ -76,6 +76,8 @@ SIGNATURES = {
     "a2m_model_forward": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
     "a2m_model_set_output_denorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "a2m_model_timeline_begin": (c_int, [c_void_p, c_i64, c_int, c_int, c_int]),
+    "a2m_model_timeline_read": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int]),
     "a2m_model_encoder_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p]),
     "a2m_model_unet_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "a2m_model_gnn_forward": (c_int, [c_void_p, c_int, c_void_p, c_i64, c_void_p, c_void_p]),

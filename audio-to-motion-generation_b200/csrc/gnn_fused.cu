@@ -822,6 +822,9 @@ gnn3_kernel(const __grid_constant__ Gnn3Params p, int* __restrict__ err_flag) {
 // TMEM (256 columns, two CTAs per SM): OUT [0,64)  Zf [64,192) (two heads, fp32)  Zb [192,256) (two heads, bf16 A
 // operand; the 16 logit columns S alias its start -- S is dead before the first Zb store).
 // Weight slices (8 KB: one head / W_rel / W_root) stream through a three-slot ring, three ahead.
+// Tried and dropped: four threads per row (512 threads, 16 features and one head each, 64 registers per thread, still two
+// CTAs per SM).  Twice the warps did not hide the round trips: 717 us instead of 509 us for the hand stack (spills, twice
+// the barrier participants); one warp polling the mbarriers while the rest park on bar.sync changed nothing either.
 // =====================================================================================================
 namespace v4 {
 
@@ -1205,6 +1208,8 @@ gnn4_kernel(const __grid_constant__ Gnn3Params p, int* __restrict__ err_flag) {
 }
 
 }  // namespace v4
+
+
 
 // U rows of the extended GAT weight: the attention logits a_src . (W_h x) = (W_h^T a_src) . x come out of the
 // same MMA as H.  Rows 256+h: src (hi), 260+h: dst (hi), 264+h: src (lo), 268+h: dst (lo); hi + lo carries

@@ -93,6 +93,9 @@ struct a2m_model {
     int* parents = nullptr;
     double* loss_scratch = nullptr;
     float* denorm = nullptr;                    // [2][104] mean | std of the optional output de-normalisation
+    // optional timeline (a2m_model_timeline_*): one event after every op of every recorded forward
+    std::vector<cudaEvent_t> tl_events;
+    int tl_capacity = 0, tl_steps = 0, tl_ops = 0;
     bool denorm_on = false;
     int* err_flag = nullptr;
     bool has_encoder = false, has_unet = false, has_decoders = false;
@@ -800,12 +803,25 @@ int check_shape(long long B, int T, int F, const char* who) {
     return A2M_OK;
 }
 
-int run_ops(ForwardPlan* P, int lo, int hi, cudaStream_t s) {
+int run_ops(ForwardPlan* P, int lo, int hi, cudaStream_t s, a2m_model* m = nullptr) {
+    const bool rec = m != nullptr && m->tl_steps < m->tl_capacity && m->tl_ops == static_cast<int>(P->ops.size());
     for (int i = lo; i < hi; ++i) {
         const int rc = P->ops[i](s);
         if (rc != A2M_OK) return rc;
+        if (rec) A2M_CUDA_CHECK(cudaEventRecord(m->tl_events[static_cast<size_t>(m->tl_steps) * (m->tl_ops + 1) + 1 + i], s));
     }
     return A2M_OK;
+}
+
+cudaEvent_t timeline_reference(int device) {          // one reference event per device, shared by every handle (lanes)
+    static cudaEvent_t ref[64] = {};
+    if (device < 0 || device >= 64) return nullptr;
+    if (!ref[device]) {
+        if (cudaEventCreate(&ref[device]) != cudaSuccess) return nullptr;
+        cudaEventRecord(ref[device], 0);
+        cudaEventSynchronize(ref[device]);
+    }
+    return ref[device];
 }
 
 }  // namespace
@@ -861,6 +877,7 @@ extern "C" void a2m_model_destroy(a2m_model* m) {
     cudaDeviceSynchronize();
     m->plans.clear();
     for (void* p : m->owned) cudaFree(p);
+    for (cudaEvent_t e : m->tl_events) cudaEventDestroy(e);
     if (m->side_stream) cudaStreamDestroy(m->side_stream);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
@@ -881,21 +898,24 @@ extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t mel_str
     m->cur_mel = mel; m->cur_stride_b = mel_stride_b; m->cur_stride_t = mel_stride_t;
     // trunk on the caller's stream, then body decoder (side stream) || hand decoder (caller's stream)
     static const bool single_stream = getenv("A2M_DEBUG_SINGLE_STREAM") != nullptr;   // debugging aid
+    const bool timeline = m->tl_steps < m->tl_capacity && m->tl_ops == static_cast<int>(P->ops.size());
+    if (timeline) A2M_CUDA_CHECK(cudaEventRecord(m->tl_events[static_cast<size_t>(m->tl_steps) * (m->tl_ops + 1)], s));    // step start
     if (single_stream) {
-        rc = run_ops(P, 0, static_cast<int>(P->ops.size()), s);
+        rc = run_ops(P, 0, static_cast<int>(P->ops.size()), s, m);
         if (rc != A2M_OK) return rc;
     } else {
-    rc = run_ops(P, 0, P->unet_end, s);
+    rc = run_ops(P, 0, P->unet_end, s, m);
     if (rc != A2M_OK) return rc;
     A2M_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
     A2M_CUDA_CHECK(cudaStreamWaitEvent(m->side_stream, m->ev_fork, 0));
-    rc = run_ops(P, P->unet_end, P->body_end, m->side_stream);
+    rc = run_ops(P, P->unet_end, P->body_end, m->side_stream, m);
     if (rc != A2M_OK) return rc;
     A2M_CUDA_CHECK(cudaEventRecord(m->ev_join, m->side_stream));
-    rc = run_ops(P, P->body_end, static_cast<int>(P->ops.size()), s);
+    rc = run_ops(P, P->body_end, static_cast<int>(P->ops.size()), s, m);
     if (rc != A2M_OK) return rc;
     A2M_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join, 0));
     }
+    if (timeline) ++m->tl_steps;
     float* stage = P->pose_stage;
     if (m->denorm_on) {     // x * std + mean (generate_motion_video.py:259-260) instead of the plain copy out of the arena
         rc = a2m_pose_denormalize_f32(stage, m->denorm, m->denorm + kPoseFeats, static_cast<int64_t>(B) * T, pose, stream);
@@ -908,6 +928,50 @@ extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t mel_str
                                 m->parents, m->loss_scratch, losses, s);
         if (rc != A2M_OK) return rc;
     }
+    return A2M_OK;
+}
+
+// Timeline of the next `steps` forwards of shape (B, T, F): an event after every op (and one at the start of each
+// forward), read back as milliseconds since a per-device reference event shared by all handles, so the lanes of a
+// pipeline line up.  Diagnostic (the events add small gaps); there is no nsys in this environment.
+extern "C" int a2m_model_timeline_begin(a2m_model* m, int64_t B, int T, int F, int steps) {
+    A2M_ARG_CHECK(m != nullptr && steps >= 1 && steps <= 64, "a2m_model_timeline_begin: bad argument");
+    int rc = check_shape(B, T, F, "a2m_model_timeline_begin");
+    if (rc != A2M_OK) return rc;
+    ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc);
+    if (!P) return rc;
+    A2M_CUDA_CHECK(cudaSetDevice(m->device));
+    A2M_ARG_CHECK(timeline_reference(m->device) != nullptr, "a2m_model_timeline_begin: no reference event");
+    for (cudaEvent_t e : m->tl_events) cudaEventDestroy(e);
+    m->tl_ops = static_cast<int>(P->ops.size());
+    m->tl_events.assign(static_cast<size_t>(steps) * (m->tl_ops + 1), nullptr);
+    for (auto& e : m->tl_events) A2M_CUDA_CHECK(cudaEventCreate(&e));
+    m->tl_capacity = steps;
+    m->tl_steps = 0;
+    return A2M_OK;
+}
+
+// out_ms_host: [recorded steps][n_ops + 1] (column 0 = the forward's start); returns the layout through the pointers.
+// Synchronises the device.  Ops [0, unet_end) and [body_end, n_ops) run on the caller's stream, [unet_end, body_end) on
+// the handle's side stream.
+extern "C" int a2m_model_timeline_read(a2m_model* m, float* out_ms_host, int capacity, int* steps_host, int* n_ops_host,
+                                       int* unet_end_host, int* body_end_host, int64_t B, int T, int F) {
+    A2M_ARG_CHECK(m != nullptr && steps_host && n_ops_host && unet_end_host && body_end_host, "a2m_model_timeline_read: NULL");
+    int rc = check_shape(B, T, F, "a2m_model_timeline_read");
+    if (rc != A2M_OK) return rc;
+    ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc);
+    if (!P) return rc;
+    A2M_CUDA_CHECK(cudaSetDevice(m->device));
+    A2M_CUDA_CHECK(cudaDeviceSynchronize());
+    *steps_host = m->tl_steps; *n_ops_host = m->tl_ops; *unet_end_host = P->unet_end; *body_end_host = P->body_end;
+    cudaEvent_t ref = timeline_reference(m->device);
+    const size_t n = static_cast<size_t>(m->tl_steps) * (m->tl_ops + 1);
+    for (size_t i = 0; i < n && static_cast<int>(i) < capacity; ++i) {
+        float ms = 0.f;
+        A2M_CUDA_CHECK(cudaEventElapsedTime(&ms, ref, m->tl_events[i]));
+        out_ms_host[i] = ms;
+    }
+    m->tl_capacity = 0;                                 // recording stops; the events stay until the next begin / destroy
     return A2M_OK;
 }
 

@@ -249,6 +249,14 @@ int a2m_model_forward(a2m_model* model, const float* mel, int64_t mel_stride_b, 
  * losses are still computed on the network's (normalised) output as in the reference.  mean, std: device
  * float[104], copied into the handle on `stream`; NULL, NULL switches it off. */
 int a2m_model_set_output_denorm(a2m_model* model, const float* mean, const float* std, void* stream);
+/* Diagnostic timeline (there is no nsys here): record an event after every launch-program op of the next `steps`
+ * forwards of shape (B, T, F); read them back as milliseconds since a per-device reference event that all handles
+ * share (so the stream lanes of a pipeline line up).  out_ms: [steps][n_ops + 1], column 0 = start of the forward;
+ * ops [0, unet_end) and [body_end, n_ops) run on the caller's stream, [unet_end, body_end) on the side stream.
+ * a2m_model_timeline_read synchronises the device.  Names: a2m_model_op_name. */
+int a2m_model_timeline_begin(a2m_model* model, int64_t B, int T, int F, int steps);
+int a2m_model_timeline_read(a2m_model* model, float* out_ms_host, int capacity, int* steps_host, int* n_ops_host,
+                            int* unet_end_host, int* body_end_host, int64_t B, int T, int F);
 int a2m_model_encoder_forward(a2m_model* model, const float* mel, int64_t B, int T, int F, float* out_nct, void* stream);
 /* UNet1D.forward (model_layers.py:341-374, D1): [B, 256, T] fp32 -> [B, 256, T] fp32 */
 int a2m_model_unet_forward(a2m_model* model, const float* x_nct, int64_t B, int T, float* out_nct, void* stream);
