@@ -514,7 +514,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, const void* w_packed, const float* bia
         // programmatically -- become resident while this layer's CTAs drain
         static const char* env = getenv("A2M_GEMM_STAGES2");
         const int mode = env ? atoi(env) : 1;
-        plan->stages = (mode && block_n == 128 && kb <= 16) ? 2 : 3;
+        plan->stages = (mode && block_n == 128 && (kb <= 16 || mode == 2)) ? 2 : 3;     // mode 2 (experiment): every 128-wide layer
     }
     plan->grid = dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>((d.N + block_n - 1) / block_n),
                       static_cast<unsigned>(d.split_k));
