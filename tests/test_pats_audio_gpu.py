@@ -83,3 +83,20 @@ def test_log_mel_512_zeros_batches_and_errors(pa):
         pa.log_mel_512(np.zeros(1024, np.float32), 44100)               # reflect needs > 1024 samples
     with pytest.raises(ValueError):
         pa.log_mel_512(wav[0], 44100, pad_mode="edge")
+
+
+def test_log_mel_512_ring_positions_and_determinism(pa):
+    """The kernel fetches only the hop's new samples per frame into a ring and walks chunks of 8 frames: a frame must
+    not depend on where it sits in its chunk.  Dropping 3 x 512 leading samples moves every interior frame to another
+    chunk position (and ring phase); zero padding keeps interior frames free of the boundary -> bit-equal.  Two runs of
+    the same launch are bit-equal too (no data race shows up as run-to-run noise)."""
+    y = torch.from_numpy(synth.wav_clip(90, 40000)).cuda()
+    a = pa.log_mel_512(y, 44100, pad_mode="constant")
+    for shift in (3, 5, 8):
+        b = pa.log_mel_512(y[512 * shift:], 44100, pad_mode="constant")
+        assert torch.equal(a[2 + shift:-2], b[2:-2 if shift == 0 else a.shape[0] - shift - 2]), shift
+    for _ in range(3):
+        assert torch.equal(pa.log_mel_512(y, 44100, pad_mode="constant"), a)
+    batch = torch.stack([y, y.flip(0), y * 0.5]).contiguous()
+    c = pa.log_mel_512(batch, 44100)
+    assert torch.equal(c[0], pa.log_mel_512(y, 44100))
