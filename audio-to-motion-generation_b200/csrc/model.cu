@@ -571,6 +571,21 @@ struct Emit {
     // ResBlock (model_layers.py:185-190): x -> conv1 -> conv2 -> attention -> + x
     void resblock(const ResW& R, const __nv_bfloat16* x, int len, int B, __nv_bfloat16* t1, __nv_bfloat16* t2,
                   __nv_bfloat16* qkv, __nv_bfloat16* out) {
+        // experimental, opt-in (A2M_RESBLOCK_FUSION=1): parity-green and 15 % faster than its three launches in isolation
+        // (50 vs 59 us), but it holds a whole SM (226 KB of shared memory) for that long, while the three small kernels
+        // interleave with the other stream lane -- in the pipeline the step got 3 % slower
+        static const bool fused = getenv("A2M_RESBLOCK_FUSION") != nullptr && atoi(getenv("A2M_RESBLOCK_FUSION")) != 0;
+        if (fused && resblock_fused_supported(len, 256) && R.c1.N == 256 && R.c2.N == 256 && R.attn.C == 256 &&
+            R.c1.act == kActLeaky && R.c2.act == kActLeaky) {                       // whole block in one kernel
+            if (dry || rc != A2M_OK) return;
+            std::shared_ptr<ResblockFusedPlan> rp;
+            rc = resblock_fused_plan(R.c1.w, R.c1.bias, R.c2.w, R.c2.bias, R.attn.qkv.w, R.attn.qkv.bias, R.attn.gamma, x, t2, B,
+                                     len, 256, out, &rp);
+            if (rc != A2M_OK) return;
+            int* flag = m->err_flag;
+            op([rp, flag](cudaStream_t s) { return resblock_fused_launch(*rp, flag, s); });
+            return;
+        }
         conv_k3(R.c1, x, 256, nullptr, 0, len, B, t1);
         conv_k3(R.c2, t1, 256, nullptr, 0, len, B, t2);
         attention(R.attn, t2, x, len, B, qkv, out);
