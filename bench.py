@@ -141,6 +141,26 @@ def run_reference(args, rank, world, out=sys.stdout):
     print(json.dumps(line), file=out, flush=True)
 
 
+def bind_to_gpu_cpus(index):
+    """One process per GPU: run (and first-touch the pinned staging memory) on the CPU cores NVML reports as local to
+    this GPU, so that eight ranks do not pull their host batches across the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cores local to GPU %d" % (len(cpus), index)
+    except Exception as exc:                      # no NVML, restricted container, ...: keep the default placement
+        return "unbound (%s)" % type(exc).__name__
+    return "unbound"
+
+
 def _claim_stdout():
     """Libraries (NCCL prints its version banner) write to fd 1: point fd 1 at stderr for the run and return a file on
     the real stdout, which then carries exactly one line -- the JSON result."""
@@ -179,6 +199,7 @@ def main():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_cpus(local) if world > 1 else None      # pinned host batches on the GPU's own NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
@@ -330,7 +351,7 @@ def main():
                 "config": {"workload": "config2: PATS-shaped batch %d (68267 samples -> 425x64 log-mel -> 64x64 -> 64x104 poses), "
                                        "mel + SelfAttention_G forward + L1/PCK" % B,
                            "clips_per_step_per_gpu": B, "parallelism": "clip-sharded x%d" % world,
-                           "stream_lanes": args.lanes, "cuda_graphs": bool(args.graphs),
+                           "stream_lanes": args.lanes, "cuda_graphs": bool(args.graphs), "host_binding": numa,
                            "mel_frames": "64 adapter frames only (shortcut)" if args.adapter_frames_only else "all 425 per clip",
                            "l2": "inputs cycle through %d distinct batches (%.0f MB each) > L2" % (POOL, h2d / 1e6)},
                 "clocks": clocks,
