@@ -26,6 +26,8 @@ if ROOT not in sys.path:
 
 METRIC = "clips/sec audio->pose (mel+fwd+eval)"
 UNIT = "clips/s"
+WORKLOAD = ("config2: PATS-shaped batch %d (68267 samples -> 425x64 log-mel -> 64x64 -> 64x104 poses), "
+            "mel + SelfAttention_G forward + L1/PCK")
 CLIP_SAMPLES = 68267
 POOL = 6                     # distinct input batches cycled through: 6 x 77 MB > 126 MB of L2
 
@@ -132,8 +134,8 @@ def run_reference(args, rank, world, out=sys.stdout):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 mel / f32 model", "data": "synthetic",
-            "config": {"workload": "config2: PATS-shaped clips, mel+UNet forward+eval", "clips_per_step": sample,
-                       "clip_samples": CLIP_SAMPLES},
+            "config": {"workload": WORKLOAD % args.batch, "clips_per_step": sample, "clip_samples": CLIP_SAMPLES,
+                       "note": "the reference's CPU path (oracle port) on a bounded sample of the same workload per step"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d clips per step x %d steps (oracle port of the reference CPU path)" % (sample, args.steps)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -348,8 +350,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16 (fp32 accumulate; mel and eval fp32)", "data": "synthetic",
-                "config": {"workload": "config2: PATS-shaped batch %d (68267 samples -> 425x64 log-mel -> 64x64 -> 64x104 poses), "
-                                       "mel + SelfAttention_G forward + L1/PCK" % B,
+                "config": {"workload": WORKLOAD % B,
                            "clips_per_step_per_gpu": B, "parallelism": "clip-sharded x%d" % world,
                            "stream_lanes": args.lanes, "cuda_graphs": bool(args.graphs), "host_binding": numa,
                            "mel_frames": "64 adapter frames only (shortcut)" if args.adapter_frames_only else "all 425 per clip",
