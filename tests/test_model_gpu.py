@@ -150,3 +150,36 @@ def test_experimental_fused_resblock_keeps_parity():
     assert len(margins) >= 2, out.stdout
     for name, rel in margins:
         assert float(rel) <= 1e-2, (name, rel)
+
+
+def test_timeline_api_orders_ops_on_one_time_axis(pkg):
+    """a2m_model_timeline_begin / _read: one event per op of the recorded forwards, milliseconds on a device-wide axis;
+    ops of one stream are ordered, the decoder fork starts after the UNet, recording stops after `steps` forwards."""
+    import ctypes
+    import importlib
+    cabi = importlib.import_module("audio-to-motion-generation_b200._cabi")
+    lib = cabi.lib()
+    mods = pkg.install_dropin()
+    m = mods["real_motion_model"].SelfAttention_G().cuda().eval()
+    x = torch.randn(4, 64, 64, device="cuda")
+    m(x)
+    h = m.native()
+    cabi.check(lib.a2m_model_timeline_begin(h.ptr, 4, 64, 64, 2))
+    for _ in range(3):                                     # the third forward is not recorded
+        m(x)
+    buf = (ctypes.c_float * 400)()
+    steps, n_ops, unet_end, body_end = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    cabi.check(lib.a2m_model_timeline_read(h.ptr, buf, 400, ctypes.byref(steps), ctypes.byref(n_ops), ctypes.byref(unet_end),
+                                           ctypes.byref(body_end), 4, 64, 64))
+    assert steps.value == 2 and 30 <= n_ops.value <= 80 and 0 < unet_end.value < body_end.value < n_ops.value
+    n = n_ops.value
+    for s in range(2):
+        row = [buf[s * (n + 1) + j] for j in range(n + 1)]
+        trunk = row[:1 + unet_end.value]
+        assert all(b >= a for a, b in zip(trunk, trunk[1:]))                       # caller's stream, in order
+        body = row[1 + unet_end.value:1 + body_end.value]
+        hand = row[1 + body_end.value:]
+        assert all(b >= a for a, b in zip(body, body[1:])) and all(b >= a for a, b in zip(hand, hand[1:]))
+        assert body[0] >= trunk[-1] and hand[0] >= trunk[-1]                       # both branches start after the UNet
+    assert buf[n + 1] >= buf[n]                                                    # second forward after the first's last trunk op
+    assert lib.a2m_model_op_name(h.ptr, 4, 64, 64, 0, None).decode().startswith("enc")
