@@ -571,9 +571,9 @@ struct Emit {
     // ResBlock (model_layers.py:185-190): x -> conv1 -> conv2 -> attention -> + x
     void resblock(const ResW& R, const __nv_bfloat16* x, int len, int B, __nv_bfloat16* t1, __nv_bfloat16* t2,
                   __nv_bfloat16* qkv, __nv_bfloat16* out) {
-        // experimental, opt-in (A2M_RESBLOCK_FUSION=1): parity-green and 15 % faster than its three launches in isolation
-        // (50 vs 59 us), but it holds a whole SM (226 KB of shared memory) for that long, while the three small kernels
-        // interleave with the other stream lane -- in the pipeline the step got 3 % slower
+        // experimental, opt-in (A2M_RESBLOCK_FUSION=1): parity-green and 24 % faster than its three launches in isolation
+        // (45 vs 59 us), but it holds a whole SM (206 KB of shared memory) for that long, while the three small kernels
+        // interleave with the other stream lane -- in the pipeline the step got 2 % slower
         static const bool fused = getenv("A2M_RESBLOCK_FUSION") != nullptr && atoi(getenv("A2M_RESBLOCK_FUSION")) != 0;
         if (fused && resblock_fused_supported(len, 256) && R.c1.N == 256 && R.c2.N == 256 && R.attn.C == 256 &&
             R.c1.act == kActLeaky && R.c2.act == kActLeaky) {                       // whole block in one kernel

@@ -8,13 +8,15 @@
 // within the clip.
 //
 // The activations never leave the SM between the layers.  A 256-channel tile lives in shared memory as four 64-channel
-// chunks of [zero row | clip 0: 64 rows | zero row | zero row | clip 1: 64 rows | zero row] 128-byte rows with the
-// 128-byte swizzle, i.e. directly as the K-major A operand of tcgen05.mma, and (tools/probes/umma_m64_probe.cu):
-//   * a convolution tap is the same tile read one row earlier / later: the descriptor's start address moves by whole
+// chunks of 132 128-byte rows with the 128-byte swizzle, i.e. directly as the K-major A operand of tcgen05.mma, with the
+// two clips' time steps INTERLEAVED: rows 0, 1 zero | row 2 (t + 1) + clip | rows 130, 131 zero.  Then
+// (tools/probes/umma_m64_probe.cu):
+//   * a convolution tap is the same tile read two rows earlier / later: the descriptor's start address moves by whole
 //     rows (base-offset field 0 -- the swizzle is a function of the absolute shared-memory address);
-//   * one M = 64 MMA per clip and tap therefore sees exactly the reference's zero padding at the clip ends;
-//   * clip 1's accumulator uses TMEM lane base 16 (M = 64 fills lanes 0-15 of each quadrant), so both clips share one
-//     column range and every epilogue thread owns one output row.
+//   * one M = 128 MMA per tap covers both clips, and the zero rows at the two ends are exactly the reference's zero
+//     padding of both (a first version used one M = 64 MMA per clip on a clip-after-clip layout with lane-offset
+//     accumulators: twice the MMAs at half rate each, 19 us of tensor time per launch);
+//   * TMEM lane i holds (t = i >> 1, clip = i & 1).
 // Only the weights stream from L2 (32 blocks of 20-32 KB through a four-stage TMA ring fed by a dedicated producer
 // warp).  (Tried: 2-CTA clusters multicasting the weight blocks -- no faster, the stream is bound by the bytes in flight
 // per SM, not by L2 bandwidth, and the cluster barriers cost 4 us.)  The epilogue of a layer writes the next layer's operand tile; from the q | k | v projection on the kernel is
@@ -35,7 +37,6 @@ namespace {
 constexpr int kWorkers = 512;
 constexpr int kThreadsRb = kWorkers + 32;                  // + one producer warp
 constexpr int kC = 256, kD = 32, kNqkv = 2 * kD + kC, kT = 64;
-constexpr int kClipRows = 66;                              // zero row, 64 time steps, zero row
 constexpr int kChunkBytes = 136 * 128;                     // 132 rows used; 17 KB keeps every chunk 1024-byte aligned
 constexpr int kTileBytes = 4 * kChunkBytes;
 constexpr int kOffA0 = 0;                                  // x, then t1, then t2 (each layer's MMAs are done before its epilogue
@@ -115,11 +116,11 @@ resblock_fused_kernel(const __grid_constant__ ResblockParams p, int* __restrict_
     if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     for (int i = tid; i < 2 * kC + kNqkv; i += kThreadsRb)
         s_bias[i] = __ldg(i < kC ? p.bias1 + i : i < 2 * kC ? p.bias2 + (i - kC) : p.bias_qkv + (i - 2 * kC));
-    {   // the padding rows of the activation tile (rows 0, 65, 66, 131 of every chunk) stay zero through all three layers
+    {   // the padding rows of the activation tile (rows 0, 1, 130, 131 of every chunk) stay zero through all three layers
         const uint4 z = make_uint4(0, 0, 0, 0);
         for (int i = tid; i < 4 * 4 * 8; i += kThreadsRb) {
             const int chunk = (i >> 5) & 3, which = (i >> 3) & 3, c16 = i & 7;
-            const int prow = which == 0 ? 0 : which == 1 ? 65 : which == 2 ? 66 : 131;
+            const int prow = which == 0 ? 0 : which == 1 ? 1 : which == 2 ? 130 : 131;
             *reinterpret_cast<uint4*>(smem + kOffA0 + chunk * kChunkBytes + prow * 128 + (c16 << 4)) = z;
         }
     }
@@ -155,16 +156,16 @@ resblock_fused_kernel(const __grid_constant__ ResblockParams p, int* __restrict_
         const int r = tid & 127, q = tid >> 7, quad = warp & 3;
         const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
         const uint32_t base = smem_u32(smem);
-        // tile row of this thread in the two lane orders: natural (M = 128 accumulators: S, O; also the x load) and the
-        // M = 64 pair (conv / q|k|v accumulators: lanes 0-15 of a quadrant = clip 0, lanes 16-31 = clip 1)
-        const int clip_m = (r & 31) >> 4, t_m = quad * 16 + (r & 15);
-        const int row_m = clip_m * kT + t_m;               // tile row held by my lane in the M = 64 layout
-        const int prow_m = clip_m * kClipRows + 1 + t_m;   // its padded row
+        // tile row of this thread in the two lane orders: natural (S, O accumulators over the unpadded Q / K / V tiles; also
+        // the x load) and interleaved (conv / q|k|v accumulators over the padded tile: lane i = time step i >> 1 of clip i & 1)
+        const int clip_m = r & 1, t_m = r >> 1;
+        const int row_m = clip_m * kT + t_m;               // natural tile row held by my lane in the interleaved layout
+        const int prow_m = r + 2;                          // its padded row
         auto worker_sync = [] { named_barrier(1, kWorkers); };
 
         {   // ---- x -> A0 (my natural row r, channel quarter q = chunk q)
             const long long row = row0 + r;
-            const int prow = (r >> 6) * kClipRows + 1 + (r & 63);
+            const int prow = 2 * ((r & 63) + 1) + (r >> 6);
             unsigned char* dst = smem + kOffA0 + q * kChunkBytes;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -179,20 +180,16 @@ resblock_fused_kernel(const __grid_constant__ ResblockParams p, int* __restrict_
         int g = 0;                                         // weight K block counter (MMA thread)
         // one k = 3 convolution: accumulators [128 lanes][256 columns] from the tile at `a_off`
         auto conv_mma = [&](int a_off) {
-            const uint32_t idesc = umma_idesc_bf16(64, 256);
+            const uint32_t idesc = umma_idesc_bf16(128, 256);
             for (int kb = 0; kb < kConvBlocks; ++kb, ++g) {
                 const int s = g % kStages, tap = kb >> 2, chunk = kb & 3;       // K offset kb * 64 = tap * 256 + chunk * 64
                 if (!mbar_wait(&full_bar[s], (g / kStages) & 1, err_flag, 52)) break;
                 tc_fence_after();
                 const uint32_t b_addr = base + kOffRing + s * kStageBytes;
+                const uint32_t a_addr = base + a_off + chunk * kChunkBytes + (2 * tap) * 128;      // time steps t - 1 + tap of both clips
 #pragma unroll
-                for (int clip = 0; clip < 2; ++clip) {
-                    const uint32_t a_addr = base + a_off + chunk * kChunkBytes + (clip * kClipRows + tap) * 128;   // rows t - 1 + tap
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base + (static_cast<uint32_t>(clip * 16) << 16), umma_desc_sw128(a_addr + k * 32),
-                                  umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
-                }
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
                 umma_commit(&empty_bar[s]);
             }
             umma_commit(acc_bar);
@@ -241,20 +238,16 @@ resblock_fused_kernel(const __grid_constant__ ResblockParams p, int* __restrict_
         // ---------------- q | k | v = t2 Wqkv^T ----------------
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t id160 = umma_idesc_bf16(64, 160);
+            const uint32_t id160 = umma_idesc_bf16(128, 160);
             for (int hb = 0; hb < 8; ++hb, ++g) {          // K block hb >> 1, weight rows (= accumulator columns) 160 (hb & 1) ...
                 const int s = g % kStages, kb = hb >> 1, j = hb & 1;
                 if (!mbar_wait(&full_bar[s], (g / kStages) & 1, err_flag, 55)) break;
                 tc_fence_after();
                 const uint32_t b_addr = base + kOffRing + s * kStageBytes;
+                const uint32_t a_addr = base + kOffA0 + kb * kChunkBytes + 2 * 128;
 #pragma unroll
-                for (int clip = 0; clip < 2; ++clip) {
-                    const uint32_t a_addr = base + kOffA0 + kb * kChunkBytes + (clip * kClipRows + 1) * 128;
-                    const uint32_t d = tmem_base + (static_cast<uint32_t>(clip * 16) << 16) + j * 160;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), id160, (kb | k) != 0);
-                }
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base + j * 160, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), id160, (kb | k) != 0);
                 umma_commit(&empty_bar[s]);
             }
             umma_commit(acc_bar);
