@@ -57,6 +57,27 @@ def test_argument_errors_without_gpu(pkg):
                                  w.ctypes.data_as(ctypes.c_void_p), 0.01, 0, ctypes.byref(out))
     assert rc == -1 and b"window" in lib.a2m_last_error()
     assert lib.a2m_eval_l1_pck_f32(None, None, 4, 64, 0.2, None, None, None, None) == -1
+    # entry points added for the "next" rows reject bad arguments before touching the device
+    rc = lib.a2m_mel_plan_create_ex(400, 160, 512, 64, hann.ctypes.data_as(ctypes.c_void_p),
+                                    w.ctypes.data_as(ctypes.c_void_p), 0.01, 7, 0, ctypes.byref(out))
+    assert rc == -1 and b"log_mode" in lib.a2m_last_error()
+    win = np.ones(2048)
+    w2 = np.zeros((1025, 128))
+    rc = lib.a2m_melspec_plan_create(1024, 512, 128, 2, 1, win.ctypes.data_as(ctypes.c_void_p),
+                                     w2.ctypes.data_as(ctypes.c_void_p), 1e-10, 1, 0, ctypes.byref(out))
+    assert rc == -3 and b"not supported" in lib.a2m_last_error()
+    rc = lib.a2m_melspec_plan_create(2048, 512, 128, 3, 1, win.ctypes.data_as(ctypes.c_void_p),
+                                     w2.ctypes.data_as(ctypes.c_void_p), 1e-10, 1, 0, ctypes.byref(out))
+    assert rc == -1 and b"power" in lib.a2m_last_error()
+    w2[10, 0] = w2[12, 0] = 1.0                            # a band whose support is not one contiguous run of bins
+    rc = lib.a2m_melspec_plan_create(2048, 512, 128, 2, 1, win.ctypes.data_as(ctypes.c_void_p),
+                                     w2.ctypes.data_as(ctypes.c_void_p), 1e-10, 1, 0, ctypes.byref(out))
+    assert rc == -3 and b"contiguous" in lib.a2m_last_error()
+    assert lib.a2m_melspec_num_frames(None, 4096) == -1
+    assert lib.a2m_motion_smoothness_f32(None, 4, 64, 200, 0, None, None) == -1      # more than 128 features
+    assert lib.a2m_motion_smoothness_f32(None, 4, 64, 104, 0, None, None) == -1      # no accumulator
+    assert lib.a2m_model_set_output_denorm(None, None, None, None) == -1
+    assert lib.a2m_model_timeline_begin(None, 4, 64, 64, 2) == -1
 
 
 def test_host_tables_match_oracle(pkg):
