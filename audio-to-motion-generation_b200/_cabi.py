@@ -54,6 +54,7 @@ SIGNATURES = {
     "a2m_mel_plan_destroy": (None, [c_void_p]),
     "a2m_mel_num_frames": (c_i64, [c_void_p, c_i64]),
     "a2m_logmel_f32": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
+    "a2m_logmel_i16": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
     "a2m_stft_magnitude_f32": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
     "a2m_melspec_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_double, c_int, c_int,
                                         ctypes.POINTER(c_void_p)]),
@@ -62,10 +63,13 @@ SIGNATURES = {
     "a2m_melspec_f32": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
     "a2m_eval_l1_pck_f32": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
+    "a2m_eval_l1_pck_f64": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_double, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     "a2m_motion_smoothness_f32": (c_int, [c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "a2m_pose_normalize_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "a2m_pose_denormalize_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "a2m_pose_stats_f64": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
+    "a2m_pose_stats_ex_f64": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "a2m_comm_unique_id": (c_int, [c_void_p]),
     "a2m_comm_init": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
     "a2m_allreduce_metrics": (c_int, [c_void_p, c_void_p, c_void_p]),

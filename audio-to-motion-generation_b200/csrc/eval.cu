@@ -17,18 +17,47 @@ constexpr int kJoints = 52;
 constexpr int kFeat = 2 * kJoints;
 constexpr int kWarpsPerBlock = 8;
 
+// IEEE single operations without FMA contraction, in the input's own width (numpy computes fp32 inputs in fp32 and
+// fp64 inputs in fp64, motion_evaluation.py:4-23)
+template <typename T> struct Ieee;
+template <> struct Ieee<float> {
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+};
+template <> struct Ieee<double> {
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+};
+template <typename T>
+__device__ __forceinline__ T warp_min_t(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max_t(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <typename T>
 struct FrameRegs {   // this lane's share of one frame: keypoints l (a) and l+32 (b)
-    float gxa, gya, pxa, pya, gxb, gyb, pxb, pyb;
+    T gxa, gya, pxa, pya, gxb, gyb, pxb, pyb;
 };
 
-__device__ __forceinline__ FrameRegs load_frame(const float* __restrict__ p, const float* __restrict__ g, int lane,
-                                                bool has_b) {
-    FrameRegs r;
+template <typename T>
+__device__ __forceinline__ FrameRegs<T> load_frame(const T* __restrict__ p, const T* __restrict__ g, int lane, bool has_b) {
+    FrameRegs<T> r;
     r.gxa = __ldcs(g + lane);
     r.gya = __ldcs(g + kJoints + lane);
     r.pxa = __ldcs(p + lane);
     r.pya = __ldcs(p + kJoints + lane);
-    r.gxb = r.gyb = r.pxb = r.pyb = 0.f;
+    r.gxb = r.gyb = r.pxb = r.pyb = T(0);
     if (has_b) {
         r.gxb = __ldcs(g + 32 + lane);
         r.gyb = __ldcs(g + kJoints + 32 + lane);
@@ -38,15 +67,19 @@ __device__ __forceinline__ FrameRegs load_frame(const float* __restrict__ p, con
     return r;
 }
 
-__device__ __forceinline__ bool pck_hit(float gx, float gy, float px, float py, float radius) {
-    const float dx = __fsub_rn(gx, px), dy = __fsub_rn(gy, py);
-    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-    return __fsqrt_rn(d2) <= radius;
+template <typename T>
+__device__ __forceinline__ bool pck_hit(T gx, T gy, T px, T py, T radius) {
+    const T dx = Ieee<T>::sub(gx, px), dy = Ieee<T>::sub(gy, py);
+    const T d2 = Ieee<T>::add(Ieee<T>::mul(dx, dx), Ieee<T>::mul(dy, dy));
+    return Ieee<T>::sqrt(d2) <= radius;
 }
 
+// T = float: the hot path (fp32 poses).  T = double: the reference called on float64 arrays; alpha arrives as the
+// Python float it was, the radius and the distances are fp64, the L1 differences are fp64.
+template <typename T>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-eval_l1_pck_kernel(const float* __restrict__ pred, const float* __restrict__ gt, long long n_clips, int T, int seg_frames,
-                   int segs, float alpha, double* __restrict__ pck_per_frame, float* __restrict__ radius_per_frame,
+eval_l1_pck_kernel(const T* __restrict__ pred, const T* __restrict__ gt, long long n_clips, int T_frames, int seg_frames,
+                   int segs, T alpha, double* __restrict__ pck_per_frame, T* __restrict__ radius_per_frame,
                    a2m_metrics* __restrict__ accum) {
     __shared__ double s_pose[kWarpsPerBlock], s_motion[kWarpsPerBlock];
     __shared__ unsigned long long s_hits[kWarpsPerBlock];
@@ -62,45 +95,44 @@ eval_l1_pck_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
          item += static_cast<long long>(gridDim.x) * kWarpsPerBlock) {
         const long long clip = item / segs;
         const int t_begin = static_cast<int>(item - clip * segs) * seg_frames;
-        const int t_end = min(T, t_begin + seg_frames);
-        const float* p = pred + clip * T * kFeat;
-        const float* g = gt + clip * T * kFeat;
-        FrameRegs cur = load_frame(p + t_begin * kFeat, g + t_begin * kFeat, lane, has_b), prev = cur;
+        const int t_end = min(T_frames, t_begin + seg_frames);
+        const T* p = pred + clip * T_frames * kFeat;
+        const T* g = gt + clip * T_frames * kFeat;
+        FrameRegs<T> cur = load_frame(p + t_begin * kFeat, g + t_begin * kFeat, lane, has_b), prev = cur;
         if (t_begin > 0) prev = load_frame(p + (t_begin - 1) * kFeat, g + (t_begin - 1) * kFeat, lane, has_b);
         for (int t = t_begin; t < t_end; ++t) {
-            FrameRegs nxt = cur;
+            FrameRegs<T> nxt = cur;
             if (t + 1 < t_end) nxt = load_frame(p + (t + 1) * kFeat, g + (t + 1) * kFeat, lane, has_b);   // prefetch
             // bounding box of the ground truth (lanes without a second keypoint contribute neutral values)
-            float mnx = has_b ? fminf(cur.gxa, cur.gxb) : cur.gxa, mxx = has_b ? fmaxf(cur.gxa, cur.gxb) : cur.gxa;
-            float mny = has_b ? fminf(cur.gya, cur.gyb) : cur.gya, mxy = has_b ? fmaxf(cur.gya, cur.gyb) : cur.gya;
-            mnx = a2m::warp_min(mnx); mxx = a2m::warp_max(mxx);
-            mny = a2m::warp_min(mny); mxy = a2m::warp_max(mxy);
-            const float side = fmaxf(fabsf(__fsub_rn(mxx, mnx)), fabsf(__fsub_rn(mxy, mny)));
-            const float radius = __fmul_rn(side, alpha);
+            T mnx = has_b ? min(cur.gxa, cur.gxb) : cur.gxa, mxx = has_b ? max(cur.gxa, cur.gxb) : cur.gxa;
+            T mny = has_b ? min(cur.gya, cur.gyb) : cur.gya, mxy = has_b ? max(cur.gya, cur.gyb) : cur.gya;
+            mnx = warp_min_t(mnx); mxx = warp_max_t(mxx);
+            mny = warp_min_t(mny); mxy = warp_max_t(mxy);
+            const T side = max(abs(Ieee<T>::sub(mxx, mnx)), abs(Ieee<T>::sub(mxy, mny)));
+            const T radius = Ieee<T>::mul(side, alpha);
             const bool ha = pck_hit(cur.gxa, cur.gya, cur.pxa, cur.pya, radius);
             const bool hb = has_b && pck_hit(cur.gxb, cur.gyb, cur.pxb, cur.pyb, radius);
             const int frame_hits = __popc(__ballot_sync(0xffffffffu, ha)) + __popc(__ballot_sync(0xffffffffu, hb));
             if (lane == 0) {
                 hits += frame_hits;
-                const long long f = clip * T + t;
+                const long long f = clip * T_frames + t;
                 if (pck_per_frame) pck_per_frame[f] = static_cast<double>(frame_hits) / static_cast<double>(kJoints);
                 if (radius_per_frame) radius_per_frame[f] = radius;
             }
-            // L1 on poses: fp32 |a-b| (torch L1Loss element op), fp64 accumulation
-            float e = fabsf(__fsub_rn(cur.pxa, cur.gxa)) ;
-            abs_pose += e;
-            abs_pose += fabsf(__fsub_rn(cur.pya, cur.gya));
+            // L1 on poses: |a-b| in the input's width (torch L1Loss element op), fp64 accumulation
+            abs_pose += abs(Ieee<T>::sub(cur.pxa, cur.gxa));
+            abs_pose += abs(Ieee<T>::sub(cur.pya, cur.gya));
             if (has_b) {
-                abs_pose += fabsf(__fsub_rn(cur.pxb, cur.gxb));
-                abs_pose += fabsf(__fsub_rn(cur.pyb, cur.gyb));
+                abs_pose += abs(Ieee<T>::sub(cur.pxb, cur.gxb));
+                abs_pose += abs(Ieee<T>::sub(cur.pyb, cur.gyb));
             }
             // L1 on motion: first differences along time inside the clip (pos_to_motion)
             if (t > 0) {
-                abs_motion += fabsf(__fsub_rn(__fsub_rn(cur.pxa, prev.pxa), __fsub_rn(cur.gxa, prev.gxa)));
-                abs_motion += fabsf(__fsub_rn(__fsub_rn(cur.pya, prev.pya), __fsub_rn(cur.gya, prev.gya)));
+                abs_motion += abs(Ieee<T>::sub(Ieee<T>::sub(cur.pxa, prev.pxa), Ieee<T>::sub(cur.gxa, prev.gxa)));
+                abs_motion += abs(Ieee<T>::sub(Ieee<T>::sub(cur.pya, prev.pya), Ieee<T>::sub(cur.gya, prev.gya)));
                 if (has_b) {
-                    abs_motion += fabsf(__fsub_rn(__fsub_rn(cur.pxb, prev.pxb), __fsub_rn(cur.gxb, prev.gxb)));
-                    abs_motion += fabsf(__fsub_rn(__fsub_rn(cur.pyb, prev.pyb), __fsub_rn(cur.gyb, prev.gyb)));
+                    abs_motion += abs(Ieee<T>::sub(Ieee<T>::sub(cur.pxb, prev.pxb), Ieee<T>::sub(cur.gxb, prev.gxb)));
+                    abs_motion += abs(Ieee<T>::sub(Ieee<T>::sub(cur.pyb, prev.pyb), Ieee<T>::sub(cur.gyb, prev.gyb)));
                 }
             }
             prev = cur;
@@ -119,24 +151,23 @@ eval_l1_pck_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
         atomicAdd(&accum->abs_pose, sp);
         atomicAdd(&accum->abs_motion, sm);
         if (blockIdx.x == 0) {      // the counts are pure functions of the shape
-            const unsigned long long frames = static_cast<unsigned long long>(n_clips) * T;
+            const unsigned long long frames = static_cast<unsigned long long>(n_clips) * T_frames;
             atomicAdd(reinterpret_cast<unsigned long long*>(&accum->n_frames), frames);
             atomicAdd(reinterpret_cast<unsigned long long*>(&accum->n_keypoints), frames * kJoints);
             atomicAdd(reinterpret_cast<unsigned long long*>(&accum->n_pose), frames * kFeat);
             atomicAdd(reinterpret_cast<unsigned long long*>(&accum->n_motion),
-                      static_cast<unsigned long long>(n_clips) * (T > 0 ? T - 1 : 0) * kFeat);
+                      static_cast<unsigned long long>(n_clips) * (T_frames > 0 ? T_frames - 1 : 0) * kFeat);
         }
     }
 }
 
-}  // namespace
-
-extern "C" int a2m_eval_l1_pck_f32(const float* pred, const float* gt, int64_t n_clips, int frames_per_clip, float alpha,
-                                   double* pck_per_frame, float* radius_per_frame, a2m_metrics* accum, void* stream) {
-    A2M_ARG_CHECK(n_clips >= 0 && frames_per_clip >= 0, "a2m_eval_l1_pck_f32: negative size");
-    A2M_ARG_CHECK(accum != nullptr, "a2m_eval_l1_pck_f32: accum is NULL");
+template <typename T>
+int launch_eval(const T* pred, const T* gt, int64_t n_clips, int frames_per_clip, T alpha, double* pck_per_frame,
+                T* radius_per_frame, a2m_metrics* accum, void* stream, const char* who) {
+    A2M_ARG_CHECK(n_clips >= 0 && frames_per_clip >= 0, "%s: negative size", who);
+    A2M_ARG_CHECK(accum != nullptr, "%s: accum is NULL", who);
     if (n_clips == 0 || frames_per_clip == 0) return A2M_OK;
-    A2M_ARG_CHECK(pred != nullptr && gt != nullptr, "a2m_eval_l1_pck_f32: NULL pose buffer");
+    A2M_ARG_CHECK(pred != nullptr && gt != nullptr, "%s: NULL pose buffer", who);
     // split clips into time segments until there are ~8 warps of work per SM sub-partition (never below 4 frames)
     const long long want = 32LL * a2m_num_sms();
     int segs = static_cast<int>((want + n_clips - 1) / n_clips);
@@ -148,11 +179,25 @@ extern "C" int a2m_eval_l1_pck_f32(const float* pred, const float* gt, int64_t n
     long long blocks = (n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const long long cap = 32LL * a2m_num_sms();
     if (blocks > cap) blocks = cap;
-    eval_l1_pck_kernel<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+    eval_l1_pck_kernel<T><<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
         pred, gt, n_clips, frames_per_clip, seg_frames, segs, alpha, pck_per_frame, radius_per_frame, accum);
     a2m_count_launch();
     A2M_LAUNCH_CHECK();
     return A2M_OK;
+}
+
+}  // namespace
+
+extern "C" int a2m_eval_l1_pck_f32(const float* pred, const float* gt, int64_t n_clips, int frames_per_clip, float alpha,
+                                   double* pck_per_frame, float* radius_per_frame, a2m_metrics* accum, void* stream) {
+    return launch_eval<float>(pred, gt, n_clips, frames_per_clip, alpha, pck_per_frame, radius_per_frame, accum, stream,
+                              "a2m_eval_l1_pck_f32");
+}
+
+extern "C" int a2m_eval_l1_pck_f64(const double* pred, const double* gt, int64_t n_clips, int frames_per_clip, double alpha,
+                                   double* pck_per_frame, double* radius_per_frame, a2m_metrics* accum, void* stream) {
+    return launch_eval<double>(pred, gt, n_clips, frames_per_clip, alpha, pck_per_frame, radius_per_frame, accum, stream,
+                               "a2m_eval_l1_pck_f64");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -38,14 +38,14 @@ pose_denormalize_kernel(const float* __restrict__ pose, const float* __restrict_
 
 // accum: double[2 * 104 + 1] = sum, sum of squares, frame count (as double)
 __global__ void __launch_bounds__(128)
-pose_stats_kernel(const float* __restrict__ pose, long long n_frames, double* __restrict__ accum) {
+pose_stats_kernel(const float* __restrict__ pose, long long n_frames, int neck_sub, double* __restrict__ accum) {
     const int c = threadIdx.x;                      // feature; 104 of 128 threads active
     if (c >= kFeat) return;
     double s = 0.0, q = 0.0;
     const int neck_col = c < kJoints ? 0 : kJoints;
     for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
         const float* row = pose + f * kFeat;
-        const float v = __fsub_rn(__ldg(row + c), __ldg(row + neck_col));
+        const float v = neck_sub ? __fsub_rn(__ldg(row + c), __ldg(row + neck_col)) : __ldg(row + c);
         s += static_cast<double>(v);
         q += static_cast<double>(__fmul_rn(v, v));   // torch: mean(pose ** 2) squares in fp32
     }
@@ -82,13 +82,18 @@ extern "C" int a2m_pose_denormalize_f32(const float* pose, const float* mean, co
     return A2M_OK;
 }
 
-extern "C" int a2m_pose_stats_f64(const float* pose, int64_t n_frames, double* accum, void* stream) {
+extern "C" int a2m_pose_stats_ex_f64(const float* pose, int64_t n_frames, int neck_sub, double* accum, void* stream) {
     A2M_ARG_CHECK(n_frames >= 0 && accum != nullptr, "a2m_pose_stats_f64: bad argument");
     if (n_frames == 0) return A2M_OK;
     A2M_ARG_CHECK(pose != nullptr, "a2m_pose_stats_f64: NULL pose");
     long long blocks = n_frames < 4LL * a2m_num_sms() ? n_frames : 4LL * a2m_num_sms();
-    pose_stats_kernel<<<static_cast<unsigned>(blocks), 128, 0, static_cast<cudaStream_t>(stream)>>>(pose, n_frames, accum);
+    pose_stats_kernel<<<static_cast<unsigned>(blocks), 128, 0, static_cast<cudaStream_t>(stream)>>>(pose, n_frames,
+                                                                                                   neck_sub ? 1 : 0, accum);
     a2m_count_launch();
     A2M_LAUNCH_CHECK();
     return A2M_OK;
+}
+
+extern "C" int a2m_pose_stats_f64(const float* pose, int64_t n_frames, double* accum, void* stream) {
+    return a2m_pose_stats_ex_f64(pose, n_frames, 1, accum, stream);
 }

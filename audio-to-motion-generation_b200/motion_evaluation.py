@@ -3,9 +3,10 @@ L1 / PCK partial-sum evaluation the multi-GPU driver all-reduces.
 
 ``compute_pck`` / ``compute_pck_radius`` keep the reference's signatures (motion_evaluation.py:4,17)
 and its numpy-in / numpy-out behaviour; arithmetic is numpy's fp32 operation order, reproduced on the
-GPU bit for bit by csrc/eval.cu (hit counts are identical to the reference for fp32 inputs).
-Inputs of another float width are converted to fp32 first (the reference would compute fp64 inputs in
-fp64; decision D7 in DESIGN.md).  torch tensors are accepted and yield torch tensors.
+GPU bit for bit by csrc/eval.cu.  The reference computes in the dtype of its inputs: float32 arrays
+in fp32 (the hot path), float64 arrays in fp64 -- both widths have a kernel instantiation, so hit counts
+equal the reference's for either; other dtypes (ints, halves) are converted to fp32 first.  torch tensors
+are accepted and yield torch tensors on their own device.
 """
 import ctypes
 
@@ -18,13 +19,30 @@ K_JOINTS = 52            # the radius is tiled to 52 keypoints, motion_evaluatio
 METRIC_FIELDS = ("pck_hits", "n_keypoints", "n_frames", "n_pose", "n_motion")
 
 
-def _frames_on_device(x, name):
-    """[N, 2, 52] (numpy / torch, any device) -> contiguous fp32 CUDA tensor."""
+def _cuda_device_of(*tensors):
+    """The CUDA device the work runs on: the inputs' own device if any of them lives on a GPU (never silently the
+    *current* device), else the current device."""
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _same_device(device, **tensors):
+    for name, t in tensors.items():
+        if t is not None and t.device != device:
+            raise ValueError("%s is on %s but the poses are on %s" % (name, t.device, device))
+
+
+def _frames_on_device(x, name, device=None, dtype=None):
+    """[N, 2, 52] (numpy / torch, any device) -> contiguous CUDA tensor, fp64 if the input is fp64 else fp32."""
     was_numpy = not isinstance(x, torch.Tensor)
     t = torch.as_tensor(np.asarray(x)) if was_numpy else x
     if t.dim() != 3 or t.shape[1] != 2 or t.shape[2] != K_JOINTS:
         raise ValueError("%s must have shape [N, 2, %d], got %s" % (name, K_JOINTS, tuple(t.shape)))
-    t = t.to(device="cuda", dtype=torch.float32).contiguous()
+    if dtype is None:
+        dtype = torch.float64 if t.dtype == torch.float64 else torch.float32
+    t = t.to(device=device or _cuda_device_of(t), dtype=dtype).contiguous()
     return t, was_numpy
 
 
@@ -50,20 +68,27 @@ def finalize_metrics(m):
 
 
 def evaluate_poses(pred, gt, alpha=0.2, accum=None, pck_per_frame=None, radius_per_frame=None):
-    """Fused evaluation of a batch of pose sequences [B, T, 104] (fp32 CUDA tensors): accumulates
-    PCK hits, |pred-gt| and |motion(pred)-motion(gt)| sums into ``accum`` (device, 64 bytes)."""
+    """Fused evaluation of a batch of pose sequences [B, T, 104] (CUDA tensors, fp32 -- or fp64, computed in fp64 like
+    the reference does for float64 arrays): accumulates PCK hits, |pred-gt| and |motion(pred)-motion(gt)| sums into
+    ``accum`` (device, 64 bytes)."""
     _cabi.require_cuda("evaluate_poses")
     if pred.shape != gt.shape or pred.dim() != 3 or pred.shape[-1] != 2 * K_JOINTS:
         raise ValueError("pred and gt must both be [B, T, %d]" % (2 * K_JOINTS))
-    pred = pred.to(device="cuda", dtype=torch.float32).contiguous()
-    gt = gt.to(device=pred.device, dtype=torch.float32).contiguous()
+    wide = pred.dtype == torch.float64 or gt.dtype == torch.float64
+    dtype = torch.float64 if wide else torch.float32
+    dev = _cuda_device_of(pred, gt)
+    pred = pred.to(device=dev, dtype=dtype).contiguous()
+    gt = gt.to(device=dev, dtype=dtype).contiguous()
     if accum is None:
-        accum = new_metrics(pred.device)
-    with torch.cuda.device(pred.device):
-        _cabi.check(_cabi.lib().a2m_eval_l1_pck_f32(
-            _cabi.ptr(pred), _cabi.ptr(gt), pred.shape[0], pred.shape[1], float(alpha),
-            _cabi.ptr(pck_per_frame), _cabi.ptr(radius_per_frame), _cabi.ptr(accum),
-            _cabi.stream_ptr(pred.device)))
+        accum = new_metrics(dev)
+    _same_device(dev, accum=accum, pck_per_frame=pck_per_frame, radius_per_frame=radius_per_frame)
+    if radius_per_frame is not None and radius_per_frame.dtype != dtype:
+        raise ValueError("radius_per_frame must be %s like the poses" % dtype)
+    entry = _cabi.lib().a2m_eval_l1_pck_f64 if wide else _cabi.lib().a2m_eval_l1_pck_f32
+    with torch.cuda.device(dev):
+        _cabi.check(entry(_cabi.ptr(pred), _cabi.ptr(gt), pred.shape[0], pred.shape[1], float(alpha),
+                          _cabi.ptr(pck_per_frame), _cabi.ptr(radius_per_frame), _cabi.ptr(accum),
+                          _cabi.stream_ptr(dev)))
     return accum
 
 
@@ -82,9 +107,10 @@ def evaluate_smoothness(seq, accum=None, from_pose=False):
     _cabi.require_cuda("evaluate_smoothness")
     if seq.dim() != 3:
         raise ValueError("motion sequence must be [B, L, F], got %s" % (tuple(seq.shape),))
-    seq = seq.to(device="cuda", dtype=torch.float32).contiguous()
+    seq = seq.to(device=_cuda_device_of(seq), dtype=torch.float32).contiguous()
     if accum is None:
         accum = new_smoothness(seq.device)
+    _same_device(seq.device, accum=accum)
     with torch.cuda.device(seq.device):
         _cabi.check(_cabi.lib().a2m_motion_smoothness_f32(
             _cabi.ptr(seq), seq.shape[0], seq.shape[1], seq.shape[2], int(bool(from_pose)), _cabi.ptr(accum),
@@ -129,13 +155,17 @@ def compute_jerk_loss(motion_seq):
 
 
 def _per_frame(pred, gt, alpha, want):
-    p, was_numpy = _frames_on_device(pred, "pred")
-    g, _ = _frames_on_device(gt, "gt")
+    g, was_numpy = _frames_on_device(gt, "gt")
+    wide = g.dtype == torch.float64 or (isinstance(pred, torch.Tensor) and pred.dtype == torch.float64) or \
+        (isinstance(pred, np.ndarray) and pred.dtype == np.float64)
+    dtype = torch.float64 if wide else torch.float32
+    g = g.to(dtype)
+    p, _ = _frames_on_device(pred, "pred", g.device, dtype)
     if p.shape != g.shape:
         raise ValueError("pred and gt differ in shape: %s vs %s" % (tuple(p.shape), tuple(g.shape)))
     n = g.shape[0]
     pck = torch.empty(n, dtype=torch.float64, device=g.device) if want == "pck" else None
-    rad = torch.empty(n, dtype=torch.float32, device=g.device) if want == "radius" else None
+    rad = torch.empty(n, dtype=dtype, device=g.device) if want == "radius" else None
     # every frame is its own "clip" of length 1: no motion term, per-frame outputs only
     evaluate_poses(p.view(n, 1, 2 * K_JOINTS), g.view(n, 1, 2 * K_JOINTS), alpha, None, pck, rad)
     return (pck if want == "pck" else rad), was_numpy

@@ -19,7 +19,8 @@ def _prep(pose, name):
     t = torch.as_tensor(pose)
     if t.shape[-1] != FEATS:
         raise ValueError("%s: last dimension must be %d (52 x then 52 y), got %s" % (name, FEATS, tuple(t.shape)))
-    return t.to(device="cuda", dtype=torch.float32).contiguous()
+    dev = t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())    # a GPU input stays on its own GPU
+    return t.to(device=dev, dtype=torch.float32).contiguous()
 
 
 def _vec(v, device, name):
@@ -53,17 +54,23 @@ def denormalize_pose(pose_norm, pose_mean, pose_std):
 
 class PoseStats:
     """Streaming version of get_mean_std_necksub (normalization_tools.py:24-45) for equal-sized batches:
-    ``update(pose_batch)`` per batch, then ``finalize() -> (pose_mean, pose_std)`` with std[0] = std[52] = 1."""
+    ``update(pose_batch)`` per batch, then ``finalize() -> (pose_mean, pose_std)`` with std[0] = std[52] = 1.
+    ``neck_sub=False`` gives get_mean_std (:5-20): no neck subtraction and no std override."""
 
-    def __init__(self, device="cuda"):
+    def __init__(self, device=None, neck_sub=True):
         _cabi.require_cuda("PoseStats")
-        self.accum = torch.zeros(2 * FEATS + 1, dtype=torch.float64, device=device)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.neck_sub = bool(neck_sub)
+        self.accum = torch.zeros(2 * FEATS + 1, dtype=torch.float64, device=self.device)
 
     def update(self, pose):
-        x = _prep(pose, "PoseStats.update")
+        t = torch.as_tensor(pose)
+        x = _prep(t if t.is_cuda else t.to(self.device), "PoseStats.update")
+        if x.device != self.accum.device:
+            raise ValueError("PoseStats lives on %s, the batch on %s" % (self.accum.device, x.device))
         with torch.cuda.device(x.device):
-            _cabi.check(_cabi.lib().a2m_pose_stats_f64(_cabi.ptr(x), x.numel() // FEATS, _cabi.ptr(self.accum),
-                                                       _cabi.stream_ptr(x.device)))
+            _cabi.check(_cabi.lib().a2m_pose_stats_ex_f64(_cabi.ptr(x), x.numel() // FEATS, int(self.neck_sub),
+                                                          _cabi.ptr(self.accum), _cabi.stream_ptr(x.device)))
         return self
 
     def finalize(self):
@@ -71,6 +78,42 @@ class PoseStats:
         n = max(float(a[2 * FEATS]), 1.0)
         mean = a[:FEATS] / n
         std = (a[FEATS:2 * FEATS] / n - mean ** 2).clamp_min(0.0) ** 0.5
-        std[0] = 1.0
-        std[52] = 1.0
+        if self.neck_sub:
+            std[0] = 1.0
+            std[52] = 1.0
         return mean.float(), std.float()
+
+
+def _dataset_stats(dataloader, neck_sub):
+    """The reference's loop: the MEAN over batches of each batch's own mean and mean square (so a ragged last batch
+    weighs as much as a full one, exactly as in normalization_tools.py:8-17,28-41), finished in fp32 like the
+    reference.  Each batch's sums come from the CUDA statistics kernel (fp64 accumulation of fp32 values)."""
+    _cabi.require_cuda("get_mean_std")
+    mean_sum = sq_sum = None
+    n_batches = 0
+    for n_batches, batch in enumerate(dataloader.train, 1):
+        stats = PoseStats(neck_sub=neck_sub).update(batch["pose/data"])
+        a = stats.accum
+        n = a[2 * FEATS].clamp_min(1.0)
+        m, q = (a[:FEATS] / n).float(), (a[FEATS:2 * FEATS] / n).float()
+        mean_sum = m if mean_sum is None else mean_sum + m
+        sq_sum = q if sq_sum is None else sq_sum + q
+    if n_batches == 0:
+        raise ValueError("dataloader.train yielded no batches")
+    pose_mean = (mean_sum / n_batches).cpu()
+    pose_std = ((sq_sum / n_batches).cpu() - pose_mean ** 2) ** 0.5
+    return pose_mean, pose_std
+
+
+def get_mean_std(dataloader):
+    """normalization_tools.py:5-20: (pose_mean [104], pose_std [104]) over ``dataloader.train`` batches
+    (dicts carrying ``'pose/data'`` [B, T, 104])."""
+    return _dataset_stats(dataloader, neck_sub=False)
+
+
+def get_mean_std_necksub(dataloader):
+    """normalization_tools.py:24-45: the same on neck-subtracted poses, std of the two neck features set to 1."""
+    pose_mean, pose_std = _dataset_stats(dataloader, neck_sub=True)
+    pose_std[0] = 1.
+    pose_std[52] = 1.
+    return pose_mean, pose_std

@@ -1,16 +1,19 @@
 """B200 drop-in for ``pose_video/mel_features.py`` of the reference (same names and argument meaning).
 
 ``log_mel_spectrogram`` and ``stft_magnitude`` run on the GPU through liba2m_b200.so (fused framing
--> periodic Hann -> 512-point real FFT -> |.| -> mel -> log, csrc/logmel.cu).  The small constant
+-> periodic Hann -> real FFT -> |.| -> mel -> log, csrc/logmel.cu: a tuned kernel for the hot path's
+512-point transform, a general one for the other power-of-two lengths the reference's rule produces).  The small constant
 tables (``periodic_hann``, ``spectrogram_to_mel_matrix``) are evaluated on the host in fp64 with the
 reference's formulas (mel_features.py:67-68, :155-189) and uploaded once per parameter set.
 
 Extensions over the reference: a leading batch dimension ([B, N] -> [B, frames, mel]) and
 torch tensors (CPU or CUDA).  numpy in -> numpy float64 out (the reference's dtype; values carry
 fp32 precision, tolerance 1e-4 per SURVEY.md D8); torch in -> torch float32 out on the GPU.
+int16 PCM (numpy or torch) is consumed as int16 by the kernel -- half the bytes to move; every other
+dtype is converted to fp32 first.
 Errors mirror the reference: bad band edges raise ValueError (:156-163); fewer samples than one
 window minus one hop raises ValueError ("negative dimensions"); anything the CUDA path does not
-implement (fft length other than 512) raises NotImplementedError -- never a silent CPU fallback.
+implement (a window longer than 4096 samples) raises NotImplementedError -- never a silent CPU fallback.
 """
 import ctypes
 import math
@@ -81,9 +84,9 @@ def _get_plan(device_index, window, hop, nfft, log_offset, mel_kwargs):
     key = (device_index, window, hop, nfft, float(log_offset), tuple(sorted(mel_kwargs.items())))
     plan = _plans.get(key)
     if plan is None:
-        if nfft != 512:
+        if nfft < 64 or nfft > 4096:
             raise NotImplementedError(
-                "the B200 log-mel kernel implements fft_length 512 (e.g. 16 kHz / 25 ms windows); got %d" % nfft)
+                "the B200 log-mel kernels implement fft lengths 64 .. 4096 (windows of 33 .. 4096 samples); got %d" % nfft)
         weights = np.ascontiguousarray(spectrogram_to_mel_matrix(num_spectrogram_bins=nfft // 2 + 1, **mel_kwargs),
                                        dtype=np.float64)
         hann = np.ascontiguousarray(periodic_hann(window), dtype=np.float64)
@@ -96,17 +99,19 @@ def _get_plan(device_index, window, hop, nfft, log_offset, mel_kwargs):
 
 
 def _to_device(data):
-    """-> (fp32 CUDA tensor [B, N] with unit inner stride, had_batch_dim, input_was_numpy)."""
+    """-> (CUDA tensor [B, N] with unit inner stride -- int16 if the input is int16, else fp32 --, had_batch_dim,
+    input_was_numpy)."""
     was_numpy = not isinstance(data, torch.Tensor)
     t = torch.as_tensor(np.asarray(data)) if was_numpy else data
     if t.dim() not in (1, 2):
         raise ValueError("expected a waveform [num_samples] or a batch [B, num_samples], got shape %s"
                          % (tuple(t.shape),))
     batched = t.dim() == 2
+    dtype = torch.int16 if t.dtype == torch.int16 else torch.float32
     if not t.is_cuda:
-        t = t.to(device="cuda", dtype=torch.float32, non_blocking=True)
-    elif t.dtype != torch.float32:
-        t = t.to(torch.float32)
+        t = t.to(device=torch.device("cuda", torch.cuda.current_device()), dtype=dtype, non_blocking=True)
+    elif t.dtype != dtype:
+        t = t.to(dtype)
     if not batched:
         t = t.unsqueeze(0)
     if t.stride(-1) != 1:
@@ -142,6 +147,8 @@ def stft_magnitude(signal, fft_length, hop_length=None, window_length=None):
     """|rfft(frames * periodic_hann, fft_length)| -> [frames, fft_length/2+1] (:71-92), on the GPU."""
     _cabi.require_cuda("stft_magnitude")
     wav, batched, was_numpy = _to_device(signal)
+    if wav.dtype != torch.float32:
+        wav = wav.to(torch.float32)
     plan = _get_plan(wav.device.index, int(window_length), int(hop_length), int(fft_length), 0.0,
                      dict(num_mel_bins=20, audio_sample_rate=8000))          # mel table unused by this entry
     out = _run(_cabi.lib().a2m_stft_magnitude_f32, plan, wav, plan.nfft // 2 + 1)
@@ -157,5 +164,6 @@ def log_mel_spectrogram(data, audio_sample_rate=8000, log_offset=0.0, window_len
     mel_kwargs.pop("num_spectrogram_bins", None)
     wav, batched, was_numpy = _to_device(data)
     plan = _get_plan(wav.device.index, window, hop, nfft, log_offset, mel_kwargs)
-    out = _run(_cabi.lib().a2m_logmel_f32, plan, wav, plan.n_mel)
+    entry = _cabi.lib().a2m_logmel_i16 if wav.dtype == torch.int16 else _cabi.lib().a2m_logmel_f32
+    out = _run(entry, plan, wav, plan.n_mel)
     return _finish(out, batched, was_numpy)

@@ -44,10 +44,12 @@ void a2m_launch_count_reset(void);
  * The plan carries the constants the reference recomputes on every call: the periodic Hann window
  * and the mel matrix, both computed by the caller on the host in fp64 with the reference formulas
  * (the Python drop-in does that) and rounded to fp32 here.
- *   nfft == 512 (the hot path's 25 ms window at 16 kHz; other lengths return A2M_ERR_UNSUPPORTED),
+ *   nfft: a power of two from 64 to 4096 (mel_features.py:212-214 picks 2^ceil(log2(window)): 512 for the hot path's
+ *   25 ms window at 16 kHz -- the tuned kernel --, 256 at the function's 8 kHz default, 1024 / 2048 at 22.05 / 44.1 kHz;
+ *   anything else returns A2M_ERR_UNSUPPORTED),
  *   1 <= window <= nfft, hop >= 1, 1 <= n_mel <= 128,
- *   mel_weights: host fp64 [nfft/2+1, n_mel] row-major; every column's non-zeros must form one contiguous run of
- *   bins below the Nyquist bin -- true of every matrix spectrogram_to_mel_matrix can produce.
+ *   mel_weights: host fp64 [nfft/2+1, n_mel] row-major (each band is evaluated over the run of bins from its first to
+ *   its last non-zero weight).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct a2m_mel_plan a2m_mel_plan;
 int a2m_mel_plan_create(int window, int hop, int nfft, int n_mel, const double* hann_host,
@@ -67,6 +69,10 @@ int64_t a2m_mel_num_frames(const a2m_mel_plan* plan, int64_t n_samples);
 /* wav: [n_clips] rows of n_samples fp32, row stride wav_stride elements;
  * out: [n_clips, num_frames, n_mel] fp32 contiguous. */
 int a2m_logmel_f32(const a2m_mel_plan* plan, const float* wav, int64_t n_clips, int64_t n_samples,
+                   int64_t wav_stride, float* out, void* stream);
+/* The same for 16-bit PCM (the reference accepts any real dtype, mel_features.py:192-197; the samples are converted
+ * exactly and multiplied by the fp32 window): half the bytes per sample on PCIe and in HBM.  wav_stride in elements. */
+int a2m_logmel_i16(const a2m_mel_plan* plan, const int16_t* wav, int64_t n_clips, int64_t n_samples,
                    int64_t wav_stride, float* out, void* stream);
 /* |STFT| only (mel_features.py:71-92 stft_magnitude): out [n_clips, num_frames, nfft/2+1] fp32 */
 int a2m_stft_magnitude_f32(const a2m_mel_plan* plan, const float* wav, int64_t n_clips, int64_t n_samples,
@@ -118,6 +124,12 @@ int a2m_eval_l1_pck_f32(const float* pred, const float* gt, int64_t n_clips, int
                         double* pck_per_frame /* nullable [n_clips*frames_per_clip] */,
                         float* radius_per_frame /* nullable [n_clips*frames_per_clip] */,
                         a2m_metrics* accum /* device */, void* stream);
+/* The same for float64 poses: the reference computes in the dtype of its inputs (numpy promotion in
+ * motion_evaluation.py:11-23: fp64 arrays -> fp64 bounding box, radius = side * alpha with alpha the Python float,
+ * fp64 distances), so hit counts on fp64 inputs can differ from the fp32 ones near the radius.  Same partial sums. */
+int a2m_eval_l1_pck_f64(const double* pred, const double* gt, int64_t n_clips, int frames_per_clip, double alpha,
+                        double* pck_per_frame /* nullable */, double* radius_per_frame /* nullable */,
+                        a2m_metrics* accum /* device */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * temporal smoothness / jerk metrics of the validation loop: replaces
@@ -154,6 +166,8 @@ int a2m_pose_normalize_f32(const float* pose, const float* mean, const float* st
 int a2m_pose_denormalize_f32(const float* pose, const float* mean, const float* std, int64_t n_frames, float* out,
                              void* stream);
 int a2m_pose_stats_f64(const float* pose, int64_t n_frames, double* accum, void* stream);
+/* neck_sub = 0: statistics of the poses as they are (normalization_tools.py:5-20 get_mean_std); 1: as above. */
+int a2m_pose_stats_ex_f64(const float* pose, int64_t n_frames, int neck_sub, double* accum, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * the one collective of the path: sum the 64-byte partials over the ranks.

@@ -83,11 +83,43 @@ def smoothness_golden():
 
 SMOOTH_CASES = [("b4", 0, 4), ("b1", 7, 1), ("b16", 20, 16)]     # (name, first clip, clips)
 
+# log_mel_spectrogram at sample rates whose 25 ms window needs another fft length (mel_features.py:212-214):
+# (name, clip index, samples, kind, kwargs)
+MEL_NFFT_CASES = [
+    ("sr4000_nfft128", 30, 3000, "noise", dict(audio_sample_rate=4000, log_offset=1e-3, num_mel_bins=16,
+                                               lower_edge_hertz=60.0, upper_edge_hertz=1900.0)),
+    ("sr8000_nfft256", 31, 6000, "noise", dict(audio_sample_rate=8000, log_offset=0.01)),
+    ("sr22050_nfft1024", 32, 12000, "noise", dict(audio_sample_rate=22050, log_offset=0.01, num_mel_bins=64,
+                                                  lower_edge_hertz=125.0, upper_edge_hertz=7500.0)),
+    ("sr44100_nfft2048", 33, 20000, "tone", dict(audio_sample_rate=44100, log_offset=0.01, num_mel_bins=128,
+                                                 lower_edge_hertz=20.0, upper_edge_hertz=20000.0)),
+    ("sr48000_nfft2048_i16", 34, 20000, "int16", dict(audio_sample_rate=48000, log_offset=1.0, num_mel_bins=80,
+                                                      lower_edge_hertz=50.0, upper_edge_hertz=12000.0)),
+]
+
+
+def mel_nfft_golden():
+    """tests/golden/melnfft_reference.npz: the UNMODIFIED mel_features.log_mel_spectrogram on seeded clips at the
+    sample rates above (fft lengths 128 / 256 / 1024 / 2048), plus one |STFT| of a 1024-point transform."""
+    mf = ref_shim.import_reference()["mel_features"]
+    out = {}
+    for name, idx, n, kind, kw in MEL_NFFT_CASES:
+        wav = synth.wav_clip(idx, n, kind)
+        if kind == "int16":
+            wav = wav.astype(np.int16)
+        out[name] = mf.log_mel_spectrogram(wav, **kw)
+    out["stft_mag_1024"] = mf.stft_magnitude(synth.wav_clip(35, 5000), fft_length=1024, hop_length=300, window_length=700)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "melnfft_reference.npz"), **out)
+    print("mel nfft goldens:", {k: v.shape for k, v in out.items()})
+
 
 def main():
     if "--smoothness-only" in sys.argv:
         os.makedirs(GOLDEN_DIR, exist_ok=True)
         return smoothness_golden()
+    if "--mel-nfft-only" in sys.argv:
+        os.makedirs(GOLDEN_DIR, exist_ok=True)
+        return mel_nfft_golden()
     ref = ref_shim.import_reference()
     mf, me, rm = ref["mel_features"], ref["motion_evaluation"], ref["real_motion_model"]
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -154,6 +186,7 @@ def main():
         print(name, pose.shape, mo[name + "_losses"], float(pose.abs().mean()))
     np.savez_compressed(os.path.join(GOLDEN_DIR, "model_reference.npz"), **mo)
     smoothness_golden()
+    mel_nfft_golden()
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
 

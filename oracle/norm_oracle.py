@@ -32,3 +32,17 @@ def mean_std_necksub(batches):
     std[0] = 1.
     std[52] = 1.
     return mean, std
+
+
+def mean_std(batches):
+    """get_mean_std over an iterable of [B, T, 104] batches (normalization_tools.py:5-20): no neck subtraction."""
+    s = torch.zeros(104)
+    q = torch.zeros(104)
+    n = 0
+    for n, pose in enumerate(batches, 1):
+        pose = torch.as_tensor(pose, dtype=torch.float32)
+        s += torch.mean(pose, dim=[0, 1])
+        q += torch.mean(pose ** 2, dim=[0, 1])
+    mean = s / n
+    std = (q / n - mean ** 2) ** 0.5
+    return mean, std

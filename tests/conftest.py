@@ -29,4 +29,4 @@ def pkg():
 def golden():
     import numpy as np
     d = os.path.join(ROOT, "tests", "golden")
-    return {n: np.load(os.path.join(d, n + "_reference.npz")) for n in ("mel", "eval", "model", "smooth")}
+    return {n: np.load(os.path.join(d, n + "_reference.npz")) for n in ("mel", "eval", "model", "smooth", "melnfft")}

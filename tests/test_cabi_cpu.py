@@ -50,7 +50,7 @@ def test_argument_errors_without_gpu(pkg):
     out = ctypes.c_void_p()
     hann = np.ones(400)
     w = np.zeros((257, 64))
-    rc = lib.a2m_mel_plan_create(400, 160, 1024, 64, hann.ctypes.data_as(ctypes.c_void_p),
+    rc = lib.a2m_mel_plan_create(400, 160, 768, 64, hann.ctypes.data_as(ctypes.c_void_p),      # not a power of two
                                  w.ctypes.data_as(ctypes.c_void_p), 0.01, 0, ctypes.byref(out))
     assert rc == -3 and b"not supported" in lib.a2m_last_error()
     rc = lib.a2m_mel_plan_create(600, 160, 512, 64, hann.ctypes.data_as(ctypes.c_void_p),

@@ -29,6 +29,33 @@ def test_compute_pck_matches_reference_golden(ev, golden):
     np.testing.assert_array_equal(rad, eval_oracle.pck_radius(gtf, 0.2))
 
 
+def test_compute_pck_float64_inputs_match_reference_golden(ev, golden):
+    """The reference computes in the dtype of its inputs (motion_evaluation.py:11-23); golden `pck_alpha02_f64` is
+    compute_pck on the float64 casts of the same poses.  fp64 kernel instantiation: bit-exact per-frame rates."""
+    g = golden["eval"]
+    gt, pred = synth.gt_pose_batch(0, 4), synth.noisy_pred_batch(0, 4)
+    gtf, prf = gt.reshape(-1, 2, 52).astype(np.float64), pred.reshape(-1, 2, 52).astype(np.float64)
+    got = ev.compute_pck(prf, gtf, 0.2)
+    assert got.dtype == np.float64
+    np.testing.assert_array_equal(got, g["pck_alpha02_f64"])
+    np.testing.assert_array_equal(got, eval_oracle.pck(prf, gtf, 0.2))
+    # inputs that are exactly representable in fp32 but sit on the radius in fp64 vs fp32 arithmetic: the two widths
+    # are separate code paths, each equal to numpy in its own width
+    rng = np.random.default_rng(3)
+    g64 = rng.normal(0, 50, (512, 2, 52))
+    p64 = g64 + rng.normal(0, 12, g64.shape)
+    np.testing.assert_array_equal(ev.compute_pck(p64, g64, 0.1), eval_oracle.pck(p64, g64, 0.1))
+    np.testing.assert_array_equal(ev.compute_pck(p64.astype(np.float32), g64.astype(np.float32), 0.1),
+                                  eval_oracle.pck(p64.astype(np.float32), g64.astype(np.float32), 0.1))
+    rad = ev.compute_pck_radius(g64, 0.2)
+    assert rad.dtype == np.float64 and rad.shape == (512, 52)
+    np.testing.assert_array_equal(rad, eval_oracle.pck_radius(g64, 0.2))
+    # torch float64 on the device -> torch float64 out, fused partial sums in fp64
+    t = ev.compute_pck(torch.from_numpy(p64).cuda(), torch.from_numpy(g64).cuda(), 0.2)
+    assert t.is_cuda and t.dtype == torch.float64
+    np.testing.assert_array_equal(t.cpu().numpy(), eval_oracle.pck(p64, g64, 0.2))
+
+
 def test_fused_metrics_match_oracle(ev, golden):
     for n_clips, T in ((4, 64), (37, 64), (3, 7), (1, 1)):
         gt, pred = synth.gt_pose_batch(50, n_clips, T), synth.noisy_pred_batch(50, n_clips, T)

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import mel_oracle, synth
-from oracle.make_golden import MEL_CASES
+from oracle.make_golden import MEL_CASES, MEL_NFFT_CASES
 
 pytestmark = pytest.mark.gpu
 
@@ -73,10 +73,60 @@ def test_logmel_edge_cases(mods):
     with pytest.raises(ValueError):
         mods["pose_video.mel_features"].log_mel_spectrogram(np.zeros(1000), audio_sample_rate=16000,
                                                            upper_edge_hertz=9000.0)
-    with pytest.raises(NotImplementedError):
-        mods["pose_video.mel_features"].log_mel_spectrogram(np.zeros(1000))       # 8 kHz default -> nfft 256
+    with pytest.raises(NotImplementedError):                                      # a 25 ms window at 200 kHz: 5000 samples
+        mods["pose_video.mel_features"].log_mel_spectrogram(np.zeros(20000), audio_sample_rate=200000,
+                                                           upper_edge_hertz=3800.0)
     int16 = (synth.wav_clip(3, 4000, "int16")).astype(np.int16)
     assert_d8(lm(int16), mel_oracle.log_mel_audio_repr(int16))
+
+
+def test_logmel_default_parameters_golden(mods, golden):
+    """The function's own defaults (8 kHz -> window 200, hop 80, fft length 256, 20 bands, 125-3800 Hz): the reference
+    golden `default_params_4000`."""
+    got = mods["pose_video.mel_features"].log_mel_spectrogram(synth.wav_clip(10, 4000), log_offset=1e-3)
+    assert got.shape == (48, 20) and got.dtype == np.float64
+    assert_d8(got, golden["mel"]["default_params_4000"])
+
+
+@pytest.mark.parametrize("name,idx,n,kind,kw", MEL_NFFT_CASES)
+def test_logmel_other_fft_lengths_golden(mods, golden, name, idx, n, kind, kw):
+    """fft lengths 128 / 256 / 1024 / 2048 against the unmodified reference (mel_features.py:212-214)."""
+    wav = synth.wav_clip(idx, n, kind)
+    if kind == "int16":
+        wav = wav.astype(np.int16)
+    ref = golden["melnfft"][name]
+    got = mods["pose_video.mel_features"].log_mel_spectrogram(wav, **kw)
+    assert_d8(got, ref)
+    both = mods["pose_video.mel_features"].log_mel_spectrogram(torch.from_numpy(np.stack([wav, wav])).cuda(), **kw)
+    assert both.shape == (2,) + ref.shape and torch.equal(both[0], both[1])
+    assert_d8(both[1].cpu().numpy(), ref)
+
+
+def test_logmel_int16_pcm_path(mods, golden):
+    """int16 PCM is consumed as int16 by the kernel (a2m_logmel_i16): golden `int16_8000`, odd / even row alignment,
+    a strided view, and equality with the fp32 path on the same (exactly representable) samples to fp32 rounding."""
+    lm = mods["pose_video.audio_repr"].log_mel_spectograms
+    pcm = synth.wav_clip(3, 8000, "int16").astype(np.int16)
+    assert_d8(lm(pcm), golden["mel"]["int16_8000"])
+    batch = np.stack([synth.wav_clip(40 + i, 5001, "int16").astype(np.int16) for i in range(5)])      # odd rows: 2-byte aligned only
+    ref = mel_oracle.log_mel_batch(batch)
+    t = torch.from_numpy(batch).cuda()
+    got = lm(t)
+    assert got.dtype == torch.float32 and got.shape == ref.shape
+    assert_d8(got.cpu().numpy(), ref)
+    assert_d8(lm(t[:, 3:4504]).cpu().numpy(), mel_oracle.log_mel_batch(batch[:, 3:4504]))
+    as_f32 = lm(t.float())
+    assert torch.allclose(got, as_f32, rtol=0, atol=2e-5)
+    full = torch.from_numpy(np.stack([synth.wav_clip(50 + i, synth.CLIP_SAMPLES, "int16").astype(np.int16) for i in range(3)])).cuda()
+    assert_d8(lm(full).cpu().numpy(), mel_oracle.log_mel_batch(full.cpu().numpy()))
+
+
+def test_stft_magnitude_1024(mods, golden):
+    got = mods["pose_video.mel_features"].stft_magnitude(synth.wav_clip(35, 5000), fft_length=1024, hop_length=300,
+                                                        window_length=700)
+    ref = golden["melnfft"]["stft_mag_1024"]
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
 def test_stft_magnitude(mods, golden):

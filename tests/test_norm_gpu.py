@@ -43,6 +43,30 @@ def test_streaming_statistics_match_reference(nt):
     assert std[0] == 1.0 and std[52] == 1.0
 
 
+def test_get_mean_std_dropins_follow_the_reference_loop(nt):
+    """normalization_tools.get_mean_std / get_mean_std_necksub(dataloader): the reference's names and loop (mean over
+    batches of per-batch means, so the ragged last batch counts as much as a full one); fp64-accumulated sums vs the
+    reference's fp32 torch.mean: rtol 1e-5 / atol 1e-4 as above."""
+    class Loader:                                                        # what the reference iterates: dataloader.train
+        def __init__(self, batches):
+            self.train = [{"pose/data": b} for b in batches]
+    batches = [torch.from_numpy(synth.gt_pose_batch(8 * i, 8)) for i in range(3)] + \
+              [torch.from_numpy(synth.gt_pose_batch(100, 3))]            # ragged tail
+    mean, std = nt.get_mean_std_necksub(Loader(batches))
+    ref_mean, ref_std = norm_oracle.mean_std_necksub(batches)
+    assert mean.shape == (104,) and mean.dtype == torch.float32 and not mean.is_cuda
+    np.testing.assert_allclose(mean.numpy(), ref_mean.numpy(), rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(std.numpy(), ref_std.numpy(), rtol=1e-5, atol=1e-4)
+    assert std[0] == 1.0 and std[52] == 1.0
+    mean, std = nt.get_mean_std(Loader([b.cuda() for b in batches]))     # device-resident batches work too
+    ref_mean, ref_std = norm_oracle.mean_std(batches)
+    np.testing.assert_allclose(mean.numpy(), ref_mean.numpy(), rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(std.numpy(), ref_std.numpy(), rtol=1e-5, atol=1e-4)
+    assert std[0] != 1.0
+    with pytest.raises(ValueError):
+        nt.get_mean_std(Loader([]))
+
+
 def test_fused_output_denorm_equals_separate_pass(pkg, nt):
     """SelfAttention_G.set_output_denorm: the forward's output pass applies pose * std + mean; bit-equal to the
     separate kernel (and to the oracle's torch restatement) on the same normalised poses; losses unchanged;

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import mel_oracle, eval_oracle, model_oracle, synth, weights
-from oracle.make_golden import MEL_CASES, MODEL_CASES, model_input, real_pose_input
+from oracle.make_golden import MEL_CASES, MEL_NFFT_CASES, MODEL_CASES, model_input, real_pose_input
 
 
 @pytest.mark.parametrize("name,kind,n,idx", MEL_CASES)
@@ -29,6 +29,17 @@ def test_mel_oracle_pieces(golden):
     assert tuple(g["frames_shape_1000"]) == mel_oracle.frames(synth.wav_clip(4, 1000), 400, 160).shape
     np.testing.assert_array_equal(mel_oracle.log_mel(synth.wav_clip(10, 4000), log_offset=1e-3),
                                   g["default_params_4000"])
+    np.testing.assert_array_equal(mel_oracle.stft_mag(synth.wav_clip(35, 5000), 1024, 300, 700),
+                                  golden["melnfft"]["stft_mag_1024"])
+
+
+@pytest.mark.parametrize("name,idx,n,kind,kw", MEL_NFFT_CASES)
+def test_mel_oracle_other_fft_lengths(golden, name, idx, n, kind, kw):
+    """fft lengths 128 / 256 / 1024 / 2048 (mel_features.py:212-214 at other sample rates)."""
+    wav = synth.wav_clip(idx, n, kind)
+    if kind == "int16":
+        wav = wav.astype(np.int16)
+    np.testing.assert_array_equal(mel_oracle.log_mel(wav, **kw), golden["melnfft"][name])
 
 
 def test_mel_self_checks():

@@ -41,6 +41,12 @@ def main():
             byt = B * (68267 * 4 + 425 * 64 * 4)
             print("mel  B=%6d  %.3f ms (best %.3f)  %.2f Mclips/s  %.0f GB/s  %.1f%% of %.0f" % (
                 B, med, best, B / med / 1e3, byt / med / 1e6, 100 * byt / med / 1e6 / PEAK, PEAK))
+            pcm = (3000 * torch.randn(B, 68267, device="cuda")).round().clamp(-32768, 32767).to(torch.int16)
+            med, best = timeit(lambda: lm(pcm), flush=flush)
+            byt = B * (68267 * 2 + 425 * 64 * 4)
+            print("mel16 B=%5d  %.3f ms (best %.3f)  %.2f Mclips/s  %.0f GB/s  %.1f%% of %.0f" % (
+                B, med, best, B / med / 1e3, byt / med / 1e6, 100 * byt / med / 1e6 / PEAK, PEAK))
+            del wav, pcm
     if "eval" in which:
         ev = mods["motion_evaluation"]
         for B in (256, 16384, 100000):
