@@ -55,6 +55,7 @@ SIGNATURES = {
     "a2m_mel_num_frames": (c_i64, [c_void_p, c_i64]),
     "a2m_logmel_f32": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
     "a2m_logmel_i16": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
+    "a2m_mel_schedule_host": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "a2m_stft_magnitude_f32": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
     "a2m_melspec_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_double, c_int, c_int,
                                         ctypes.POINTER(c_void_p)]),

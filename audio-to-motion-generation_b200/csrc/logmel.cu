@@ -18,14 +18,18 @@
 //      through padded shared memory (16-byte accesses, conflict-free both ways).
 //    * the real-input untangle needs Z[256 - k] next to Z[k]: lane l and lane 16 - l swap HALF of their registers
 //      with warp shuffles and each computes both |X[k]| and |X[256 - k]| from one (A, B) pair -- no spectrum dump.
-//    * magnitudes of the pair go to shared memory once ([bin] -> (A, B)); lane l sums bands l, l + 16, ... with one
-//      16-byte load per two bins (both frames) and writes log(mel + offset) straight to global memory.
+//    * magnitudes of the pair go to shared memory once ([bin] -> (A, B)) and are read back ONCE: a triangular filterbank
+//      feeds every bin to at most two adjacent bands, so bin k belongs to "segment" g (band g - 1 with weight v_k, band g
+//      with weight u_k); lane l sums segments l, l + 16, ... (R = sum u mag, F = sum v mag), band g - 1 = R[g - 1] + F[g]
+//      arrives by one shuffle.  The order in which a lane visits its bins is fixed at plan time by an edge colouring of
+//      the (lane, bin mod 16) graph, so the 16 lanes of a step always hit 16 different banks; log(mel + offset) goes
+//      straight to global memory.
 //    fp32 and int16 PCM input (the reference accepts any real dtype; int16 halves the HBM / PCIe bytes per sample).
 //
 //  logmel_generic_kernel  (any power-of-two fft length 64 .. 4096; also |STFT| only)
-//    one CTA per frame, radix-2 Stockham FFT of the even/odd-packed frame in shared memory.  Correct for every
-//    geometry log_mel_spectrogram can ask for (its 8 kHz default -> 256, 22.05 kHz -> 1024, 44.1 / 48 kHz -> 2048);
-//    not tuned.
+//    one CTA per frame, radix-2 Stockham FFT of the even/odd-packed frame in shared memory, in fp64 like the
+//    reference's numpy path.  Correct for every geometry log_mel_spectrogram can ask for (its 8 kHz default -> 256,
+//    22.05 kHz -> 1024, 44.1 / 48 kHz -> 2048); not tuned.
 #include <cmath>
 #include <vector>
 #include <cstring>
@@ -52,12 +56,17 @@ struct FastTables {               // device-resident constants of a plan (512-po
     const float* window;          // [512]  window, zero padded past the window length
     const float2* tw;             // [16][16] exp(-2 pi i m2 k1 / 256) at [k1][m2]
     const float2* untangle;       // [256]  (-sin, -cos)(2 pi k / 512)
-    const int4* col_meta;         // [n_mel] {first bin (even), bin pairs, offset into weights (even), 0}
-    const float* weights;         // [nnz]  0.5 * mel weight (the kernel keeps |2 X|)
+    const int* sched_bin;         // [steps][16] bin a lane reads at a step (257 = none: zero magnitude, zero weights)
+    const float2* sched_uv;       // [steps][16] (u, v) = 0.5 * (weight into band g, weight into band g - 1); the kernel keeps |2 X|
+    const int* round_steps;       // [n_rounds] schedule rows of each round
 };
+constexpr int kMaxRounds = 9;                         // ceil((128 + 1) / 16)
 
 struct FastGeom {
-    int window, hop, n_mel, nnz;
+    int window, hop, n_mel;
+    int n_steps;                  // rows of the mel schedule
+    int n_rounds;                 // segment rounds: round r, lane l -> segment 16 r + l
+    int dist_last;                // the last round holds one segment only: its bins are spread over the lanes instead
     int n_m1;                     // rows of the 16 x 16 input that are not all zero padding: ceil(window / 32)
     int span_bytes;               // per-warp sample buffer (multiple of 16)
     int tables_bytes;             // offset of the first warp's private region
@@ -78,20 +87,20 @@ __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
     }
 }
 
-template <typename InT> __device__ __forceinline__ float to_f32(InT v);
-template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
-template <> __device__ __forceinline__ float to_f32<int16_t>(int16_t v) { return static_cast<float>(v); }
-
-// samples (x[i], x[i + 1]) of a staged span; `aligned`: i is even (fp32: 8-byte aligned, int16: 4-byte aligned)
+// samples (x[i], x[i + 1]) of a staged span; `aligned`: i is even (fp32: 8-byte aligned, int16: 4-byte aligned).
+// Unaligned fp32 pairs are two 4-byte loads; the two 16-lane groups of the warp (grp) take them in opposite order, so
+// that one instruction covers the even banks from one group and the odd banks from the other instead of colliding.
 template <typename InT>
-__device__ __forceinline__ float2 load_pair(const InT* __restrict__ s, int i, bool aligned);
+__device__ __forceinline__ float2 load_pair(const InT* __restrict__ s, int i, bool aligned, int grp);
 template <>
-__device__ __forceinline__ float2 load_pair<float>(const float* __restrict__ s, int i, bool aligned) {
+__device__ __forceinline__ float2 load_pair<float>(const float* __restrict__ s, int i, bool aligned, int grp) {
     if (aligned) return *reinterpret_cast<const float2*>(s + i);
-    return make_float2(s[i], s[i + 1]);
+    const float first = s[i + grp], second = s[i + 1 - grp];
+    return grp ? make_float2(second, first) : make_float2(first, second);
 }
 template <>
-__device__ __forceinline__ float2 load_pair<int16_t>(const int16_t* __restrict__ s, int i, bool aligned) {
+__device__ __forceinline__ float2 load_pair<int16_t>(const int16_t* __restrict__ s, int i, bool aligned, int grp) {
+    (void)grp;
     if (aligned) {
         const uint32_t u = *reinterpret_cast<const uint32_t*>(s + i);
         return make_float2(static_cast<float>(static_cast<int16_t>(u & 0xffffu)), static_cast<float>(static_cast<int16_t>(u >> 16)));
@@ -108,14 +117,15 @@ logmel512_kernel(const InT* __restrict__ wav, long long wav_stride, long long n_
     float* s_window = reinterpret_cast<float*>(smem);
     float2* s_tw = reinterpret_cast<float2*>(smem + 2048);
     float2* s_unt = reinterpret_cast<float2*>(smem + 4096);
-    int4* s_meta = reinterpret_cast<int4*>(smem + 6144);
-    float* s_weights = reinterpret_cast<float*>(smem + 8192);
+    float2* s_uv = reinterpret_cast<float2*>(smem + 6144);                   // [n_steps][16]
+    int* s_bin = reinterpret_cast<int*>(smem + 6144 + g.n_steps * 128);      // [n_steps][16]
+    int* s_round = s_bin + g.n_steps * 16;                                   // [n_rounds]
 
     const int tid = threadIdx.x;
     for (int i = tid; i < kFastNfft; i += kWarps * 32) s_window[i] = tab.window[i];
     for (int i = tid; i < 256; i += kWarps * 32) { s_tw[i] = tab.tw[i]; s_unt[i] = tab.untangle[i]; }
-    for (int i = tid; i < g.n_mel; i += kWarps * 32) s_meta[i] = tab.col_meta[i];
-    for (int i = tid; i < g.nnz; i += kWarps * 32) s_weights[i] = tab.weights[i];
+    for (int i = tid; i < g.n_steps * 16; i += kWarps * 32) { s_uv[i] = tab.sched_uv[i]; s_bin[i] = tab.sched_bin[i]; }
+    if (tid < g.n_rounds) s_round[tid] = tab.round_steps[tid];
 
     const int warp = tid >> 5, lane = tid & 31;
     const int l = lane & 15, grp = lane >> 4;
@@ -195,8 +205,8 @@ logmel512_kernel(const InT* __restrict__ wav, long long wav_stride, long long n_
                     const float2 w = *reinterpret_cast<const float2*>(s_window + n);
                     // past the window (last row) the buffer holds samples of later frames or of an earlier tile: finite
                     // values (the buffer is zeroed once, then only ever holds copied input), times the zero padding
-                    const float2 xa = load_pair<InT>(s, rel_a + n, al_a);
-                    const float2 xb = load_pair<InT>(s, rel_b + n, al_b);
+                    const float2 xa = load_pair<InT>(s, rel_a + n, al_a, grp);
+                    const float2 xb = load_pair<InT>(s, rel_b + n, al_b, grp);
                     v[m1] = a2m_fft::make(a2m_fft::pack(xa.x * w.x, xb.x * w.x), a2m_fft::pack(xa.y * w.y, xb.y * w.y));
                 } else {
                     v[m1] = a2m_fft::make(a2m_fft::pack(0.f, 0.f), a2m_fft::pack(0.f, 0.f));
@@ -258,25 +268,42 @@ logmel512_kernel(const InT* __restrict__ wav, long long wav_stride, long long n_
         }
         __syncwarp();
 
-        // ---- mel bands l, l + 16, ...: one 16-byte load = two bins of both frames ----------------------------------
+        // ---- mel: segment g = 16 r + l per round; band g - 1 = R[g - 1] + F[g] ---------------------------------------
         {
             const int fa = f0 + 2 * grp;
             float* row_a = out + (static_cast<long long>(clip) * frames_per_clip + fa) * g.n_mel;
             const bool has_a = fa < frames_per_clip, has_b = fa + 1 < frames_per_clip;
-            for (int c = l; c < g.n_mel; c += 16) {
-                const int4 m = s_meta[c];
-                const ulonglong2* mg = reinterpret_cast<const ulonglong2*>(mag + m.x);
-                const float2* w = reinterpret_cast<const float2*>(s_weights + m.z);
-                pair_t acc = a2m_fft::pack(0.f, 0.f);
-                for (int j = 0; j < m.y; ++j) {
-                    const ulonglong2 q = mg[j];
-                    const float2 ww = w[j];
-                    acc = a2m_fft::fma2(q.x, a2m_fft::bcast(ww.x), acc);
-                    acc = a2m_fft::fma2(q.y, a2m_fft::bcast(ww.y), acc);
+            const pair_t zero = a2m_fft::pack(0.f, 0.f);
+            pair_t carry = zero;                                             // R of lane 15 of the previous round
+            int step = 0;
+            for (int r = 0; r < g.n_rounds; ++r) {
+                const int n_t = s_round[r];
+                pair_t acc_r = zero, acc_f = zero;
+                for (int t = 0; t < n_t; ++t, ++step) {
+                    const int bin = s_bin[step * 16 + l];
+                    const float2 uv = s_uv[step * 16 + l];
+                    const pair_t m = *reinterpret_cast<const pair_t*>(mag + bin);
+                    acc_r = a2m_fft::fma2(m, a2m_fft::bcast(uv.x), acc_r);
+                    acc_f = a2m_fft::fma2(m, a2m_fft::bcast(uv.y), acc_f);
                 }
-                const float ea = a2m_fft::lo(acc), eb = a2m_fft::hi(acc);
-                if (has_a) row_a[c] = __logf(g.log_mode ? (ea == 0.f ? g.log_offset : ea) : ea + g.log_offset);
-                if (has_b) row_a[g.n_mel + c] = __logf(g.log_mode ? (eb == 0.f ? g.log_offset : eb) : eb + g.log_offset);
+                int band = 16 * r + l - 1;
+                pair_t e;
+                if (g.dist_last && r == g.n_rounds - 1) {                    // one segment spread over the lanes: band n_mel - 1
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) acc_f = a2m_fft::add2(acc_f, __shfl_xor_sync(0xffffffffu, acc_f, o, 16));
+                    e = a2m_fft::add2(carry, acc_f);
+                    band = lane0 ? g.n_mel - 1 : -1;
+                } else {
+                    pair_t r_prev = __shfl_sync(0xffffffffu, acc_r, (l + 15) & 15, 16);
+                    if (lane0) r_prev = carry;
+                    carry = __shfl_sync(0xffffffffu, acc_r, 15, 16);
+                    e = a2m_fft::add2(r_prev, acc_f);
+                }
+                if (band >= 0 && band < g.n_mel) {
+                    const float ea = a2m_fft::lo(e), eb = a2m_fft::hi(e);
+                    if (has_a) row_a[band] = __logf(g.log_mode ? (ea == 0.f ? g.log_offset : ea) : ea + g.log_offset);
+                    if (has_b) row_a[g.n_mel + band] = __logf(g.log_mode ? (eb == 0.f ? g.log_offset : eb) : eb + g.log_offset);
+                }
             }
         }
         __syncwarp();                                                        // the magnitudes are exchange rows again
@@ -284,18 +311,18 @@ logmel512_kernel(const InT* __restrict__ wav, long long wav_stride, long long n_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// generic kernel
+// generic kernel: fp64 arithmetic like the reference's numpy path (window, FFT, magnitude, mel sum), fp32 in / out
 // ---------------------------------------------------------------------------------------------------------------
 struct GenTables {
-    const float* window;          // [nfft] zero padded
-    const float2* tw;             // [n/2]  exp(-2 pi i t / n), n = nfft / 2
-    const float2* untangle;       // [n+1]  (-sin, -cos)(2 pi k / nfft)
+    const double* window;         // [nfft] zero padded
+    const double2* tw;            // [n/2]  exp(-2 pi i t / n), n = nfft / 2
+    const double2* untangle;      // [n+1]  (-sin, -cos)(2 pi k / nfft)
     const int4* col_meta;         // [n_mel] {first bin, bins, offset into weights, 0}
-    const float* weights;         // [nnz]
+    const double* weights;        // [nnz]
 };
 struct GenGeom {
     int window, hop, nfft, n_mel;
-    float log_offset;
+    double log_offset;
     int log_mode;
 };
 constexpr int kGenThreads = 128;
@@ -306,9 +333,9 @@ logmel_generic_kernel(const InT* __restrict__ wav, long long wav_stride, long lo
                       GenTables tab, GenGeom g, float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int n = g.nfft / 2;
-    float2* buf0 = reinterpret_cast<float2*>(smem);
-    float2* buf1 = buf0 + n;
-    float* mag = reinterpret_cast<float*>(buf1 + n);                         // [n + 1]
+    double2* buf0 = reinterpret_cast<double2*>(smem);
+    double2* buf1 = buf0 + n;
+    double* mag = reinterpret_cast<double*>(buf1 + n);                       // [n + 1]
     const int tid = threadIdx.x;
     const long long total = n_clips * frames_per_clip;
     for (long long fr = blockIdx.x; fr < total; fr += gridDim.x) {
@@ -316,49 +343,169 @@ logmel_generic_kernel(const InT* __restrict__ wav, long long wav_stride, long lo
         const InT* src = wav + clip * wav_stride + (fr - clip * frames_per_clip) * g.hop;
         for (int m = tid; m < n; m += kGenThreads) {                         // even/odd packing, window, zero padding
             const int i = 2 * m;
-            const float a = i < g.window ? to_f32<InT>(src[i]) * __ldg(tab.window + i) : 0.f;
-            const float b = i + 1 < g.window ? to_f32<InT>(src[i + 1]) * __ldg(tab.window + i + 1) : 0.f;
-            buf0[m] = make_float2(a, b);
+            const double a = i < g.window ? static_cast<double>(src[i]) * __ldg(tab.window + i) : 0.0;
+            const double b = i + 1 < g.window ? static_cast<double>(src[i + 1]) * __ldg(tab.window + i + 1) : 0.0;
+            buf0[m] = make_double2(a, b);
         }
         __syncthreads();
-        float2* x = buf0;
-        float2* y = buf1;
+        double2* x = buf0;
+        double2* y = buf1;
         for (int len = 1; len < n; len <<= 1) {                              // radix-2 Stockham, autosort
             const int tw_step = n / (2 * len);
             for (int j = tid; j < n / 2; j += kGenThreads) {
                 const int k = j & (len - 1);
-                const float2 w = __ldg(tab.tw + k * tw_step);
-                const float2 a = x[j], b0 = x[j + n / 2];
-                const float2 b = make_float2(b0.x * w.x - b0.y * w.y, b0.x * w.y + b0.y * w.x);
+                const double2 w = __ldg(tab.tw + k * tw_step);
+                const double2 a = x[j], b0 = x[j + n / 2];
+                const double2 b = make_double2(b0.x * w.x - b0.y * w.y, b0.x * w.y + b0.y * w.x);
                 const int idx = ((j - k) << 1) + k;
-                y[idx] = make_float2(a.x + b.x, a.y + b.y);
-                y[idx + len] = make_float2(a.x - b.x, a.y - b.y);
+                y[idx] = make_double2(a.x + b.x, a.y + b.y);
+                y[idx + len] = make_double2(a.x - b.x, a.y - b.y);
             }
             __syncthreads();
-            float2* t = x; x = y; y = t;
+            double2* t = x; x = y; y = t;
         }
         for (int k = tid; k <= n; k += kGenThreads) {                        // real-input untangle, bins 0..n
-            const float2 zk = x[k & (n - 1)], zq = x[(n - k) & (n - 1)];
-            const float2 t = __ldg(tab.untangle + k);
-            const float ar = zk.x + zq.x, ai = zk.y - zq.y, br = zk.x - zq.x, bi = zk.y + zq.y;
-            const float xr = ar + (t.x * br - t.y * bi), xi = ai + (t.x * bi + t.y * br);
-            mag[k] = 0.5f * sqrtf(xr * xr + xi * xi);
+            const double2 zk = x[k & (n - 1)], zq = x[(n - k) & (n - 1)];
+            const double2 t = __ldg(tab.untangle + k);
+            const double ar = zk.x + zq.x, ai = zk.y - zq.y, br = zk.x - zq.x, bi = zk.y + zq.y;
+            const double xr = ar + (t.x * br - t.y * bi), xi = ai + (t.x * bi + t.y * br);
+            mag[k] = 0.5 * sqrt(xr * xr + xi * xi);
         }
         __syncthreads();
         if (kMagOnly) {
             float* o = out + fr * (n + 1);
-            for (int k = tid; k <= n; k += kGenThreads) o[k] = mag[k];
+            for (int k = tid; k <= n; k += kGenThreads) o[k] = static_cast<float>(mag[k]);
         } else {
             float* o = out + fr * g.n_mel;
             for (int c = tid; c < g.n_mel; c += kGenThreads) {
                 const int4 m = __ldg(tab.col_meta + c);
-                float acc = 0.f;
-                for (int j = 0; j < m.y; ++j) acc = fmaf(mag[m.x + j], __ldg(tab.weights + m.z + j), acc);
-                o[c] = logf(g.log_mode ? (acc == 0.f ? g.log_offset : acc) : acc + g.log_offset);
+                double acc = 0.0;
+                for (int j = 0; j < m.y; ++j) acc = fma(mag[m.x + j], __ldg(tab.weights + m.z + j), acc);
+                o[c] = static_cast<float>(log(g.log_mode ? (acc == 0.0 ? g.log_offset : acc) : acc + g.log_offset));
             }
         }
         __syncthreads();                                                     // mag / buffers are rewritten by the next frame
     }
+}
+
+}  // namespace
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// mel schedule of the 512-point kernel (host, plan time)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct MelSchedule {
+    bool ok = false;
+    std::vector<int> bin;          // [steps][16]
+    std::vector<float2> uv;        // [steps][16]
+    int n_rounds = 0, dist_last = 0;
+    int round_steps[kMaxRounds + 3] = {};
+};
+
+// Proper edge colouring of a bipartite multigraph (16 lanes x 16 residues, one edge per bin) with max-degree many
+// colours (Koenig): colour = the step at which the lane reads the bin.  Returns the number of colours.
+int colour_edges(const std::vector<int>& eu, const std::vector<int>& ev, std::vector<int>& colour) {
+    const int n_e = static_cast<int>(eu.size());
+    int deg_u[16] = {}, deg_v[16] = {}, delta = 0;
+    for (int e = 0; e < n_e; ++e) { ++deg_u[eu[e]]; ++deg_v[ev[e]]; }
+    for (int i = 0; i < 16; ++i) { if (deg_u[i] > delta) delta = deg_u[i]; if (deg_v[i] > delta) delta = deg_v[i]; }
+    std::vector<int> at_u(16 * (delta + 1), -1), at_v(16 * (delta + 1), -1);   // [vertex][colour] -> edge
+    colour.assign(n_e, -1);
+    for (int e = 0; e < n_e; ++e) {
+        const int u = eu[e], v = ev[e];
+        int a = 0, b = 0;
+        while (at_u[u * delta + a] >= 0) ++a;               // free at u
+        while (at_v[v * delta + b] >= 0) ++b;               // free at v
+        if (a != b) {
+            // flip the a/b alternating path that starts at v with colour a (it cannot reach u: the graph is bipartite)
+            std::vector<int> path;
+            int x = v, c = a;
+            bool on_v = true;
+            for (;;) {
+                const int f = on_v ? at_v[x * delta + c] : at_u[x * delta + c];
+                if (f < 0) break;
+                path.push_back(f);
+                x = on_v ? eu[f] : ev[f];
+                on_v = !on_v;
+                c = (c == a) ? b : a;
+            }
+            for (int f : path) { at_u[eu[f] * delta + colour[f]] = -1; at_v[ev[f] * delta + colour[f]] = -1; }
+            for (int f : path) {
+                colour[f] = (colour[f] == a) ? b : a;
+                at_u[eu[f] * delta + colour[f]] = f;
+                at_v[ev[f] * delta + colour[f]] = f;
+            }
+        }
+        colour[e] = a;
+        at_u[u * delta + a] = e;
+        at_v[v * delta + a] = e;
+    }
+    return delta;
+}
+
+// weights: fp64 [257, n_mel] row-major.  Fails (ok = false) when a bin feeds more than two bands or two bands that are
+// not adjacent -- not a triangular filterbank; the generic kernel handles such a matrix.
+MelSchedule build_mel_schedule(const double* w, int n_mel) {
+    MelSchedule s;
+    const int bins = 257, n_seg = n_mel + 1;
+    std::vector<int> seg(bins, -1);
+    std::vector<float> u(bins, 0.f), v(bins, 0.f);
+    std::vector<int> peak(n_mel, 0);                        // bin of each band's largest weight
+    for (int c = 0; c < n_mel; ++c)
+        for (int k = 0; k < bins; ++k)
+            if (w[static_cast<size_t>(k) * n_mel + c] > w[static_cast<size_t>(peak[c]) * n_mel + c]) peak[c] = k;
+    for (int k = 0; k < bins; ++k) {
+        int c0 = -1, c1 = -1, cnt = 0;
+        for (int c = 0; c < n_mel; ++c)
+            if (w[static_cast<size_t>(k) * n_mel + c] != 0.0) { if (cnt == 0) c0 = c; c1 = c; ++cnt; }
+        if (cnt == 0) continue;
+        if (cnt > 2 || c1 - c0 > 1) return s;
+        // segment g feeds band g - 1 with v and band g with u: a bin of two bands (c, c + 1) is in segment c + 1; a bin
+        // of one band c is in segment c (rising edge, u) or c + 1 (falling edge past the peak, v)
+        if (cnt == 2) {
+            seg[k] = c1;
+            v[k] = 0.5f * static_cast<float>(w[static_cast<size_t>(k) * n_mel + c0]);      // 0.5: the kernel keeps |2 X|
+            u[k] = 0.5f * static_cast<float>(w[static_cast<size_t>(k) * n_mel + c1]);
+        } else if (k > peak[c0]) {
+            seg[k] = c0 + 1;
+            v[k] = 0.5f * static_cast<float>(w[static_cast<size_t>(k) * n_mel + c0]);
+        } else {
+            seg[k] = c0;
+            u[k] = 0.5f * static_cast<float>(w[static_cast<size_t>(k) * n_mel + c0]);
+        }
+    }
+    s.n_rounds = (n_seg + 15) / 16;
+    // a last round that holds segment n_mel alone (n_mel a multiple of 16: the falling edge of the last band) would
+    // keep one lane busy for all its bins: spread them over the 16 lanes, the kernel adds the lanes up
+    int n_last = 0;
+    for (int k = 0; k < bins; ++k) n_last += seg[k] == n_mel;
+    s.dist_last = (n_seg % 16 == 1 && n_last > 1) ? 1 : 0;
+    for (int r = 0; r < s.n_rounds; ++r) {
+        std::vector<int> eu, ev, ek, colour;
+        int spread = 0;
+        for (int k = 0; k < bins; ++k)
+            if (seg[k] >= 0 && seg[k] / 16 == r) {
+                eu.push_back(s.dist_last && r == s.n_rounds - 1 ? (spread++) % 16 : seg[k] % 16);
+                ev.push_back(k % 16);
+                ek.push_back(k);
+            }
+        const int steps = eu.empty() ? 0 : colour_edges(eu, ev, colour);
+        if (steps > 255) return s;
+        s.round_steps[r] = steps;
+        const size_t base = s.bin.size();
+        s.bin.resize(base + static_cast<size_t>(steps) * 16, 257);
+        s.uv.resize(base + static_cast<size_t>(steps) * 16, make_float2(0.f, 0.f));
+        for (size_t e = 0; e < eu.size(); ++e) {
+            const size_t slot = base + static_cast<size_t>(colour[e]) * 16 + eu[e];
+            if (s.bin[slot] != 257) return s;               // colouring bug guard
+            s.bin[slot] = ek[e];
+            s.uv[slot] = make_float2(u[ek[e]], v[ek[e]]);
+        }
+    }
+    s.ok = true;
+    return s;
 }
 
 }  // namespace
@@ -370,13 +517,35 @@ struct a2m_mel_plan {
     int device;
     int window, hop, nfft, n_mel;
     float log_offset;
+    double log_offset64;
     int log_mode;
     void* blob;           // one device allocation holding all tables
     bool fast;            // the 512-point kernel's tables are present
-    int fast_nnz;
+    int n_steps, n_rounds, dist_last;
     FastTables ftab;
     GenTables gtab;
 };
+
+// Host-only diagnostic: the mel schedule the 512-point kernel would use for this filterbank (tests check on the CPU
+// that it reproduces the matrix and that the 16 lanes of a step read 16 different banks).
+extern "C" int a2m_mel_schedule_host(const double* mel_weights_host, int n_mel, int capacity_steps, int* bin_out,
+                                     float* uv_out, int* round_steps_out, int* n_rounds_out, int* dist_last_out) {
+    A2M_ARG_CHECK(mel_weights_host && bin_out && uv_out && round_steps_out && n_rounds_out && dist_last_out,
+                  "a2m_mel_schedule_host: NULL argument");
+    A2M_ARG_CHECK(n_mel >= 1 && n_mel <= kMaxMel, "a2m_mel_schedule_host: n_mel %d must be in [1, %d]", n_mel, kMaxMel);
+    const MelSchedule s = build_mel_schedule(mel_weights_host, n_mel);
+    if (!s.ok) {
+        a2m_set_error("a2m_mel_schedule_host: not a triangular filterbank (a bin feeds more than two adjacent bands)");
+        return A2M_ERR_UNSUPPORTED;
+    }
+    const int steps = static_cast<int>(s.bin.size() / 16);
+    A2M_ARG_CHECK(steps <= capacity_steps, "a2m_mel_schedule_host: %d steps, capacity %d", steps, capacity_steps);
+    for (size_t i = 0; i < s.bin.size(); ++i) { bin_out[i] = s.bin[i]; uv_out[2 * i] = s.uv[i].x; uv_out[2 * i + 1] = s.uv[i].y; }
+    for (int r = 0; r < s.n_rounds; ++r) round_steps_out[r] = s.round_steps[r];
+    *n_rounds_out = s.n_rounds;
+    *dist_last_out = s.dist_last;
+    return steps;
+}
 
 extern "C" int a2m_mel_plan_create(int window, int hop, int nfft, int n_mel, const double* hann_host,
                                    const double* mel_weights_host, double log_offset, int device,
@@ -407,37 +576,29 @@ extern "C" int a2m_mel_plan_create_ex(int window, int hop, int nfft, int n_mel, 
         for (int k = 0; k < bins; ++k)
             if (mel_weights_host[static_cast<size_t>(k) * n_mel + c] != 0.0) { if (first[c] < 0) first[c] = k; last[c] = k; }
     }
-    auto weight = [&](int k, int c) { return k < bins ? static_cast<float>(mel_weights_host[static_cast<size_t>(k) * n_mel + c]) : 0.f; };
+    auto weight = [&](int k, int c) { return k < bins ? mel_weights_host[static_cast<size_t>(k) * n_mel + c] : 0.0; };
 
     // generic kernel: exact runs
     std::vector<int4> gmeta(kMaxMel, make_int4(0, 0, 0, 0));
-    std::vector<float> gweights;
+    std::vector<double> gweights;
     for (int c = 0; c < n_mel; ++c) {
         if (first[c] < 0) continue;                         // empty band: log(offset)
         gmeta[c] = make_int4(first[c], last[c] - first[c] + 1, static_cast<int>(gweights.size()), 0);
         for (int k = first[c]; k <= last[c]; ++k) gweights.push_back(weight(k, c));
     }
-    // 512-point kernel: runs padded (zero weights) to whole bin PAIRS starting on an even bin; 0.5 folded in (exact)
-    const bool fast = nfft == kFastNfft;
-    std::vector<int4> fmeta(kMaxMel, make_int4(0, 0, 0, 0));
-    std::vector<float> fweights;
-    if (fast) {
-        for (int c = 0; c < n_mel; ++c) {
-            if (first[c] < 0) continue;
-            const int lo = first[c] & ~1, hi = last[c] | 1;                 // hi <= 257
-            fmeta[c] = make_int4(lo, (hi - lo + 1) / 2, static_cast<int>(fweights.size()), 0);
-            for (int k = lo; k <= hi; ++k) fweights.push_back(0.5f * weight(k, c));
-        }
-    }
+    // 512-point kernel: the mel sum as a plan-time schedule (see build_mel_schedule); a matrix that is not a triangular
+    // filterbank runs on the generic kernel
+    MelSchedule sched;
+    if (nfft == kFastNfft) sched = build_mel_schedule(mel_weights_host, n_mel);
+    const bool fast = sched.ok;
 
     const double two_pi = 6.283185307179586476925286766559;
     std::vector<float> win(nfft, 0.f);                      // zero padded: samples past the window contribute nothing
-    for (int i = 0; i < window; ++i) win[i] = static_cast<float>(hann_host[i]);
-    std::vector<float2> gtw(n / 2), gunt(n + 1);
-    for (int t = 0; t < n / 2; ++t)
-        gtw[t] = make_float2(static_cast<float>(std::cos(two_pi * t / n)), static_cast<float>(-std::sin(two_pi * t / n)));
-    for (int k = 0; k <= n; ++k)
-        gunt[k] = make_float2(static_cast<float>(-std::sin(two_pi * k / nfft)), static_cast<float>(-std::cos(two_pi * k / nfft)));
+    std::vector<double> gwin(nfft, 0.0);
+    for (int i = 0; i < window; ++i) { win[i] = static_cast<float>(hann_host[i]); gwin[i] = hann_host[i]; }
+    std::vector<double2> gtw(n / 2), gunt(n + 1);
+    for (int t = 0; t < n / 2; ++t) gtw[t] = make_double2(std::cos(two_pi * t / n), -std::sin(two_pi * t / n));
+    for (int k = 0; k <= n; ++k) gunt[k] = make_double2(-std::sin(two_pi * k / nfft), -std::cos(two_pi * k / nfft));
     std::vector<float2> ftw(256), funt(256);
     for (int k1 = 0; k1 < 16; ++k1)
         for (int m2 = 0; m2 < 16; ++m2) {                   // [k1][m2]: a 16-lane group reads one contiguous row
@@ -450,38 +611,45 @@ extern "C" int a2m_mel_plan_create_ex(int window, int hop, int nfft, int n_mel, 
     A2M_CUDA_CHECK(cudaSetDevice(device));
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
-    const size_t o_win = carve(nfft * 4), o_gtw = carve((n / 2) * 8), o_gunt = carve((n + 1) * 8), o_gmeta = carve(kMaxMel * 16),
-                 o_gw = carve((gweights.size() + 4) * 4), o_ftw = carve(256 * 8), o_funt = carve(256 * 8),
-                 o_fmeta = carve(kMaxMel * 16), o_fw = carve((fweights.size() + 4) * 4);
+    const size_t o_win = carve(nfft * 4), o_gwin = carve(nfft * 8), o_gtw = carve((n / 2) * 16), o_gunt = carve((n + 1) * 16),
+                 o_gmeta = carve(kMaxMel * 16), o_gw = carve((gweights.size() + 4) * 8), o_ftw = carve(256 * 8),
+                 o_funt = carve(256 * 8), o_sbin = carve((sched.bin.size() + 4) * 4), o_suv = carve((sched.uv.size() + 4) * 8),
+                 o_srnd = carve(sizeof(sched.round_steps));
     unsigned char* blob = nullptr;
     A2M_CUDA_CHECK(cudaMalloc(&blob, off));
     std::vector<unsigned char> host(off, 0);
     memcpy(host.data() + o_win, win.data(), nfft * 4);
-    memcpy(host.data() + o_gtw, gtw.data(), gtw.size() * 8);
-    memcpy(host.data() + o_gunt, gunt.data(), gunt.size() * 8);
+    memcpy(host.data() + o_gwin, gwin.data(), nfft * 8);
+    memcpy(host.data() + o_gtw, gtw.data(), gtw.size() * 16);
+    memcpy(host.data() + o_gunt, gunt.data(), gunt.size() * 16);
     memcpy(host.data() + o_gmeta, gmeta.data(), kMaxMel * 16);
-    if (!gweights.empty()) memcpy(host.data() + o_gw, gweights.data(), gweights.size() * 4);
+    if (!gweights.empty()) memcpy(host.data() + o_gw, gweights.data(), gweights.size() * 8);
     memcpy(host.data() + o_ftw, ftw.data(), 256 * 8);
     memcpy(host.data() + o_funt, funt.data(), 256 * 8);
-    memcpy(host.data() + o_fmeta, fmeta.data(), kMaxMel * 16);
-    if (!fweights.empty()) memcpy(host.data() + o_fw, fweights.data(), fweights.size() * 4);
+    if (!sched.bin.empty()) {
+        memcpy(host.data() + o_sbin, sched.bin.data(), sched.bin.size() * 4);
+        memcpy(host.data() + o_suv, sched.uv.data(), sched.uv.size() * 8);
+    }
+    memcpy(host.data() + o_srnd, sched.round_steps, sizeof(sched.round_steps));
     cudaError_t e = cudaMemcpy(blob, host.data(), off, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(blob); a2m_set_error("a2m_mel_plan_create: upload failed: %s", cudaGetErrorString(e)); return (int)e; }
 
     a2m_mel_plan* p = new a2m_mel_plan();
     p->device = device; p->window = window; p->hop = hop; p->nfft = nfft; p->n_mel = n_mel;
-    p->log_offset = static_cast<float>(log_offset); p->log_mode = log_mode; p->blob = blob;
-    p->fast = fast; p->fast_nnz = static_cast<int>(fweights.size());
-    p->gtab.window = reinterpret_cast<const float*>(blob + o_win);
-    p->gtab.tw = reinterpret_cast<const float2*>(blob + o_gtw);
-    p->gtab.untangle = reinterpret_cast<const float2*>(blob + o_gunt);
+    p->log_offset = static_cast<float>(log_offset); p->log_offset64 = log_offset; p->log_mode = log_mode; p->blob = blob;
+    p->fast = fast; p->n_steps = static_cast<int>(sched.bin.size() / 16); p->n_rounds = sched.n_rounds;
+    p->dist_last = sched.dist_last;
+    p->gtab.window = reinterpret_cast<const double*>(blob + o_gwin);
+    p->gtab.tw = reinterpret_cast<const double2*>(blob + o_gtw);
+    p->gtab.untangle = reinterpret_cast<const double2*>(blob + o_gunt);
     p->gtab.col_meta = reinterpret_cast<const int4*>(blob + o_gmeta);
-    p->gtab.weights = reinterpret_cast<const float*>(blob + o_gw);
-    p->ftab.window = p->gtab.window;
+    p->gtab.weights = reinterpret_cast<const double*>(blob + o_gw);
+    p->ftab.window = reinterpret_cast<const float*>(blob + o_win);
     p->ftab.tw = reinterpret_cast<const float2*>(blob + o_ftw);
     p->ftab.untangle = reinterpret_cast<const float2*>(blob + o_funt);
-    p->ftab.col_meta = reinterpret_cast<const int4*>(blob + o_fmeta);
-    p->ftab.weights = reinterpret_cast<const float*>(blob + o_fw);
+    p->ftab.sched_bin = reinterpret_cast<const int*>(blob + o_sbin);
+    p->ftab.sched_uv = reinterpret_cast<const float2*>(blob + o_suv);
+    p->ftab.round_steps = reinterpret_cast<const int*>(blob + o_srnd);
     *out = p;
     return A2M_OK;
 }
@@ -509,13 +677,14 @@ constexpr int kSmemCap = 227 * 1024;
 template <typename InT>
 int fast_geometry(const a2m_mel_plan* plan, FastGeom* g) {
     if (!plan->fast) return 0;
-    g->window = plan->window; g->hop = plan->hop; g->n_mel = plan->n_mel; g->nnz = plan->fast_nnz;
+    g->window = plan->window; g->hop = plan->hop; g->n_mel = plan->n_mel;
+    g->n_steps = plan->n_steps; g->n_rounds = plan->n_rounds; g->dist_last = plan->dist_last;
     g->n_m1 = (plan->window + 31) / 32;
     g->log_offset = plan->log_offset; g->log_mode = plan->log_mode;
     // the furthest element a tile reads: alignment shift (< 16 bytes) + 3 hops + the padded rows of the last frame
     const long long span_elems = 16 / static_cast<int>(sizeof(InT)) + 3LL * plan->hop + 32LL * g->n_m1;
     const long long span_bytes = (span_elems * static_cast<long long>(sizeof(InT)) + 15) & ~15LL;
-    g->tables_bytes = (8192 + ((plan->fast_nnz + 3) / 4) * 16 + 15) & ~15;
+    g->tables_bytes = (6144 + plan->n_steps * (128 + 64) + (kMaxRounds + 3) * 4 + 15) & ~15;
     const long long total = g->tables_bytes + static_cast<long long>(kWarps) * (2 * kXchgGroupBytes + span_bytes + 16);
     if (total > kSmemCap) return 0;
     g->span_bytes = static_cast<int>(span_bytes);
@@ -554,11 +723,11 @@ int launch_logmel(const a2m_mel_plan* plan, const InT* wav, int64_t n_clips, int
     } else {
         GenGeom g;
         g.window = plan->window; g.hop = plan->hop; g.nfft = plan->nfft; g.n_mel = plan->n_mel;
-        g.log_offset = plan->log_offset; g.log_mode = plan->log_mode;
-        const int smem = plan->nfft * 8 + (plan->nfft / 2 + 4) * 4;
+        g.log_offset = plan->log_offset64; g.log_mode = plan->log_mode;
+        const int smem = plan->nfft * 16 + (plan->nfft / 2 + 4) * 8;
         static A2mPerDeviceOnce attr_set;
         if (attr_set.first())
-            A2M_CUDA_CHECK(cudaFuncSetAttribute(logmel_generic_kernel<InT, kMagOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            A2M_CUDA_CHECK(cudaFuncSetAttribute(logmel_generic_kernel<InT, kMagOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         long long grid = n_clips * frames;
         const long long cap = 16LL * a2m_num_sms();
         if (grid > cap) grid = cap;

@@ -110,7 +110,8 @@ def log_mel_400(y, sr=16000, eps=1e-6):
     if wav.shape[1] < 512:
         raise ValueError("log_mel_400: %d samples are fewer than one 512-sample frame" % wav.shape[1])
     plan = _plan_400(wav.device.index, eps)
-    out = mel_features._run(_cabi.lib().a2m_logmel_f32, plan, wav, 64)
+    entry = _cabi.lib().a2m_logmel_i16 if wav.dtype == torch.int16 else _cabi.lib().a2m_logmel_f32
+    out = mel_features._run(entry, plan, wav, 64)
     if not batched:
         out = out[0]
     return out.cpu().numpy() if was_numpy else out
@@ -145,6 +146,8 @@ def log_mel_512(y, sr, eps=1e-10, pad_mode="reflect"):
     if pad_mode not in ("reflect", "constant", "zeros"):
         raise ValueError("log_mel_512: pad_mode must be 'reflect' or 'constant', got %r" % (pad_mode,))
     wav, batched, was_numpy = mel_features._to_device(y)
+    if wav.dtype != torch.float32:
+        wav = wav.to(torch.float32)                 # the 2048-point kernel reads fp32
     if pad_mode == "reflect" and wav.shape[1] <= 1024:
         raise ValueError("log_mel_512: reflect padding needs more than 1024 samples, got %d" % wav.shape[1])
     plan = _plan_512(wav.device.index, float(sr), eps, pad_mode)

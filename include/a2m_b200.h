@@ -74,6 +74,13 @@ int a2m_logmel_f32(const a2m_mel_plan* plan, const float* wav, int64_t n_clips, 
  * exactly and multiplied by the fp32 window): half the bytes per sample on PCIe and in HBM.  wav_stride in elements. */
 int a2m_logmel_i16(const a2m_mel_plan* plan, const int16_t* wav, int64_t n_clips, int64_t n_samples,
                    int64_t wav_stride, float* out, void* stream);
+/* Host-only diagnostic (no GPU needed): the plan-time schedule of the 512-point kernel's mel sum for a [257, n_mel]
+ * filterbank -- per step and lane the bin read (257 = none) and its weights (u into band g, v into band g - 1, both
+ * carrying the factor 0.5 of the kernel's |2 X|), for segment g = 16 * round + lane.  Returns the number of steps
+ * (rows of 16), or A2M_ERR_UNSUPPORTED when the matrix is not a triangular filterbank (then the general kernel runs).
+ * bin_out: int[capacity_steps * 16]; uv_out: float[capacity_steps * 32]; round_steps_out: int[12]. */
+int a2m_mel_schedule_host(const double* mel_weights_host, int n_mel, int capacity_steps, int* bin_out, float* uv_out,
+                          int* round_steps_out, int* n_rounds_out, int* dist_last_out);
 /* |STFT| only (mel_features.py:71-92 stft_magnitude): out [n_clips, num_frames, nfft/2+1] fp32 */
 int a2m_stft_magnitude_f32(const a2m_mel_plan* plan, const float* wav, int64_t n_clips, int64_t n_samples,
                            int64_t wav_stride, float* out, void* stream);

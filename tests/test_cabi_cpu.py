@@ -103,3 +103,55 @@ def test_audio_repr_registry(pkg):
     assert ar.get_repr(ar.RAW) is ar.raw_repr and ar.SR == 16000
     with pytest.raises(KeyError):
         ar.get_repr("nope")
+
+
+def test_mel_schedule_reproduces_the_filterbank_and_is_conflict_free(pkg):
+    """The plan-time schedule of the 512-point kernel's mel sum (a2m_mel_schedule_host, no GPU): every weight of the
+    reference's filterbank (and of the Slaney one of log_mel_400) is visited exactly once -- band c = R[c] + F[c + 1]
+    reproduces 0.5 * mag . W to fp32 rounding --, the 16 lanes of a step read bins in 16 different banks, and a
+    matrix that is not a triangular filterbank is refused (the general kernel takes it)."""
+    import importlib
+    from oracle import mel_oracle
+    lib = pkg.load_library()
+    pa = importlib.import_module(pkg.__name__ + ".pats_audio")
+
+    def schedule(w):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        cap = 256
+        b, uv, rs = np.zeros(cap * 16, np.int32), np.zeros(cap * 32, np.float32), np.zeros(12, np.int32)
+        nr, dl = ctypes.c_int(), ctypes.c_int()
+        n = lib.a2m_mel_schedule_host(w.ctypes.data_as(ctypes.c_void_p), w.shape[1], cap, b.ctypes.data_as(ctypes.c_void_p),
+                                      uv.ctypes.data_as(ctypes.c_void_p), rs.ctypes.data_as(ctypes.c_void_p),
+                                      ctypes.byref(nr), ctypes.byref(dl))
+        if n < 0:
+            return n, None, None, None, None
+        return n, b[:n * 16].reshape(n, 16), uv[:n * 32].reshape(n, 16, 2), rs[:nr.value], dl.value
+
+    cases = [mel_oracle.mel_matrix(64, 257, 16000, 125, 7500), mel_oracle.mel_matrix(40, 257, 16000, 60, 7000),
+             mel_oracle.mel_matrix(128, 257, 22050, 20, 10000), mel_oracle.mel_matrix(20, 257, 16000, 125, 3800),
+             pa.mel_filterbank(16000, 512, n_mels=64, fmin=125.0, fmax=7500.0, norm=None).T.astype(np.float64)]
+    rng = np.random.default_rng(0)
+    for w in cases:
+        n_mel = w.shape[1]
+        n, b, uv, rs, dist = schedule(w)
+        assert n == rs.sum() and n <= np.count_nonzero(w.any(axis=1))
+        for t in range(n):
+            banks = [k % 16 for k in b[t] if k != 257]
+            assert len(set(banks)) == len(banks), (t, b[t])
+        visited = b[b != 257]
+        assert len(set(visited.tolist())) == len(visited) == np.count_nonzero(w.any(axis=1))
+        mag = np.append(rng.random(257), 0.0)
+        r_sum, f_sum = np.zeros(n_mel + 17), np.zeros(n_mel + 17)
+        step = 0
+        for r, nt in enumerate(rs):
+            for _ in range(nt):
+                for lane in range(16):
+                    g = n_mel if (dist and r == len(rs) - 1) else 16 * r + lane
+                    r_sum[g] += mag[b[step, lane]] * uv[step, lane, 0]
+                    f_sum[g] += mag[b[step, lane]] * uv[step, lane, 1]
+                step += 1
+        got = r_sum[:n_mel] + f_sum[1:n_mel + 1]
+        np.testing.assert_allclose(got, 0.5 * (mag[:257] @ w), rtol=0, atol=2e-7)
+    dense = np.zeros((257, 8))
+    dense[10:20, 0] = dense[10:20, 1] = dense[10:20, 2] = 1.0            # a bin feeding three bands
+    assert schedule(dense)[0] == -3 and b"triangular" in lib.a2m_last_error()
