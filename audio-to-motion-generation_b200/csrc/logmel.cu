@@ -49,14 +49,15 @@ constexpr int kWarps = 8;                             // warps per CTA of the 51
 constexpr int kTileFrames = 4;                        // frames per warp tile: two 16-lane groups x (A, B)
 constexpr int kXchgRow = 17;                          // 16-byte units per exchange row (16 + 1 pad)
 constexpr int kXchgGroupBytes = 16 * kXchgRow * 16;   // 4352 B per 16-lane group; later the group's magnitudes
-constexpr int kMagEntries = 258;                      // (A, B) magnitudes of bins 0..256 (+1 pad) alias the exchange rows
+constexpr int kMagZeroSlots = 272;                    // (A, B) magnitudes of bins 0..256 alias the exchange rows; entries
+constexpr int kMagEntries = kMagZeroSlots + 16;       // 272..287 are zeros, one per bank: what idle schedule slots read
 static_assert(kMagEntries * 8 <= kXchgGroupBytes, "magnitudes must fit the exchange region");
 
 struct FastTables {               // device-resident constants of a plan (512-point kernel)
     const float* window;          // [512]  window, zero padded past the window length
     const float2* tw;             // [16][16] exp(-2 pi i m2 k1 / 256) at [k1][m2]
     const float2* untangle;       // [256]  (-sin, -cos)(2 pi k / 512)
-    const int* sched_bin;         // [steps][16] bin a lane reads at a step (257 = none: zero magnitude, zero weights)
+    const int* sched_bin;         // [steps][16] bin a lane reads at a step (kMagZeroSlots + bank = none: zero magnitude, zero weights)
     const float2* sched_uv;       // [steps][16] (u, v) = 0.5 * (weight into band g, weight into band g - 1); the kernel keeps |2 X|
     const int* round_steps;       // [n_rounds] schedule rows of each round
 };
@@ -108,7 +109,28 @@ __device__ __forceinline__ float2 load_pair<int16_t>(const int16_t* __restrict__
     return make_float2(static_cast<float>(s[i]), static_cast<float>(s[i + 1]));
 }
 
-template <typename InT>
+// samples * window of rows m1 < kRows (kRows == 0: g.n_m1 rows, decided at run time) -> z[16 m1 + l] of frames A and B
+template <typename InT, int kRows, bool kAligned>
+__device__ __forceinline__ void load_windowed(cpx (&v)[16], const InT* __restrict__ s, const float* __restrict__ s_window,
+                                              int rel_a, int rel_b, int l, int grp, int n_m1) {
+    const bool al_a = kAligned || (rel_a & 1) == 0, al_b = kAligned || (rel_b & 1) == 0;       // warp-uniform
+#pragma unroll
+    for (int m1 = 0; m1 < 16; ++m1) {
+        if (kRows ? m1 < kRows : m1 < n_m1) {                                // uniform
+            const int n = 32 * m1 + 2 * l;
+            const float2 w = *reinterpret_cast<const float2*>(s_window + n);
+            // past the window (last row) the buffer holds samples of later frames or of an earlier tile: finite values
+            // (the buffer is zeroed once, then only ever holds copied input), times the window's zero padding
+            const float2 xa = load_pair<InT>(s, rel_a + n, al_a, grp);
+            const float2 xb = load_pair<InT>(s, rel_b + n, al_b, grp);
+            v[m1] = a2m_fft::make(a2m_fft::pack(xa.x * w.x, xb.x * w.x), a2m_fft::pack(xa.y * w.y, xb.y * w.y));
+        } else {
+            v[m1] = a2m_fft::make(a2m_fft::pack(0.f, 0.f), a2m_fft::pack(0.f, 0.f));
+        }
+    }
+}
+
+template <typename InT, int kRows>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 logmel512_kernel(const InT* __restrict__ wav, long long wav_stride, long long n_samples, long long n_clips,
                  int frames_per_clip, int tiles_per_clip, long long n_tiles, FastTables tab, FastGeom g,
@@ -118,13 +140,13 @@ logmel512_kernel(const InT* __restrict__ wav, long long wav_stride, long long n_
     float2* s_tw = reinterpret_cast<float2*>(smem + 2048);
     float2* s_unt = reinterpret_cast<float2*>(smem + 4096);
     float2* s_uv = reinterpret_cast<float2*>(smem + 6144);                   // [n_steps][16]
-    int* s_bin = reinterpret_cast<int*>(smem + 6144 + g.n_steps * 128);      // [n_steps][16]
-    int* s_round = s_bin + g.n_steps * 16;                                   // [n_rounds]
+    int* s_off = reinterpret_cast<int*>(smem + 6144 + g.n_steps * 128);      // [n_steps][16] byte offset of the bin's magnitudes
+    int* s_round = s_off + g.n_steps * 16;                                   // [n_rounds]
 
     const int tid = threadIdx.x;
     for (int i = tid; i < kFastNfft; i += kWarps * 32) s_window[i] = tab.window[i];
     for (int i = tid; i < 256; i += kWarps * 32) { s_tw[i] = tab.tw[i]; s_unt[i] = tab.untangle[i]; }
-    for (int i = tid; i < g.n_steps * 16; i += kWarps * 32) { s_uv[i] = tab.sched_uv[i]; s_bin[i] = tab.sched_bin[i]; }
+    for (int i = tid; i < g.n_steps * 16; i += kWarps * 32) { s_uv[i] = tab.sched_uv[i]; s_off[i] = 8 * tab.sched_bin[i]; }
     if (tid < g.n_rounds) s_round[tid] = tab.round_steps[tid];
 
     const int warp = tid >> 5, lane = tid & 31;
@@ -142,51 +164,67 @@ logmel512_kernel(const InT* __restrict__ wav, long long wav_stride, long long n_
     for (int i = lane; i < g.span_bytes / 4; i += 32) reinterpret_cast<uint32_t*>(s_samples)[i] = 0u;
     __syncthreads();                                                         // tables and barriers are in place
 
-    const uintptr_t buf_lo = (reinterpret_cast<uintptr_t>(wav) + 15) & ~uintptr_t(15);          // 16-byte blocks fully
-    const uintptr_t buf_hi = reinterpret_cast<uintptr_t>(wav + (n_clips - 1) * wav_stride + n_samples) & ~uintptr_t(15);  // inside the caller's buffer
+    const uintptr_t wav_addr = reinterpret_cast<uintptr_t>(wav);
+    const uintptr_t buf_lo = (wav_addr + 15) & ~uintptr_t(15);               // 16-byte blocks fully inside the caller's buffer
+    const uintptr_t buf_hi = reinterpret_cast<uintptr_t>(wav + (n_clips - 1) * wav_stride + n_samples) & ~uintptr_t(15);
+
+    // tiles of this warp: tile = clip * tiles_per_clip + tq, advanced by n_warps without a division
+    const unsigned n_warps = gridDim.x * kWarps;
+    const unsigned step_clip = n_warps / static_cast<unsigned>(tiles_per_clip), step_tq = n_warps % static_cast<unsigned>(tiles_per_clip);
+    const unsigned first = blockIdx.x * kWarps + warp;
+    unsigned clip = first / static_cast<unsigned>(tiles_per_clip), tq = first % static_cast<unsigned>(tiles_per_clip);
+    auto advance = [&](unsigned& c, unsigned& q) {
+        c += step_clip;
+        q += step_tq;
+        if (q >= static_cast<unsigned>(tiles_per_clip)) { q -= tiles_per_clip; ++c; }
+    };
+    auto tile_addr = [&](unsigned c, unsigned q) {
+        return wav_addr + (static_cast<long long>(c) * wav_stride + static_cast<long long>(q) * (kTileFrames * g.hop)) * static_cast<long long>(sizeof(InT));
+    };
 
     // Stage the samples of one tile: element i of the tile's span lands at byte (src & 15) + i * sizeof(InT) of the
-    // warp's buffer.  Whole warp; lane 0 issues the bulk copy.
-    auto stage = [&](long long tile) {
-        const unsigned clip = static_cast<unsigned>(tile) / static_cast<unsigned>(tiles_per_clip);         // n_tiles < 2^31
-        const int f0 = static_cast<int>(static_cast<unsigned>(tile) - clip * tiles_per_clip) * kTileFrames;
-        const int nf = min(kTileFrames, frames_per_clip - f0);
-        const InT* src = wav + static_cast<long long>(clip) * wav_stride + static_cast<long long>(f0) * g.hop;
-        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-        const uintptr_t a_end = a + (static_cast<uintptr_t>(nf - 1) * g.hop + g.window) * sizeof(InT);
+    // warp's buffer.  Lane 0 issues one bulk copy; the 16-byte blocks at the two ends of the CALLER's buffer that the
+    // copy must not touch (first tile of a misaligned buffer, last tile) are copied by hand by the whole warp.
+    auto stage = [&](unsigned c, unsigned q) {
+        const uintptr_t a = tile_addr(c, q);
+        const int nf = min(kTileFrames, frames_per_clip - static_cast<int>(q) * kTileFrames);
+        const uintptr_t a_end = a + static_cast<uintptr_t>((nf - 1) * g.hop + g.window) * sizeof(InT);
         const uintptr_t a0 = a & ~uintptr_t(15);
         uintptr_t lo = a0, hi = (a_end + 15) & ~uintptr_t(15);
-        if (lo < buf_lo) lo = buf_lo;
-        if (hi > buf_hi) hi = buf_hi;
+        const bool edge = lo < buf_lo || hi > buf_hi;
+        if (edge) {
+            if (lo < buf_lo) lo = buf_lo;
+            if (hi > buf_hi) hi = buf_hi;
+        }
         const bool bulk = hi > lo;
         if (lane == 0) {
             a2m::fence_proxy_async_smem();                  // the warp's reads of the previous tile precede the async writes
             a2m::mbar_expect_tx(bar, bulk ? static_cast<uint32_t>(hi - lo) : 0u);
             if (bulk) a2m::bulk_load_1d(s_samples + (lo - a0), reinterpret_cast<const void*>(lo), static_cast<uint32_t>(hi - lo), bar);
         }
-        if (!bulk) { lo = a_end; hi = a_end; }             // everything by hand
-        for (uintptr_t p = a + lane * sizeof(InT); p < lo && p < a_end; p += 32 * sizeof(InT))          // head
-            *reinterpret_cast<InT*>(s_samples + (p - a0)) = *reinterpret_cast<const InT*>(p);
-        for (uintptr_t p = (hi > a ? hi : a) + lane * sizeof(InT); p < a_end; p += 32 * sizeof(InT))     // tail
-            *reinterpret_cast<InT*>(s_samples + (p - a0)) = *reinterpret_cast<const InT*>(p);
+        if (edge) {
+            if (!bulk) { lo = a_end; hi = a_end; }         // everything by hand
+            for (uintptr_t p = a + lane * sizeof(InT); p < lo && p < a_end; p += 32 * sizeof(InT))          // head
+                *reinterpret_cast<InT*>(s_samples + (p - a0)) = *reinterpret_cast<const InT*>(p);
+            for (uintptr_t p = (hi > a ? hi : a) + lane * sizeof(InT); p < a_end; p += 32 * sizeof(InT))     // tail
+                *reinterpret_cast<InT*>(s_samples + (p - a0)) = *reinterpret_cast<const InT*>(p);
+        }
     };
 
-    const long long warp_global = static_cast<long long>(blockIdx.x) * kWarps + warp;
-    const long long n_warps = static_cast<long long>(gridDim.x) * kWarps;
-    long long tile = warp_global;
-    if (tile < n_tiles) stage(tile);
+    if (clip < n_clips) stage(clip, tq);
     uint32_t phase = 0;
     const ulonglong2* xq = reinterpret_cast<const ulonglong2*>(xchg);
     ulonglong2* xw = reinterpret_cast<ulonglong2*>(xchg);
     float2* mag = reinterpret_cast<float2*>(xchg);
     const int pl = (16 - l) & 15;                                            // lane holding Z[256 - k] of this lane's k
     const bool lane0 = l == 0;
+    const int n_mel = g.n_mel;
+    const float log_offset = g.log_offset;
+    const bool floor_zeros = g.log_mode != 0;
 
-    for (; tile < n_tiles; tile += n_warps) {
-        const unsigned clip = static_cast<unsigned>(tile) / static_cast<unsigned>(tiles_per_clip);
-        const int f0 = static_cast<int>(static_cast<unsigned>(tile) - clip * tiles_per_clip) * kTileFrames;
-        const InT* src = wav + static_cast<long long>(clip) * wav_stride + static_cast<long long>(f0) * g.hop;
-        const int shift = static_cast<int>((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(InT));
+    for (; clip < n_clips; advance(clip, tq)) {
+        const int f0 = static_cast<int>(tq) * kTileFrames;
+        const int shift = static_cast<int>((tile_addr(clip, tq) & 15) / sizeof(InT));
         wait_or_trap(bar, phase);
         phase ^= 1;
         __syncwarp();                                                        // hand-copied head / tail of the other lanes
@@ -196,25 +234,15 @@ logmel512_kernel(const InT* __restrict__ wav, long long wav_stride, long long n_
         {
             const InT* s = reinterpret_cast<const InT*>(s_samples);
             const int rel_a = shift + 2 * grp * g.hop, rel_b = rel_a + g.hop;
-            const bool al_a = (rel_a & 1) == 0, al_b = (rel_b & 1) == 0;     // warp-uniform
-            const int last = g.n_m1 - 1;
-#pragma unroll
-            for (int m1 = 0; m1 < 16; ++m1) {
-                if (m1 <= last) {                                            // uniform
-                    const int n = 32 * m1 + 2 * l;
-                    const float2 w = *reinterpret_cast<const float2*>(s_window + n);
-                    // past the window (last row) the buffer holds samples of later frames or of an earlier tile: finite
-                    // values (the buffer is zeroed once, then only ever holds copied input), times the zero padding
-                    const float2 xa = load_pair<InT>(s, rel_a + n, al_a, grp);
-                    const float2 xb = load_pair<InT>(s, rel_b + n, al_b, grp);
-                    v[m1] = a2m_fft::make(a2m_fft::pack(xa.x * w.x, xb.x * w.x), a2m_fft::pack(xa.y * w.y, xb.y * w.y));
-                } else {
-                    v[m1] = a2m_fft::make(a2m_fft::pack(0.f, 0.f), a2m_fft::pack(0.f, 0.f));
-                }
-            }
+            if (((shift | g.hop) & 1) == 0) load_windowed<InT, kRows, true>(v, s, s_window, rel_a, rel_b, l, grp, g.n_m1);
+            else load_windowed<InT, kRows, false>(v, s, s_window, rel_a, rel_b, l, grp, g.n_m1);
         }
         __syncwarp();                                                        // every lane has its samples in registers
-        if (tile + n_warps < n_tiles) stage(tile + n_warps);                 // overlaps everything below
+        {
+            unsigned c2 = clip, q2 = tq;
+            advance(c2, q2);
+            if (c2 < n_clips) stage(c2, q2);                                 // overlaps everything below
+        }
 
         // ---- pass 1: DFT16 over m1, twiddle W256^(l k1), exchange [k1][m2] ----------------------------------------
         a2m_fft::dft16(v);
@@ -239,10 +267,8 @@ logmel512_kernel(const InT* __restrict__ wav, long long wav_stride, long long n_
         // ---- untangle: lane l and lane 16 - l swap registers 8..15; |2 X[k]| and |2 X[256 - k]| per pair -----------
         {   // bin 128 pairs with itself: |X[128]| = |Z[128]| (register 8 of lane 0)
             const pair_t sq = a2m_fft::fma2(v[8].im, v[8].im, a2m_fft::mul2(v[8].re, v[8].re));
-            if (lane0) {
-                mag[128] = make_float2(2.f * fast_sqrt(a2m_fft::lo(sq)), 2.f * fast_sqrt(a2m_fft::hi(sq)));
-                mag[257] = make_float2(0.f, 0.f);
-            }
+            if (lane0) mag[128] = make_float2(2.f * fast_sqrt(a2m_fft::lo(sq)), 2.f * fast_sqrt(a2m_fft::hi(sq)));
+            mag[kMagZeroSlots + l] = make_float2(0.f, 0.f);                  // what the idle slots of the mel schedule read
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -271,38 +297,44 @@ logmel512_kernel(const InT* __restrict__ wav, long long wav_stride, long long n_
         // ---- mel: segment g = 16 r + l per round; band g - 1 = R[g - 1] + F[g] ---------------------------------------
         {
             const int fa = f0 + 2 * grp;
-            float* row_a = out + (static_cast<long long>(clip) * frames_per_clip + fa) * g.n_mel;
+            float* row_a = out + (static_cast<long long>(clip) * frames_per_clip + fa) * n_mel;
             const bool has_a = fa < frames_per_clip, has_b = fa + 1 < frames_per_clip;
             const pair_t zero = a2m_fft::pack(0.f, 0.f);
             pair_t carry = zero;                                             // R of lane 15 of the previous round
-            int step = 0;
-            for (int r = 0; r < g.n_rounds; ++r) {
+            const unsigned char* magb = reinterpret_cast<const unsigned char*>(mag);
+            const int* off_p = s_off + l;
+            const float2* uv_p = s_uv + l;
+            const int n_rounds = g.n_rounds;
+            for (int r = 0; r < n_rounds; ++r) {
                 const int n_t = s_round[r];
                 pair_t acc_r = zero, acc_f = zero;
-                for (int t = 0; t < n_t; ++t, ++step) {
-                    const int bin = s_bin[step * 16 + l];
-                    const float2 uv = s_uv[step * 16 + l];
-                    const pair_t m = *reinterpret_cast<const pair_t*>(mag + bin);
+#pragma unroll 4
+                for (int t = 0; t < n_t; ++t) {
+                    const int off = off_p[t * 16];
+                    const float2 uv = uv_p[t * 16];
+                    const pair_t m = *reinterpret_cast<const pair_t*>(magb + off);
                     acc_r = a2m_fft::fma2(m, a2m_fft::bcast(uv.x), acc_r);
                     acc_f = a2m_fft::fma2(m, a2m_fft::bcast(uv.y), acc_f);
                 }
+                off_p += n_t * 16;
+                uv_p += n_t * 16;
                 int band = 16 * r + l - 1;
                 pair_t e;
-                if (g.dist_last && r == g.n_rounds - 1) {                    // one segment spread over the lanes: band n_mel - 1
+                if (g.dist_last && r == n_rounds - 1) {                      // one segment spread over the lanes: band n_mel - 1
 #pragma unroll
                     for (int o = 8; o > 0; o >>= 1) acc_f = a2m_fft::add2(acc_f, __shfl_xor_sync(0xffffffffu, acc_f, o, 16));
                     e = a2m_fft::add2(carry, acc_f);
-                    band = lane0 ? g.n_mel - 1 : -1;
+                    band = lane0 ? n_mel - 1 : -1;
                 } else {
                     pair_t r_prev = __shfl_sync(0xffffffffu, acc_r, (l + 15) & 15, 16);
                     if (lane0) r_prev = carry;
                     carry = __shfl_sync(0xffffffffu, acc_r, 15, 16);
                     e = a2m_fft::add2(r_prev, acc_f);
                 }
-                if (band >= 0 && band < g.n_mel) {
+                if (band >= 0 && band < n_mel) {
                     const float ea = a2m_fft::lo(e), eb = a2m_fft::hi(e);
-                    if (has_a) row_a[band] = __logf(g.log_mode ? (ea == 0.f ? g.log_offset : ea) : ea + g.log_offset);
-                    if (has_b) row_a[g.n_mel + band] = __logf(g.log_mode ? (eb == 0.f ? g.log_offset : eb) : eb + g.log_offset);
+                    if (has_a) row_a[band] = __logf(floor_zeros ? (ea == 0.f ? log_offset : ea) : ea + log_offset);
+                    if (has_b) row_a[n_mel + band] = __logf(floor_zeros ? (eb == 0.f ? log_offset : eb) : eb + log_offset);
                 }
             }
         }
@@ -495,13 +527,24 @@ MelSchedule build_mel_schedule(const double* w, int n_mel) {
         if (steps > 255) return s;
         s.round_steps[r] = steps;
         const size_t base = s.bin.size();
-        s.bin.resize(base + static_cast<size_t>(steps) * 16, 257);
+        s.bin.resize(base + static_cast<size_t>(steps) * 16, -1);
         s.uv.resize(base + static_cast<size_t>(steps) * 16, make_float2(0.f, 0.f));
         for (size_t e = 0; e < eu.size(); ++e) {
             const size_t slot = base + static_cast<size_t>(colour[e]) * 16 + eu[e];
-            if (s.bin[slot] != 257) return s;               // colouring bug guard
+            if (s.bin[slot] != -1) return s;                // colouring bug guard
             s.bin[slot] = ek[e];
             s.uv[slot] = make_float2(u[ek[e]], v[ek[e]]);
+        }
+        for (int t = 0; t < steps; ++t) {                   // idle slots read a zero entry in a bank no lane of the step uses
+            bool used[16] = {};
+            for (int ln = 0; ln < 16; ++ln) { const int k = s.bin[base + t * 16 + ln]; if (k >= 0) used[k % 16] = true; }
+            int free_bank = 0;
+            for (int ln = 0; ln < 16; ++ln) {
+                if (s.bin[base + t * 16 + ln] >= 0) continue;
+                while (used[free_bank]) ++free_bank;
+                used[free_bank] = true;
+                s.bin[base + t * 16 + ln] = kMagZeroSlots + free_bank;
+            }
         }
     }
     s.ok = true;
@@ -711,15 +754,25 @@ int launch_logmel(const a2m_mel_plan* plan, const InT* wav, int64_t n_clips, int
     const int tiles_per_clip = static_cast<int>((frames + kTileFrames - 1) / kTileFrames);
     const long long n_tiles = static_cast<long long>(tiles_per_clip) * n_clips;
     if (fast_smem > 0 && n_tiles <= 0x7fffffffLL) {
-        static A2mPerDeviceOnce attr_set;                     // one instance per template instantiation
-        if (attr_set.first())
-            A2M_CUDA_CHECK(cudaFuncSetAttribute(logmel512_kernel<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap));
         const int ctas_per_sm = 2 * (fast_smem + 1024) <= 228 * 1024 ? 2 : 1;
         long long grid = static_cast<long long>(ctas_per_sm) * a2m_num_sms();
         const long long need = (n_tiles + kWarps - 1) / kWarps;
         if (grid > need) grid = need;
-        logmel512_kernel<InT><<<static_cast<unsigned>(grid), kWarps * 32, fast_smem, st>>>(
-            wav, wav_stride, n_samples, n_clips, static_cast<int>(frames), tiles_per_clip, n_tiles, plan->ftab, fg, out);
+        auto launch = [&](auto kernel) -> int {
+            static A2mPerDeviceOnce attr_set;                 // one instance per kernel instantiation
+            if (attr_set.first())
+                A2M_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap));
+            kernel<<<static_cast<unsigned>(grid), kWarps * 32, fast_smem, st>>>(
+                wav, wav_stride, n_samples, n_clips, static_cast<int>(frames), tiles_per_clip, n_tiles, plan->ftab, fg, out);
+            return A2M_OK;
+        };
+        // the rows of the 16 x 16 input that hold window samples are a compile-time constant for the two geometries of the
+        // path (25 ms at 16 kHz: 400 samples = 13 rows; log_mel_400: the 512-sample centred window = 16 rows)
+        int rc;
+        if (fg.n_m1 == 13) rc = launch(logmel512_kernel<InT, 13>);
+        else if (fg.n_m1 == 16) rc = launch(logmel512_kernel<InT, 16>);
+        else rc = launch(logmel512_kernel<InT, 0>);
+        if (rc != A2M_OK) return rc;
     } else {
         GenGeom g;
         g.window = plan->window; g.hop = plan->hop; g.nfft = plan->nfft; g.n_mel = plan->n_mel;

@@ -75,7 +75,7 @@ int a2m_logmel_f32(const a2m_mel_plan* plan, const float* wav, int64_t n_clips, 
 int a2m_logmel_i16(const a2m_mel_plan* plan, const int16_t* wav, int64_t n_clips, int64_t n_samples,
                    int64_t wav_stride, float* out, void* stream);
 /* Host-only diagnostic (no GPU needed): the plan-time schedule of the 512-point kernel's mel sum for a [257, n_mel]
- * filterbank -- per step and lane the bin read (257 = none) and its weights (u into band g, v into band g - 1, both
+ * filterbank -- per step and lane the bin read (272 + b = none: a zero entry in bank b) and its weights (u into band g, v into band g - 1, both
  * carrying the factor 0.5 of the kernel's |2 X|), for segment g = 16 * round + lane.  Returns the number of steps
  * (rows of 16), or A2M_ERR_UNSUPPORTED when the matrix is not a triangular filterbank (then the general kernel runs).
  * bin_out: int[capacity_steps * 16]; uv_out: float[capacity_steps * 32]; round_steps_out: int[12]. */
