@@ -31,6 +31,8 @@
 //    reference's numpy path.  Correct for every geometry log_mel_spectrogram can ask for (its 8 kHz default -> 256,
 //    22.05 kHz -> 1024, 44.1 / 48 kHz -> 2048); not tuned.
 #include <cmath>
+#include <mutex>
+#include <utility>
 #include <vector>
 #include <cstring>
 #include "a2m_common.cuh"
@@ -79,6 +81,13 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     float y;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// natural log of a positive normal number (every caller adds an offset or floors zeros first): one MUFU + one multiply
+__device__ __forceinline__ float fast_log(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * 0.69314718055994530942f;
 }
 
 __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
@@ -218,9 +227,9 @@ logmel512_kernel(const InT* __restrict__ wav, long long wav_stride, long long n_
     float2* mag = reinterpret_cast<float2*>(xchg);
     const int pl = (16 - l) & 15;                                            // lane holding Z[256 - k] of this lane's k
     const bool lane0 = l == 0;
-    const int n_mel = g.n_mel;
+    const int n_mel = g.n_mel, n_rounds = g.n_rounds;
     const float log_offset = g.log_offset;
-    const bool floor_zeros = g.log_mode != 0;
+    const bool floor_zeros = g.log_mode != 0, dist_last = g.dist_last != 0;
 
     for (; clip < n_clips; advance(clip, tq)) {
         const int f0 = static_cast<int>(tq) * kTileFrames;
@@ -295,47 +304,57 @@ logmel512_kernel(const InT* __restrict__ wav, long long wav_stride, long long n_
         __syncwarp();
 
         // ---- mel: segment g = 16 r + l per round; band g - 1 = R[g - 1] + F[g] ---------------------------------------
+        // The schedule rows of a round are padded to PAIRS (idle slots read zeros); the (offset, weights) of the next pair
+        // are fetched while the current pair's magnitudes are in flight.
         {
             const int fa = f0 + 2 * grp;
-            float* row_a = out + (static_cast<long long>(clip) * frames_per_clip + fa) * n_mel;
+            float* out_p = out + (static_cast<long long>(clip) * frames_per_clip + fa) * n_mel + (l - 1);   // band 16 r + l - 1
             const bool has_a = fa < frames_per_clip, has_b = fa + 1 < frames_per_clip;
             const pair_t zero = a2m_fft::pack(0.f, 0.f);
             pair_t carry = zero;                                             // R of lane 15 of the previous round
             const unsigned char* magb = reinterpret_cast<const unsigned char*>(mag);
             const int* off_p = s_off + l;
             const float2* uv_p = s_uv + l;
-            const int n_rounds = g.n_rounds;
+            int off0 = off_p[0], off1 = off_p[16];
+            float2 uv0 = uv_p[0], uv1 = uv_p[16];
+            int band = l - 1;
             for (int r = 0; r < n_rounds; ++r) {
-                const int n_t = s_round[r];
+                const int n_pairs = s_round[r];
                 pair_t acc_r = zero, acc_f = zero;
-#pragma unroll 4
-                for (int t = 0; t < n_t; ++t) {
-                    const int off = off_p[t * 16];
-                    const float2 uv = uv_p[t * 16];
-                    const pair_t m = *reinterpret_cast<const pair_t*>(magb + off);
-                    acc_r = a2m_fft::fma2(m, a2m_fft::bcast(uv.x), acc_r);
-                    acc_f = a2m_fft::fma2(m, a2m_fft::bcast(uv.y), acc_f);
+                for (int t = 0; t < n_pairs; ++t) {
+                    const pair_t m0 = *reinterpret_cast<const pair_t*>(magb + off0);
+                    const pair_t m1 = *reinterpret_cast<const pair_t*>(magb + off1);
+                    const float2 w0 = uv0, w1 = uv1;
+                    off_p += 32;
+                    uv_p += 32;
+                    off0 = off_p[0]; off1 = off_p[16];                       // one pair of rows past the end exists (zeros)
+                    uv0 = uv_p[0]; uv1 = uv_p[16];
+                    acc_r = a2m_fft::fma2(m0, a2m_fft::bcast(w0.x), acc_r);
+                    acc_f = a2m_fft::fma2(m0, a2m_fft::bcast(w0.y), acc_f);
+                    acc_r = a2m_fft::fma2(m1, a2m_fft::bcast(w1.x), acc_r);
+                    acc_f = a2m_fft::fma2(m1, a2m_fft::bcast(w1.y), acc_f);
                 }
-                off_p += n_t * 16;
-                uv_p += n_t * 16;
-                int band = 16 * r + l - 1;
                 pair_t e;
-                if (g.dist_last && r == n_rounds - 1) {                      // one segment spread over the lanes: band n_mel - 1
+                bool write = band >= 0 && band < n_mel;
+                float* dst = out_p;
+                if (dist_last && r == n_rounds - 1) {                        // one segment spread over the lanes: band n_mel - 1
 #pragma unroll
                     for (int o = 8; o > 0; o >>= 1) acc_f = a2m_fft::add2(acc_f, __shfl_xor_sync(0xffffffffu, acc_f, o, 16));
                     e = a2m_fft::add2(carry, acc_f);
-                    band = lane0 ? n_mel - 1 : -1;
+                    write = lane0;                                           // band 16 r - 1 = n_mel - 1: lane 0's slot
                 } else {
                     pair_t r_prev = __shfl_sync(0xffffffffu, acc_r, (l + 15) & 15, 16);
                     if (lane0) r_prev = carry;
                     carry = __shfl_sync(0xffffffffu, acc_r, 15, 16);
                     e = a2m_fft::add2(r_prev, acc_f);
                 }
-                if (band >= 0 && band < n_mel) {
+                if (write) {
                     const float ea = a2m_fft::lo(e), eb = a2m_fft::hi(e);
-                    if (has_a) row_a[band] = __logf(floor_zeros ? (ea == 0.f ? log_offset : ea) : ea + log_offset);
-                    if (has_b) row_a[n_mel + band] = __logf(floor_zeros ? (eb == 0.f ? log_offset : eb) : eb + log_offset);
+                    if (has_a) dst[0] = fast_log(floor_zeros ? (ea == 0.f ? log_offset : ea) : ea + log_offset);
+                    if (has_b) dst[n_mel] = fast_log(floor_zeros ? (eb == 0.f ? log_offset : eb) : eb + log_offset);
                 }
+                band += 16;
+                out_p += 16;
             }
         }
         __syncwarp();                                                        // the magnitudes are exchange rows again
@@ -523,9 +542,10 @@ MelSchedule build_mel_schedule(const double* w, int n_mel) {
                 ev.push_back(k % 16);
                 ek.push_back(k);
             }
-        const int steps = eu.empty() ? 0 : colour_edges(eu, ev, colour);
-        if (steps > 255) return s;
-        s.round_steps[r] = steps;
+        const int used_steps = eu.empty() ? 0 : colour_edges(eu, ev, colour);
+        const int steps = (used_steps + 1) & ~1;            // the kernel walks the rows in pairs
+        if (steps > 254) return s;
+        s.round_steps[r] = steps / 2;
         const size_t base = s.bin.size();
         s.bin.resize(base + static_cast<size_t>(steps) * 16, -1);
         s.uv.resize(base + static_cast<size_t>(steps) * 16, make_float2(0.f, 0.f));
@@ -547,6 +567,9 @@ MelSchedule build_mel_schedule(const double* w, int n_mel) {
             }
         }
     }
+    // the kernel's look-ahead reads one pair of rows past the last round
+    for (int t = 0; t < 2; ++t)
+        for (int ln = 0; ln < 16; ++ln) { s.bin.push_back(kMagZeroSlots + ln); s.uv.push_back(make_float2(0.f, 0.f)); }
     s.ok = true;
     return s;
 }
@@ -581,10 +604,10 @@ extern "C" int a2m_mel_schedule_host(const double* mel_weights_host, int n_mel, 
         a2m_set_error("a2m_mel_schedule_host: not a triangular filterbank (a bin feeds more than two adjacent bands)");
         return A2M_ERR_UNSUPPORTED;
     }
-    const int steps = static_cast<int>(s.bin.size() / 16);
+    const int steps = static_cast<int>(s.bin.size() / 16) - 2;            // without the look-ahead rows
     A2M_ARG_CHECK(steps <= capacity_steps, "a2m_mel_schedule_host: %d steps, capacity %d", steps, capacity_steps);
-    for (size_t i = 0; i < s.bin.size(); ++i) { bin_out[i] = s.bin[i]; uv_out[2 * i] = s.uv[i].x; uv_out[2 * i + 1] = s.uv[i].y; }
-    for (int r = 0; r < s.n_rounds; ++r) round_steps_out[r] = s.round_steps[r];
+    for (size_t i = 0; i < static_cast<size_t>(steps) * 16; ++i) { bin_out[i] = s.bin[i]; uv_out[2 * i] = s.uv[i].x; uv_out[2 * i + 1] = s.uv[i].y; }
+    for (int r = 0; r < s.n_rounds; ++r) round_steps_out[r] = 2 * s.round_steps[r];     // rows (the kernel walks them in pairs)
     *n_rounds_out = s.n_rounds;
     *dist_last_out = s.dist_last;
     return steps;
@@ -716,6 +739,19 @@ namespace {
 
 constexpr int kSmemCap = 227 * 1024;
 
+// cudaFuncSetAttribute is per (kernel, device): true the first time this pair is seen
+bool first_use(const void* kernel) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, int>> seen;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto& e : seen)
+        if (e.first == kernel && e.second == dev) return false;
+    seen.emplace_back(kernel, dev);
+    return true;
+}
+
 // shared memory of the 512-point kernel for this geometry; 0 if it cannot run (the generic kernel takes over)
 template <typename InT>
 int fast_geometry(const a2m_mel_plan* plan, FastGeom* g) {
@@ -759,8 +795,7 @@ int launch_logmel(const a2m_mel_plan* plan, const InT* wav, int64_t n_clips, int
         const long long need = (n_tiles + kWarps - 1) / kWarps;
         if (grid > need) grid = need;
         auto launch = [&](auto kernel) -> int {
-            static A2mPerDeviceOnce attr_set;                 // one instance per kernel instantiation
-            if (attr_set.first())
+            if (first_use(reinterpret_cast<const void*>(kernel)))
                 A2M_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap));
             kernel<<<static_cast<unsigned>(grid), kWarps * 32, fast_smem, st>>>(
                 wav, wav_stride, n_samples, n_clips, static_cast<int>(frames), tiles_per_clip, n_tiles, plan->ftab, fg, out);
