@@ -12,7 +12,6 @@ build defines, written against the drop-in modules of this package:
 One process per GPU (torchrun); ranks own contiguous clip ranges; weights are replicated; the only
 collective is ``allreduce_metrics`` (NCCL over NVLink through liba2m_b200's run-time binding).
 """
-import copy
 import ctypes
 
 import torch
@@ -137,9 +136,10 @@ class AudioToPosePipeline:
 
     def __init__(self, model, alpha=0.2, comm=None, lanes=2, graphs=False, smoothness=False, front_end="vggish",
                  sample_rate=None, adapter_frames_only=False):
-        """`lanes` > 1 runs consecutive batches on alternating CUDA streams, each lane with its own packed
-        weights and activation arena, so the latency-bound tail of one batch (graph decoders, small GEMMs)
-        overlaps the head of the next.  `graphs=True` captures each lane's whole step (about 60 launches, the
+        """`lanes` > 1 runs consecutive batches on alternating CUDA streams, each lane with its own native handle
+        (packed weights and activation arena) built from the SAME module, so the latency-bound tail of one batch
+        (graph decoders, small GEMMs) overlaps the head of the next, and a later load_state_dict / weight edit /
+        set_output_denorm on `model` reaches every lane.  `graphs=True` captures each lane's whole step (about 60 launches, the
         two-stream decoder fork and the programmatic-dependent-launch edges included) into a CUDA graph per input
         shape and replays it; inputs are copied into the graph's static buffers.  Results depend on neither.
         `front_end` selects the audio features: "vggish" (pose_video/audio_repr.py, 64 bands -- the path BASELINE's
@@ -168,12 +168,8 @@ class AudioToPosePipeline:
         self.smooth = motion_evaluation.new_smoothness(self.device) if smoothness else None
         self._copy_stream = torch.cuda.Stream(self.device)
         self._staging = {}                      # (wav shape, gt shape, depth) -> ring of [wav_dev, gt_dev, last-use event]
-        self._lane_models = [model]
-        for _ in range(max(1, int(lanes)) - 1):
-            twin = copy.deepcopy(model).eval()
-            twin.repack()                       # its own native handle (weights + arena)
-            self._lane_models.append(twin)
-        self._lane_streams = [torch.cuda.Stream(self.device) for _ in self._lane_models]
+        self._n_lanes = max(1, int(lanes))
+        self._lane_streams = [torch.cuda.Stream(self.device) for _ in range(self._n_lanes)]
         self._turn = 0
         self._use_graphs = bool(graphs)
         self._graphs = {}                       # (lane, wav shape, gt shape) -> (graph, static wav, gt, pose, kernels per replay)
@@ -199,8 +195,8 @@ class AudioToPosePipeline:
             return pats_audio.log_mel_400(wav, self.sample_rate)
         return audio_repr.log_mel_spectograms(wav, audio_sample_rate=self.sample_rate)
 
-    def generate(self, wav, model=None):
-        """wav [B, N] fp32 CUDA tensor -> pose [B, 64, 104] fp32 (on the current stream)."""
+    def generate(self, wav, lane=0):
+        """wav [B, N] fp32 (or int16 PCM) CUDA tensor -> pose [B, 64, 104] fp32 (on the current stream)."""
         if self.adapter_frames_only:
             # frames 0, 6, 12, ... only: same window, hop = ADAPTER_STRIDE x 10 ms
             logmel = audio_repr.log_mel_spectograms(wav, audio_sample_rate=self.sample_rate,
@@ -210,29 +206,28 @@ class AudioToPosePipeline:
             x = logmel[:, :POSE_FRAMES, :]
         else:
             x = adapter(self.features(wav))
-        pose, _ = (model or self.model)(x)
+        pose, _ = self.model(x, lane=lane)
         return pose
 
-    def generate_long(self, wav, window_hop=WINDOW_HOP, model=None):
+    def generate_long(self, wav, window_hop=WINDOW_HOP, lane=0):
         """Long-form audio (BASELINE config 4): wav [B, N] (e.g. 60 s = 960 000 samples) -> poses
         [B, n_windows, 64, 104].  The log-mel of every stream is computed once; each clip's overlapping windows
         (384-frame span, stride 6, hop window_hop * 6 frames -- the reference's window arithmetic) are fed to the
         generator as one strided view per clip, so no window is ever materialised."""
         logmel = self.features(wav)                                        # [B, frames, 64 | 128]
-        net = model or self.model
         out = []
         for b in range(logmel.shape[0]):
             x = sliding_windows(logmel[b], window_hop=window_hop)
             if x.shape[0] == 0:
                 raise ValueError("the audio is shorter than one window (%d log-mel frames)" % logmel.shape[1])
-            out.append(net(x)[0])
+            out.append(self.model(x, lane=lane)[0])
         return torch.stack(out)
 
     def step(self, wav, gt_pose, done_event=None):
         """One batch, inputs already on the device: enqueues mel -> generator -> evaluation on the next lane and
         accumulates the metric partials.  Returns the poses; they (and the metrics) are complete once
         ``sync_lanes()`` / ``finish()`` has been called on the consuming stream."""
-        lane = self._turn % len(self._lane_models)
+        lane = self._turn % self._n_lanes
         self._turn += 1
         st = self._lane_streams[lane]
         st.wait_stream(torch.cuda.current_stream(self.device))      # inputs were produced on the caller's stream
@@ -240,7 +235,7 @@ class AudioToPosePipeline:
             if self._use_graphs:
                 pose = self._replay(lane, st, wav, gt_pose)
             else:
-                pose = self.generate(wav, self._lane_models[lane])
+                pose = self.generate(wav, lane)
                 motion_evaluation.evaluate_poses(pose, gt_pose, self.alpha, accum=self.accum)
             if self.smooth is not None:
                 motion_evaluation.evaluate_smoothness(pose, accum=self.smooth, from_pose=True)
@@ -254,22 +249,21 @@ class AudioToPosePipeline:
         """Run one step of `lane` through its CUDA graph (captured on first use for this input shape).  Called with
         `st` current.  The returned poses live in the graph's static output buffer: they are overwritten by the
         lane's next step."""
-        key = (lane, tuple(wav.shape), tuple(gt_pose.shape))
+        key = (lane, tuple(wav.shape), wav.dtype, tuple(gt_pose.shape))
         entry = self._graphs.get(key)
-        model = self._lane_models[lane]
         if entry is None:
-            s_wav = torch.empty(wav.shape, dtype=torch.float32, device=self.device)
+            s_wav = torch.empty(wav.shape, dtype=wav.dtype, device=self.device)
             s_gt = torch.empty(gt_pose.shape, dtype=torch.float32, device=self.device)
             s_wav.copy_(wav)
             s_gt.copy_(gt_pose)
             scratch = motion_evaluation.new_metrics(self.device)
             for _ in range(2):                  # warm up outside the capture: plans, attributes, allocator pools
-                motion_evaluation.evaluate_poses(self.generate(s_wav, model), s_gt, self.alpha, accum=scratch)
+                motion_evaluation.evaluate_poses(self.generate(s_wav, lane), s_gt, self.alpha, accum=scratch)
             st.synchronize()
             graph = torch.cuda.CUDAGraph()
             before = _cabi.lib().a2m_launch_count()
             with torch.cuda.graph(graph, stream=st):
-                s_pose = self.generate(s_wav, model)
+                s_pose = self.generate(s_wav, lane)
                 motion_evaluation.evaluate_poses(s_pose, s_gt, self.alpha, accum=self.accum)
             entry = (graph, s_wav, s_gt, s_pose, int(_cabi.lib().a2m_launch_count() - before))
             self._graphs[key] = entry
@@ -292,11 +286,12 @@ class AudioToPosePipeline:
 
         def stage(pair):
             nonlocal turn
-            key = (tuple(pair[0].shape), tuple(pair[1].shape), depth)
+            key = (tuple(pair[0].shape), pair[0].dtype, tuple(pair[1].shape), depth)
             ring = self._staging.get(key)
             if ring is None:
-                ring = self._staging[key] = [
-                    [torch.empty(pair[0].shape, dtype=torch.float32, device=self.device),
+                ring = self._staging[key] = [                       # int16 PCM stays int16: half the bytes over PCIe
+                    [torch.empty(pair[0].shape, dtype=pair[0].dtype if pair[0].dtype == torch.int16 else torch.float32,
+                                 device=self.device),
                      torch.empty(pair[1].shape, dtype=torch.float32, device=self.device), None] for _ in range(depth)]
             slot = ring[turn % depth]
             turn += 1
@@ -326,7 +321,8 @@ class AudioToPosePipeline:
         """All-reduce (if sharded) and read the 64-byte result: {'pck', 'l1_pose', 'l1_motion', counts...}."""
         self.sync_lanes()
         allreduce_metrics(self.accum, self.comm)
-        m = motion_evaluation.read_metrics(self.accum)
+        m = motion_evaluation.read_metrics(self.accum)          # D2H copy: every lane's kernels have completed
+        self.model.check_device_status()                        # a kernel's bounded barrier wait expired -> A2MError
         m.update(motion_evaluation.finalize_metrics(m))
         if self.smooth is not None:
             allreduce_smoothness(self.smooth, self.comm)

@@ -195,11 +195,12 @@ class SelfAttention_G(NativeModule):
                 std.record_stream(torch.cuda.current_stream(h.device))
         h.denorm_token = token
 
-    def forward(self, audio, real_pose=None):
+    def forward(self, audio, real_pose=None, lane=0):
         """audio [B, T, F] (log-mel) -> (pose [B, T, 104] fp32, [angle_loss]) or
-        (pose, [bone_loss, angle_loss]) when real_pose [B, T, 104] is given."""
+        (pose, [bone_loss, angle_loss]) when real_pose [B, T, 104] is given.  `lane` (an extension) selects one of
+        the module's native handles, so that forwards enqueued on different CUDA streams do not share an arena."""
         self._require_eval()
-        h = self.native()
+        h = self.native(lane)
         self._sync_denorm(h)
         x = as_input(audio, h.device, "SelfAttention_G expects audio [B, T, F], got %s", keep_strides=True)
         B, T, F = x.shape

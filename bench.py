@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the audio->pose hot path (mel + SelfAttention_G forward + L1/PCK eval).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch 256]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch 256] [--config 2|3]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one batch of synthetic PATS-shaped clips (BASELINE config 2:
@@ -9,6 +9,12 @@ One "step" = one pass of the hot path over one batch of synthetic PATS-shaped cl
 against synthetic ground truth).  Weak scaling: every rank runs its own batch each step (clips shard
 naturally, weights replicated); the only collective is the 64-byte metric all-reduce at the end of the
 timed region.  Prints ONE JSON line (rank 0).
+
+Every synthetic clip is a function of its GLOBAL index only (torch.Generator seeded with 1234 + index for the waveform,
+4321 + index for the ground truth), so any sharding sees the same clips.  The line therefore also
+carries `sharded_check`: a fixed evaluation set (clips 0 .. 2047) split over the N ranks, whose integer hit count is the
+same for every N.  `--config 3` runs BASELINE config 3 instead: the 100 000-clip evaluation set, STRONG scaling (rank r
+takes clips [r * ceil(n / N), (r + 1) * ceil(n / N))), one all-reduce at the end.
 """
 import argparse
 import importlib
@@ -32,11 +38,32 @@ CLIP_SAMPLES = 68267
 POOL = 6                     # distinct input batches cycled through: 6 x 77 MB > 126 MB of L2
 
 
+def synth_clips(lo, hi, device, dtype=None):
+    """Clips [lo, hi) of the synthetic set, generated ON THE DEVICE from per-clip seeds: wav 0.1 * N(0, 1) (seed
+    1234 + index), ground truth 50 * N(0, 1) (seed 4321 + index).  dtype torch.int16: the waveform as 16-bit PCM
+    (round(wav * 32767 / 0.5), i.e. +-0.5 full scale -- 5 sigma)."""
+    import torch
+    n = hi - lo
+    wav = torch.empty(n, CLIP_SAMPLES, device=device)
+    gt = torch.empty(n, 64, 104, device=device)
+    g = torch.Generator(device=device)
+    for i in range(n):
+        g.manual_seed(1234 + lo + i)
+        wav[i].normal_(0.0, 0.1, generator=g)
+        g.manual_seed(4321 + lo + i)
+        gt[i].normal_(0.0, 50.0, generator=g)
+    if dtype is not None and dtype == torch.int16:
+        wav = (wav * (32767.0 / 0.5)).round_().clamp_(-32768, 32767).to(torch.int16)
+    return wav, gt
+
+
 def ncu_traffic():
     """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel class, summed over its
     launches in one step, from the committed ncu capture (profiles/r1_traffic.json; ncu serialises launches and
     starts each one cold, so this is an upper bound for the pipelined run).  None if the file is absent."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if not os.path.exists(path):
         return None
     try:
@@ -100,19 +127,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(n_clips, threads):
+def cpu_reference_run(n_clips, threads, first_clip=0):
     """The reference's CPU path through the oracle port: per-clip fp64 log-mel (the reference has no batch
-    dimension), adapter D2, fp32 generator forward in eval mode, compute_pck + L1.  Returns seconds."""
+    dimension; the clips are spread over the host threads -- numpy's FFT releases the GIL), adapter D2, fp32 generator
+    forward in eval mode on all threads, compute_pck + L1.  Returns seconds."""
+    import concurrent.futures
     import numpy as np
     import torch
     from oracle import mel_oracle, model_oracle, eval_oracle, synth, weights
     torch.set_num_threads(threads)
     sd = cpu_reference_run.sd if hasattr(cpu_reference_run, "sd") else weights.make_state_dict(0, "stress")
     cpu_reference_run.sd = sd
-    wav = synth.wav_batch(0, n_clips)
-    gt = synth.gt_pose_batch(0, n_clips)
+    wav = synth.wav_batch(first_clip, n_clips)
+    gt = synth.gt_pose_batch(first_clip, n_clips)
     t0 = time.perf_counter()
-    mel = np.stack([mel_oracle.log_mel_audio_repr(w) for w in wav])
+    if n_clips >= 4 and threads > 1:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=threads) as ex:
+            mel = np.stack(list(ex.map(mel_oracle.log_mel_audio_repr, wav)))
+    else:
+        mel = np.stack([mel_oracle.log_mel_audio_repr(w) for w in wav])
     x = torch.from_numpy(synth.adapter(mel).astype(np.float32))
     pose, _ = model_oracle.generator_forward(sd, x)
     eval_oracle.finalize(eval_oracle.metric_partials(pose.numpy(), gt))
@@ -120,24 +153,38 @@ def cpu_reference_run(n_clips, threads):
 
 
 def run_reference(args, rank, world, out=sys.stdout):
-    """--impl reference: the reference algorithm on the host cores (oracle port; the reference itself is
-    pure Python and not importable as shipped)."""
+    """--impl reference: the reference algorithm on the host cores (oracle port; the reference itself is pure Python
+    and not importable as shipped).  BASELINE.md section 4: one step = ONE batch of config 2
+    (256 clips, the same configuration as the B200 arm); the config-1 latency (batch 1) is reported beside it.
+    If a step takes so long that K steps would not end within a few minutes, the remaining steps run on a
+    quarter batch and the line says so."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = max(4, min(args.ref_clips, 32))
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_run(sample, threads)
-    t = [cpu_reference_run(sample, threads) for _ in range(args.steps)]
-    total = sum(t)
-    value = sample * args.steps / total
+    B = args.batch
+    budget_s = 240.0
+    cpu_reference_run(4, threads)                                            # imports, weights, thread pools
+    warm = min(args.warmup, 1)
+    times, clips = [], []
+    t_first = cpu_reference_run(B, threads, 0) if warm else None              # the warm-up step doubles as the probe
+    per_step = t_first if t_first is not None else cpu_reference_run(B, threads, 0)
+    n_step = B if per_step * args.steps <= budget_s else max(16, B // 4)
+    for i in range(args.steps):
+        times.append(cpu_reference_run(n_step, threads, (i + 1) * B))
+        clips.append(n_step)
+    total = sum(times)
+    value = sum(clips) / total
+    b1 = sorted(cpu_reference_run(1, threads, 7) for _ in range(5))[2]
+    sample = "%d steps x %d clips (oracle port of the reference CPU path, %d threads)" % (args.steps, n_step, threads)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+            "warmup": warm, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 mel / f32 model", "data": "synthetic",
-            "config": {"workload": WORKLOAD % args.batch, "clips_per_step": sample, "clip_samples": CLIP_SAMPLES,
-                       "note": "the reference's CPU path (oracle port) on a bounded sample of the same workload per step"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d clips per step x %d steps (oracle port of the reference CPU path)" % (sample, args.steps)},
+            "config": {"workload": WORKLOAD % B, "clips_per_step": n_step, "clip_samples": CLIP_SAMPLES,
+                       "note": "the reference's CPU path (oracle port); one step = one batch of the workload"
+                               + ("" if n_step == B else " -- reduced to %d clips per step to bound the run" % n_step)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config1_batch1": {"ms_per_clip": 1e3 * b1, "clips_per_s": 1.0 / b1,
+                               "note": "BASELINE config 1: one 4.27 s clip, log-mel + forward + eval, median of 5"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), file=out, flush=True)
@@ -186,6 +233,10 @@ def main():
     ap.add_argument("--adapter-frames-only", type=int, default=0, help="1: compute only the 64 log-mel frames the adapter "
                     "feeds to the generator (an end-to-end shortcut; NOT the headline configuration, which produces all 425)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="2: the headline (weak scaling, batches of 256 "
+                    "per rank and step); 3: BASELINE config 3, the 100 000-clip evaluation set strong-scaled over the ranks")
+    ap.add_argument("--eval-clips", type=int, default=100000, help="size of the config-3 evaluation set")
+    ap.add_argument("--sustain-seconds", type=float, default=3.0, help="length of the sustained leg (0: skip)")
     args = ap.parse_args()
     out = _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
@@ -229,13 +280,7 @@ def main():
     pipe = pipeline.AudioToPosePipeline(model, comm=comm, lanes=args.lanes, graphs=bool(args.graphs),
                                         adapter_frames_only=bool(args.adapter_frames_only))
 
-    # ---- synthetic inputs: per-clip seeds make any sharding reproduce the same clips -----------------
     B = args.batch
-    gen = torch.Generator(device=device).manual_seed(1234 + rank)
-    wav_dev = [0.1 * torch.randn(B, CLIP_SAMPLES, device=device, generator=gen) for _ in range(POOL)]
-    gt_dev = [50.0 * torch.randn(B, 64, 104, device=device, generator=gen) for _ in range(POOL)]
-    wav_host = [w.cpu().pin_memory() for w in wav_dev]
-    gt_host = [g_.cpu().pin_memory() for g_ in gt_dev]
 
     def barrier():
         if world > 1:
@@ -249,6 +294,72 @@ def main():
             return t.item()
         return ms
 
+    def sharded_eval(n_clips):
+        """Strong-scaled evaluation of clips [0, n_clips): rank r owns [r * ceil(n / W), (r + 1) * ceil(n / W)), batches
+        of B, one all-reduce.  Inputs are generated into HBM before the timed region.  Returns (ms, result)."""
+        lo, hi = pipeline.shard_range(n_clips, rank, world)
+        chunks = [synth_clips(c, min(hi, c + B), device) for c in range(lo, hi, B)]
+        pipe.reset()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for w, g_ in chunks:
+            pipe.step(w, g_)
+        res = pipe.finish()
+        t1.record()
+        barrier()
+        return max_over_ranks(t0.elapsed_time(t1)), res
+
+    if args.config == 3:
+        # ---- BASELINE config 3: the full synthetic evaluation set, clip-sharded, strong scaling -------------
+        for i in range(max(args.warmup, args.lanes)):
+            w, g_ = synth_clips(i * B, (i + 1) * B, device)
+            pipe.step(w, g_)
+        pipe.finish()
+        lib.a2m_launch_count_reset()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ms, res = sharded_eval(args.eval_clips)
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            line = {"metric": METRIC, "value": args.eval_clips / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+                    "steps": -(-args.eval_clips // (B * world)), "warmup": max(args.warmup, args.lanes),
+                    "ms_per_step": ms / max(1, -(-args.eval_clips // (B * world))), "ms_total": ms, "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "bf16 (fp32 accumulate; mel and eval fp32)",
+                    "data": "synthetic",
+                    "config": {"workload": "config3: full synthetic eval set, %d clips with L1/PCK, clip-sharded x%d, "
+                                           "batches of %d, per-clip seeds" % (args.eval_clips, world, B),
+                               "parallelism": "clip-sharded x%d" % world, "stream_lanes": args.lanes,
+                               "l2": "each rank's shard (%.1f GB of waveforms) is read once" %
+                                     (-(-args.eval_clips // world) * CLIP_SAMPLES * 4 / 1e9)},
+                    "clocks": clocks, "gpu_launches": int(lib.a2m_launch_count()),
+                    "result": {k: res[k] for k in ("pck_hits", "n_keypoints", "pck", "l1_pose", "l1_motion", "n_frames")}}
+            print(json.dumps(line), file=out, flush=True)
+        if comm is not None:
+            comm.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- synthetic inputs: per-clip seeds make any sharding reproduce the same clips; batch j of rank r holds the
+    # global clips [(j * world + r) * B, +B) ---------------------------------------------------------------------
+    pairs = [synth_clips((j * world + rank) * B, (j * world + rank + 1) * B, device) for j in range(POOL)]
+    wav_dev, gt_dev = [p_[0] for p_ in pairs], [p_[1] for p_ in pairs]
+    wav_host = [w.cpu().pin_memory() for w in wav_dev]
+    gt_host = [g_.cpu().pin_memory() for g_ in gt_dev]
+    pcm_host = [(w * (32767.0 / 0.5)).round().clamp(-32768, 32767).to(torch.int16).cpu().pin_memory() for w in wav_dev]
+
+    def timed_steps(n_steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_steps):
+            pipe.step(wav_dev[i % POOL], gt_dev[i % POOL])
+        res = pipe.finish()                      # all-reduce + 64-byte D2H inside the timed region
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), res
+
     # ---- device-resident arm -------------------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
@@ -256,40 +367,58 @@ def main():
     for i in range(args.warmup):
         pipe.step(wav_dev[i % POOL], gt_dev[i % POOL])
     pipe.finish()
-    model.check_device_status()
     pipe.reset()
     barrier()
     if rank == 0:
         sampler.mark()                           # samples from here on are "under load"
     lib.a2m_launch_count_reset()
     pipe.replayed_launches = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        pipe.step(wav_dev[i % POOL], gt_dev[i % POOL])
-    result = pipe.finish()                       # all-reduce + 64-byte D2H inside the timed region
-    e1.record()
-    barrier()
+    ms_total, result = timed_steps(args.steps)
     launches = int(lib.a2m_launch_count()) + int(pipe.replayed_launches)
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms_total / 1e3)
 
+    # ---- sustained leg: the same loop for >= --sustain-seconds (clocks settle under the power cap) ------------
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(args.sustain_seconds / (ms_total / args.steps / 1e3)) + 1)
+        pipe.reset()
+        barrier()
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
+            time.sleep(0.2)
+            sampler2.mark()
+        ms_sus, _ = timed_steps(n_sus)
+        clocks2 = sampler2.stop() if rank == 0 else None
+        sustained = {"value": world * B * n_sus / (ms_sus / 1e3), "unit": UNIT, "steps": n_sus, "seconds": ms_sus / 1e3,
+                     "ms_per_step": ms_sus / n_sus, "clocks": clocks2}
+
     # ---- end-to-end arm: pinned host inputs, H2D inside the timed region, result read back ------------
-    pipe.reset()
-    pipe.run_host_batches([(wav_host[i % POOL], gt_host[i % POOL]) for i in range(2)])
-    pipe.finish(); pipe.reset()
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    pipe.run_host_batches((wav_host[i % POOL], gt_host[i % POOL]) for i in range(args.steps))
-    result_e2e = pipe.finish()
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
-    wall_e2e = time.perf_counter() - t0
+    def e2e_run(wavs):
+        pipe.reset()
+        pipe.run_host_batches([(wavs[i % POOL], gt_host[i % POOL]) for i in range(2)])
+        pipe.finish(); pipe.reset()
+        barrier()
+        t0 = time.perf_counter()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        pipe.run_host_batches((wavs[i % POOL], gt_host[i % POOL]) for i in range(args.steps))
+        res = pipe.finish()
+        b_.record()
+        barrier()
+        ms = max_over_ranks(max(a.elapsed_time(b_), 0.0))
+        return ms, time.perf_counter() - t0, res
+
+    ms_e2e, wall_e2e, result_e2e = e2e_run(wav_host)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     h2d = wav_host[0].numel() * 4 + gt_host[0].numel() * 4
+    ms_e2e16, wall_e2e16, result_e2e16 = e2e_run(pcm_host)
+    h2d16 = pcm_host[0].numel() * 2 + gt_host[0].numel() * 4
+
+    # ---- the same fixed evaluation set for every N (per-clip seeds): integer hit counts must not depend on N ----
+    check_clips = 2048
+    _, check = sharded_eval(check_clips)
 
     # ---- roofline of the dominant kernel (tcgen05 conv GEMM) and of the two HBM-bound kernels ----------
     pk = peaks()
@@ -306,30 +435,49 @@ def main():
                                          out_ms, ctypes.byref(n_gemm), cabi.stream_ptr(device)))
         flops = int(lib.a2m_model_gemm_flops(h.ptr, B, 64, 64))
         achieved = flops / (out_ms[1] * 1e-3) / 1e12
+        # a2m_model_profile times every launch between its own pair of events on an otherwise idle GPU: each kernel is
+        # timed ALONE, so the burst peak is the denominator; the sustained one is given beside it
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, %d launches/step)" % n_gemm.value,
-                "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                "peak_kind": pk["src"] + " sustained (kernel timed inside a long step)",
+                "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
+                "peak_kind": pk["src"] + " burst (every launch timed alone between its own events)",
+                "frac_of_sustained_peak": achieved / pk["tf_sustained"], "sustained_peak": pk["tf_sustained"],
                 "traffic": (ncu_traffic() or {}).get("conv_gemm_bytes_per_step"),
                 "traffic_note": (ncu_traffic() or {}).get("note"),
-                "gemm_ms_per_step": out_ms[1], "other_ms_per_step": out_ms[2], "algorithmic_gflop_per_step": flops / 1e9}
+                "gemm_ms_per_step": out_ms[1], "other_ms_per_step": out_ms[2], "algorithmic_gflop_per_step": flops / 1e9,
+                "whole_forward": {"algorithmic_gflop_per_step": 3.434 * B, "achieved_tflops_in_step": 3.434 * B / (ms_total / args.steps) ,
+                                  "frac_of_burst": 3.434 * B / (ms_total / args.steps) / pk["tf_burst"]}}
 
         def ev_time(fn, n=10):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             fn(0); torch.cuda.synchronize()
             a.record()
             for i in range(n):
                 fn(i)
-            b.record(); torch.cuda.synchronize()
-            return a.elapsed_time(b) / n
-        mel_ms = ev_time(lambda i: pipeline.audio_repr.log_mel_spectograms(wav_dev[i % POOL]))
+            b_.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b_) / n
+        lm = pipeline.audio_repr.log_mel_spectograms
+        mel_ms = ev_time(lambda i: lm(wav_dev[i % POOL]))
         mel_bytes = B * (CLIP_SAMPLES * 4 + 425 * 64 * 4)
+        pcm_dev = [p_.to(device) for p_ in pcm_host[:3]]
+        mel16_ms = ev_time(lambda i: lm(pcm_dev[i % 3]))
+        mel16_bytes = B * (CLIP_SAMPLES * 2 + 425 * 64 * 4)
+        sweep = []
+        for nb in (1, 16, 4096):                 # BASELINE config 5 (bandwidth sweep); 256 is the line above
+            wv = torch.empty(nb, CLIP_SAMPLES, device=device).normal_(0.0, 0.1)
+            ms = ev_time(lambda i: lm(wv), n=5)
+            sweep.append({"clips": nb, "ms": ms, "gbs": nb * (CLIP_SAMPLES * 4 + 425 * 64 * 4) / ms / 1e6,
+                          "frac": nb * (CLIP_SAMPLES * 4 + 425 * 64 * 4) / ms / 1e6 / pk["hbm"]})
+            del wv
         acc = pipe.accum
         ev_ms = ev_time(lambda i: pipeline.motion_evaluation.evaluate_poses(gt_dev[i % POOL], gt_dev[(i + 1) % POOL], accum=acc))
         ev_bytes = B * 64 * 104 * 4 * 2
         extra = {"roofline_mel": {"bound": "hbm", "achieved": mel_bytes / mel_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
                                   "frac": mel_bytes / mel_ms / 1e6 / pk["hbm"], "ms": mel_ms,
-                                  "note": "HBM-bound by contract, fp32-issue / shared-memory bound in practice (DESIGN.md section 4): "
-                                          "the FFT butterflies alone need more issue slots than 50 % of the HBM roofline leaves"},
+                                  "int16_pcm": {"achieved": mel16_bytes / mel16_ms / 1e6, "frac": mel16_bytes / mel16_ms / 1e6 / pk["hbm"],
+                                                "ms": mel16_ms, "bytes_per_clip": CLIP_SAMPLES * 2 + 425 * 64 * 4},
+                                  "sweep": sweep,
+                                  "note": "HBM-bound by contract; in practice shared-memory-crossbar / issue bound (DESIGN.md "
+                                          "section 4): ncu shows 68 % of the shared-memory wavefront peak, 61 % issue, 42 % fp32 pipe"},
                  "roofline_eval": {"bound": "hbm", "achieved": ev_bytes / ev_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
                                    "frac": ev_bytes / ev_ms / 1e6 / pk["hbm"], "ms": ev_ms}}
         pipe.reset()
@@ -354,14 +502,26 @@ def main():
                            "clips_per_step_per_gpu": B, "parallelism": "clip-sharded x%d" % world,
                            "stream_lanes": args.lanes, "cuda_graphs": bool(args.graphs), "host_binding": numa,
                            "mel_frames": "64 adapter frames only (shortcut)" if args.adapter_frames_only else "all 425 per clip",
+                           "clip_seeds": "per clip: 1234 + global index (wav), 4321 + global index (ground truth)",
                            "l2": "inputs cycle through %d distinct batches (%.0f MB each) > L2" % (POOL, h2d / 1e6)},
                 "clocks": clocks,
+                "value_sustained": sustained,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 64,
-                        "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": 1e3 * wall_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": 1e3 * wall_e2e / args.steps,
+                        "input": "fp32 waveforms from pinned host memory"},
+                "e2e_int16": {"value": world * B * args.steps / (ms_e2e16 / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d16,
+                              "d2h_bytes_per_step": 64, "ms_per_step": ms_e2e16 / args.steps,
+                              "input": "16-bit PCM waveforms (the source format; a2m_logmel_i16) from pinned host memory",
+                              "result": {k: result_e2e16[k] for k in ("pck", "n_frames")}},
                 "gpu_launches": launches,
                 "roofline": roof, "cpu_baseline": cpu,
+                "cpu_baseline_note": None if cpu is not None else "measured on rank 0 at N = 1 only (see the N = 1 line)",
                 "result": {k: result[k] for k in ("pck", "l1_pose", "l1_motion", "n_frames")},
-                "result_e2e": {k: result_e2e[k] for k in ("pck", "n_frames")}}
+                "result_e2e": {k: result_e2e[k] for k in ("pck", "n_frames")},
+                "sharded_check": {"clips": check_clips, "note": "clips 0 .. %d split over the %d rank(s), per-clip seeds: "
+                                  "identical integers for every N" % (check_clips - 1, world),
+                                  "pck_hits": check["pck_hits"], "n_keypoints": check["n_keypoints"], "pck": check["pck"],
+                                  "l1_pose": check["l1_pose"]}}
         line.update(extra)
         print(json.dumps(line), file=out, flush=True)
     if comm is not None:

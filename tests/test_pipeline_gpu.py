@@ -181,3 +181,53 @@ def test_adapter_frames_only_is_bit_identical(setup):
     out = pipe.finish()
     assert torch.equal(p_sparse.cpu(), p_full[0])
     assert out["pck_hits"] == full["pck_hits"] and out["abs_pose"] == full["abs_pose"]
+
+
+def test_lanes_follow_later_changes_of_the_model(pkg):
+    """The stream lanes are native handles of ONE module: load_state_dict, an in-place weight edit and
+    set_output_denorm made after the pipeline was built reach every lane (alternating batches would otherwise run on
+    stale weights)."""
+    mods = pkg.install_dropin()
+    pipeline = importlib.import_module(PKG + ".pipeline")
+    model = mods["real_motion_model"].SelfAttention_G().cuda().eval()
+    model.load_state_dict(weights.make_state_dict(0, "stress"))
+    pipe = pipeline.AudioToPosePipeline(model, lanes=2)
+    wav = torch.from_numpy(synth.wav_batch(60, 2)).cuda()
+    gt = torch.from_numpy(synth.gt_pose_batch(60, 2)).cuda()
+    a0, a1 = pipe.step(wav, gt).clone(), pipe.step(wav, gt).clone()      # lane 0, lane 1
+    pipe.finish()
+    assert torch.equal(a0, a1)
+    model.load_state_dict(weights.make_state_dict(5, "stress"))          # new weights after construction
+    b0, b1 = pipe.step(wav, gt).clone(), pipe.step(wav, gt).clone()
+    pipe.finish()
+    assert torch.equal(b0, b1) and not torch.equal(b0, a0)
+    fresh = mods["real_motion_model"].SelfAttention_G().cuda().eval()
+    fresh.load_state_dict(weights.make_state_dict(5, "stress"))
+    assert torch.equal(b0, pipeline.AudioToPosePipeline(fresh, lanes=1).step(wav, gt))
+    with torch.no_grad():
+        model.body_logits.bias.add_(1.0)                                 # in-place edit
+    c0, c1 = pipe.step(wav, gt).clone(), pipe.step(wav, gt).clone()
+    pipe.finish()
+    assert torch.equal(c0, c1) and torch.allclose(c0[..., :20], b0[..., :20] + 1.0, atol=1e-5)
+    mean, std = torch.full((104,), 3.0), torch.full((104,), 2.0)
+    model.set_output_denorm(mean, std)
+    d0, d1 = pipe.step(wav, gt).clone(), pipe.step(wav, gt).clone()
+    pipe.finish()
+    assert torch.equal(d0, d1) and torch.equal(d0, c0 * 2.0 + 3.0)
+    model.set_output_denorm()
+
+
+def test_int16_pcm_batches_end_to_end(setup):
+    """Pinned int16 host batches (half the H2D bytes) give the metrics of the same samples fed as fp32."""
+    pipeline, model, _ = setup
+    pcm = np.stack([synth.wav_clip(70 + i, synth.CLIP_SAMPLES, "int16").astype(np.int16) for i in range(4)])
+    gt = synth.gt_pose_batch(70, 4)
+    ref, p_ref = run(pipeline, model, 1, [(pcm.astype(np.float32), gt)])
+    pipe = pipeline.AudioToPosePipeline(model, lanes=2)
+    host = [(torch.from_numpy(pcm[i:i + 2]).pin_memory(), torch.from_numpy(gt[i:i + 2]).pin_memory()) for i in (0, 2)]
+    assert host[0][0].dtype == torch.int16
+    assert pipe.run_host_batches(host) == 4
+    out = pipe.finish()
+    assert out["n_frames"] == ref["n_frames"]
+    assert abs(out["pck_hits"] - ref["pck_hits"]) <= 2                   # the two mel paths agree to fp32 rounding
+    np.testing.assert_allclose(out["abs_pose"], ref["abs_pose"], rtol=1e-3)

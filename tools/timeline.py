@@ -23,7 +23,7 @@ gt = [50 * torch.randn(B, 64, 104, device="cuda") for _ in range(3)]
 for i in range(2 * lanes + 2):
     pipe.step(wav[i % 3], gt[i % 3])
 pipe.finish()
-handles = [m.native() for m in pipe._lane_models]
+handles = [pipe.model.native(i) for i in range(pipe._n_lanes)]
 per_lane = (steps + lanes - 1) // lanes
 for h in handles:
     cabi.check(lib.a2m_model_timeline_begin(h.ptr, B, 64, 64, per_lane))
