@@ -194,25 +194,28 @@ def test_lanes_follow_later_changes_of_the_model(pkg):
     pipe = pipeline.AudioToPosePipeline(model, lanes=2)
     wav = torch.from_numpy(synth.wav_batch(60, 2)).cuda()
     gt = torch.from_numpy(synth.gt_pose_batch(60, 2)).cuda()
-    a0, a1 = pipe.step(wav, gt).clone(), pipe.step(wav, gt).clone()      # lane 0, lane 1
-    pipe.finish()
+
+    def two_lanes(p):
+        x, y = p.step(wav, gt), p.step(wav, gt)                          # lane 0, lane 1
+        p.finish()                                                       # the poses are complete after the lanes are joined
+        return x.clone(), y.clone()
+
+    a0, a1 = two_lanes(pipe)
     assert torch.equal(a0, a1)
     model.load_state_dict(weights.make_state_dict(5, "stress"))          # new weights after construction
-    b0, b1 = pipe.step(wav, gt).clone(), pipe.step(wav, gt).clone()
-    pipe.finish()
+    b0, b1 = two_lanes(pipe)
     assert torch.equal(b0, b1) and not torch.equal(b0, a0)
     fresh = mods["real_motion_model"].SelfAttention_G().cuda().eval()
     fresh.load_state_dict(weights.make_state_dict(5, "stress"))
-    assert torch.equal(b0, pipeline.AudioToPosePipeline(fresh, lanes=1).step(wav, gt))
+    assert torch.equal(b0, two_lanes(pipeline.AudioToPosePipeline(fresh, lanes=1))[0])
     with torch.no_grad():
         model.body_logits.bias.add_(1.0)                                 # in-place edit
-    c0, c1 = pipe.step(wav, gt).clone(), pipe.step(wav, gt).clone()
-    pipe.finish()
+    c0, c1 = two_lanes(pipe)
     assert torch.equal(c0, c1) and torch.allclose(c0[..., :20], b0[..., :20] + 1.0, atol=1e-5)
+    assert torch.equal(c0[..., 20:], b0[..., 20:])
     mean, std = torch.full((104,), 3.0), torch.full((104,), 2.0)
     model.set_output_denorm(mean, std)
-    d0, d1 = pipe.step(wav, gt).clone(), pipe.step(wav, gt).clone()
-    pipe.finish()
+    d0, d1 = two_lanes(pipe)
     assert torch.equal(d0, d1) and torch.equal(d0, c0 * 2.0 + 3.0)
     model.set_output_denorm()
 
