@@ -84,6 +84,11 @@ SIGNATURES = {
     "a2m_model_timeline_begin": (c_int, [c_void_p, c_i64, c_int, c_int, c_int]),
     "a2m_model_timeline_read": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int]),
     "a2m_model_encoder_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p]),
+    "a2m_model_encoder_forward_ex": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "a2m_model_plan_generation": (c_i64, [c_void_p]),
+    "a2m_block_create": (c_int, [c_int, ctypes.POINTER(TensorDesc), c_int, c_int, c_int, c_int, c_int,
+                                 ctypes.POINTER(c_void_p)]),
+    "a2m_block_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "a2m_model_unet_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "a2m_model_gnn_forward": (c_int, [c_void_p, c_int, c_void_p, c_i64, c_void_p, c_void_p]),
     "a2m_model_status": (c_int, [c_void_p]),

@@ -9,9 +9,10 @@ from . import _cabi
 
 
 class NativeHandle:
-    """Owns one a2m_model*; destroyed with the Python object."""
+    """Owns one a2m_model*; destroyed with the Python object.  `block`: (kind, in_channels, out_channels, leaky) makes
+    it a stand-alone building block (a2m_block_create) instead of a generator section (a2m_model_create)."""
 
-    def __init__(self, state, device):
+    def __init__(self, state, device, block=None):
         descs = (_cabi.TensorDesc * len(state))()
         keep = []                                   # tensors (possibly converted copies) alive during create
         for i, (name, t) in enumerate(state.items()):
@@ -21,7 +22,7 @@ class NativeHandle:
                 dtype = 0
                 if t.dtype != torch.float32:
                     t = t.to(torch.float32)
-            t = t.to(device).contiguous()
+            t = t.detach().to(device).contiguous()
             keep.append(t)
             descs[i].name = name.encode()
             descs[i].data = t.data_ptr()
@@ -31,7 +32,12 @@ class NativeHandle:
                 descs[i].shape[k] = s
         out = ctypes.c_void_p()
         with torch.cuda.device(device):
-            _cabi.check(_cabi.lib().a2m_model_create(descs, len(state), device.index, ctypes.byref(out)))
+            if block is None:
+                _cabi.check(_cabi.lib().a2m_model_create(descs, len(state), device.index, ctypes.byref(out)))
+            else:
+                kind, cin, cout, leaky = block
+                _cabi.check(_cabi.lib().a2m_block_create(kind, descs, len(state), cin, cout, int(leaky), device.index,
+                                                         ctypes.byref(out)))
         self.ptr = out
         self.device = device
 
@@ -49,6 +55,7 @@ class NativeModule(nn.Module):
     BatchNorm running statistics, dropout off); forward raises while the module is in training mode."""
 
     _state_prefix = ""              # prefix that maps this module's keys onto SelfAttention_G's names
+    _block = None                   # stand-alone building blocks: (kind, in_channels, out_channels, leaky), set per instance
 
     def _native_state(self):
         sd = self.state_dict()
@@ -90,7 +97,7 @@ class NativeModule(nn.Module):
             if dev.type != "cuda":
                 raise RuntimeError("%s: parameters are on %s; move the module to a CUDA device (.cuda()) -- "
                                    "there is no CPU fallback" % (type(self).__name__, dev))
-            entry = handles[lane] = (NativeHandle(self._native_state(), dev), fp)
+            entry = handles[lane] = (NativeHandle(self._native_state(), dev, self._block), fp)
         return entry[0]
 
     def repack(self):

@@ -340,6 +340,80 @@ attention_generic_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
     }
 }
 
+// Sequences longer than 64 steps (the reference has no limit, model_layers.py:133-146): one CTA per (clip, 8 query
+// rows); the 8 x T score rows live in shared memory, softmax by one warp per row, then P.v with two channels per thread.
+constexpr int kLongRows = 8;
+__global__ void __launch_bounds__(256)
+attention_long_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ x,
+                      const __nv_bfloat16* __restrict__ res2, const float* __restrict__ gamma_p, int T, int C,
+                      __nv_bfloat16* __restrict__ out) {
+    extern __shared__ __align__(16) float s_long[];
+    const int d = C / 8, ld = 2 * d + C;
+    float* s_q = s_long;                                   // [8][d]
+    float* s_p = s_long + kLongRows * d;                   // [8][T]
+    const long long b = blockIdx.x;
+    const int i0 = blockIdx.y * kLongRows, rows = min(kLongRows, T - i0);
+    const __nv_bfloat16* base = qkv + b * T * ld;
+    for (int idx = threadIdx.x; idx < rows * d; idx += blockDim.x) {
+        const int r = idx / d, c = idx - r * d;
+        s_q[idx] = __bfloat162float(base[static_cast<long long>(i0 + r) * ld + c]);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < rows) {
+        const float* q = s_q + warp * d;
+        float* prow = s_p + warp * T;
+        float m = -INFINITY;
+        for (int j = lane; j < T; j += 32) {
+            const uint4* k8 = reinterpret_cast<const uint4*>(base + static_cast<long long>(j) * ld + d);   // d % 8 == 0, ld % 8 == 0
+            float acc = 0.f;
+            for (int c = 0; c < d / 8; ++c) {
+                const uint4 u = __ldg(k8 + c);
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc = fmaf(q[c * 8 + 2 * e], __uint_as_float(w4[e] << 16), acc);
+                    acc = fmaf(q[c * 8 + 2 * e + 1], __uint_as_float(w4[e] & 0xffff0000u), acc);
+                }
+            }
+            prow[j] = acc;                                  // no 1/sqrt(d): model_layers.py:140
+            m = fmaxf(m, acc);
+        }
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int j = lane; j < T; j += 32) { const float e = __expf(prow[j] - m); prow[j] = e; sum += e; }
+        const float inv = 1.f / warp_sum(sum);
+        for (int j = lane; j < T; j += 32) prow[j] *= inv;
+    }
+    __syncthreads();
+    const float gamma = *gamma_p;
+    const __nv_bfloat16* vbase = base + 2 * d;
+    for (int c = 2 * threadIdx.x; c < C; c += 2 * blockDim.x) {
+        float acc[kLongRows][2];
+#pragma unroll
+        for (int r = 0; r < kLongRows; ++r) acc[r][0] = acc[r][1] = 0.f;
+        for (int j = 0; j < T; ++j) {
+            const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(vbase + static_cast<long long>(j) * ld + c));
+            const float v0 = __uint_as_float(u << 16), v1 = __uint_as_float(u & 0xffff0000u);
+#pragma unroll
+            for (int r = 0; r < kLongRows; ++r) {
+                const float pj = s_p[r * T + j];
+                acc[r][0] = fmaf(pj, v0, acc[r][0]);
+                acc[r][1] = fmaf(pj, v1, acc[r][1]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kLongRows; ++r) {
+            if (r < rows) {
+                const long long o = (b * T + i0 + r) * C + c;
+                float r0 = gamma * acc[r][0] + __bfloat162float(x[o]), r1 = gamma * acc[r][1] + __bfloat162float(x[o + 1]);
+                if (res2) { r0 += __bfloat162float(res2[o]); r1 += __bfloat162float(res2[o + 1]); }
+                *reinterpret_cast<__nv_bfloat162*>(out + o) = __floats2bfloat162_rn(r0, r1);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ channel attention
 // One CTA (256 threads = 8 warps) per clip.  Pooling and the final scaling move 8 channels per thread as 16-byte
 // vectors, warp w taking the time steps w, w + 8, ...; the per-warp partial sums / maxima meet in shared memory.
@@ -562,9 +636,59 @@ int launch_conv0(const float* mel, long long stride_b, long long stride_t, int B
     A2M_AFTER_LAUNCH();
 }
 
+// Any output length (T not a multiple of Hc: T % 8 != 0, or AudioEncoder.forward(x, time_steps != T),
+// model_layers.py:267-279): one thread per (clip, output step, 8 channels), the two source rows read directly.
+__global__ void __launch_bounds__(256)
+time_interp_general_kernel(const float* __restrict__ in, int n_planes, long long plane_stride, int Hc, int T, int C,
+                           long long total, __nv_bfloat16* __restrict__ out) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c8 = C / 8;
+    const int c = static_cast<int>(idx % c8) * 8;
+    const long long bt = idx / c8;
+    const int t = static_cast<int>(bt % T);
+    const long long b = bt / T;
+    float src = (static_cast<float>(Hc) / static_cast<float>(T)) * (static_cast<float>(t) + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    const int i0 = min(static_cast<int>(src), Hc - 1);
+    const int i1 = i0 + (i0 < Hc - 1 ? 1 : 0);
+    const float l1 = src - static_cast<float>(i0), l0 = 1.f - l1;
+    float v[2][8];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[r][e] = 0.f;
+    for (int pl = 0; pl < n_planes; ++pl) {                   // fixed summation order over the split-K planes
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float4* p4 = reinterpret_cast<const float4*>(in + pl * plane_stride + (b * Hc + (r ? i1 : i0)) * C + c);
+            const float4 a0 = __ldg(p4), a1 = __ldg(p4 + 1);
+            v[r][0] += a0.x; v[r][1] += a0.y; v[r][2] += a0.z; v[r][3] += a0.w;
+            v[r][4] += a1.x; v[r][5] += a1.y; v[r][6] += a1.z; v[r][7] += a1.w;
+        }
+    }
+    uint4 o;
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float f0 = l0 * leaky(v[0][2 * e]) + l1 * leaky(v[1][2 * e]);
+        const float f1 = l0 * leaky(v[0][2 * e + 1]) + l1 * leaky(v[1][2 * e + 1]);
+        __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+        w[e] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    o.x = w[0]; o.y = w[1]; o.z = w[2]; o.w = w[3];
+    *reinterpret_cast<uint4*>(out + (b * T + t) * C + c) = o;
+}
+
 int launch_time_interp(const float* in, int n_planes, int B, int Hc, int T, int C, __nv_bfloat16* out, cudaStream_t stream) {
-    A2M_ARG_CHECK(C % 8 == 0 && Hc >= 1 && T % Hc == 0 && n_planes >= 1 && n_planes <= kMaxPlanes,
+    A2M_ARG_CHECK(C % 8 == 0 && Hc >= 1 && T >= 1 && n_planes >= 1 && n_planes <= kMaxPlanes,
                   "time_interp: C = %d, Hc = %d, T = %d, planes = %d", C, Hc, T, n_planes);
+    if (T % Hc != 0) {
+        const long long total = static_cast<long long>(B) * T * (C / 8);
+        time_interp_general_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+            in, n_planes, static_cast<long long>(B) * Hc * C, Hc, T, C, total, out);
+        A2M_AFTER_LAUNCH();
+    }
     const long long total = static_cast<long long>(B) * Hc * (C / 8);
     time_interp_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, n_planes, static_cast<long long>(B) * Hc * C, Hc, T, C, total, out);
     A2M_AFTER_LAUNCH();
@@ -597,10 +721,20 @@ int launch_attention(const __nv_bfloat16* qkv, const __nv_bfloat16* x, const __n
         case 56: return launch_attention_t<56>(qkv, x, res2, gamma, B, C, out, stream);
         case 64: return launch_attention_t<64>(qkv, x, res2, gamma, B, C, out, stream);
         default:
-            A2M_ARG_CHECK(T >= 1 && T <= 64, "attention: T = %d; this build implements T <= 64", T);
-            attention_generic_kernel<<<B, 256, 0, stream>>>(qkv, x, res2, gamma, T, C, out);
-            A2M_AFTER_LAUNCH();
+            break;
     }
+    A2M_ARG_CHECK(T >= 1 && T <= 4096, "attention: T = %d; this build implements T <= 4096", T);
+    if (T <= 64) {
+        attention_generic_kernel<<<B, 256, 0, stream>>>(qkv, x, res2, gamma, T, C, out);
+        A2M_AFTER_LAUNCH();
+    }
+    const size_t smem = static_cast<size_t>(kLongRows) * (C / 8 + T) * sizeof(float);
+    A2M_ARG_CHECK(smem <= 200 * 1024 && C % 64 == 0, "attention: T %d x C %d needs %zu B of shared memory", T, C, smem);
+    static A2mPerDeviceOnce configured;
+    if (configured.first())
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attention_long_kernel<<<dim3(B, (T + kLongRows - 1) / kLongRows), 256, smem, stream>>>(qkv, x, res2, gamma, T, C, out);
+    A2M_AFTER_LAUNCH();
 }
 
 int launch_channel_attention(const __nv_bfloat16* x, int B, int T, int C, int hidden, const float* w0, const float* b0,

@@ -62,6 +62,8 @@ struct DecoderW {
 
 struct ForwardPlan {
     int B, T, F;
+    int T_out = 0;                              // AudioEncoder.forward(x, time_steps): length of the encoder output (= T in the generator)
+    unsigned long long last_use = 0;            // plan cache: least recently used goes first
     void* arena = nullptr;
     std::vector<std::function<int(cudaStream_t)>> ops;
     std::vector<int> op_is_gemm;                // parallel to ops
@@ -89,6 +91,12 @@ struct a2m_model {
     LayerW ds[4], bott, up0_even, up0_odd, up1, up2_even, up2_odd, up3, final_conv;
     AttnW bott_attn, up_attn;
     DecoderW dec[2];
+    // stand-alone building block (a2m_block_*): one layer class of model_layers.py with its own forward
+    int blk_kind = 0, blk_cin = 0, blk_cout = 0;
+    LayerW blk_conv, blk_even, blk_odd;
+    AttnW blk_attn;
+    ChanW blk_chan;
+    ResW blk_res;
     int* triples = nullptr; int n_hand_triples = 0, n_body_triples = 0;
     int* parents = nullptr;
     double* loss_scratch = nullptr;
@@ -104,6 +112,8 @@ struct a2m_model {
     long long cur_stride_b = 0, cur_stride_t = 0;
     float* cur_pose = nullptr;
     std::map<std::string, std::unique_ptr<ForwardPlan>> plans;
+    unsigned long long plan_clock = 0;
+    long long plan_generation = 0;              // bumped whenever a cached plan (and its arena) is released
     std::string build_error;
     // the two decoder branches are independent: the body branch runs on a side stream, forked / joined with events
     cudaStream_t side_stream = nullptr;
@@ -586,15 +596,20 @@ struct Emit {
             op([rp, flag](cudaStream_t s) { return resblock_fused_launch(*rp, flag, s); });
             return;
         }
-        conv_k3(R.c1, x, 256, nullptr, 0, len, B, t1);
-        conv_k3(R.c2, t1, 256, nullptr, 0, len, B, t2);
+        const int C = R.attn.C;
+        conv_k3(R.c1, x, C, nullptr, 0, len, B, t1);
+        conv_k3(R.c2, t1, C, nullptr, 0, len, B, t2);
         attention(R.attn, t2, x, len, B, qkv, out);
     }
 };
 
 int build_plan(a2m_model* m, ForwardPlan* P) {
-    const int B = P->B, T = P->T, F = P->F;
-    const int H1 = T / 2, W1 = F / 2, H2 = T / 4, W2 = F / 4, H3 = T / 8, W3 = F / 8;
+    const int B = P->B, T = P->T, F = P->F, T_out = P->T_out;
+    // three k4 s2 p1 stages: H -> floor(H / 2) (model_layers.py:252-256).  T % 4 == 0 makes H1 and H2 exact; H2 may be odd,
+    // then the third stage drops its last row pair like the reference does.  The parity view of a stride-2 stage needs an
+    // even number of allocated rows: a1 gets one zero row of padding per clip when H2 is odd.
+    const int H1 = T / 2, W1 = F / 2, H2 = T / 4, W2 = F / 4, H3 = H2 / 2, W3 = F / 8;
+    const int H2a = H2 + (H2 & 1);
     const int w_out = W3 - 1;                                   // conv 4: W + 2*3 - 8 + 1
     A2M_ARG_CHECK(w_out >= 1 && (w_out % 2) == 1, "model: F = %d gives an even number (%d) of encoder output columns; "
                   "only odd widths (F/8 even) are implemented", F, w_out);
@@ -616,11 +631,13 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
         const size_t BT = static_cast<size_t>(B) * T;
         auto* mel_stage = bufs.get<float>(BT * F);
         auto* a0 = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * H1 * W1 * 64);
-        auto* a1 = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * H2 * W2 * 128);
+        auto* a1 = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * H2a * W2 * 128);
+        if (pass == 1 && H2a != H2)               // the padding rows are never written: zero them once
+            A2M_CUDA_CHECK(cudaMemset(a1, 0, static_cast<size_t>(B) * H2a * W2 * 128 * sizeof(__nv_bfloat16)));
         auto* a2 = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * H3 * W3 * 256);
         auto* a3 = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * H3 * W3 * 512);
         auto* a4 = bufs.get<float>(static_cast<size_t>(kConv4Splits) * B * H3 * 256);
-        auto* e0 = bufs.get<__nv_bfloat16>(BT * 256);
+        auto* e0 = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * std::max(T, T_out) * 256);
         auto* s0 = bufs.get<__nv_bfloat16>(BT * 512);
         auto* u1 = bufs.get<__nv_bfloat16>(BT / 2 * 512);
         auto* s1 = bufs.get<__nv_bfloat16>(BT / 2 * 1024);
@@ -643,23 +660,24 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
             a2m_model* mm = m;
             E.tag = "enc.conv0";
             E.op([=](cudaStream_t s) { return launch_conv0(mm->cur_mel, mm->cur_stride_b, mm->cur_stride_t, B, T, F, mm->conv0_w, mm->conv0_b, a0, s); });
-            auto conv2d_s2 = [&](const LayerW& L, const __nv_bfloat16* in, int H, int W, int C, __nv_bfloat16* out) {
-                const int Ho = H / 2, Wo = W / 2;
+            // in: [B, H (allocated rows, even), W, C]; out: [B, Ho_alloc, W / 2, N], rows [0, Ho) written
+            auto conv2d_s2 = [&](const LayerW& L, const __nv_bfloat16* in, int H, int W, int C, __nv_bfloat16* out, int Ho, int Ho_alloc) {
+                const int Wo = W / 2;
                 AView v[2];
                 for (int ph = 0; ph < 2; ++ph) {
                     v[ph].ptr = in + static_cast<size_t>(ph) * W * C; v[ph].rank = 5;
-                    const long long dims[5] = {C, 2, Wo, Ho, B}, str[5] = {1, C, 2LL * C, 2LL * W * C, static_cast<long long>(H) * W * C};
+                    const long long dims[5] = {C, 2, Wo, H / 2, B}, str[5] = {1, C, 2LL * C, 2LL * W * C, static_cast<long long>(H) * W * C};
                     for (int i = 0; i < 5; ++i) { v[ph].dims[i] = dims[i]; v[ph].strides[i] = str[i]; }
                 }
                 const int wb = std::min(128, pow2_at_least(Wo)), hb = std::min(128 / wb, pow2_at_least(Ho));
                 const int box[4] = {1, wb, hb, 128 / (wb * hb)}, ext[4] = {1, Wo, Ho, B};
-                const long long os[4] = {0, L.N, static_cast<long long>(Wo) * L.N, static_cast<long long>(Ho) * Wo * L.N};
+                const long long os[4] = {0, L.N, static_cast<long long>(Wo) * L.N, static_cast<long long>(Ho_alloc) * Wo * L.N};
                 E.gemm(L, L.taps, v, 2, box, ext, out, os, 0, kOutBf16);
             };
             E.tag = "enc.conv1";
-            conv2d_s2(m->enc[1], a0, H1, W1, 64, a1);
+            conv2d_s2(m->enc[1], a0, H1, W1, 64, a1, H2, H2a);
             E.tag = "enc.conv2";
-            conv2d_s2(m->enc[2], a1, H2, W2, 128, a2);
+            conv2d_s2(m->enc[2], a1, H2a, W2, 128, a2, H3, H3);
             E.tag = "enc.conv3";
             {   // conv 3
                 AView v; v.ptr = a2; v.rank = 4;
@@ -687,7 +705,7 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
                        static_cast<long long>(B) * H3 * 256);
             }
             E.tag = "enc.interp";
-            E.op([=](cudaStream_t s) { return launch_time_interp(a4, kConv4Splits, B, H3, T, 256, e0, s); });
+            E.op([=](cudaStream_t s) { return launch_time_interp(a4, kConv4Splits, B, H3, T_out, 256, e0, s); });
         }
         if (pass == 1) P->enc_end = static_cast<int>(P->ops.size());
 
@@ -794,26 +812,36 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
     return A2M_OK;
 }
 
-ForwardPlan* get_plan(a2m_model* m, int B, int T, int F, int* rc_out) {
-    char key[64];
-    snprintf(key, sizeof(key), "%d:%d:%d", B, T, F);
+ForwardPlan* get_plan(a2m_model* m, int B, int T, int F, int* rc_out, int T_out = 0) {
+    if (T_out <= 0) T_out = T;
+    char key[80];
+    snprintf(key, sizeof(key), "%d:%d:%d:%d", B, T, F, T_out);
     auto it = m->plans.find(key);
-    if (it != m->plans.end()) { *rc_out = A2M_OK; return it->second.get(); }
+    if (it != m->plans.end()) { *rc_out = A2M_OK; it->second->last_use = ++m->plan_clock; return it->second.get(); }
     std::unique_ptr<ForwardPlan> P(new ForwardPlan());
-    P->B = B; P->T = T; P->F = F;
+    P->B = B; P->T = T; P->F = F; P->T_out = T_out;
     *rc_out = build_plan(m, P.get());
     if (*rc_out != A2M_OK) return nullptr;
     ForwardPlan* raw = P.get();
-    if (m->plans.size() >= 8) m->plans.clear();          // bound the cache: shapes rarely change
+    raw->last_use = ++m->plan_clock;
+    // bound the cache: evict the least recently used shape only (a CUDA graph captured over a plan bakes its arena
+    // pointers in: a2m_model_plan_generation lets the caller notice that one of its shapes was evicted)
+    if (m->plans.size() >= 16) {
+        auto victim = m->plans.begin();
+        for (auto jt = m->plans.begin(); jt != m->plans.end(); ++jt)
+            if (jt->second->last_use < victim->second->last_use) victim = jt;
+        m->plans.erase(victim);
+        ++m->plan_generation;
+    }
     m->plans[key] = std::move(P);
     return raw;
 }
 
 int check_shape(long long B, int T, int F, const char* who) {
     A2M_ARG_CHECK(B >= 1 && B <= 65535, "%s: batch %lld out of range [1, 65535]", who, (long long)B);
-    A2M_ARG_CHECK(T >= 8 && T % 8 == 0, "%s: T = %d; the time axis must be a multiple of 8 (three stride-2 encoder "
-                  "stages; the reference itself needs T %% 4 == 0 for the UNet skip concat)", who, T);
-    A2M_ARG_CHECK(T <= 64, "%s: T = %d; this build implements T <= 64 (attention tile)", who, T);
+    A2M_ARG_CHECK(T >= 8 && T % 4 == 0, "%s: T = %d; the time axis must be a multiple of 4 (the reference's UNet skip "
+                  "concats, model_layers.py:341-374) and at least 8 (three stride-2 encoder stages)", who, T);
+    A2M_ARG_CHECK(T <= 4096, "%s: T = %d; this build implements T <= 4096", who, T);
     A2M_ARG_CHECK(F >= 16 && F % 8 == 0, "%s: F = %d; the mel axis must be a multiple of 8 and >= 16", who, F);
     return A2M_OK;
 }
@@ -1006,19 +1034,28 @@ extern "C" int a2m_model_set_output_denorm(a2m_model* m, const float* mean, cons
     return A2M_OK;
 }
 
-extern "C" int a2m_model_encoder_forward(a2m_model* m, const float* mel, int64_t B, int T, int F, float* out_nct, void* stream) {
+extern "C" int a2m_model_encoder_forward_ex(a2m_model* m, const float* mel, int64_t B, int T, int F, int time_steps,
+                                            float* out_nct, void* stream) {
     A2M_ARG_CHECK(m != nullptr && mel != nullptr && out_nct != nullptr, "a2m_model_encoder_forward: NULL argument");
     A2M_ARG_CHECK(m->has_encoder, "a2m_model_encoder_forward: no audio_encoder.* tensors in the state_dict");
     int rc = check_shape(B, T, F, "a2m_model_encoder_forward");
     if (rc != A2M_OK) return rc;
-    ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc);
+    if (time_steps <= 0) time_steps = T;
+    A2M_ARG_CHECK(time_steps <= 65536, "a2m_model_encoder_forward: time_steps %d", time_steps);
+    ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc, time_steps);
     if (!P) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     m->cur_mel = mel; m->cur_stride_b = static_cast<long long>(T) * F; m->cur_stride_t = F;
     rc = run_ops(P, 0, P->enc_end, s);
     if (rc != A2M_OK) return rc;
-    return launch_btc_to_ncw(P->enc_out, static_cast<int>(B), 256, T, out_nct, s);
+    return launch_btc_to_ncw(P->enc_out, static_cast<int>(B), 256, time_steps, out_nct, s);
 }
+
+extern "C" int a2m_model_encoder_forward(a2m_model* m, const float* mel, int64_t B, int T, int F, float* out_nct, void* stream) {
+    return a2m_model_encoder_forward_ex(m, mel, B, T, F, T, out_nct, stream);
+}
+
+extern "C" int64_t a2m_model_plan_generation(a2m_model* m) { return m ? m->plan_generation : -1; }
 
 extern "C" int a2m_model_unet_forward(a2m_model* m, const float* x_nct, int64_t B, int T, float* out_nct, void* stream) {
     A2M_ARG_CHECK(m != nullptr && x_nct != nullptr && out_nct != nullptr, "a2m_model_unet_forward: NULL argument");
@@ -1160,4 +1197,130 @@ extern "C" const char* a2m_model_op_name(a2m_model* m, int64_t B, int T, int F, 
     if (!P || index < 0 || index >= static_cast<int>(P->op_name.size())) return nullptr;
     if (flops_host) *flops_host = P->op_flops[index];
     return P->op_name[index].c_str();
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stand-alone building blocks: the layer classes of model_layers.py with their own forward (ConvNormRelu :112-118,
+// SelfAttention :133-146, ChannelAttention :167-174, ResBlock :185-190, ConvTranspose1D :211-215), on the same
+// kernels the generator uses.  x, out: fp32 [B, C, T] (the reference's NCW layout).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+int block_out_length(int kind, int T) {
+    return kind == A2M_BLOCK_CONV_K4S2 ? T / 2 : kind == A2M_BLOCK_CONV_TRANSPOSE ? 2 * T : T;
+}
+
+int build_block_plan(a2m_model* m, ForwardPlan* P) {
+    const int B = P->B, T = P->T, kind = m->blk_kind, cin = m->blk_cin, cout = m->blk_cout;
+    const int To = block_out_length(kind, T);
+    Bufs bufs;
+    for (int pass = 0; pass < 2; ++pass) {
+        Emit E{m, P, pass == 0};
+        if (pass == 1) {
+            P->ops.clear(); P->op_is_gemm.clear(); P->op_name.clear(); P->op_flops.clear();
+            P->gemm_flops = 0;
+            cudaError_t e = cudaMalloc(&P->arena, bufs.off + 256);
+            if (e != cudaSuccess) { a2m_set_error("block: arena cudaMalloc(%zu) failed: %s", bufs.off, cudaGetErrorString(e)); return (int)e; }
+            bufs.base = static_cast<unsigned char*>(P->arena);
+        }
+        bufs.off = 0;
+        const size_t BT = static_cast<size_t>(B) * T;
+        auto* xin = bufs.get<__nv_bfloat16>(BT * cin);
+        auto* xout = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * To * cout);
+        auto* t1 = bufs.get<__nv_bfloat16>(BT * cin);
+        auto* t2 = bufs.get<__nv_bfloat16>(BT * cin);
+        auto* qkv = bufs.get<__nv_bfloat16>(BT * (cin + 2 * (cin / 8)));
+        P->enc_out = xin; P->unet_out = xout;
+        E.tag = "block";
+        switch (kind) {
+            case A2M_BLOCK_CONV_K3: E.conv_k3(m->blk_conv, xin, cin, nullptr, 0, T, B, xout); break;
+            case A2M_BLOCK_CONV_K4S2: E.conv_k4s2(m->blk_conv, xin, cin, T, B, xout); break;
+            case A2M_BLOCK_CONV_TRANSPOSE: E.conv_transpose(m->blk_even, m->blk_odd, xin, cin, T, B, xout); break;
+            case A2M_BLOCK_SELF_ATTENTION: E.attention(m->blk_attn, xin, nullptr, T, B, qkv, xout); break;
+            case A2M_BLOCK_CHANNEL_ATTENTION: E.channel(m->blk_chan, xin, T, B, xout); break;
+            case A2M_BLOCK_RESBLOCK: E.resblock(m->blk_res, xin, T, B, t1, t2, qkv, xout); break;
+            default: a2m_set_error("block: kind %d", kind); return A2M_ERR_ARGUMENT;
+        }
+        if (E.rc != A2M_OK) return E.rc;
+    }
+    return A2M_OK;
+}
+
+}  // namespace
+
+extern "C" int a2m_block_create(int kind, const a2m_tensor_desc* tensors, int n_tensors, int in_channels, int out_channels,
+                                int leaky, int device, a2m_model** out) {
+    A2M_ARG_CHECK(out != nullptr && tensors != nullptr && n_tensors > 0, "a2m_block_create: NULL argument");
+    *out = nullptr;
+    A2M_ARG_CHECK(kind >= A2M_BLOCK_CONV_K3 && kind <= A2M_BLOCK_RESBLOCK, "a2m_block_create: kind %d", kind);
+    A2M_ARG_CHECK(in_channels >= 64 && in_channels % 64 == 0 && in_channels <= 4096, "a2m_block_create: in_channels %d must be a "
+                  "multiple of 64 (one 128-byte swizzle row of bf16 per K step)", in_channels);
+    A2M_ARG_CHECK(out_channels >= 8 && out_channels % 8 == 0 && out_channels <= 8192, "a2m_block_create: out_channels %d", out_channels);
+    const bool same = kind == A2M_BLOCK_SELF_ATTENTION || kind == A2M_BLOCK_CHANNEL_ATTENTION || kind == A2M_BLOCK_RESBLOCK;
+    A2M_ARG_CHECK(!same || in_channels == out_channels, "a2m_block_create: this block keeps its channel count");
+    A2M_ARG_CHECK(kind != A2M_BLOCK_CHANNEL_ATTENTION || in_channels <= 1024, "a2m_block_create: ChannelAttention up to 1024 channels");
+    A2M_CUDA_CHECK(cudaSetDevice(device));
+    std::unique_ptr<a2m_model> m(new a2m_model());
+    m->device = device;
+    for (int i = 0; i < n_tensors; ++i) {
+        const a2m_tensor_desc& t = tensors[i];
+        A2M_ARG_CHECK(t.name != nullptr && t.ndim >= 0 && t.ndim <= 4 && t.dtype == A2M_DTYPE_F32, "a2m_block_create: bad descriptor %d", i);
+        Param p;
+        p.ndim = t.ndim;
+        for (int k = 0; k < t.ndim; ++k) p.shape[k] = t.shape[k];
+        p.f32 = static_cast<const float*>(t.data);
+        m->params[t.name] = p;
+    }
+    m->blk_kind = kind; m->blk_cin = in_channels; m->blk_cout = out_channels;
+    Builder b{m.get(), nullptr};
+    const std::string p = "blk";
+    switch (kind) {
+        case A2M_BLOCK_CONV_K3: b.conv1d_k3(m->blk_conv, p, in_channels, 0, out_channels); break;
+        case A2M_BLOCK_CONV_K4S2: b.conv1d_k4s2(m->blk_conv, p, in_channels, out_channels); break;
+        case A2M_BLOCK_CONV_TRANSPOSE: b.conv_transpose(m->blk_even, m->blk_odd, p, in_channels, out_channels); break;
+        case A2M_BLOCK_SELF_ATTENTION: b.attention(m->blk_attn, p, in_channels); break;
+        case A2M_BLOCK_CHANNEL_ATTENTION: b.channel(m->blk_chan, p, in_channels); break;
+        default: b.resblock(m->blk_res, p, in_channels); break;
+    }
+    if (kind == A2M_BLOCK_CONV_K3 || kind == A2M_BLOCK_CONV_K4S2) m->blk_conv.act = leaky ? kActLeaky : kActRelu;
+    m->err_flag = b.alloc<int>(1);
+    if (b.rc == A2M_OK) cudaMemset(m->err_flag, 0, 4);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (b.rc == A2M_OK && e != cudaSuccess) { a2m_set_error("a2m_block_create: %s", cudaGetErrorString(e)); b.rc = (int)e; }
+    if (b.rc != A2M_OK) {
+        for (void* q : m->owned) cudaFree(q);
+        return b.rc;
+    }
+    m->params.clear();
+    *out = m.release();
+    return A2M_OK;
+}
+
+extern "C" int a2m_block_forward(a2m_model* m, const float* x_nct, int64_t B, int T, float* out_nct, void* stream) {
+    A2M_ARG_CHECK(m != nullptr && x_nct != nullptr && out_nct != nullptr, "a2m_block_forward: NULL argument");
+    A2M_ARG_CHECK(m->blk_kind != 0, "a2m_block_forward: the handle is not a building block");
+    A2M_ARG_CHECK(B >= 1 && B <= 65535 && T >= 1 && T <= 4096, "a2m_block_forward: B = %lld, T = %d", (long long)B, T);
+    A2M_ARG_CHECK(m->blk_kind != A2M_BLOCK_CONV_K4S2 || T % 2 == 0, "a2m_block_forward: the stride-2 block needs an even T (got %d)", T);
+    char key[64];
+    snprintf(key, sizeof(key), "blk:%lld:%d", (long long)B, T);
+    ForwardPlan* P = nullptr;
+    auto it = m->plans.find(key);
+    if (it != m->plans.end()) {
+        P = it->second.get();
+    } else {
+        std::unique_ptr<ForwardPlan> np(new ForwardPlan());
+        np->B = static_cast<int>(B); np->T = T; np->F = 0;
+        const int rc = build_block_plan(m, np.get());
+        if (rc != A2M_OK) return rc;
+        if (m->plans.size() >= 16) m->plans.clear();
+        P = np.get();
+        m->plans[key] = std::move(np);
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = launch_ncw_to_btc(x_nct, static_cast<int>(B), m->blk_cin, T, P->enc_out, s);
+    if (rc != A2M_OK) return rc;
+    rc = run_ops(P, 0, static_cast<int>(P->ops.size()), s);
+    if (rc != A2M_OK) return rc;
+    return launch_btc_to_ncw(P->unet_out, static_cast<int>(B), m->blk_cout, block_out_length(m->blk_kind, T), out_nct, s);
 }

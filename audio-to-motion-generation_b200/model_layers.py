@@ -3,10 +3,12 @@
 The classes keep the reference's constructor signatures, attribute names and state_dict keys
 (model_layers.py:53-118 ConvNormRelu, :125-131 SelfAttention, :155-165 ChannelAttention, :179-183
 ResBlock, :198-209 ConvTranspose1D, :249-261 AudioEncoder, :303-339 UNet1D), so checkpoints written
-by the reference load unchanged.  They are parameter containers: the arithmetic of a whole
-``AudioEncoder`` / ``UNet1D`` / ``SelfAttention_G`` forward runs in liba2m_b200.so (tcgen05 implicit-GEMM
-convolutions with folded BatchNorm + fused activations, csrc/conv_gemm.cu, and the kernels of
-csrc/layers.cu).  The small building blocks have no stand-alone forward on this path.
+by the reference load unchanged.  The arithmetic of a whole ``AudioEncoder`` / ``UNet1D`` / ``SelfAttention_G`` forward runs as one native launch program
+in liba2m_b200.so (tcgen05 implicit-GEMM convolutions with folded BatchNorm + fused activations, csrc/conv_gemm.cu, and
+the kernels of csrc/layers.cu).  The small building blocks (ConvNormRelu, SelfAttention, ChannelAttention, ResBlock,
+ConvTranspose1D) also run on their own -- ``forward(x[B, C, T]) -> [B, C', T']`` like the reference's, eval semantics
+(a2m_block_forward) -- on the same kernels, for the 1-D geometries the generator uses; anything else raises
+NotImplementedError, never a PyTorch fallback.
 
 Decision D1: ``UNet1D.up_attention`` (declared with 4*C channels, :339) is applied to the
 ConvTranspose output *before* the skip concat; the reference's own forward (:364-365) raises.
@@ -18,11 +20,42 @@ from . import _cabi
 from ._native_module import NativeModule, as_input
 
 
-class _Block(nn.Module):
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError(
-            "%s is a parameter container on the B200 path; run it through AudioEncoder, UNet1D or "
-            "SelfAttention_G (fused native forward)" % type(self).__name__)
+BLOCK_CONV_K3, BLOCK_CONV_K4S2, BLOCK_CONV_TRANSPOSE, BLOCK_SELF_ATTENTION, BLOCK_CHANNEL_ATTENTION, BLOCK_RESBLOCK = range(1, 7)
+
+
+class _Block(NativeModule):
+    """A layer class with the reference's parameters and a native stand-alone forward.  Subclasses set
+    ``self._block = (kind, in_channels, out_channels, leaky)`` when their geometry is one the kernels implement,
+    or leave it None (then forward raises NotImplementedError; the module still works as a parameter container
+    inside AudioEncoder / UNet1D / SelfAttention_G)."""
+
+    _state_prefix = "blk."
+
+    def forward(self, x, **kwargs):
+        if self._block is None:
+            raise NotImplementedError(
+                "%s: this geometry has no stand-alone forward on the B200 path (1-D blocks with channel counts that are "
+                "multiples of 64 do); run it through AudioEncoder, UNet1D or SelfAttention_G" % type(self).__name__)
+        self._require_eval()
+        h = self.native()
+        kind, cin, cout, _ = self._block
+        x = as_input(x, h.device, type(self).__name__ + " expects [B, C, T], got %s")
+        B, C, T = x.shape
+        if C != cin:
+            raise ValueError("%s expects %d input channels, got %d" % (type(self).__name__, cin, C))
+        if kind == BLOCK_CONV_K4S2 and T % 2:
+            raise NotImplementedError("the stride-2 block needs an even number of steps on the native path, got %d" % T)
+        t_out = T // 2 if kind == BLOCK_CONV_K4S2 else 2 * T if kind == BLOCK_CONV_TRANSPOSE else T
+        out = torch.empty((B, cout, t_out), dtype=torch.float32, device=h.device)
+        if B == 0 or T == 0:
+            return out
+        with torch.cuda.device(h.device):
+            _cabi.check(_cabi.lib().a2m_block_forward(h.ptr, _cabi.ptr(x), B, T, _cabi.ptr(out), _cabi.stream_ptr(h.device)))
+        return out
+
+
+def _channels_ok(*cs):
+    return all(c >= 64 and c % 64 == 0 for c in cs)
 
 
 def _auto_padding(kernel_size, stride):
@@ -39,7 +72,8 @@ def _auto_padding(kernel_size, stride):
 
 
 class ConvNormRelu(_Block):
-    """conv -> dropout -> BatchNorm -> (Leaky)ReLU block (parameters only)."""
+    """conv -> dropout -> BatchNorm -> (Leaky)ReLU block (model_layers.py:51-118).  Stand-alone forward for the 1-D
+    k3 s1 p1 and k4 s2 p1 (downsample) geometries."""
 
     def __init__(self, in_channels, out_channels, type='1d', leaky=False, downsample=False,
                  kernel_size=None, stride=None, padding=None, p=0, groups=1):
@@ -56,6 +90,11 @@ class ConvNormRelu(_Block):
         self.norm = norm(out_channels)
         self.dropout = drop(p=p)
         self.relu = nn.LeakyReLU(negative_slope=0.2) if leaky else nn.ReLU()
+        if type == '1d' and _channels_ok(in_channels) and out_channels % 8 == 0:
+            if (kernel_size, stride, padding) == (3, 1, 1):
+                self._block = (BLOCK_CONV_K3, in_channels, out_channels, bool(leaky))
+            elif (kernel_size, stride, padding) == (4, 2, 1):
+                self._block = (BLOCK_CONV_K4S2, in_channels, out_channels, bool(leaky))
 
 
 class SelfAttention(_Block):
@@ -68,6 +107,8 @@ class SelfAttention(_Block):
         self.value_conv = nn.Conv1d(in_channels, in_channels, kernel_size=1)
         self.gamma = nn.Parameter(torch.zeros(1))
         self.softmax = nn.Softmax(dim=-1)
+        if _channels_ok(in_channels):
+            self._block = (BLOCK_SELF_ATTENTION, in_channels, in_channels, False)
 
 
 class ChannelAttention(_Block):
@@ -77,6 +118,8 @@ class ChannelAttention(_Block):
         self.max_pool = nn.AdaptiveMaxPool1d(1)
         self.fc = nn.Sequential(nn.Linear(channel, channel // reduction), nn.ReLU(inplace=True),
                                 nn.Linear(channel // reduction, channel), nn.Sigmoid())
+        if _channels_ok(channel) and channel <= 1024 and reduction == 8:
+            self._block = (BLOCK_CHANNEL_ATTENTION, channel, channel, False)
 
 
 class ResBlock(_Block):
@@ -85,6 +128,8 @@ class ResBlock(_Block):
         self.conv1 = ConvNormRelu(channels, channels, type=type, leaky=True, p=p)
         self.conv2 = ConvNormRelu(channels, channels, type=type, leaky=True, p=p)
         self.attention = SelfAttention(channels)
+        if type == '1d' and _channels_ok(channels):
+            self._block = (BLOCK_RESBLOCK, channels, channels, True)
 
 
 class ConvTranspose1D(_Block):
@@ -96,6 +141,8 @@ class ConvTranspose1D(_Block):
                                                  padding=padding, output_padding=output_padding)
         self.bn = nn.BatchNorm1d(out_channels)
         self.relu = nn.ReLU(inplace=True)
+        if _channels_ok(in_channels) and out_channels % 8 == 0:
+            self._block = (BLOCK_CONV_TRANSPOSE, in_channels, out_channels, False)
 
 
 class AudioEncoder(NativeModule):
@@ -123,12 +170,13 @@ class AudioEncoder(NativeModule):
         h = self.native()
         x = as_input(x, h.device, "AudioEncoder expects [B, T, F], got %s")
         B, T, F = x.shape
-        if time_steps is not None and time_steps != T:
-            raise NotImplementedError("time_steps != input T is not implemented on the native path")
-        out = torch.empty((B, 256, T), dtype=torch.float32, device=h.device)
+        steps = T if time_steps is None else int(time_steps)        # model_layers.py:268-269
+        if steps < 1:
+            raise ValueError("time_steps must be positive, got %d" % steps)
+        out = torch.empty((B, 256, steps), dtype=torch.float32, device=h.device)
         with torch.cuda.device(h.device):
-            _cabi.check(_cabi.lib().a2m_model_encoder_forward(h.ptr, _cabi.ptr(x), B, T, F, _cabi.ptr(out),
-                                                              _cabi.stream_ptr(h.device)))
+            _cabi.check(_cabi.lib().a2m_model_encoder_forward_ex(h.ptr, _cabi.ptr(x), B, T, F, steps, _cabi.ptr(out),
+                                                                 _cabi.stream_ptr(h.device)))
         return out
 
 

@@ -251,6 +251,12 @@ class AudioToPosePipeline:
         lane's next step."""
         key = (lane, tuple(wav.shape), wav.dtype, tuple(gt_pose.shape))
         entry = self._graphs.get(key)
+        handle = self.model.native(lane)
+        # a captured graph has the arena pointers of its launch plan baked in: if the handle was rebuilt (weights
+        # changed) or released a cached plan since the capture, capture again
+        if entry is not None and (entry[5] is not handle or
+                                  entry[6] != int(_cabi.lib().a2m_model_plan_generation(handle.ptr))):
+            entry = None
         if entry is None:
             s_wav = torch.empty(wav.shape, dtype=wav.dtype, device=self.device)
             s_gt = torch.empty(gt_pose.shape, dtype=torch.float32, device=self.device)
@@ -265,9 +271,11 @@ class AudioToPosePipeline:
             with torch.cuda.graph(graph, stream=st):
                 s_pose = self.generate(s_wav, lane)
                 motion_evaluation.evaluate_poses(s_pose, s_gt, self.alpha, accum=self.accum)
-            entry = (graph, s_wav, s_gt, s_pose, int(_cabi.lib().a2m_launch_count() - before))
+            handle = self.model.native(lane)
+            entry = (graph, s_wav, s_gt, s_pose, int(_cabi.lib().a2m_launch_count() - before), handle,
+                     int(_cabi.lib().a2m_model_plan_generation(handle.ptr)))
             self._graphs[key] = entry
-        graph, s_wav, s_gt, s_pose, n_kernels = entry
+        graph, s_wav, s_gt, s_pose, n_kernels = entry[:5]
         s_wav.copy_(wav, non_blocking=True)
         s_gt.copy_(gt_pose, non_blocking=True)
         graph.replay()

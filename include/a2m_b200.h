@@ -279,6 +279,13 @@ int a2m_model_timeline_begin(a2m_model* model, int64_t B, int T, int F, int step
 int a2m_model_timeline_read(a2m_model* model, float* out_ms_host, int capacity, int* steps_host, int* n_ops_host,
                             int* unet_end_host, int* body_end_host, int64_t B, int T, int F);
 int a2m_model_encoder_forward(a2m_model* model, const float* mel, int64_t B, int T, int F, float* out_nct, void* stream);
+/* The same with the reference's optional argument: AudioEncoder.forward(x, time_steps) resizes the encoder output to
+ * time_steps steps (bilinear, model_layers.py:267-279) -> [B, 256, time_steps]; time_steps <= 0 means T. */
+int a2m_model_encoder_forward_ex(a2m_model* model, const float* mel, int64_t B, int T, int F, int time_steps,
+                                 float* out_nct, void* stream);
+/* Counts the cached launch plans (activation arenas) this handle has released: a caller that captured a CUDA graph
+ * over a forward must re-capture when the number changes. */
+int64_t a2m_model_plan_generation(a2m_model* model);
 /* UNet1D.forward (model_layers.py:341-374, D1): [B, 256, T] fp32 -> [B, 256, T] fp32 */
 int a2m_model_unet_forward(a2m_model* model, const float* x_nct, int64_t B, int T, float* out_nct, void* stream);
 /* The fused five-layer graph stack of one decoder branch (real_motion_model.py:172-201 body / :224-253 hand:
@@ -301,6 +308,26 @@ int a2m_model_profile(a2m_model* model, const float* mel, int64_t mel_stride_b, 
 int a2m_model_profile_ops(a2m_model* model, const float* mel, int64_t mel_stride_b, int64_t mel_stride_t, int64_t B,
                           int T, int F, int iters, float* out_ms_host, int capacity, int* n_ops_host, void* stream);
 const char* a2m_model_op_name(a2m_model* model, int64_t B, int T, int F, int index, int64_t* flops_host /* nullable */);
+
+/* ------------------------------------------------------------------------------------------------
+ * stand-alone building blocks: the layer classes of model_layers.py with their own forward, on the kernels the
+ * generator uses (eval semantics: BatchNorm running statistics, dropout off).  The state_dict of the module is passed
+ * with the prefix "blk." (e.g. "blk.conv.weight"); x, out: fp32 [B, C, T] (the reference's NCW layout).
+ *   A2M_BLOCK_CONV_K3 / _K4S2    ConvNormRelu 1-D, k3 s1 p1 / k4 s2 p1 (downsample), :94-118; leaky: LeakyReLU(0.2) or ReLU
+ *   A2M_BLOCK_CONV_TRANSPOSE     ConvTranspose1D k3 s2 p1 op1 + BatchNorm + ReLU, :200-215          T -> 2 T
+ *   A2M_BLOCK_SELF_ATTENTION     SelfAttention, :133-146          A2M_BLOCK_CHANNEL_ATTENTION  ChannelAttention, :167-174
+ *   A2M_BLOCK_RESBLOCK           ResBlock, :185-190
+ * in_channels: a multiple of 64; handles are destroyed with a2m_model_destroy.
+ * ---------------------------------------------------------------------------------------------- */
+#define A2M_BLOCK_CONV_K3 1
+#define A2M_BLOCK_CONV_K4S2 2
+#define A2M_BLOCK_CONV_TRANSPOSE 3
+#define A2M_BLOCK_SELF_ATTENTION 4
+#define A2M_BLOCK_CHANNEL_ATTENTION 5
+#define A2M_BLOCK_RESBLOCK 6
+int a2m_block_create(int kind, const a2m_tensor_desc* tensors, int n_tensors, int in_channels, int out_channels, int leaky,
+                     int device, a2m_model** out);
+int a2m_block_forward(a2m_model* block, const float* x_nct, int64_t B, int T, float* out_nct, void* stream);
 
 #ifdef __cplusplus
 }

@@ -113,7 +113,63 @@ def mel_nfft_golden():
     print("mel nfft goldens:", {k: v.shape for k, v in out.items()})
 
 
+# stand-alone building blocks of model_layers.py: (name, class, ctor args, ctor kwargs, C_in, T)
+BLOCK_CASES = [
+    ("conv_k3_leaky", "ConvNormRelu", (64, 128), dict(type="1d", leaky=True), 64, 24),
+    ("conv_k3_relu", "ConvNormRelu", (128, 64), dict(type="1d", leaky=False), 128, 20),
+    ("conv_down", "ConvNormRelu", (128, 128), dict(type="1d", leaky=True, downsample=True), 128, 32),
+    ("conv_transpose", "ConvTranspose1D", (128, 64), dict(), 128, 16),
+    ("self_attention", "SelfAttention", (128,), dict(), 128, 24),
+    ("self_attention_long", "SelfAttention", (64,), dict(), 64, 100),
+    ("channel_attention", "ChannelAttention", (128,), dict(), 128, 32),
+    ("res_block", "ResBlock", (64,), dict(type="1d", p=0.1), 64, 32),
+]
+
+
+def randomize_block(module, seed):
+    """Non-trivial BatchNorm statistics / affine parameters and attention gates (the defaults make BatchNorm and
+    gamma = 0 attention almost the identity)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, t in module.state_dict().items():
+            if name.endswith("running_var"):
+                t.copy_(0.5 + torch.rand(t.shape, generator=g))
+            elif name.endswith("running_mean"):
+                t.copy_(0.2 * torch.randn(t.shape, generator=g))
+            elif name.endswith("norm.weight") or name.endswith("bn.weight"):
+                t.copy_(0.8 + 0.4 * torch.rand(t.shape, generator=g))
+            elif name.endswith("norm.bias") or name.endswith("bn.bias"):
+                t.copy_(0.1 * torch.randn(t.shape, generator=g))
+            elif name.endswith("gamma"):
+                t.fill_(0.5)
+
+
+def block_golden():
+    """tests/golden/blocks_reference.npz: the UNMODIFIED layer classes of model_layers.py (eval mode) on seeded inputs;
+    per case the module's state_dict (small channel counts keep the fixture small), the input and the output."""
+    ml = ref_shim.import_reference()["model_layers"]
+    out = {}
+    for i, (name, cls, args, kwargs, cin, T) in enumerate(BLOCK_CASES):
+        torch.manual_seed(100 + i)
+        mod = getattr(ml, cls)(*args, **kwargs).eval()
+        randomize_block(mod, 200 + i)
+        g = torch.Generator().manual_seed(300 + i)
+        x = torch.randn(3, cin, T, generator=g)
+        with torch.no_grad():
+            y = mod(x)
+        for k, v in mod.state_dict().items():
+            if not k.endswith("num_batches_tracked"):
+                out["%s/sd/%s" % (name, k)] = v.numpy()
+        out[name + "/x"] = x.numpy()
+        out[name + "/y"] = y.numpy()
+        print(name, tuple(x.shape), "->", tuple(y.shape), float(y.abs().mean()))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "blocks_reference.npz"), **out)
+
+
 def main():
+    if "--blocks-only" in sys.argv:
+        os.makedirs(GOLDEN_DIR, exist_ok=True)
+        return block_golden()
     if "--smoothness-only" in sys.argv:
         os.makedirs(GOLDEN_DIR, exist_ok=True)
         return smoothness_golden()
@@ -187,6 +243,7 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN_DIR, "model_reference.npz"), **mo)
     smoothness_golden()
     mel_nfft_golden()
+    block_golden()
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
 

@@ -92,6 +92,36 @@ def test_other_sequence_lengths_vs_oracle(stress_model, T, F, B):
     assert rel_l1(pose, ref) <= REL_L1
 
 
+@pytest.mark.parametrize("T,F,B", [(12, 64, 3), (20, 64, 2), (28, 64, 2), (36, 32, 2), (44, 64, 1), (60, 64, 2),
+                                   (68, 64, 2), (100, 64, 1), (128, 64, 2), (192, 32, 1)])
+def test_reference_lengths_beyond_the_fast_path(stress_model, T, F, B):
+    """Every T the reference accepts is T % 4 == 0 (UNet skip concats, model_layers.py:341-374), of any length.
+    T % 8 != 0 makes the second stride-2 encoder stage odd (the third drops a row like the reference's conv does,
+    and the (T, 1) resize no longer divides evenly); T > 64 runs the long-sequence attention kernel and more than one
+    128-row tile per clip."""
+    sd = weights.make_state_dict(0, "stress")
+    x = model_input(40 + T, B, T, F)
+    pose, _ = stress_model(x.cuda())
+    stress_model.check_device_status()
+    ref, _ = model_oracle.generator_forward(sd, x)
+    assert pose.shape == (B, T, 104)
+    assert rel_l1(pose, ref) <= REL_L1
+
+
+def test_audio_encoder_time_steps_argument(mods):
+    """AudioEncoder.forward(x, time_steps) resizes to any length (model_layers.py:267-279)."""
+    sd = weights.make_state_dict(0, "stress")
+    enc = mods["model_layers"].AudioEncoder().cuda().eval()
+    enc.load_state_dict({k[len("audio_encoder."):]: v for k, v in sd.items() if k.startswith("audio_encoder.")})
+    x = model_input(5, 2, 64, 64)
+    for steps in (64, 32, 100, 7):
+        got = enc(x.cuda(), time_steps=steps)
+        ref = model_oracle.audio_encoder(sd, x, time_steps=steps)
+        assert got.shape == ref.shape == (2, 256, steps)
+        assert rel_l1(got, ref) <= 4e-3
+    assert torch.equal(enc(x.cuda()), enc(x.cuda(), time_steps=64))
+
+
 def test_batch_invariance_and_config2_size(stress_model):
     """BASELINE config 2 (B = 256, T = 64, F = 64): each clip's pose is independent of the batch it is in."""
     x = model_input(11, 8, 64, 64).cuda().repeat(32, 1, 1)
@@ -117,7 +147,7 @@ def test_error_behaviour(mods, stress_model):
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         cpu_model(torch.zeros(1, 64, 64))
     with pytest.raises(NotImplementedError):
-        mods["model_layers"].ConvNormRelu(4, 4)(torch.zeros(1, 4, 8))
+        mods["model_layers"].ConvNormRelu(4, 4).eval()(torch.zeros(1, 4, 8))
 
 
 def test_weight_update_repacks(mods):

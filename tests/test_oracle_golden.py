@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import mel_oracle, eval_oracle, model_oracle, synth, weights
-from oracle.make_golden import MEL_CASES, MEL_NFFT_CASES, MODEL_CASES, model_input, real_pose_input
+from oracle.make_golden import BLOCK_CASES, MEL_CASES, MEL_NFFT_CASES, MODEL_CASES, model_input, real_pose_input
 
 
 @pytest.mark.parametrize("name,kind,n,idx", MEL_CASES)
@@ -128,3 +128,20 @@ def test_model_oracle_matches_reference(golden, name, seed, mode, B, T, F, with_
 def test_model_oracle_rejects_bad_t():
     with pytest.raises(ValueError):
         model_oracle.generator_forward({}, torch.zeros(1, 62, 64))
+
+
+@pytest.mark.parametrize("name,cls,args,kwargs,cin,T", BLOCK_CASES)
+def test_block_oracles_match_reference_classes(name, cls, args, kwargs, cin, T):
+    """The functional restatements of the layer classes (model_oracle.conv_norm_act, self_attention, ...) against the
+    unmodified reference classes' outputs on the same parameters (tests/golden/blocks_reference.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "blocks_reference.npz"))
+    sd = {"p." + k[len(name) + 4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(name + "/sd/")}
+    x = torch.from_numpy(g[name + "/x"])
+    fn = {"ConvNormRelu": lambda: model_oracle.conv_norm_act(sd, "p", x, stride=2 if kwargs.get("downsample") else 1,
+                                                             padding=1, leaky=kwargs.get("leaky", False)),
+          "ConvTranspose1D": lambda: model_oracle.conv_transpose_block(sd, "p", x),
+          "SelfAttention": lambda: model_oracle.self_attention(sd, "p", x),
+          "ChannelAttention": lambda: model_oracle.channel_attention(sd, "p", x),
+          "ResBlock": lambda: model_oracle.res_block(sd, "p", x)}[cls]
+    torch.testing.assert_close(fn(), torch.from_numpy(g[name + "/y"]), rtol=1e-5, atol=1e-5)
