@@ -89,6 +89,9 @@ SIGNATURES = {
     "a2m_block_create": (c_int, [c_int, ctypes.POINTER(TensorDesc), c_int, c_int, c_int, c_int, c_int,
                                  ctypes.POINTER(c_void_p)]),
     "a2m_block_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
+    "a2m_disc_create": (c_int, [ctypes.POINTER(TensorDesc), c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "a2m_disc_out_length": (c_int, [c_int, c_int]),
+    "a2m_disc_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "a2m_model_unet_forward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "a2m_model_gnn_forward": (c_int, [c_void_p, c_int, c_void_p, c_i64, c_void_p, c_void_p]),
     "a2m_model_status": (c_int, [c_void_p]),

@@ -711,7 +711,9 @@ static int launch_attention_t(const __nv_bfloat16* qkv, const __nv_bfloat16* x, 
 int launch_attention(const __nv_bfloat16* qkv, const __nv_bfloat16* x, const __nv_bfloat16* res2, const float* gamma,
                      int B, int T, int C, __nv_bfloat16* out, cudaStream_t stream) {
     A2M_ARG_CHECK(C % 64 == 0, "attention: C = %d must be a multiple of 64", C);
-    switch (T) {
+    // the tiled kernel keeps q, k ([T][C/8 + 4] each) and the scores in shared memory; wide layers at long T fall through
+    const size_t tiled_smem = (2 * static_cast<size_t>(T) * (C / 8 + 4) + static_cast<size_t>(T) * (T + 1)) * sizeof(float);
+    switch (tiled_smem <= 100 * 1024 ? T : 0) {
         case 8: return launch_attention_t<8>(qkv, x, res2, gamma, B, C, out, stream);
         case 16: return launch_attention_t<16>(qkv, x, res2, gamma, B, C, out, stream);
         case 24: return launch_attention_t<24>(qkv, x, res2, gamma, B, C, out, stream);
@@ -776,6 +778,138 @@ int launch_bf16_to_f32(const __nv_bfloat16* in, long long n, float* out, cudaStr
     bf16_to_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, n, out);
     A2M_AFTER_LAUNCH();
 }
+// ------------------------------------------------------------------------------ discriminator (SelfAttention_D)
+// pose [B, T, 104] fp32 -> [B, T_alloc, 128] bf16 (channels 104..127 zero; rows T..T_alloc-1 are never written)
+__global__ void pose_pad_kernel(const float* __restrict__ pose, long long total, int T, int T_alloc, int C, int C_pad,
+                                __nv_bfloat16* __restrict__ out) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = static_cast<int>(idx % C_pad);
+    const long long bt = idx / C_pad;
+    const int t = static_cast<int>(bt % T);
+    const long long b = bt / T;
+    out[(b * T_alloc + t) * C_pad + c] = __float2bfloat16_rn(c < C ? pose[bt * C + c] : 0.f);
+}
+// mean over the T rows of [B, T, C] bf16 -> [B, C] bf16 (x.mean(dim=2) of real_motion_model.py:599,609)
+__global__ void mean_time_kernel(const __nv_bfloat16* __restrict__ x, long long total, int T, int C, __nv_bfloat16* __restrict__ out) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = static_cast<int>(idx % C);
+    const long long b = idx / C;
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += __bfloat162float(x[(b * T + t) * C + c]);
+    out[idx] = __float2bfloat16_rn(s / static_cast<float>(T));
+}
+// One GATConv(64, 64, heads=4, concat=False) layer on its own (no LayerNorm / residual: real_motion_model.py:604,616),
+// one CTA per graph, fp32 arithmetic.  wt: lin.weight transposed to [64][256]; att_src / att_dst: [4][64].
+__global__ void __launch_bounds__(256)
+gat_single_kernel(const __nv_bfloat16* __restrict__ x, int J, const float* __restrict__ wt, const float* __restrict__ att_src,
+                  const float* __restrict__ att_dst, const float* __restrict__ bias, const int* __restrict__ nbr,
+                  const int* __restrict__ deg, __nv_bfloat16* __restrict__ out) {
+    extern __shared__ __align__(16) float s_gat[];
+    float* s_x = s_gat;                          // [J][64]
+    float* s_h = s_x + J * 64;                   // [J][256]
+    float* s_src = s_h + J * 256;                // [J][4]
+    float* s_dst = s_src + J * 4;                // [J][4]
+    const long long g = blockIdx.x;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < J * 64; i += 256) s_x[i] = __bfloat162float(x[g * J * 64 + i]);
+    __syncthreads();
+    {   // h[j][o] = sum_f W[o][f] x[j][f]; thread o keeps its weight row in registers
+        float w[64];
+#pragma unroll
+        for (int f = 0; f < 64; ++f) w[f] = __ldg(wt + f * 256 + tid);
+        for (int j = 0; j < J; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int f = 0; f < 64; ++f) acc = fmaf(w[f], s_x[j * 64 + f], acc);
+            s_h[j * 256 + tid] = acc;
+        }
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int item = warp; item < J * 4; item += 8) {          // attention logits per (node, head)
+        const int j = item >> 2, h = item & 3;
+        const float h0 = s_h[j * 256 + h * 64 + lane], h1 = s_h[j * 256 + h * 64 + 32 + lane];
+        const float a = warp_sum(h0 * __ldg(att_src + h * 64 + lane) + h1 * __ldg(att_src + h * 64 + 32 + lane));
+        const float d = warp_sum(h0 * __ldg(att_dst + h * 64 + lane) + h1 * __ldg(att_dst + h * 64 + 32 + lane));
+        if (lane == 0) { s_src[item] = a; s_dst[item] = d; }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < J * 64; idx += 256) {           // out[i][o] = mean_h sum_j alpha^h_ij h[j][h][o] + bias[o]
+        const int i = idx >> 6, o = idx & 63;
+        const int dg = deg[i];
+        float acc = 0.f;
+        for (int h = 0; h < 4; ++h) {
+            const float sd = s_dst[i * 4 + h];
+            float e[kMaxDeg + 1];
+            float m = leaky(s_src[i * 4 + h] + sd);
+            e[0] = m;
+            for (int k = 0; k < dg; ++k) { e[k + 1] = leaky(s_src[nbr[i * kMaxDeg + k] * 4 + h] + sd); m = fmaxf(m, e[k + 1]); }
+            float den = 0.f, num = 0.f;
+            for (int k = 0; k <= dg; ++k) {
+                const float w = __expf(e[k] - m);
+                const int j = k == 0 ? i : nbr[i * kMaxDeg + k - 1];
+                den += w;
+                num = fmaf(w, s_h[j * 256 + h * 64 + o], num);
+            }
+            acc += num / den;
+        }
+        out[g * J * 64 + idx] = __float2bfloat16_rn(0.25f * acc + __ldg(bias + o));
+    }
+}
+// logits Conv1d(2 C -> 1, k3 p1) over cat([x, graph features repeated over time]) (real_motion_model.py:619-630):
+// one warp per (clip, step).  w: [3][2 C] fp32 (tap-major), x [B, T, C] bf16, xg [B, C] bf16 -> out [B, T] fp32
+__global__ void __launch_bounds__(256)
+disc_logits_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ xg, const float* __restrict__ w,
+                   const float* __restrict__ bias, long long n_items, int T, int C, float* __restrict__ out) {
+    const long long item = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (item >= n_items) return;
+    const int lane = threadIdx.x & 31;
+    const int t = static_cast<int>(item % T);
+    const long long b = item / T;
+    float acc = 0.f;
+    for (int tap = 0; tap < 3; ++tap) {
+        const int tt = t + tap - 1;
+        if (tt < 0 || tt >= T) continue;                      // zero padding covers the graph channels too
+        const __nv_bfloat16* xr = x + (b * T + tt) * C;
+        const __nv_bfloat16* gr = xg + b * C;
+        const float* w0 = w + tap * 2 * C;
+        for (int c = lane; c < C; c += 32)
+            acc = fmaf(__ldg(w0 + c), __bfloat162float(xr[c]), fmaf(__ldg(w0 + C + c), __bfloat162float(gr[c]), acc));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[item] = acc + __ldg(bias);
+}
+
+int launch_pose_pad(const float* pose, int B, int T, int T_alloc, int C, int C_pad, __nv_bfloat16* out, cudaStream_t stream) {
+    const long long total = static_cast<long long>(B) * T * C_pad;
+    pose_pad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(pose, total, T, T_alloc, C, C_pad, out);
+    A2M_AFTER_LAUNCH();
+}
+int launch_mean_time(const __nv_bfloat16* x, int B, int T, int C, __nv_bfloat16* out, cudaStream_t stream) {
+    const long long total = static_cast<long long>(B) * C;
+    mean_time_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, total, T, C, out);
+    A2M_AFTER_LAUNCH();
+}
+int launch_gat_single(const __nv_bfloat16* x, long long n_graphs, int J, const float* wt, const float* att_src,
+                      const float* att_dst, const float* bias, const int* nbr, const int* deg, __nv_bfloat16* out,
+                      cudaStream_t stream) {
+    A2M_ARG_CHECK(J >= 1 && J <= 48 && n_graphs >= 1 && n_graphs <= 0x7fffffffLL, "gat: %lld graphs of %d nodes", n_graphs, J);
+    const size_t smem = static_cast<size_t>(J) * (64 + 256 + 8) * sizeof(float);
+    static A2mPerDeviceOnce configured;
+    if (configured.first())
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(gat_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * (64 + 256 + 8) * 4));
+    gat_single_kernel<<<static_cast<unsigned>(n_graphs), 256, smem, stream>>>(x, J, wt, att_src, att_dst, bias, nbr, deg, out);
+    A2M_AFTER_LAUNCH();
+}
+int launch_disc_logits(const __nv_bfloat16* x, const __nv_bfloat16* xg, const float* w, const float* bias, int B, int T,
+                       int C, float* out, cudaStream_t stream) {
+    const long long n_items = static_cast<long long>(B) * T;
+    disc_logits_kernel<<<static_cast<unsigned>((n_items + 7) / 8), 256, 0, stream>>>(x, xg, w, bias, n_items, T, C, out);
+    A2M_AFTER_LAUNCH();
+}
+
 int launch_ncw_to_btc(const float* in, int B, int C, int T, __nv_bfloat16* out, cudaStream_t stream) {
     ncw_to_btc_kernel<<<dim3((T + 31) / 32, (C + 31) / 32, B), dim3(32, 8), 0, stream>>>(in, C, T, out);
     A2M_AFTER_LAUNCH();

@@ -95,6 +95,17 @@ int gnn_fused_launch(const GnnFusedPlan& plan, int* err_flag, cudaStream_t strea
 int launch_pose_losses(const float* pose, const float* real_pose, int B, int T, const int* triples, int n_hand,
                        int n_body, const int* parents, double* scratch, float* losses_out, cudaStream_t stream);
 
+// Small kernels of the discriminator forward (SelfAttention_D, real_motion_model.py:580-642)
+int launch_pose_pad(const float* pose, int B, int T, int T_alloc, int C, int C_pad, __nv_bfloat16* out, cudaStream_t stream);
+int launch_mean_time(const __nv_bfloat16* x, int B, int T, int C, __nv_bfloat16* out, cudaStream_t stream);
+// one GATConv(64, 64, heads=4, concat=False) layer alone; wt = lin.weight transposed [64][256] fp32
+int launch_gat_single(const __nv_bfloat16* x, long long n_graphs, int J, const float* wt, const float* att_src,
+                      const float* att_dst, const float* bias, const int* nbr, const int* deg, __nv_bfloat16* out,
+                      cudaStream_t stream);
+// Conv1d(2 C -> 1, k3 p1) over cat([x, graph features repeated over time]); w [3][2 C] fp32 tap-major
+int launch_disc_logits(const __nv_bfloat16* x, const __nv_bfloat16* xg, const float* w, const float* bias, int B, int T,
+                       int C, float* out, cudaStream_t stream);
+
 int launch_f32_to_bf16(const float* in, long long n, __nv_bfloat16* out, cudaStream_t stream);
 int launch_bf16_to_f32(const __nv_bfloat16* in, long long n, float* out, cudaStream_t stream);
 // [B, C, T] fp32 (reference NCW layout) <-> [B, T, C] bf16 for the AudioEncoder / UNet1D drop-in surfaces

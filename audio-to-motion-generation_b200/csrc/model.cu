@@ -91,6 +91,16 @@ struct a2m_model {
     LayerW ds[4], bott, up0_even, up0_odd, up1, up2_even, up2_odd, up3, final_conv;
     AttnW bott_attn, up_attn;
     DecoderW dec[2];
+    // discriminator (a2m_disc_*): SelfAttention_D, real_motion_model.py:464-642
+    bool has_disc = false;
+    int disc_down = 0, disc_c = 0;              // n_downsampling; channels after conv2 (512 for the defaults)
+    std::vector<LayerW> disc_conv;              // conv1 (2), conv2 (2 per stage), conv3 (3)
+    AttnW disc_attn;
+    LayerW disc_proj[2], disc_out[2];
+    const float *disc_gat_wt[2] = {nullptr, nullptr}, *disc_gat_src[2] = {nullptr, nullptr},
+                *disc_gat_dst[2] = {nullptr, nullptr}, *disc_gat_bias[2] = {nullptr, nullptr};
+    int *disc_nbr[2] = {nullptr, nullptr}, *disc_deg[2] = {nullptr, nullptr};
+    const float *disc_logit_w = nullptr, *disc_logit_b = nullptr;
     // stand-alone building block (a2m_block_*): one layer class of model_layers.py with its own forward
     int blk_kind = 0, blk_cin = 0, blk_cout = 0;
     LayerW blk_conv, blk_even, blk_odd;
@@ -201,6 +211,27 @@ struct Builder {
         L.N = N; L.act = kActLeaky;
         const float* scale = fold_bn(p + ".conv", p + ".norm", N, &L.bias);
         pack(L, f32(p + ".conv.weight", static_cast<long long>(N) * C * 4), C * 4LL, 4, scale);
+    }
+    // Conv1d + BatchNorm1d + LeakyReLU of the discriminator's nn.Sequential stacks (real_motion_model.py:504-550), names
+    // given explicitly.  kind 0: k4 s2 p1 (view [B, T/2, 2, C]); 1: k4 s1 p1 (taps -1..2, one step shorter); 2: k3 s1 p1.
+    // c_pad > c_in: the input tensor carries zero channels up to c_pad (104 pose features -> 128).
+    void conv_bn(LayerW& L, const std::string& conv, const std::string& bn, int kind, int c_in, int c_pad, int N) {
+        const int k = kind == 2 ? 3 : 4;
+        if (kind == 0) L.taps = {tap(0, 1, -1, 0, c_pad, 0), tap(0, 0, 0, 0, c_pad, 1), tap(0, 1, 0, 0, c_pad, 2), tap(0, 0, 1, 0, c_pad, 3)};
+        else for (int j = 0; j < k; ++j) L.taps.push_back(tap(0, j - 1, 0, 0, c_pad, j));
+        L.N = N; L.act = kActLeaky;
+        const float* scale = fold_bn(conv, bn, N, &L.bias);
+        const float* w = f32(conv + ".weight", static_cast<long long>(N) * c_in * k);
+        if (rc != A2M_OK) return;
+        if (c_pad != c_in) {                                   // zero-padded copy [N][c_pad][k]
+            float* wp = alloc<float>(static_cast<size_t>(N) * c_pad * k);
+            if (rc != A2M_OK) return;
+            cudaMemsetAsync(wp, 0, static_cast<size_t>(N) * c_pad * k * sizeof(float), s);
+            cudaMemcpy2DAsync(wp, static_cast<size_t>(c_pad) * k * 4, w, static_cast<size_t>(c_in) * k * 4,
+                              static_cast<size_t>(c_in) * k * 4, N, cudaMemcpyDeviceToDevice, s);
+            w = wp;
+        }
+        pack(L, w, static_cast<long long>(c_pad) * k, k, scale);
     }
     // ConvTranspose1D k3 s2 p1 op1 + BN + ReLU (model_layers.py:200-215) as two parity GEMMs:
     //   out[2j] = W[:,:,1] x[j];  out[2j+1] = W[:,:,2] x[j] + W[:,:,0] x[j+1];  weight layout [C_in, C_out, 3]
@@ -517,6 +548,28 @@ struct Emit {
         const int lt = std::min(128, pow2_at_least(lo));
         const int box[4] = {1, lt, 128 / lt, 1}, ext[4] = {1, lo, B, 1};
         const long long os[4] = {0, L.N, static_cast<long long>(lo) * L.N, 0};
+        gemm(L, L.taps, &v, 1, box, ext, out, os, 0, kOutBf16);
+    }
+    // input [B, in_alloc, C] with rows [0, in_len) valid -> rows [0, out_len) of out [B, out_alloc, N]; taps shift along the rows
+    void conv_rows_io(const LayerW& L, const __nv_bfloat16* a, int C, int in_len, int in_alloc, int out_len, int out_alloc,
+                      int B, __nv_bfloat16* out) {
+        AView v;
+        v.ptr = a; v.rank = 3; v.dims[0] = C; v.dims[1] = in_len; v.dims[2] = B;
+        v.strides[0] = 1; v.strides[1] = C; v.strides[2] = static_cast<long long>(in_alloc) * C;
+        const int lt = std::min(128, pow2_at_least(out_len));
+        const int box[4] = {lt, 128 / lt, 1, 1}, ext[4] = {out_len, B, 1, 1};
+        const long long os[4] = {L.N, static_cast<long long>(out_alloc) * L.N, 0, 0};
+        gemm(L, L.taps, &v, 1, box, ext, out, os, 0, kOutBf16);
+    }
+    // the same for k4 s2 p1: in_alloc is even and rows [in_len, in_alloc) are zero
+    void conv_k4s2_io(const LayerW& L, const __nv_bfloat16* a, int C, int in_alloc, int out_len, int out_alloc, int B,
+                      __nv_bfloat16* out) {
+        AView v;
+        v.ptr = a; v.rank = 4; v.dims[0] = C; v.dims[1] = 2; v.dims[2] = in_alloc / 2; v.dims[3] = B;
+        v.strides[0] = 1; v.strides[1] = C; v.strides[2] = 2LL * C; v.strides[3] = static_cast<long long>(in_alloc) * C;
+        const int lt = std::min(128, pow2_at_least(out_len));
+        const int box[4] = {1, lt, 128 / lt, 1}, ext[4] = {1, out_len, B, 1};
+        const long long os[4] = {0, L.N, static_cast<long long>(out_alloc) * L.N, 0};
         gemm(L, L.taps, &v, 1, box, ext, out, os, 0, kOutBf16);
     }
     void conv_transpose(const LayerW& even, const LayerW& odd, const __nv_bfloat16* a, int C, int len, int B,
@@ -1323,4 +1376,266 @@ extern "C" int a2m_block_forward(a2m_model* m, const float* x_nct, int64_t B, in
     rc = run_ops(P, 0, static_cast<int>(P->ops.size()), s);
     if (rc != A2M_OK) return rc;
     return launch_btc_to_ncw(P->unet_out, static_cast<int>(B), m->blk_cout, block_out_length(m->blk_kind, T), out_nct, s);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Discriminator: SelfAttention_D.forward(x) (real_motion_model.py:580-642, eval mode, audio = None, aux_labels = None --
+// the two optional arguments cannot work as shipped: the concat with audio has 6144 channels where `logits` takes 4096,
+// and the aux classifier is handed a [B] tensor).  pose [B, T, 104] fp32 -> scores [B, T'] fp32.
+// Grouped convolutions with groups = 1 (the only value the reference instantiates); every Conv1d + BatchNorm + LeakyReLU
+// is one tcgen05 implicit GEMM; the k4 s1 p1 layers shorten the sequence by one step each.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct DiscLengths { int len[12]; int n; };      // sequence length after the input and after every conv
+
+int disc_lengths(int T, int n_down, DiscLengths* L) {
+    int t = T < 4 ? T + (4 - T % 4) : T;         // F.pad(x, (0, 4 - T % 4)) for T < 4 (:583-584)
+    int n = 0;
+    L->len[n++] = t;
+    auto s2 = [&](int v) { return (v + 2 - 4) / 2 + 1; };
+    auto s1 = [&](int v) { return v + 2 - 4 + 1; };
+    t = s2(t); L->len[n++] = t;
+    t = s1(t); L->len[n++] = t;
+    for (int i = 0; i < n_down; ++i) { t = s2(t); L->len[n++] = t; t = s1(t); L->len[n++] = t; }
+    t = s1(t); L->len[n++] = t;
+    t = s1(t); L->len[n++] = t;
+    L->len[n++] = t;                              // k3 s1 p1 keeps the length
+    L->n = n;
+    for (int i = 0; i < n; ++i)
+        if (L->len[i] < 1) return -1;
+    return t;
+}
+
+int build_disc_plan(a2m_model* m, ForwardPlan* P) {
+    const int B = P->B, T = P->T, nd = m->disc_down, c = m->disc_c;
+    DiscLengths L;
+    const int To = disc_lengths(T, nd, &L);
+    A2M_ARG_CHECK(To >= 1, "discriminator: %d steps are too few for %d downsampling stages", T, nd);
+    Bufs bufs;
+    for (int pass = 0; pass < 2; ++pass) {
+        Emit E{m, P, pass == 0};
+        if (pass == 1) {
+            P->ops.clear(); P->op_is_gemm.clear(); P->op_name.clear(); P->op_flops.clear();
+            P->gemm_flops = 0;
+            cudaError_t e = cudaMalloc(&P->arena, bufs.off + 256);
+            if (e != cudaSuccess) { a2m_set_error("discriminator: arena cudaMalloc(%zu) failed: %s", bufs.off, cudaGetErrorString(e)); return (int)e; }
+            // rows past a sequence's length (the padding that makes stride-2 views even) are never written: zero once
+            e = cudaMemset(P->arena, 0, bufs.off + 256);
+            if (e != cudaSuccess) { a2m_set_error("discriminator: arena memset: %s", cudaGetErrorString(e)); return (int)e; }
+            bufs.base = static_cast<unsigned char*>(P->arena);
+        }
+        bufs.off = 0;
+        auto even = [](int v) { return v + (v & 1); };
+        const int n_conv = static_cast<int>(m->disc_conv.size());
+        // buffer i holds the input of conv i (i = 0: the padded pose); channels per buffer
+        std::vector<int> chan(n_conv + 1);
+        chan[0] = 128;
+        for (int i = 0; i < n_conv; ++i) chan[i + 1] = m->disc_conv[i].N;
+        std::vector<__nv_bfloat16*> buf(n_conv + 1);
+        for (int i = 0; i <= n_conv; ++i) buf[i] = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * even(L.len[i]) * chan[i]);
+        const int C4 = 4 * c, Tl = To;                 // 2048 channels, final length
+        auto* attn_out = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * Tl * C4);
+        auto* qkv = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * Tl * (C4 + 2 * (C4 / 8)));
+        auto* pooled = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * C4);
+        auto* nodes_in = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * (kBodyJoints + kHandJoints) * kJointFeat);
+        auto* nodes_out = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * (kBodyJoints + kHandJoints) * kJointFeat);
+        auto* xg = bufs.get<__nv_bfloat16>(static_cast<size_t>(B) * C4);
+        auto* scores = bufs.get<float>(static_cast<size_t>(B) * Tl);
+        P->enc_out = buf[0]; P->pose_stage = scores; P->T_out = Tl;
+
+        // conv stack.  Layer kinds in order: conv1 (s2, s1), conv2 stages (s2, s1), conv3 (s1, s1, [attention], k3)
+        int li = 0;
+        auto s2 = [&](const char* tag) {
+            E.tag = tag;
+            E.conv_k4s2_io(m->disc_conv[li], buf[li], chan[li], even(L.len[li]), L.len[li + 1], even(L.len[li + 1]), B, buf[li + 1]);
+            ++li;
+        };
+        auto s1 = [&](const char* tag, __nv_bfloat16* in = nullptr, int in_alloc = 0) {
+            E.tag = tag;
+            E.conv_rows_io(m->disc_conv[li], in ? in : buf[li], chan[li], L.len[li], in ? in_alloc : even(L.len[li]), L.len[li + 1],
+                           even(L.len[li + 1]), B, buf[li + 1]);
+            ++li;
+        };
+        s2("disc.conv1.0"); s1("disc.conv1.4");
+        for (int i = 0; i < nd; ++i) { s2("disc.conv2.a"); s1("disc.conv2.b"); }
+        s1("disc.conv3.0");
+        // conv3.4 writes a dense [B, Tl, 4c] tensor (the attention's layout): out_alloc = Tl
+        E.tag = "disc.conv3.4";
+        E.conv_rows_io(m->disc_conv[li], buf[li], chan[li], L.len[li], even(L.len[li]), L.len[li + 1], L.len[li + 1], B, buf[li + 1]);
+        ++li;
+        E.tag = "disc.conv3.8";
+        E.attention(m->disc_attn, buf[li], nullptr, Tl, B, qkv, attn_out);
+        E.tag = "disc.conv3.9";
+        E.conv_rows_io(m->disc_conv[li], attn_out, C4, Tl, Tl, Tl, Tl, B, buf[li + 1]);
+        __nv_bfloat16* feat = buf[li + 1];             // [B, Tl, 4c] dense (k3 keeps the length; allocated even(Tl) rows, used Tl)
+        ++li;
+        E.tag = "disc.pool";
+        E.op([=](cudaStream_t st) { return launch_mean_time(feat, B, Tl, C4, pooled, st); });
+        // graph branches: body = channels [0, 2c), hand = [2c, 4c)  (:595-616)
+        for (int part = 0; part < 2; ++part) {
+            const int J = part == 0 ? kBodyJoints : kHandJoints;
+            __nv_bfloat16* nin = nodes_in + (part == 0 ? 0 : static_cast<size_t>(B) * kBodyJoints * kJointFeat);
+            __nv_bfloat16* nout = nodes_out + (part == 0 ? 0 : static_cast<size_t>(B) * kBodyJoints * kJointFeat);
+            {
+                E.tag = part == 0 ? "disc.body_proj" : "disc.hand_proj";
+                AView v;
+                v.ptr = pooled + part * 2 * c; v.rank = 2; v.dims[0] = 2 * c; v.dims[1] = B; v.strides[0] = 1; v.strides[1] = C4;
+                const int box[4] = {128, 1, 1, 1}, ext[4] = {B, 1, 1, 1};
+                const long long os[4] = {static_cast<long long>(J) * kJointFeat, 0, 0, 0};
+                E.gemm(m->disc_proj[part], m->disc_proj[part].taps, &v, 1, box, ext, nin, os, 0, kOutBf16);
+            }
+            E.tag = part == 0 ? "disc.body_gat" : "disc.hand_gat";
+            const float *wt = m->disc_gat_wt[part], *as = m->disc_gat_src[part], *ad = m->disc_gat_dst[part], *gb = m->disc_gat_bias[part];
+            const int *nbr = m->disc_nbr[part], *deg = m->disc_deg[part];
+            E.op([=](cudaStream_t st) { return launch_gat_single(nin, B, J, wt, as, ad, gb, nbr, deg, nout, st); });
+            E.tag = part == 0 ? "disc.body_graph_out" : "disc.hand_graph_out";
+            E.linear_rows(m->disc_out[part], nout, nullptr, J * kJointFeat, B, xg, C4, part * 2 * c, kOutBf16);
+        }
+        E.tag = "disc.logits";
+        const float *lw = m->disc_logit_w, *lb = m->disc_logit_b;
+        E.op([=](cudaStream_t st) { return launch_disc_logits(feat, xg, lw, lb, B, Tl, C4, scores, st); });
+        if (E.rc != A2M_OK) return E.rc;
+    }
+    return A2M_OK;
+}
+
+}  // namespace
+
+extern "C" int a2m_disc_create(const a2m_tensor_desc* tensors, int n_tensors, int n_downsampling, int device, a2m_model** out) {
+    A2M_ARG_CHECK(out != nullptr && tensors != nullptr && n_tensors > 0, "a2m_disc_create: NULL argument");
+    *out = nullptr;
+    A2M_ARG_CHECK(n_downsampling >= 0 && n_downsampling <= 2, "a2m_disc_create: n_downsampling %d (0..2: the channel count "
+                  "grows by 2^n per stage)", n_downsampling);
+    A2M_CUDA_CHECK(cudaSetDevice(device));
+    std::unique_ptr<a2m_model> m(new a2m_model());
+    m->device = device;
+    for (int i = 0; i < n_tensors; ++i) {
+        const a2m_tensor_desc& t = tensors[i];
+        A2M_ARG_CHECK(t.name != nullptr && t.ndim >= 0 && t.ndim <= 4, "a2m_disc_create: bad descriptor %d", i);
+        Param p;
+        p.ndim = t.ndim;
+        for (int k = 0; k < t.ndim; ++k) p.shape[k] = t.shape[k];
+        if (t.dtype == A2M_DTYPE_F32) p.f32 = static_cast<const float*>(t.data);
+        else if (t.dtype == A2M_DTYPE_I64) p.i64 = static_cast<const long long*>(t.data);
+        else { a2m_set_error("a2m_disc_create: tensor '%s' has unsupported dtype %d", t.name, t.dtype); return A2M_ERR_ARGUMENT; }
+        m->params[t.name] = p;
+    }
+    Builder b{m.get(), nullptr};
+    const Param* w0 = b.find("conv1.0.weight");
+    A2M_ARG_CHECK(w0 && w0->ndim == 3 && w0->shape[1] == kPoseFeats && w0->shape[2] == 4 && w0->shape[0] == 64,
+                  "a2m_disc_create: conv1.0.weight must be [64, 104, 4] (in_channels 104, out_channels 64, groups 1)");
+    m->has_disc = true; m->disc_down = n_downsampling;
+    int c = 64;
+    m->disc_conv.resize(2 + 2 * n_downsampling + 3);
+    int li = 0;
+    b.conv_bn(m->disc_conv[li++], "conv1.0", "conv1.1", 0, kPoseFeats, 128, c);
+    b.conv_bn(m->disc_conv[li++], "conv1.4", "conv1.5", 1, c, c, c);
+    for (int n = 1; n <= n_downsampling; ++n) {
+        const int mul = 1 << n;
+        const std::string p = "conv2." + std::to_string(n - 1);
+        b.conv_bn(m->disc_conv[li++], p + ".0", p + ".1", 0, c, c, c * mul);
+        b.conv_bn(m->disc_conv[li++], p + ".4", p + ".5", 1, c * mul, c * mul, c * mul);
+        c *= mul;
+    }
+    m->disc_c = c;
+    b.conv_bn(m->disc_conv[li++], "conv3.0", "conv3.1", 1, c, c, 2 * c);
+    b.conv_bn(m->disc_conv[li++], "conv3.4", "conv3.5", 1, 2 * c, 2 * c, 4 * c);
+    b.attention(m->disc_attn, "conv3.8", 4 * c);
+    b.conv_bn(m->disc_conv[li++], "conv3.9", "conv3.10", 2, 4 * c, 4 * c, 4 * c);
+    const char* parts[2] = {"body", "hand"};
+    for (int part = 0; part < 2 && b.rc == A2M_OK; ++part) {
+        const int J = part == 0 ? kBodyJoints : kHandJoints;
+        const std::string p = parts[part];
+        b.linear(m->disc_proj[part], p + "_proj.weight", p + "_proj.bias", 2 * c, J * kJointFeat, kActNone);
+        b.linear(m->disc_out[part], p + "_graph_out.weight", p + "_graph_out.bias", J * kJointFeat, 2 * c, kActNone);
+        m->disc_gat_src[part] = b.keep(p + "_gat.att_src", kGatHeads * kJointFeat);
+        m->disc_gat_dst[part] = b.keep(p + "_gat.att_dst", kGatHeads * kJointFeat);
+        m->disc_gat_bias[part] = b.keep(p + "_gat.bias", kJointFeat);
+        std::string wname = p + "_gat.lin.weight";
+        if (!b.find(wname, false))
+            for (const char* alt : {"_gat.lin_src.weight", "_gat.lin_l.weight"})
+                if (b.find(p + alt, false)) { wname = p + alt; break; }
+        const float* w = b.f32(wname, static_cast<long long>(kGatHeads) * kJointFeat * kJointFeat);
+        float* wt = b.alloc<float>(static_cast<size_t>(kGatHeads) * kJointFeat * kJointFeat);
+        if (b.rc == A2M_OK) {                          // transpose [256][64] -> [64][256] on the host (64 KB, once)
+            std::vector<float> h(256 * 64), ht(256 * 64);
+            cudaError_t e = cudaMemcpy(h.data(), w, h.size() * 4, cudaMemcpyDeviceToHost);
+            for (int o = 0; o < 256; ++o)
+                for (int f = 0; f < 64; ++f) ht[f * 256 + o] = h[o * 64 + f];
+            if (e == cudaSuccess) e = cudaMemcpy(wt, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { a2m_set_error("a2m_disc_create: %s", cudaGetErrorString(e)); b.rc = (int)e; }
+        }
+        m->disc_gat_wt[part] = wt;
+        DecoderW topo;
+        b.topology(topo, p + "_edge_index_template", J);
+        m->disc_nbr[part] = topo.nbr; m->disc_deg[part] = topo.deg;
+    }
+    if (b.rc == A2M_OK) {                              // logits Conv1d(8c -> 1, k3): [1][8c][3] -> tap-major [3][8c]
+        const int C8 = 8 * c;
+        const Param* lp = b.find("logits.weight");
+        if (lp && (lp->ndim != 3 || lp->shape[0] != 1 || lp->shape[1] != C8 || lp->shape[2] != 3)) {
+            a2m_set_error("a2m_disc_create: logits.weight must be [1, %d, 3] (out_shape 1, groups 1)", C8);
+            b.rc = A2M_ERR_UNSUPPORTED;
+        }
+        const float* w = b.f32("logits.weight", 3LL * C8);
+        float* wt = b.alloc<float>(3 * static_cast<size_t>(C8));
+        if (b.rc == A2M_OK) {
+            std::vector<float> h(3 * static_cast<size_t>(C8)), ht(h.size());
+            cudaError_t e = cudaMemcpy(h.data(), w, h.size() * 4, cudaMemcpyDeviceToHost);
+            for (int ch = 0; ch < C8; ++ch)
+                for (int k = 0; k < 3; ++k) ht[static_cast<size_t>(k) * C8 + ch] = h[static_cast<size_t>(ch) * 3 + k];
+            if (e == cudaSuccess) e = cudaMemcpy(wt, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { a2m_set_error("a2m_disc_create: %s", cudaGetErrorString(e)); b.rc = (int)e; }
+        }
+        m->disc_logit_w = wt;
+        m->disc_logit_b = b.keep("logits.bias", 1);
+    }
+    m->err_flag = b.alloc<int>(1);
+    if (b.rc == A2M_OK) cudaMemset(m->err_flag, 0, 4);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (b.rc == A2M_OK && e != cudaSuccess) { a2m_set_error("a2m_disc_create: %s", cudaGetErrorString(e)); b.rc = (int)e; }
+    if (b.rc != A2M_OK) {
+        for (void* q : m->owned) cudaFree(q);
+        return b.rc;
+    }
+    m->params.clear();
+    *out = m.release();
+    return A2M_OK;
+}
+
+extern "C" int a2m_disc_out_length(int T, int n_downsampling) {
+    DiscLengths L;
+    return T >= 1 && n_downsampling >= 0 && n_downsampling <= 2 ? disc_lengths(T, n_downsampling, &L) : -1;
+}
+
+extern "C" int a2m_disc_forward(a2m_model* m, const float* pose, int64_t B, int T, float* scores, void* stream) {
+    A2M_ARG_CHECK(m != nullptr && pose != nullptr && scores != nullptr, "a2m_disc_forward: NULL argument");
+    A2M_ARG_CHECK(m->has_disc, "a2m_disc_forward: the handle is not a discriminator");
+    A2M_ARG_CHECK(B >= 1 && B <= 65535 && T >= 4 && T <= 4096, "a2m_disc_forward: B = %lld, T = %d (4 <= T <= 4096)", (long long)B, T);
+    char key[64];
+    snprintf(key, sizeof(key), "disc:%lld:%d", (long long)B, T);
+    ForwardPlan* P = nullptr;
+    auto it = m->plans.find(key);
+    if (it != m->plans.end()) {
+        P = it->second.get();
+    } else {
+        std::unique_ptr<ForwardPlan> np(new ForwardPlan());
+        np->B = static_cast<int>(B); np->T = T; np->F = 0;
+        const int rc = build_disc_plan(m, np.get());
+        if (rc != A2M_OK) return rc;
+        if (m->plans.size() >= 16) m->plans.clear();
+        P = np.get();
+        m->plans[key] = std::move(np);
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DiscLengths L;
+    disc_lengths(T, m->disc_down, &L);
+    int rc = launch_pose_pad(pose, static_cast<int>(B), T, L.len[0] + (L.len[0] & 1), kPoseFeats, 128, P->enc_out, s);
+    if (rc != A2M_OK) return rc;
+    rc = run_ops(P, 0, static_cast<int>(P->ops.size()), s);
+    if (rc != A2M_OK) return rc;
+    A2M_CUDA_CHECK(cudaMemcpyAsync(scores, P->pose_stage, static_cast<size_t>(B) * P->T_out * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return A2M_OK;
 }

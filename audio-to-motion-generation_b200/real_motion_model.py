@@ -1,4 +1,5 @@
-"""B200 drop-in for ``real_motion_model.py`` of the reference: the ``SelfAttention_G`` generator.
+"""B200 drop-in for ``real_motion_model.py`` of the reference: the ``SelfAttention_G`` generator and the
+``SelfAttention_D`` discriminator (inference forward).
 
 Same constructor and ``forward(audio, real_pose=None) -> (pose [B, T, 104], [losses])`` contract
 (real_motion_model.py:22,154-278) and the same 340 state_dict keys, so reference
@@ -219,3 +220,123 @@ class SelfAttention_G(NativeModule):
                                                       _cabi.stream_ptr(h.device)))
         internal = [losses[1], losses[0]] if rp is not None else [losses[0]]
         return pose, internal
+
+
+
+class SelfAttention_D(NativeModule):
+    """The discriminator of the reference (real_motion_model.py:464-642), eval-mode forward on the B200 path:
+    ``forward(x [B, T, 104]) -> (scores [B, T'], [])`` with T' = a2m_disc_out_length(T) (4 for T = 64).  Same constructor
+    and state_dict keys (conv1.0.weight ... aux_classifier.3.bias), so reference checkpoints load.
+
+    ``audio`` and ``aux_labels`` cannot work in the reference as shipped (with audio the concatenated tensor has 6144
+    channels where ``logits`` takes 4096, :625-630; the auxiliary classifier is handed a [B] tensor, :637-638); here they
+    raise NotImplementedError instead of a shape error.  ``audio_fusion`` / ``aux_classifier`` parameters are kept for
+    checkpoint compatibility only."""
+
+    def __init__(self, in_channels=104, out_channels=64, n_downsampling=2, p=0.3, groups=1, aux_classes=10, **kwargs):
+        super().__init__()
+        if (in_channels, out_channels, groups) != (104, 64, 1) or not 0 <= n_downsampling <= 2 or kwargs.get("out_shape", 1) != 1:
+            raise NotImplementedError("the native discriminator implements in_channels 104, out_channels 64, groups 1, "
+                                      "n_downsampling <= 2, out_shape 1")
+        self.n_downsampling, self.groups, self.p = n_downsampling, groups, p
+        self.num_body_joints, self.num_hand_joints, self.joint_feat_dim = 10, 42, 64
+        self.body_edge_index = _edge_index(SKELETON_PARENTS, 0, 10)
+        self.hand_edge_index = _edge_index(SKELETON_PARENTS, 10, 42)
+        self.register_buffer('body_edge_index_template', self.body_edge_index)
+        self.register_buffer('hand_edge_index_template', self.hand_edge_index)
+
+        def stack(cin, cout, first_stride):
+            return [nn.Conv1d(cin, cout, kernel_size=4, stride=first_stride, padding=1), nn.BatchNorm1d(cout),
+                    nn.LeakyReLU(negative_slope=0.2), nn.Dropout(p=p)]
+        c = out_channels
+        self.conv1 = nn.Sequential(*(stack(in_channels, c, 2) + stack(c, c, 1)))
+        self.conv2 = nn.ModuleList()
+        for n in range(1, n_downsampling + 1):
+            mul = min(2 ** n, 16)
+            self.conv2.append(nn.Sequential(*(stack(c, c * mul, 2) + stack(c * mul, c * mul, 1))))
+            c *= mul
+        self.conv3 = nn.Sequential(*(stack(c, 2 * c, 1) + stack(2 * c, 4 * c, 1) + [SelfAttention(4 * c)] +
+                                     [nn.Conv1d(4 * c, 4 * c, kernel_size=3, stride=1, padding=1), nn.BatchNorm1d(4 * c),
+                                      nn.LeakyReLU(negative_slope=0.2), nn.Dropout(p=p)]))
+        self.body_proj = nn.Linear(2 * c, 10 * 64)
+        self.hand_proj = nn.Linear(2 * c, 42 * 64)
+        self.body_gat = GATConv(64, 64, heads=4, concat=False)
+        self.hand_gat = GATConv(64, 64, heads=4, concat=False)
+        self.body_graph_out = nn.Linear(10 * 64, 2 * c)
+        self.hand_graph_out = nn.Linear(42 * 64, 2 * c)
+        self.audio_fusion = nn.Conv1d(256, 4 * c, kernel_size=1)
+        self.logits = nn.Conv1d(8 * c, 1, kernel_size=3, stride=1, padding=1)
+        self.aux_classifier = nn.Sequential(nn.Linear(4 * c, 512), nn.LeakyReLU(0.2), nn.Dropout(p), nn.Linear(512, aux_classes))
+        self.aux_loss_fn = nn.CrossEntropyLoss()
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        for part in ("body", "hand"):                                # torch_geometric version-dependent key names
+            base = "%s%s_gat." % (prefix, part)
+            for alt in ("lin_src.weight", "lin_l.weight"):
+                if base + alt in state_dict and base + "lin.weight" not in state_dict:
+                    state_dict[base + "lin.weight"] = state_dict.pop(base + alt)
+            for dup in ("lin_dst.weight", "lin_r.weight"):
+                state_dict.pop(base + dup, None)
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def native(self, lane=0):
+        _cabi.require_cuda(type(self).__name__)
+        fp = self._fingerprint()
+        handles = self.__dict__.setdefault("_handles", {})
+        entry = handles.get(lane)
+        if entry is None or entry[1] != fp:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("SelfAttention_D: parameters are on %s; move the module to a CUDA device (.cuda()) -- "
+                                   "there is no CPU fallback" % dev)
+            entry = handles[lane] = (_DiscHandle(self._native_state(), dev, self.n_downsampling), fp)
+        return entry[0]
+
+    def forward(self, x, audio=None, aux_labels=None):
+        if audio is not None or aux_labels is not None:
+            raise NotImplementedError("SelfAttention_D: the audio / aux_labels branches raise shape errors in the reference "
+                                      "as shipped (real_motion_model.py:625-639) and are not implemented")
+        self._require_eval()
+        h = self.native()
+        x = as_input(x, h.device, "SelfAttention_D expects poses [B, T, 104], got %s")
+        B, T, feats = x.shape
+        if feats != 104:
+            raise ValueError("SelfAttention_D expects 104 pose features, got %d" % feats)
+        t_out = int(_cabi.lib().a2m_disc_out_length(T, self.n_downsampling))
+        if t_out < 1:
+            raise ValueError("SelfAttention_D: %d steps are too few for the convolution stack" % T)
+        out = torch.empty((B, t_out), dtype=torch.float32, device=h.device)
+        if B:
+            with torch.cuda.device(h.device):
+                _cabi.check(_cabi.lib().a2m_disc_forward(h.ptr, _cabi.ptr(x), B, T, _cabi.ptr(out), _cabi.stream_ptr(h.device)))
+        return out, []
+
+
+class _DiscHandle:
+    """Owns the a2m_model* of a discriminator (a2m_disc_create)."""
+
+    def __init__(self, state, device, n_downsampling):
+        import ctypes
+        descs = (_cabi.TensorDesc * len(state))()
+        keep = []
+        for i, (name, t) in enumerate(state.items()):
+            dtype = 1 if t.dtype == torch.int64 else 0
+            if not dtype and t.dtype != torch.float32:
+                t = t.to(torch.float32)
+            t = t.detach().to(device).contiguous()
+            keep.append(t)
+            descs[i].name, descs[i].data, descs[i].dtype, descs[i].ndim = name.encode(), t.data_ptr(), dtype, t.dim()
+            for k, sdim in enumerate(t.shape):
+                descs[i].shape[k] = sdim
+        out = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _cabi.check(_cabi.lib().a2m_disc_create(descs, len(state), int(n_downsampling), device.index, ctypes.byref(out)))
+        self.ptr, self.device = out, device
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr:
+            try:
+                _cabi.lib().a2m_model_destroy(ptr)
+            except Exception:
+                pass

@@ -329,6 +329,19 @@ int a2m_block_create(int kind, const a2m_tensor_desc* tensors, int n_tensors, in
                      int device, a2m_model** out);
 int a2m_block_forward(a2m_model* block, const float* x_nct, int64_t B, int T, float* out_nct, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * the discriminator: replaces real_motion_model.py:464-642 SelfAttention_D, eval-mode
+ * forward(x) with audio = None and aux_labels = None (neither optional argument can work in the reference as shipped:
+ * the concat with audio features has 6144 channels where `logits` takes 4096, and the auxiliary classifier is handed
+ * a [B] tensor).  State_dict with the reference's key names (conv1.0.weight ... logits.bias; groups = 1,
+ * in_channels 104, out_channels 64); pose [B, T, 104] fp32 -> scores [B, a2m_disc_out_length(T)] fp32.
+ * Every Conv1d + BatchNorm1d + LeakyReLU is one tcgen05 implicit GEMM; the two single-layer GAT branches run in fp32.
+ * Handles are destroyed with a2m_model_destroy.
+ * ---------------------------------------------------------------------------------------------- */
+int a2m_disc_create(const a2m_tensor_desc* tensors, int n_tensors, int n_downsampling, int device, a2m_model** out);
+int a2m_disc_out_length(int T, int n_downsampling);      /* < 1: the sequence is too short */
+int a2m_disc_forward(a2m_model* disc, const float* pose, int64_t B, int T, float* scores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

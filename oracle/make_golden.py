@@ -166,7 +166,37 @@ def block_golden():
     np.savez_compressed(os.path.join(GOLDEN_DIR, "blocks_reference.npz"), **out)
 
 
+DISC_CASES = [("disc_b3_t64", 11, 3, 64), ("disc_b2_t40", 12, 2, 40)]      # (name, weight seed, B, T)
+
+
+def disc_golden():
+    """tests/golden/disc_reference.npz: the UNMODIFIED SelfAttention_D (eval mode, torch_geometric stand-ins of
+    oracle/ref_shim.py) on seeded poses; weights from oracle/weights.make_state_dict(seed, discriminator=True)."""
+    rm = ref_shim.import_reference()["real_motion_model"]
+    torch.manual_seed(0)
+    model = rm.SelfAttention_D().eval()
+    ref_sd = model.state_dict()
+    con = weights.disc_contract()
+    assert [n for n, _, _ in con] == list(ref_sd.keys()), "discriminator contract differs from the reference state_dict"
+    for n, shape, _ in con:
+        assert tuple(ref_sd[n].shape) == tuple(shape), (n, ref_sd[n].shape, shape)
+    out = {"n_tensors": np.array(len(con))}
+    for name, seed, B, T in DISC_CASES:
+        model.load_state_dict(weights.make_state_dict(seed, "stress", discriminator=True), strict=True)
+        model.eval()
+        pose = real_pose_input(seed, B, T)
+        with torch.no_grad():
+            y, losses = model(pose)
+        assert losses == []
+        out[name] = y.numpy()
+        print(name, tuple(pose.shape), "->", tuple(y.shape), y.numpy().ravel()[:4])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "disc_reference.npz"), **out)
+
+
 def main():
+    if "--disc-only" in sys.argv:
+        os.makedirs(GOLDEN_DIR, exist_ok=True)
+        return disc_golden()
     if "--blocks-only" in sys.argv:
         os.makedirs(GOLDEN_DIR, exist_ok=True)
         return block_golden()
@@ -244,6 +274,7 @@ def main():
     smoothness_golden()
     mel_nfft_golden()
     block_golden()
+    disc_golden()
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
 

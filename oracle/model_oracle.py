@@ -242,3 +242,41 @@ def generator_forward(sd, mel, real_pose=None):
         losses.append(bone_loss(real_pose, out))
     losses.append(angle_loss(out))
     return out, losses
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# discriminator
+# ---------------------------------------------------------------------------------------------------------------
+def _conv_bn_act(sd, p, i, x, stride, padding):
+    """nn.Sequential entries i (Conv1d), i + 1 (BatchNorm1d), LeakyReLU(0.2), Dropout (identity in eval mode)."""
+    y = F.conv1d(x, sd[f"{p}.{i}.weight"], sd[f"{p}.{i}.bias"], stride, padding)
+    return F.leaky_relu(_bn(sd, f"{p}.{i + 1}", y), SLOPE)
+
+
+def discriminator_forward(sd, pose, n_downsampling=2):
+    """SelfAttention_D.forward(x) with audio = None, aux_labels = None (real_motion_model.py:580-642; the two optional
+    arguments cannot work as shipped: with audio the concat has 6144 channels but `logits` takes 4096, and the aux
+    classifier is fed a [B] tensor).  pose [B, T, 104] -> scores [B, T']."""
+    x = pose.transpose(-1, -2)                                               # :582
+    if x.size(2) < 4:
+        x = F.pad(x, (0, 4 - x.size(2) % 4))                                 # :583-584
+    x = _conv_bn_act(sd, "conv1", 0, x, 2, 1)                                # :586, ctor :504-513
+    x = _conv_bn_act(sd, "conv1", 4, x, 1, 1)
+    for n in range(n_downsampling):                                          # :587-588, ctor :518-532
+        x = _conv_bn_act(sd, f"conv2.{n}", 0, x, 2, 1)
+        x = _conv_bn_act(sd, f"conv2.{n}", 4, x, 1, 1)
+    x = _conv_bn_act(sd, "conv3", 0, x, 1, 1)                                # :590, ctor :535-550
+    x = _conv_bn_act(sd, "conv3", 4, x, 1, 1)
+    x = self_attention(sd, "conv3.8", x)
+    x = _conv_bn_act(sd, "conv3", 9, x, 1, 1)
+    B, C, T = x.shape
+    body_e, hand_e = edge_templates()
+    outs = []
+    for part, nj, e, feats in (("body", N_BODY, body_e, x[:, :C // 2]), ("hand", N_HAND, hand_e, x[:, C // 2:])):
+        h = F.linear(feats.mean(dim=2), sd[f"{part}_proj.weight"], sd[f"{part}_proj.bias"])            # :599-600
+        h = gat(sd, f"{part}_gat", h.view(B, nj, JOINT_FEAT), dense_adjacency(e, nj))                  # :601-604
+        outs.append(F.linear(h.reshape(B, -1), sd[f"{part}_graph_out.weight"], sd[f"{part}_graph_out.bias"]))
+    xg = torch.cat(outs, dim=1).unsqueeze(2).repeat(1, 1, T)                                            # :619-621
+    x = torch.cat([x, xg], dim=1)
+    x = F.conv1d(x, sd["logits.weight"], sd["logits.bias"], 1, 1)                                       # :630
+    return x.transpose(-1, -2).squeeze(dim=-1)

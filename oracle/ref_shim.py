@@ -110,6 +110,29 @@ def _unet_forward_d1(self, x):
     return self.final_conv(x)
 
 
+class _Data:
+    """torch_geometric.data.Data as the discriminator uses it (real_motion_model.py:602,614): a bag of x and edge_index."""
+
+    def __init__(self, x=None, edge_index=None):
+        self.x, self.edge_index = x, edge_index
+
+
+class _Batch:
+    """torch_geometric.data.Batch.from_data_list: node features concatenated, edge indices offset per graph."""
+
+    def __init__(self, x, edge_index):
+        self.x, self.edge_index = x, edge_index
+
+    @classmethod
+    def from_data_list(cls, data_list):
+        xs, es, off = [], [], 0
+        for d in data_list:
+            xs.append(d.x)
+            es.append(d.edge_index + off)
+            off += d.x.shape[0]
+        return cls(torch.cat(xs, dim=0), torch.cat(es, dim=1))
+
+
 def available():
     return os.path.isdir(REFERENCE_ROOT)
 
@@ -126,7 +149,7 @@ def import_reference():
     tg_nn = types.ModuleType("torch_geometric.nn")
     tg_data = types.ModuleType("torch_geometric.data")
     tg_nn.GATConv, tg_nn.GraphConv = GATConv, GraphConv
-    tg_data.Data, tg_data.Batch = object, object              # imported but never used by G
+    tg_data.Data, tg_data.Batch = _Data, _Batch               # used by SelfAttention_D.forward only
     tg.nn, tg.data = tg_nn, tg_data
     pats = types.ModuleType("pats")
     pats_dl = types.ModuleType("pats.data_loading")

@@ -114,6 +114,38 @@ def contract(in_channels=256, out_channels=256, out_feats=104):
     return e
 
 
+def _conv_bn(prefix, i, c_out, c_in, k):
+    """nn.Sequential entries i (Conv1d) and i + 1 (BatchNorm1d) of the discriminator's conv stacks."""
+    return [(f"{prefix}.{i}.weight", (c_out, c_in, k), "w"), (f"{prefix}.{i}.bias", (c_out,), "b"),
+            (f"{prefix}.{i + 1}.weight", (c_out,), "bn_w"), (f"{prefix}.{i + 1}.bias", (c_out,), "bn_b"),
+            (f"{prefix}.{i + 1}.running_mean", (c_out,), "bn_m"), (f"{prefix}.{i + 1}.running_var", (c_out,), "bn_v"),
+            (f"{prefix}.{i + 1}.num_batches_tracked", (), "bn_n")]
+
+
+def disc_contract(in_channels=104, out_channels=64, n_downsampling=2, aux_classes=10):
+    """Ordered [(name, shape, kind)] of every state_dict entry of SelfAttention_D with groups = 1
+    (real_motion_model.py:464-577)."""
+    e = [("body_edge_index_template", (2, 18), "edge_body"), ("hand_edge_index_template", (2, 80), "edge_hand")]
+    c = out_channels
+    e += _conv_bn("conv1", 0, c, in_channels, 4) + _conv_bn("conv1", 4, c, c, 4)
+    for n in range(1, n_downsampling + 1):
+        mul = min(2 ** n, 16)
+        e += _conv_bn(f"conv2.{n - 1}", 0, c * mul, c, 4) + _conv_bn(f"conv2.{n - 1}", 4, c * mul, c * mul, 4)
+        c *= mul
+    e += _conv_bn("conv3", 0, 2 * c, c, 4) + _conv_bn("conv3", 4, 4 * c, 2 * c, 4) + _attn("conv3.8", 4 * c)
+    e += _conv_bn("conv3", 9, 4 * c, 4 * c, 3)
+    e += [("body_proj.weight", (N_BODY * JOINT_FEAT, 2 * c), "w"), ("body_proj.bias", (N_BODY * JOINT_FEAT,), "b"),
+          ("hand_proj.weight", (N_HAND * JOINT_FEAT, 2 * c), "w"), ("hand_proj.bias", (N_HAND * JOINT_FEAT,), "b")]
+    e += _gat("body_gat") + _gat("hand_gat")
+    e += [("body_graph_out.weight", (2 * c, N_BODY * JOINT_FEAT), "w"), ("body_graph_out.bias", (2 * c,), "b"),
+          ("hand_graph_out.weight", (2 * c, N_HAND * JOINT_FEAT), "w"), ("hand_graph_out.bias", (2 * c,), "b"),
+          ("audio_fusion.weight", (4 * c, 256, 1), "w"), ("audio_fusion.bias", (4 * c,), "b"),
+          ("logits.weight", (1, 8 * c, 3), "w"), ("logits.bias", (1,), "b"),
+          ("aux_classifier.0.weight", (512, 4 * c), "w"), ("aux_classifier.0.bias", (512,), "b"),
+          ("aux_classifier.3.weight", (aux_classes, 512), "w"), ("aux_classifier.3.bias", (aux_classes,), "b")]
+    return e
+
+
 def _fan_in(shape, name):
     if "conv_transpose" in name:             # weight is [C_in, C_out, k]
         return shape[1] * math.prod(shape[2:])
@@ -135,7 +167,8 @@ def make_state_dict(seed=0, mode="stress", **kw):
     body_e, hand_e = edge_templates()
     sd = OrderedDict()
     stress = mode == "stress"
-    for name, shape, kind in contract(**kw):
+    entries = disc_contract() if kw.pop("discriminator", False) else contract(**kw)
+    for name, shape, kind in entries:
         if kind == "edge_body":
             t = body_e.clone()
         elif kind == "edge_hand":

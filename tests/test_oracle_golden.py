@@ -145,3 +145,17 @@ def test_block_oracles_match_reference_classes(name, cls, args, kwargs, cin, T):
           "ChannelAttention": lambda: model_oracle.channel_attention(sd, "p", x),
           "ResBlock": lambda: model_oracle.res_block(sd, "p", x)}[cls]
     torch.testing.assert_close(fn(), torch.from_numpy(g[name + "/y"]), rtol=1e-5, atol=1e-5)
+
+
+def test_discriminator_oracle_matches_reference():
+    """model_oracle.discriminator_forward (dense-adjacency GAT, functional convs) against the unmodified SelfAttention_D
+    run through the scatter-style stand-ins (tests/golden/disc_reference.npz); fp32 round-off only."""
+    import os
+    from oracle.make_golden import DISC_CASES
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "disc_reference.npz"))
+    assert int(g["n_tensors"]) == len(weights.disc_contract())
+    for name, seed, B, T in DISC_CASES:
+        sd = weights.make_state_dict(seed, "stress", discriminator=True)
+        y = model_oracle.discriminator_forward(sd, real_pose_input(seed, B, T))
+        assert tuple(y.shape) == g[name].shape
+        np.testing.assert_allclose(y.numpy(), g[name], rtol=1e-3, atol=2e-5)
