@@ -62,6 +62,10 @@ SIGNATURES = {
     "a2m_melspec_plan_destroy": (None, [c_void_p]),
     "a2m_melspec_num_frames": (c_i64, [c_void_p, c_i64]),
     "a2m_melspec_f32": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
+    "a2m_resample_plan_create": (c_int, [c_double, c_double, c_int, ctypes.POINTER(c_void_p)]),
+    "a2m_resample_plan_destroy": (None, [c_void_p]),
+    "a2m_resample_out_length": (c_i64, [c_void_p, c_i64]),
+    "a2m_resample_f32": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
     "a2m_eval_l1_pck_f32": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
     "a2m_eval_l1_pck_f64": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_double, c_void_p, c_void_p, c_void_p,
@@ -80,6 +84,8 @@ SIGNATURES = {
     "a2m_model_destroy": (None, [c_void_p]),
     "a2m_model_forward": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
+    "a2m_model_forward_windows": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_void_p,
+                                          c_void_p, c_void_p]),
     "a2m_model_set_output_denorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "a2m_model_timeline_begin": (c_int, [c_void_p, c_i64, c_int, c_int, c_int]),
     "a2m_model_timeline_read": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int]),

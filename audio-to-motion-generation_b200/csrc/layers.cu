@@ -35,19 +35,21 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
 // same 4 x 10 input window as broadcast vector loads (12 loads for 8 x 16 FMAs per lane).
 constexpr int kConv0Rows = 8;
 __global__ void __launch_bounds__(256)
-conv0_kernel(const float* __restrict__ mel, long long stride_b, long long stride_t, int T, int F,
-             const float* __restrict__ w, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+conv0_kernel(const float* __restrict__ mel, long long stride_b, long long stride_t, int n_inner, long long stride_outer,
+             int T, int F, const float* __restrict__ w, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
     extern __shared__ __align__(16) float s_rows[];   // [2R + 2][stride]: column c of the input at index c + 1
     const int ho0 = blockIdx.x * kConv0Rows;
     const long long b = blockIdx.y;
     const int Ho = T / 2, Wo = F / 2;
     const int stride = ((F + 2 + 3) / 4) * 4 + 4;     // multiple of 4 floats, room for the 10-wide window of the last group
     const int n_in = 2 * kConv0Rows + 2;
+    // clip b = window (b % n_inner) of stream (b / n_inner): sliding windows over one log-mel per stream are read in place
+    const float* clip = mel + (b / n_inner) * stride_outer + (b % n_inner) * stride_b;
     for (int i = threadIdx.x; i < n_in * stride; i += blockDim.x) {
         const int r = i / stride, col = i - r * stride - 1;
         const int h = 2 * ho0 + r - 1;
         float v = 0.f;
-        if (h >= 0 && h < T && col >= 0 && col < F) v = __ldg(mel + b * stride_b + h * stride_t + col);
+        if (h >= 0 && h < T && col >= 0 && col < F) v = __ldg(clip + h * stride_t + col);
         s_rows[i] = v;
     }
     const int cp = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -628,11 +630,12 @@ __global__ void btc_to_ncw_kernel(const __nv_bfloat16* __restrict__ in, int C, i
     return A2M_OK
 
 int launch_conv0(const float* mel, long long stride_b, long long stride_t, int B, int T, int F, const float* w_folded,
-                 const float* bias_folded, __nv_bfloat16* out, cudaStream_t stream) {
+                 const float* bias_folded, __nv_bfloat16* out, cudaStream_t stream, int n_inner, long long stride_outer) {
+    if (n_inner <= 0) { n_inner = B > 0 ? B : 1; stride_outer = 0; }
     A2M_ARG_CHECK(T % 2 == 0 && F % 2 == 0 && B <= 65535, "conv0: T %d, F %d, B %d", T, F, B);
     const int stride = ((F + 2 + 3) / 4) * 4 + 4;
     conv0_kernel<<<dim3((T / 2 + kConv0Rows - 1) / kConv0Rows, B), 256, (2 * kConv0Rows + 2) * stride * sizeof(float), stream>>>(
-        mel, stride_b, stride_t, T, F, w_folded, bias_folded, out);
+        mel, stride_b, stride_t, n_inner, stride_outer, T, F, w_folded, bias_folded, out);
     A2M_AFTER_LAUNCH();
 }
 

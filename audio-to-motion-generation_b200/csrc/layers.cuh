@@ -10,8 +10,9 @@ namespace a2m {
 // AudioEncoder conv 0: Conv2d(1 -> 64, k4, s2, p1) + BatchNorm(eval) + LeakyReLU(0.2)  (model_layers.py:252)
 //   mel [B, T, F] fp32 (element strides stride_b, stride_t, 1: the D2 adapter slice is read in place)
 //   -> out [B, T/2, F/2, 64] bf16.  w_folded [16 taps][64 channels] fp32 (BN scale folded), bias_folded [64].
+//   n_inner > 0: clip b is window (b % n_inner) of stream (b / n_inner), at mel + stream * stride_outer + window * stride_b
 int launch_conv0(const float* mel, long long stride_b, long long stride_t, int B, int T, int F, const float* w_folded,
-                 const float* bias_folded, __nv_bfloat16* out, cudaStream_t stream);
+                 const float* bias_folded, __nv_bfloat16* out, cudaStream_t stream, int n_inner = 0, long long stride_outer = 0);
 
 // LeakyReLU(0.2) + F.interpolate(size=(T,1), mode='bilinear') + squeeze (model_layers.py:107,277-279) applied
 // to the centre column computed by the last encoder conv (pre-activation, split-K sums):

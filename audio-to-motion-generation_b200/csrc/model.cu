@@ -120,6 +120,10 @@ struct a2m_model {
     // per-forward mutable slots read by the op closures
     const float* cur_mel = nullptr;
     long long cur_stride_b = 0, cur_stride_t = 0;
+    int cur_n_inner = 0;                        // > 0: the batch is (streams x windows), a2m_model_forward_windows
+    long long cur_stride_outer = 0;
+    int next_n_inner = 0;
+    long long next_stride_outer = 0;
     float* cur_pose = nullptr;
     std::map<std::string, std::unique_ptr<ForwardPlan>> plans;
     unsigned long long plan_clock = 0;
@@ -712,7 +716,10 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
         if (m->has_encoder) {
             a2m_model* mm = m;
             E.tag = "enc.conv0";
-            E.op([=](cudaStream_t s) { return launch_conv0(mm->cur_mel, mm->cur_stride_b, mm->cur_stride_t, B, T, F, mm->conv0_w, mm->conv0_b, a0, s); });
+            E.op([=](cudaStream_t s) {
+                return launch_conv0(mm->cur_mel, mm->cur_stride_b, mm->cur_stride_t, B, T, F, mm->conv0_w, mm->conv0_b, a0, s,
+                                    mm->cur_n_inner, mm->cur_stride_outer);
+            });
             // in: [B, H (allocated rows, even), W, C]; out: [B, Ho_alloc, W / 2, N], rows [0, Ho) written
             auto conv2d_s2 = [&](const LayerW& L, const __nv_bfloat16* in, int H, int W, int C, __nv_bfloat16* out, int Ho, int Ho_alloc) {
                 const int Wo = W / 2;
@@ -992,6 +999,8 @@ extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t mel_str
     A2M_ARG_CHECK(mel_stride_t >= F && (B == 1 || mel_stride_b >= mel_stride_t), "a2m_model_forward: mel strides (%lld, %lld)",
                   (long long)mel_stride_b, (long long)mel_stride_t);
     m->cur_mel = mel; m->cur_stride_b = mel_stride_b; m->cur_stride_t = mel_stride_t;
+    m->cur_n_inner = m->next_n_inner; m->cur_stride_outer = m->next_stride_outer;
+    m->next_n_inner = 0; m->next_stride_outer = 0;
     // trunk on the caller's stream, then body decoder (side stream) || hand decoder (caller's stream)
     static const bool single_stream = getenv("A2M_DEBUG_SINGLE_STREAM") != nullptr;   // debugging aid
     const bool timeline = m->tl_steps < m->tl_capacity && m->tl_ops == static_cast<int>(P->ops.size());
@@ -1025,6 +1034,26 @@ extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t mel_str
         if (rc != A2M_OK) return rc;
     }
     return A2M_OK;
+}
+
+// Sliding-window generation over long streams (BASELINE config 4; the reference's window arithmetic, dataUtils.py:585-620,
+// 648-654): clip (s, w) reads log-mel rows start_w + t * stride_t of stream s IN PLACE -- one launch program for all
+// n_streams * n_windows clips, no window is ever gathered.
+extern "C" int a2m_model_forward_windows(a2m_model* m, const float* mel, int64_t stride_stream, int64_t stride_window,
+                                         int64_t stride_t, int64_t n_streams, int64_t n_windows, int T, int F, float* pose,
+                                         float* losses, void* stream) {
+    A2M_ARG_CHECK(m != nullptr, "a2m_model_forward_windows: NULL model");
+    A2M_ARG_CHECK(n_streams >= 1 && n_windows >= 1 && n_streams * n_windows <= 65535, "a2m_model_forward_windows: %lld streams x "
+                  "%lld windows (at most 65535 clips per call)", (long long)n_streams, (long long)n_windows);
+    A2M_ARG_CHECK(stride_window >= 1 && stride_stream >= 1 && stride_t >= F, "a2m_model_forward_windows: strides (%lld, %lld, %lld)",
+                  (long long)stride_stream, (long long)stride_window, (long long)stride_t);
+    A2M_ARG_CHECK(stride_window >= stride_t, "a2m_model_forward_windows: window stride %lld below the row stride %lld",
+                  (long long)stride_window, (long long)stride_t);
+    m->next_n_inner = static_cast<int>(n_windows);
+    m->next_stride_outer = stride_stream;
+    const int rc = a2m_model_forward(m, mel, stride_window, stride_t, n_streams * n_windows, T, F, pose, losses, nullptr, stream);
+    m->next_n_inner = 0;
+    return rc;
 }
 
 // Timeline of the next `steps` forwards of shape (B, T, F): an event after every op (and one at the start of each
@@ -1099,6 +1128,7 @@ extern "C" int a2m_model_encoder_forward_ex(a2m_model* m, const float* mel, int6
     if (!P) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     m->cur_mel = mel; m->cur_stride_b = static_cast<long long>(T) * F; m->cur_stride_t = F;
+    m->cur_n_inner = 0; m->cur_stride_outer = 0;
     rc = run_ops(P, 0, P->enc_end, s);
     if (rc != A2M_OK) return rc;
     return launch_btc_to_ncw(P->enc_out, static_cast<int>(B), 256, time_steps, out_nct, s);
@@ -1187,6 +1217,7 @@ int profile_impl(a2m_model* m, const float* mel, int64_t mel_stride_b, int64_t m
     ForwardPlan* P = get_plan(m, static_cast<int>(B), T, F, &rc);
     if (!P) return rc;
     m->cur_mel = mel; m->cur_stride_b = mel_stride_b; m->cur_stride_t = mel_stride_t;
+    m->cur_n_inner = 0; m->cur_stride_outer = 0;
     const int n = static_cast<int>(P->ops.size());
     std::vector<cudaEvent_t> ev(2 * n);
     for (auto& e : ev) A2M_CUDA_CHECK(cudaEventCreate(&e));

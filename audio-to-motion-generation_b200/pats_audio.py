@@ -95,18 +95,50 @@ def _plan_400(device_index, eps):
     return plan
 
 
+_resamplers = {}
+
+
+def resample(y, orig_sr, target_sr):
+    """librosa.core.resample(y, orig_sr=..., target_sr=...) on the GPU (band-limited sinc interpolation, resampy's
+    'kaiser_best' table; csrc/resample.cu): waveform [N] or batch [B, N] -> [ceil(N * target_sr / orig_sr)] fp32.
+    numpy in -> numpy out, torch in -> torch (CUDA) out."""
+    _cabi.require_cuda("resample")
+    wav, batched, was_numpy = mel_features._to_device(y)
+    if wav.dtype != torch.float32:
+        wav = wav.to(torch.float32)
+    if float(orig_sr) == float(target_sr):
+        out = wav.clone()
+    else:
+        key = (wav.device.index, float(orig_sr), float(target_sr))
+        plan = _resamplers.get(key)
+        if plan is None:
+            handle = ctypes.c_void_p()
+            _cabi.check(_cabi.lib().a2m_resample_plan_create(float(orig_sr), float(target_sr), wav.device.index,
+                                                             ctypes.byref(handle)))
+            plan = _resamplers[key] = handle
+        n_out = int(_cabi.lib().a2m_resample_out_length(plan, wav.shape[1]))
+        out = torch.empty((wav.shape[0], n_out), dtype=torch.float32, device=wav.device)
+        with torch.cuda.device(wav.device):
+            _cabi.check(_cabi.lib().a2m_resample_f32(plan, _cabi.ptr(wav), wav.shape[0], wav.shape[1], wav.stride(0),
+                                                     _cabi.ptr(out), _cabi.stream_ptr(wav.device)))
+    if not batched:
+        out = out[0]
+    return out.cpu().numpy() if was_numpy else out
+
+
 def log_mel_400(y, sr=16000, eps=1e-6):
     """pats/data_loading/audio.py:86-120 on the GPU: waveform [N] (or batch [B, N]) at 16 kHz ->
     log-mel [frames, 64] (``np.log(spec).transpose(1, 0)``), frames = 1 + (N - 512) // 160."""
     _cabi.require_cuda("log_mel_400")
-    if int(sr) != 16000:
-        raise NotImplementedError("log_mel_400: resampling from %s Hz is not implemented on the GPU path; "
-                                  "resample to 16 kHz first" % (sr,))
     if not isinstance(y, torch.Tensor):
         y = np.asarray(y)
         if y.ndim == 2 and y.shape[0] != 1 and y.shape[1] == 1:
             y = y.reshape(-1)                       # the reference flattens with y.reshape((-1))
     wav, batched, was_numpy = mel_features._to_device(y)
+    if float(sr) != 16000.0:                        # audio.py:87: resample to 16 kHz first
+        wav = resample(wav if batched else wav[0], sr, 16000)
+        if not batched:
+            wav = wav.unsqueeze(0)
     if wav.shape[1] < 512:
         raise ValueError("log_mel_400: %d samples are fewer than one 512-sample frame" % wav.shape[1])
     plan = _plan_400(wav.device.index, eps)

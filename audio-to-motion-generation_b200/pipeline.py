@@ -213,15 +213,16 @@ class AudioToPosePipeline:
         """Long-form audio (BASELINE config 4): wav [B, N] (e.g. 60 s = 960 000 samples) -> poses
         [B, n_windows, 64, 104].  The log-mel of every stream is computed once; each clip's overlapping windows
         (384-frame span, stride 6, hop window_hop * 6 frames -- the reference's window arithmetic) are fed to the
-        generator as one strided view per clip, so no window is ever materialised."""
+        generator in place by ONE launch program for all streams (SelfAttention_G.forward_windows), so no window is ever
+        materialised and nothing loops over clips."""
         logmel = self.features(wav)                                        # [B, frames, 64 | 128]
-        out = []
-        for b in range(logmel.shape[0]):
-            x = sliding_windows(logmel[b], window_hop=window_hop)
-            if x.shape[0] == 0:
-                raise ValueError("the audio is shorter than one window (%d log-mel frames)" % logmel.shape[1])
-            out.append(self.model(x, lane=lane)[0])
-        return torch.stack(out)
+        n_win = len(window_starts(logmel.shape[1], window_hop=window_hop))
+        if n_win == 0:
+            raise ValueError("the audio is shorter than one window (%d log-mel frames)" % logmel.shape[1])
+        per_call = max(1, 65535 // n_win)                                  # streams per launch program
+        out = [self.model.forward_windows(logmel[b:b + per_call], n_win, POSE_FRAMES, ADAPTER_STRIDE, window_hop, lane=lane)
+               for b in range(0, logmel.shape[0], per_call)]
+        return out[0] if len(out) == 1 else torch.cat(out)
 
     def step(self, wav, gt_pose, done_event=None):
         """One batch, inputs already on the device: enqueues mel -> generator -> evaluation on the next lane and

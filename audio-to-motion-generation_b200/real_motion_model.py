@@ -196,6 +196,27 @@ class SelfAttention_G(NativeModule):
                 std.record_stream(torch.cuda.current_stream(h.device))
         h.denorm_token = token
 
+    def forward_windows(self, logmel, n_windows, frames=64, stride=6, window_hop=5, lane=0):
+        """Sliding windows over long streams in ONE launch program: logmel [S, n_frames, F] (unit inner stride) -> pose
+        [S, n_windows, frames, 104]; window w of stream s reads log-mel rows w * window_hop * stride + t * stride in place
+        (the reference's window arithmetic, dataUtils.py:585-620,648-654; S * n_windows <= 65535)."""
+        self._require_eval()
+        h = self.native(lane)
+        self._sync_denorm(h)
+        x = as_input(logmel, h.device, "forward_windows expects log-mel [S, n_frames, F], got %s", keep_strides=True)
+        S, n_frames, F = x.shape
+        last = (n_windows - 1) * window_hop * stride + (frames - 1) * stride
+        if n_windows < 1 or last >= n_frames:
+            raise ValueError("%d windows of %d frames (stride %d, hop %d) need %d log-mel frames, got %d"
+                             % (n_windows, frames, stride, window_hop, last + 1, n_frames))
+        pose = torch.empty((S, n_windows, frames, 104), dtype=torch.float32, device=h.device)
+        losses = torch.empty(2, dtype=torch.float32, device=h.device)
+        with torch.cuda.device(h.device):
+            _cabi.check(_cabi.lib().a2m_model_forward_windows(
+                h.ptr, _cabi.ptr(x), x.stride(0), window_hop * stride * x.stride(1), stride * x.stride(1), S, n_windows, frames, F,
+                _cabi.ptr(pose), _cabi.ptr(losses), _cabi.stream_ptr(h.device)))
+        return pose
+
     def forward(self, audio, real_pose=None, lane=0):
         """audio [B, T, F] (log-mel) -> (pose [B, T, 104] fp32, [angle_loss]) or
         (pose, [bone_loss, angle_loss]) when real_pose [B, T, 104] is given.  `lane` (an extension) selects one of

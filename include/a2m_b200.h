@@ -108,6 +108,19 @@ int a2m_melspec_f32(const a2m_melspec_plan* plan, const float* wav, int64_t n_cl
 
 
 /* ------------------------------------------------------------------------------------------------
+ * resampling: replaces the first step of pats/data_loading/audio.py:86-120 log_mel_400,
+ * librosa.core.resample(y, orig_sr=sr, target_sr=16000) -- band-limited sinc interpolation with resampy's
+ * 'kaiser_best' table (third-party, absent and unpinned in the reference: restated from its published algorithm).
+ * wav: [n_clips] rows of n_samples fp32 (row stride wav_stride) -> out [n_clips, a2m_resample_out_length()] fp32.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct a2m_resample_plan a2m_resample_plan;
+int a2m_resample_plan_create(double orig_sr, double target_sr, int device, a2m_resample_plan** out);
+void a2m_resample_plan_destroy(a2m_resample_plan* plan);
+int64_t a2m_resample_out_length(const a2m_resample_plan* plan, int64_t n_samples);     /* ceil(n * target / orig) */
+int a2m_resample_f32(const a2m_resample_plan* plan, const float* wav, int64_t n_clips, int64_t n_samples,
+                     int64_t wav_stride, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * evaluation: replaces motion_evaluation.py:4-23 compute_pck()/compute_pck_radius() and the
  * nn.L1Loss() metric of version5_model_train.py:264,367,467 (on poses and on pos_to_motion :208-213).
  *
@@ -263,6 +276,13 @@ void a2m_model_destroy(a2m_model* model);
 int a2m_model_forward(a2m_model* model, const float* mel, int64_t mel_stride_b, int64_t mel_stride_t, int64_t B, int T,
                       int F, float* pose, float* losses, const float* real_pose /* nullable [B, T, 104] */,
                       void* stream);
+/* Sliding-window generation over long streams (BASELINE config 4; window arithmetic of pats/data_loading/dataUtils.py:
+ * 585-620,648-654): clip (s, w) = rows w * (stride_window / row) + t * (stride_t / row) of stream s, read in place --
+ * mel element (s, w, t, f) at mel[s * stride_stream + w * stride_window + t * stride_t + f]; one launch program for all
+ * n_streams * n_windows (<= 65535) clips.  pose: [n_streams * n_windows, T, 104]. */
+int a2m_model_forward_windows(a2m_model* model, const float* mel, int64_t stride_stream, int64_t stride_window,
+                              int64_t stride_t, int64_t n_streams, int64_t n_windows, int T, int F, float* pose,
+                              float* losses, void* stream);
 /* AudioEncoder.forward (model_layers.py:267-280): mel [B, T, F] -> [B, 256, T] fp32 (reference NCW layout) */
 /* Optional fused output de-normalisation (generate_motion_video.py:259-260): when
  * set, a2m_model_forward writes pose * std + mean (single fp32 multiply then add, equal to

@@ -79,3 +79,60 @@ def log_mel_512(y, sr, eps=1e-10, pad_mode="reflect"):
     spec = stft_power_centred(y, 2048, 512, pad_mode) @ filterbank(sr, 2048, 128, 0.0, sr / 2.0, area_norm=True).T
     spec = np.where(spec == 0, eps, spec)
     return np.log(spec)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# resampling (log_mel_400's first step, audio.py:87: librosa.core.resample(y, orig_sr=sr, target_sr=16000))
+# PARITY UNPINNED like the rest of this file: librosa (and resampy, which implements its 'kaiser_best' mode, the
+# default up to librosa 0.9) are absent.  Restated from resampy's published algorithm: band-limited sinc interpolation
+# (J. O. Smith) with a Kaiser-windowed sinc table -- 64 zero crossings, 2^9 table entries per crossing, beta
+# 14.769656459379492, roll-off 0.9475937167399596 -- linearly interpolated between table entries; the output has
+# ceil(n * ratio) samples (librosa's fix_length of resampy's int(n * ratio)), no amplitude scaling (scale=False).
+# ---------------------------------------------------------------------------------------------------------------
+KAISER_BEST = dict(num_zeros=64, precision=9, beta=14.769656459379492, rolloff=0.9475937167399596)
+
+
+def sinc_table(num_zeros=64, precision=9, beta=14.769656459379492, rolloff=0.9475937167399596):
+    """resampy.filters.sinc_window with a Kaiser taper: (interp_win [num_zeros * 2^precision + 1], 2^precision)."""
+    num_bits = 2 ** precision
+    n = num_bits * num_zeros
+    sinc_win = rolloff * np.sinc(rolloff * np.linspace(0, num_zeros, num=n + 1, endpoint=True))
+    taper = np.kaiser(2 * n + 1, beta)[n:]
+    return taper * sinc_win, num_bits
+
+
+def resample(y, orig_sr, target_sr):
+    """fp64 restatement of resampy.resample(y, orig_sr, target_sr, filter='kaiser_best') + librosa's fix_length."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    if orig_sr == target_sr:
+        return y.copy()
+    ratio = float(target_sr) / orig_sr
+    interp_win, num_table = sinc_table(**KAISER_BEST)
+    if ratio < 1:
+        interp_win = interp_win * ratio
+    interp_delta = np.zeros_like(interp_win)
+    interp_delta[:-1] = np.diff(interp_win)
+    n_orig, n_out = y.size, int(y.size * ratio)
+    out = np.zeros(int(np.ceil(y.size * ratio)))
+    scale = min(1.0, ratio)
+    index_step = int(scale * num_table)
+    nwin = interp_win.size
+    for t in range(n_out):
+        time_register = t / ratio
+        n = int(time_register)
+        frac = scale * (time_register - n)
+        index_frac = frac * num_table
+        offset = int(index_frac)
+        eta = index_frac - offset
+        i = np.arange(min(n + 1, (nwin - offset) // index_step))
+        idx = offset + i * index_step
+        acc = np.dot(interp_win[idx] + eta * interp_delta[idx], y[n - i])
+        frac = scale - frac
+        index_frac = frac * num_table
+        offset = int(index_frac)
+        eta = index_frac - offset
+        k = np.arange(min(n_orig - n - 1, (nwin - offset) // index_step))
+        idx = offset + k * index_step
+        acc += np.dot(interp_win[idx] + eta * interp_delta[idx], y[n + k + 1])
+        out[t] = acc
+    return out

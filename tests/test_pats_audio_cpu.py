@@ -87,3 +87,20 @@ def test_log_mel_512_oracle_known_answers():
     zr = pats_oracle.stft_power_centred(y, 2048, 512, "reflect")
     np.testing.assert_allclose(zc[3:-3], zr[3:-3], rtol=1e-12)          # interior frames never see the padding
     assert not np.allclose(zc[0], zr[0])
+
+
+def test_resample_oracle_known_answers():
+    """The restated resampler: output length ceil(n * ratio); a sine below both Nyquist rates survives a 44.1 -> 16 kHz
+    conversion to within the filter's gain error (resampy's integer table step: < 0.5 %); equal rates are the identity;
+    the Kaiser-windowed sinc table starts at the roll-off and ends at zero."""
+    win, bits = pats_oracle.sinc_table(**pats_oracle.KAISER_BEST)
+    assert bits == 512 and win.size == 64 * 512 + 1 and abs(win[0] - 0.9475937167399596) < 1e-15 and abs(win[-1]) < 1e-7
+    n, sr = 5000, 44100
+    t = np.arange(n) / sr
+    y = np.sin(2 * np.pi * 440 * t)
+    out = pats_oracle.resample(y, sr, 16000)
+    assert out.size == int(np.ceil(n * 16000 / sr))
+    ref = np.sin(2 * np.pi * 440 * np.arange(out.size) / 16000)
+    assert np.abs(out[200:-200] - ref[200:-200]).max() < 5e-3
+    assert np.array_equal(pats_oracle.resample(y, sr, sr), y)
+    assert pats_oracle.resample(y[:1000], 8000, 16000).size == 2000

@@ -51,10 +51,32 @@ def test_zeros_floor_and_batches(pa):
     for b in (0, 4):
         close(got[b].cpu().numpy(), pats_oracle.log_mel_400(wav[b]))
     assert torch.equal(got[2], pa.log_mel_400(torch.from_numpy(wav[2]).cuda()))       # batch invariance
-    with pytest.raises(NotImplementedError):
-        pa.log_mel_400(wav[0], 44100)
     with pytest.raises(ValueError):
         pa.log_mel_400(np.zeros(511, np.float32), 16000)
+
+
+@pytest.mark.parametrize("orig,target,n", [(44100, 16000, 9000), (22050, 16000, 7001), (8000, 16000, 3000), (48000, 16000, 6000)])
+def test_resample_matches_oracle(pa, orig, target, n):
+    """librosa.core.resample (audio.py:87) restated from resampy's published 'kaiser_best' algorithm (parity unpinned:
+    librosa / resampy are absent).  fp32 taps against the fp64 oracle: max|a - b| <= 2e-6 * max|b| + 1e-6."""
+    y = synth.wav_clip(60, n)
+    got = pa.resample(y, orig, target)
+    ref = pats_oracle.resample(y, orig, target)
+    assert isinstance(got, np.ndarray) and got.shape == ref.shape == (int(np.ceil(n * target / orig)),)
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max() + 1e-6, np.abs(got - ref).max()
+    both = pa.resample(torch.from_numpy(np.stack([y, 2 * y])).cuda(), orig, target)
+    assert both.is_cuda and torch.equal(both[0].cpu(), torch.from_numpy(got)) and torch.allclose(both[1], 2 * both[0])
+
+
+def test_log_mel_400_resamples_first(pa):
+    """log_mel_400(y, sr != 16000) = log_mel_400(resample(y, sr, 16000), 16000) (audio.py:87-120)."""
+    y = synth.wav_clip(61, 30000)
+    got = pa.log_mel_400(y, 44100)
+    y16 = pats_oracle.resample(y, 44100, 16000)
+    ref = pats_oracle.log_mel_400(y16)
+    assert got.shape == ref.shape
+    close(got, ref)
+    assert np.array_equal(pa.resample(y, 16000, 16000), y)
 
 
 @pytest.mark.parametrize("kind,n,idx,sr,pad", [("noise", 30000, 21, 44100, "reflect"), ("noise", 30000, 21, 44100, "constant"),

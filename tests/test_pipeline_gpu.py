@@ -113,6 +113,8 @@ def test_long_form_sliding_windows(setup):
     gathered = torch.stack([lm[s:s + 384:6] for s in starts]).contiguous()
     assert torch.equal(view, gathered)
     assert torch.equal(model(view)[0], model(gathered)[0])
+    # one launch program over all streams x windows gives, clip for clip, what a forward per clip gives
+    assert torch.equal(poses[0], model(view)[0].cpu())
 
 
 def test_long_form_full_size_shape(setup):
