@@ -59,38 +59,8 @@ inline cudaError_t a2m_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr.val.programmaticStreamSerializationAllowed = 1;
-    static const bool no_pdl = getenv("A2M_DEBUG_NO_PDL") != nullptr;       // debugging aid: plain stream order
     cfg.attrs = &attr;
-    cfg.numAttrs = no_pdl ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
-// The same for a kernel launched in thread-block clusters of `cluster_x` CTAs along x (1 = no cluster attribute).
-template <typename... KArgs, typename... Args>
-inline cudaError_t a2m_launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                          int cluster_x, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    int n = 0;
-    static const bool no_pdl = getenv("A2M_DEBUG_NO_PDL") != nullptr;
-    if (!no_pdl) {
-        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[n].val.programmaticStreamSerializationAllowed = 1;
-        ++n;
-    }
-    if (cluster_x > 1) {
-        attr[n].id = cudaLaunchAttributeClusterDimension;
-        attr[n].val.clusterDim.x = cluster_x;
-        attr[n].val.clusterDim.y = 1;
-        attr[n].val.clusterDim.z = 1;
-        ++n;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = n;
+    cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -196,26 +166,6 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const void* desc, uint64_
         "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
-// The same load delivered to the same shared-memory offset (and signalling the mbarrier at the same offset) of every CTA
-// of the cluster named in cta_mask
-__device__ __forceinline__ void tma_load_5d_multicast(void* dst, const void* desc, uint64_t* bar, int c0, int c1, int c2,
-                                                      int c3, int c4, uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
-        "r"(c2), "r"(c3), "r"(c4), "h"(cta_mask)
-        : "memory");
-}
-// ------------------------------- thread-block clusters -----------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {      // every thread of every CTA of the cluster
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // TMA store shared -> global (bulk async group); OOB parts of the box are clipped
 __device__ __forceinline__ void tma_store_5d(const void* desc, const void* src, int c0, int c1, int c2, int c3, int c4) {
     asm volatile(
@@ -276,12 +226,6 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// the same arrive delivered to the mbarrier at this offset in every CTA of cta_mask
-__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(cta_mask)
                  : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

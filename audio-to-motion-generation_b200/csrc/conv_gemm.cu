@@ -38,12 +38,9 @@ struct Smem {
     static constexpr int kTotal = kBiasOffset + BLOCK_N * 4 + 1024;      // + alignment slack
 };
 
-// CLUSTER = 2: the two CTAs of a cluster own neighbouring M tiles of the same N tile, so they need the same weight
-// tile: each fetches half of it and TMA-multicasts that half into both CTAs' rings (operand bytes from L2 per CTA and
-// K block: 16 + BLOCK_N / 16 KB instead of 16 + BLOCK_N / 8 KB).  A ring slot is then written by both producers, so its
-// "empty" barrier collects the release of both MMA issuers (tcgen05.commit multicast), and neither CTA may exit while
-// the other can still signal it.
-template <int BLOCK_N, int STAGES, int CLUSTER>
+// (A 2-CTA-cluster variant that multicast the shared weight tile was measured and retired: the coupling of the two CTAs
+// cost more than the halved weight traffic saved on every layer class of this model -- DESIGN.md section 4.)
+template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kThreads)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restrict__ bias, void* __restrict__ out,
                  int* __restrict__ err_flag) {
@@ -80,7 +77,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
         tma_prefetch_desc(&p.a_map[0]);
         tma_prefetch_desc(&p.a_map[1]);
         tma_prefetch_desc(&p.b_map);
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CLUSTER); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(accum_bar, 1);
         mbar_fence_init();
     }
@@ -89,10 +86,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
         tmem_relinquish();
     }
     tc_fence_before();
-    if (CLUSTER > 1) cluster_sync_all();             // the peer's barriers exist before anything is multicast to them
-    else __syncthreads();
+    __syncthreads();
     tc_fence_after();
-    const uint32_t cta_rank = CLUSTER > 1 ? cluster_ctarank() : 0;
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();                                      // the prologue above overlapped the previous kernel's tail
 
@@ -112,15 +107,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
                     mbar_expect_tx(&full_bar[s], S::kStageBytes);
                     unsigned char* stage = smem + s * S::kStageBytes;
                     tma_load_5d(stage, amap, &full_bar[s], ch * kBlockK, c1, c2, c3, c4);
-                    if (CLUSTER > 1) {               // my half of the weight tile (box = BLOCK_N / 2 rows) to both CTAs
-                        constexpr int kHalf = BLOCK_N / 2;
-                        tma_load_5d_multicast(stage + kABytes + cta_rank * (kHalf * kBlockK * 2), &p.b_map, &full_bar[s],
-                                              kb * kBlockK, n0 + static_cast<int>(cta_rank) * kHalf, 0, 0, 0, 0x3);
-                    } else {
-                        tma_load_5d(stage + kABytes, &p.b_map, &full_bar[s], kb * kBlockK, n0, 0, 0, 0);   // all maps are rank 5
-                        if (BLOCK_N > 128)           // the weight box is 128 rows: second half of a 256-wide tile
-                            tma_load_5d(stage + kABytes + 128 * kBlockK * 2, &p.b_map, &full_bar[s], kb * kBlockK, n0 + 128, 0, 0, 0);
-                    }
+                    tma_load_5d(stage + kABytes, &p.b_map, &full_bar[s], kb * kBlockK, n0, 0, 0, 0);   // all maps are rank 5
+                    if (BLOCK_N > 128)               // the weight box is 128 rows: second half of a 256-wide tile
+                        tma_load_5d(stage + kABytes + 128 * kBlockK * 2, &p.b_map, &full_bar[s], kb * kBlockK, n0 + 128, 0, 0, 0);
                 }
             }
         }
@@ -139,8 +128,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
                     umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
                               (kb | k) != 0);
                 }
-                if (CLUSTER > 1) umma_commit_multicast(&empty_bar[s], 0x3);     // both producers write this slot
-                else umma_commit(&empty_bar[s]);     // slot reusable once these MMAs have read it
+                umma_commit(&empty_bar[s]);          // slot reusable once these MMAs have read it
             }
             umma_commit(accum_bar);                  // accumulator complete
         }
@@ -261,8 +249,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
         }
     }
     tc_fence_before();
-    if (CLUSTER > 1) cluster_sync_all();             // the peer may still release ring slots of this CTA until it is done
-    else __syncthreads();
+    __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -352,15 +339,15 @@ int make_map(CUtensorMap* map, const void* ptr, int rank, const long long* dims,
     return A2M_OK;
 }
 
-template <int BLOCK_N, int STAGES, int CLUSTER>
+template <int BLOCK_N, int STAGES>
 int launch_variant(const ConvGemmPlan& plan, int* err_flag, cudaStream_t stream) {
     static A2mPerDeviceOnce configured;
     if (configured.first()) {
-        A2M_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Smem<BLOCK_N, STAGES>::kTotal));
     }
-    A2M_CUDA_CHECK(a2m_launch_pdl_cluster(conv_gemm_kernel<BLOCK_N, STAGES, CLUSTER>, plan.grid, dim3(kThreads),
-                                          Smem<BLOCK_N, STAGES>::kTotal, stream, CLUSTER, plan.p, plan.bias, plan.out, err_flag));
+    A2M_CUDA_CHECK(a2m_launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES>, plan.grid, dim3(kThreads), Smem<BLOCK_N, STAGES>::kTotal,
+                                  stream, plan.p, plan.bias, plan.out, err_flag));
     a2m_count_launch();
     return A2M_OK;
 }
@@ -441,17 +428,9 @@ int conv_gemm_plan(const ConvGemmDesc& d, const void* w_packed, const float* bia
     if (d.N <= 32) block_n = 32;
     else if (d.N <= 64) block_n = 64;
     else if (d.block_n_hint == 256 && d.N % 256 == 0 && d.out_type == kOutBf16 && d.split_k == 1) block_n = 256;
-    // neighbouring M tiles pair up in a 2-CTA cluster that shares (multicasts) the weight tile
-    long long m_tiles_x = 1;
-    for (int i = 0; i < 4; ++i) m_tiles_x *= (d.m_extent[i] + d.box[i] - 1) / d.box[i];
-    static const char* cluster_env = getenv("A2M_GEMM_CLUSTER");
-    // measured: the coupling of the two CTAs and the cluster barriers cost more than the halved
-    // weight traffic saves on every layer class of this model, so the variant is opt-in (A2M_GEMM_CLUSTER=1)
-    const int cluster = (block_n >= 128 && m_tiles_x % 2 == 0 && cluster_env && atoi(cluster_env) != 0) ? 2 : 1;
-    plan->cluster = cluster;
     {
         long long wd[2] = {K, d.N}, ws[2] = {1, K};
-        int wb[5] = {kBlockK, cluster == 2 ? block_n / 2 : (block_n > 128 ? 128 : block_n), 1, 1, 1};
+        int wb[5] = {kBlockK, block_n > 128 ? 128 : block_n, 1, 1, 1};
         const int rc = make_map(&p.b_map, w_packed, 2, wd, ws, wb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "weight map");
         if (rc != A2M_OK) return rc;
     }
@@ -512,9 +491,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, const void* w_packed, const float* bia
     plan->block_n = block_n;
     {   // short K loops (decoder layers): two 32 KB stages let a third CTA -- typically the next layer's, launched
         // programmatically -- become resident while this layer's CTAs drain
-        static const char* env = getenv("A2M_GEMM_STAGES2");
-        const int mode = env ? atoi(env) : 1;
-        plan->stages = (mode && block_n == 128 && (kb <= 16 || mode == 2)) ? 2 : 3;     // mode 2 (experiment): every 128-wide layer
+        plan->stages = (block_n == 128 && kb <= 16) ? 2 : 3;
     }
     plan->grid = dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>((d.N + block_n - 1) / block_n),
                       static_cast<unsigned>(d.split_k));
@@ -524,13 +501,10 @@ int conv_gemm_plan(const ConvGemmDesc& d, const void* w_packed, const float* bia
 
 int conv_gemm_launch(const ConvGemmPlan& plan, int* err_flag, cudaStream_t stream) {
     switch (plan.block_n) {
-        case 32: return launch_variant<32, 3, 1>(plan, err_flag, stream);
-        case 64: return launch_variant<64, 3, 1>(plan, err_flag, stream);
-        case 128:
-            if (plan.cluster == 2)
-                return plan.stages == 2 ? launch_variant<128, 2, 2>(plan, err_flag, stream) : launch_variant<128, 3, 2>(plan, err_flag, stream);
-            return plan.stages == 2 ? launch_variant<128, 2, 1>(plan, err_flag, stream) : launch_variant<128, 3, 1>(plan, err_flag, stream);
-        case 256: return plan.cluster == 2 ? launch_variant<256, 4, 2>(plan, err_flag, stream) : launch_variant<256, 4, 1>(plan, err_flag, stream);
+        case 32: return launch_variant<32, 3>(plan, err_flag, stream);
+        case 64: return launch_variant<64, 3>(plan, err_flag, stream);
+        case 128: return plan.stages == 2 ? launch_variant<128, 2>(plan, err_flag, stream) : launch_variant<128, 3>(plan, err_flag, stream);
+        case 256: return launch_variant<256, 4>(plan, err_flag, stream);
         default: a2m_set_error("conv_gemm_launch: block_n %d", plan.block_n); return A2M_ERR_STATE;
     }
 }

@@ -85,7 +85,6 @@ struct ConvGemmPlan {
     void* out;
     int block_n;
     int stages;                 // shared-memory ring depth of the 128 x 128 variant (2 or 3)
-    int cluster;                // 2: pairs of M tiles share the weight tile by TMA multicast; 1: no cluster
     dim3 grid;
     long long flops;            // 2 * M * N * K of the valid output rows
 };

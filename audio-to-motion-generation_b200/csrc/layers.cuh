@@ -35,15 +35,6 @@ int attn_fused_plan(const __nv_bfloat16* w_qkv, const float* bias_qkv, const flo
                     const float* ca_b2 = nullptr);      // ca_*: optional ChannelAttention (hidden 32) fused into the epilogue
 int attn_fused_launch(const AttnFusedPlan& plan, int* err_flag, cudaStream_t stream);
 
-// Fused ResBlock (conv3 -> conv3 -> SelfAttention + skip) for T = 64, C = 256 (csrc/resblock_fused.cu): the activations
-// stay in shared memory between the layers, only the weights stream.  t2 is a [B * T][256] scratch the kernel writes.
-struct ResblockFusedPlan;
-bool resblock_fused_supported(int T, int C);
-int resblock_fused_plan(const __nv_bfloat16* w1, const float* bias1, const __nv_bfloat16* w2, const float* bias2,
-                        const __nv_bfloat16* w_qkv, const float* bias_qkv, const float* gamma, const __nv_bfloat16* x,
-                        __nv_bfloat16* t2, int B, int T, int C, __nv_bfloat16* out, std::shared_ptr<ResblockFusedPlan>* plan);
-int resblock_fused_launch(const ResblockFusedPlan& plan, int* err_flag, cudaStream_t stream);
-
 // Tensor-core attention core for the wide UNet attentions (csrc/attn_core.cu), after the q|k|v GEMM: T must divide
 // 128, C a multiple of 256 with C / 8 in {64, 128, 192, 256}.
 struct AttnCorePlan;

@@ -512,11 +512,9 @@ struct Emit {
         d.taps = std::move(taps);
         d.N = L.N; d.out_base = obase; d.act = act >= 0 ? act : L.act; d.out_type = out_type; d.split_k = split_k; d.split_stride = split_stride;
         {   // wide layers with enough tiles to fill the SMs run 128 x 256 tiles (one CTA per SM, fewer operand bytes per FLOP)
-            static const char* env = getenv("A2M_GEMM_BN256");
-            const int mode = env ? atoi(env) : 1;
             long long m_tiles = 1;
             for (int i = 0; i < 4; ++i) m_tiles *= (ext[i] + box[i] - 1) / box[i];
-            if (mode && L.N % 256 == 0 && L.N >= (mode == 2 ? 256 : 512) && m_tiles * (L.N / 256) >= 120) d.block_n_hint = 256;
+            if (L.N % 256 == 0 && L.N >= 512 && m_tiles * (L.N / 256) >= 120) d.block_n_hint = 256;
         }
         auto plan = std::make_shared<ConvGemmPlan>();
         rc = conv_gemm_plan(d, L.w, L.bias, out, plan.get());
@@ -600,8 +598,7 @@ struct Emit {
 
     // SelfAttention followed by ChannelAttention (the hand decoder's order): one kernel when the fused block applies
     bool attention_then_channel(const AttnW& A, const ChanW& W, const __nv_bfloat16* x, int len, int B, __nv_bfloat16* out) {
-        static const bool unfused = getenv("A2M_NO_CHAN_FUSION") != nullptr;       // A/B aid
-        if (unfused || !attn_fused_supported(len, A.C) || W.C != A.C || W.hidden != 32) return false;
+        if (!attn_fused_supported(len, A.C) || W.C != A.C || W.hidden != 32) return false;
         attention(A, x, nullptr, len, B, nullptr, out, &W);
         return true;
     }
@@ -620,8 +617,7 @@ struct Emit {
             return;
         }
         linear_rows(A.qkv, x, nullptr, C, static_cast<long long>(B) * len, qkv, ld, 0, kOutBf16);
-        static const bool no_core = getenv("A2M_ATTN_CUDA_CORES") != nullptr;     // A/B aid
-        if (attn_core_supported(len, C) && !no_core) {    // wide UNet attentions: S, P.v on the tensor cores
+        if (attn_core_supported(len, C)) {                // wide UNet attentions: S, P.v on the tensor cores
             if (dry || rc != A2M_OK) return;
             std::shared_ptr<AttnCorePlan> cp;
             rc = attn_core_plan(qkv, gamma, x, res2, B, len, C, out, &cp);
@@ -638,21 +634,8 @@ struct Emit {
     // ResBlock (model_layers.py:185-190): x -> conv1 -> conv2 -> attention -> + x
     void resblock(const ResW& R, const __nv_bfloat16* x, int len, int B, __nv_bfloat16* t1, __nv_bfloat16* t2,
                   __nv_bfloat16* qkv, __nv_bfloat16* out) {
-        // experimental, opt-in (A2M_RESBLOCK_FUSION=1): parity-green and 24 % faster than its three launches in isolation
-        // (45 vs 59 us), but it holds a whole SM (206 KB of shared memory) for that long, while the three small kernels
-        // interleave with the other stream lane -- in the pipeline the step got 2 % slower
-        static const bool fused = getenv("A2M_RESBLOCK_FUSION") != nullptr && atoi(getenv("A2M_RESBLOCK_FUSION")) != 0;
-        if (fused && resblock_fused_supported(len, 256) && R.c1.N == 256 && R.c2.N == 256 && R.attn.C == 256 &&
-            R.c1.act == kActLeaky && R.c2.act == kActLeaky) {                       // whole block in one kernel
-            if (dry || rc != A2M_OK) return;
-            std::shared_ptr<ResblockFusedPlan> rp;
-            rc = resblock_fused_plan(R.c1.w, R.c1.bias, R.c2.w, R.c2.bias, R.attn.qkv.w, R.attn.qkv.bias, R.attn.gamma, x, t2, B,
-                                     len, 256, out, &rp);
-            if (rc != A2M_OK) return;
-            int* flag = m->err_flag;
-            op([rp, flag](cudaStream_t s) { return resblock_fused_launch(*rp, flag, s); });
-            return;
-        }
+        // (a one-kernel ResBlock with the activations resident in shared memory was built and retired:
+        // tools/probes/retired/resblock_fused.cu)
         const int C = R.attn.C;
         conv_k3(R.c1, x, C, nullptr, 0, len, B, t1);
         conv_k3(R.c2, t1, C, nullptr, 0, len, B, t2);
@@ -1002,13 +985,8 @@ extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t mel_str
     m->cur_n_inner = m->next_n_inner; m->cur_stride_outer = m->next_stride_outer;
     m->next_n_inner = 0; m->next_stride_outer = 0;
     // trunk on the caller's stream, then body decoder (side stream) || hand decoder (caller's stream)
-    static const bool single_stream = getenv("A2M_DEBUG_SINGLE_STREAM") != nullptr;   // debugging aid
     const bool timeline = m->tl_steps < m->tl_capacity && m->tl_ops == static_cast<int>(P->ops.size());
     if (timeline) A2M_CUDA_CHECK(cudaEventRecord(m->tl_events[static_cast<size_t>(m->tl_steps) * (m->tl_ops + 1)], s));    // step start
-    if (single_stream) {
-        rc = run_ops(P, 0, static_cast<int>(P->ops.size()), s, m);
-        if (rc != A2M_OK) return rc;
-    } else {
     rc = run_ops(P, 0, P->unet_end, s, m);
     if (rc != A2M_OK) return rc;
     A2M_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
@@ -1019,7 +997,6 @@ extern "C" int a2m_model_forward(a2m_model* m, const float* mel, int64_t mel_str
     rc = run_ops(P, P->body_end, static_cast<int>(P->ops.size()), s, m);
     if (rc != A2M_OK) return rc;
     A2M_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join, 0));
-    }
     if (timeline) ++m->tl_steps;
     float* stage = P->pose_stage;
     if (m->denorm_on) {     // x * std + mean (generate_motion_video.py:259-260) instead of the plain copy out of the arena

@@ -163,25 +163,6 @@ def test_weight_update_repacks(mods):
     assert rel_l1(b, ref) <= REL_L1
 
 
-def test_experimental_fused_resblock_keeps_parity():
-    """The opt-in fused ResBlock kernel (csrc/resblock_fused.cu: conv -> conv -> attention + skip with the activations
-    resident in shared memory, convolution taps as row-shifted descriptors, one M = 64 MMA per clip) is selected by an
-    environment variable the library reads once, so it is exercised in a child process: same golden cases, same bar."""
-    import os
-    import re
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, A2M_RESBLOCK_FUSION="1")
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "parity_report.py")], env=env, capture_output=True,
-                         text=True, timeout=300)
-    assert out.returncode == 0, out.stderr[-2000:]
-    margins = re.findall(r"model (\S+)\s+pose rel-L1 ([0-9.e+-]+)", out.stdout)
-    assert len(margins) >= 2, out.stdout
-    for name, rel in margins:
-        assert float(rel) <= 1e-2, (name, rel)
-
-
 def test_timeline_api_orders_ops_on_one_time_axis(pkg):
     """a2m_model_timeline_begin / _read: one event per op of the recorded forwards, milliseconds on a device-wide axis;
     ops of one stream are ordered, the decoder fork starts after the UNet, recording stops after `steps` forwards."""
