@@ -80,6 +80,15 @@ __device__ __forceinline__ uint32_t idesc_b_mn(uint32_t m, uint32_t n) { return 
 // =====================================================================================================
 namespace v4 {
 
+#ifdef A2M_GNN_TRACE            // probe build only (tools/probes/gnn_trace.sh): clock stamps of CTA 0's MMA issuer
+__device__ long long g_gnn_trace[128];
+#define GNN_STAMP(i) do { if (blockIdx.x == 0 && tid == 0 && it == 1) g_gnn_trace[(i)] = clock64(); } while (0)
+#define GNN_TILE_STAMP(i) do { if (blockIdx.x == 0 && tid == 0 && it < 20) g_gnn_trace[64 + it * 3 + (i)] = clock64(); } while (0)
+#else
+#define GNN_STAMP(i) do { } while (0)
+#define GNN_TILE_STAMP(i) do { } while (0)
+#endif
+
 constexpr int kThreads4 = 256;
 constexpr int kOffW4 = 0;                               // 3 x 8 KB weight slots
 constexpr int kOffU4 = 24576;                           // GAT attention rows [16][64] bf16
@@ -237,7 +246,9 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
         const int group = static_cast<int>(tile / p.tiles_per_group);
         const int row0 = static_cast<int>(tile - static_cast<long long>(group) * p.tiles_per_group) * rows_per_tile;
         const bool live = valid_row && row0 + r < group_rows;
+        GNN_TILE_STAMP(0);
         mbar_wait(x_bar, static_cast<uint32_t>(it & 1), err_flag, 40);
+        GNN_TILE_STAMP(1);
         float x[32];                                   // residual stream: this thread's 32 features in fp32
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -255,6 +266,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                                             : tid < 128 ? p.ln_w[layer] : p.ln_b[layer];
                 s_par[tid] = __ldg(src + (tid & 63));
             }
+            GNN_STAMP(layer * 12);
             if ((layer & 1) == 0) {
                 // ================= GATConv =================
                 if (tid == 0) {
@@ -268,6 +280,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 mbar_wait(s_bar, spar, err_flag, 43);
                 spar ^= 1;
                 tc_fence_after();
+                GNN_STAMP(layer * 12 + 1);
                 if (tid == 0 && !(layer == 4 && it + 1 == my_tiles)) load_u(layer == 4 ? 0 : (layer >> 1) + 1);
                 float sd0, sd1;                          // destination logits of my heads: half, half + 2
                 {
@@ -284,9 +297,11 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 }
                 tc_fence_before();
                 __syncthreads();                        // s_src visible
+                GNN_STAMP(layer * 12 + 2);
                 write_p(half, sd0);                     // round 1: heads 0 (buffer 0) and 1 (buffer 1)
                 fence_proxy_async_smem();
                 __syncthreads();
+                GNN_STAMP(layer * 12 + 3);
                 if (tid == 0) {
                     tc_fence_after();
 #pragma unroll
@@ -300,6 +315,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 mbar_wait(z_bar, zpar, err_flag, 44);
                 zpar ^= 1;
                 tc_fence_after();
+                GNN_STAMP(layer * 12 + 4);
                 write_p(half + 2, sd1);                 // round 2: heads 2 and 3 (the MMAs that read round 1 are done)
                 convert(half * 64, half * 32);
                 convert(half * 64 + 32, half * 32 + 16);
@@ -307,6 +323,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncthreads();
+                GNN_STAMP(layer * 12 + 5);
                 if (tid == 0) {
                     tc_fence_after();
 #pragma unroll
@@ -327,6 +344,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 mbar_wait(z_bar, zpar, err_flag, 45);
                 zpar ^= 1;
                 tc_fence_after();
+                GNN_STAMP(layer * 12 + 6);
                 if (tid == 0) { load_item(item + 3); load_item(item + 4); }     // slices 0, 1 are consumed
                 if (layer < 4 && half == 0) {              // P buffer 0 is drained: the adjacency (no self loops) of the
                     const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);    // GraphConv layer that follows
@@ -341,6 +359,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncthreads();
+                GNN_STAMP(layer * 12 + 7);
                 if (tid == 0) {
                     tc_fence_after();
 #pragma unroll
@@ -355,6 +374,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 mbar_wait(o_bar, opar, err_flag, 46);
                 opar ^= 1;
                 tc_fence_after();
+                GNN_STAMP(layer * 12 + 8);
                 if (tid == 0) { load_item(item + 5); load_item(item + 6); item += 4; }
             } else {
                 // ================= GraphConv =================
@@ -370,10 +390,12 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 mbar_wait(z_bar, zpar, err_flag, 47);
                 zpar ^= 1;
                 tc_fence_after();
+                GNN_STAMP(layer * 12 + 4);
                 convert(half * 32, half * 16);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncthreads();
+                GNN_STAMP(layer * 12 + 7);
                 if (tid == 0) {
                     tc_fence_after();
                     const uint64_t wrel = wait_item(item), wroot = wait_item(item + 1);
@@ -388,6 +410,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 mbar_wait(o_bar, opar, err_flag, 48);
                 opar ^= 1;
                 tc_fence_after();
+                GNN_STAMP(layer * 12 + 8);
                 if (tid == 0) { load_item(item + 3); load_item(item + 4); item += 2; }
             }
             {
@@ -441,7 +464,9 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
             tc_fence_before();
             fence_proxy_async_smem();
             __syncthreads();
+            GNN_STAMP(layer * 12 + 9);
         }
+        GNN_TILE_STAMP(2);
         if (tid == 0) {                                // store this tile, then (same buffer) fetch the next one
             tma_store_5d(&p.x_out, s_x, 0, row0, group, 0, 0);
             tma_store_commit();
@@ -537,6 +562,12 @@ int gnn_fused_plan(const GnnFusedWeights& w, GraphTopo topo, long long n_groups,
     *out = plan;
     return A2M_OK;
 }
+
+#ifdef A2M_GNN_TRACE
+extern "C" int a2m_gnn_trace_read(long long* out) {
+    return cudaMemcpyFromSymbol(out, v4::g_gnn_trace, sizeof(long long) * 128) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int gnn_fused_launch(const GnnFusedPlan& plan, int* err_flag, cudaStream_t stream) {
     static A2mPerDeviceOnce configured;
