@@ -37,7 +37,7 @@ class GemmDesc(ctypes.Structure):
                 ("m_extent", ctypes.c_int32 * 4), ("n_taps", ctypes.c_int32), ("tap_src", ctypes.c_int32 * 24),
                 ("tap_off", (ctypes.c_int32 * 4) * 24), ("tap_channels", ctypes.c_int32 * 24),
                 ("tap_w_off", c_i64 * 24), ("N", ctypes.c_int32), ("act", ctypes.c_int32),
-                ("out_type", ctypes.c_int32), ("reserved", ctypes.c_int32), ("out_stride", c_i64 * 4),
+                ("out_type", ctypes.c_int32), ("tile_hint", ctypes.c_int32), ("out_stride", c_i64 * 4),
                 ("out_base", c_i64)]
 
 

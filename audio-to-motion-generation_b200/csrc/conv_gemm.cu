@@ -257,6 +257,349 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2), persistent: two neighbouring M tiles and a 256-wide N tile are ONE 256 x 256 MMA tile.
+// Each CTA stages its own 128 activation rows and its own half of the weight tile (128 of the 256 rows): 32 KB per K
+// block instead of 48 KB for the same 128 x 256 x 64 of work per SM.  The leader (even) CTA's elected thread issues the
+// MMAs for the pair; tcgen05.commit is multicast, so each CTA's producer sees its own ring slots released and each
+// CTA's epilogue warps see their own accumulator half (rows 0..127 in the leader's tensor memory, 128..255 in the
+// peer's).  Both producers count their bytes on the LEADER's "full" barrier.
+// One cluster per SM pair walks the tile list (tile = cluster + i * clusters).  The accumulator is double-buffered in
+// tensor memory (2 x 256 columns): the epilogue of tile i (tcgen05.ld -> bias / activation -> bf16 -> swizzled staging
+// -> TMA store) runs while the MMAs of tile i + 1 fill the other buffer; both CTAs' epilogues hand a drained buffer back
+// to the leader's MMA thread through a cluster-scope mbarrier arrive.  Five 32 KB ring stages + 2 x 16 KB staging.
+// Layers whose tile list fits one round (every cluster has exactly one tile: the short decoder layers) use
+// conv_gemm_pair_single_kernel below instead.
+// ---------------------------------------------------------------------------------------------
+struct SmemPair {
+    static constexpr int kStages = 5;
+    static constexpr int kStageBytes = 2 * kABytes;             // A: 128 rows, B: my 128 of the tile's 256 rows
+    static constexpr int kStagingOffset = kStages * kStageBytes;            // 2 x [128 rows][64 cols] bf16, 128B-swizzled
+    static constexpr int kBarOffset = kStagingOffset + 2 * 16384;
+    static constexpr int kBiasOffset = kBarOffset + 256;
+    static constexpr int kTotal = kBiasOffset + 256 * 4 + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
+conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p, const float* __restrict__ bias, int* __restrict__ err_flag) {
+    using S = SmemPair;
+    constexpr int kStages = S::kStages;
+    constexpr int kN = 256;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);     // waited on in the leader only
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* acc_full = empty_bar + kStages;          // [2] accumulator buffer complete (multicast commit)
+    uint64_t* acc_empty = acc_full + 2;                // [2] buffer drained by BOTH CTAs' epilogues (leader's copy is used)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int m_tiles = p.tiles[0] * p.tiles[1] * p.tiles[2] * p.tiles[3];
+    const int n_tiles = p.N / kN;
+    const int work_total = ((m_tiles + 1) >> 1) * n_tiles;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    // work item -> my M tile's base coordinates (dims 1..4), the N offset, and whether my half exists (odd tile count)
+    auto decode = [&](int w, int (&base)[4], int& n0) {
+        n0 = (w % n_tiles) * kN;
+        int t = (w / n_tiles) * 2 + static_cast<int>(rank);
+        const bool valid = t < m_tiles;
+        if (!valid) t = 0;                              // the idle half of the last pair recomputes tile 0 and stores nothing
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            base[i] = (t % p.tiles[i]) * p.box[i];
+            t /= p.tiles[i];
+        }
+        return valid;
+    };
+
+    pdl_launch_dependents();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.a_map[0]);
+        tma_prefetch_desc(&p.a_map[1]);
+        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.c_map);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 2); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_pair(tmem_slot, 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();                               // both CTAs' barriers exist before either signals the other
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int g = 0;                                // K blocks issued so far (ring position carries over from tile to tile)
+            bool ok = true;
+            for (int w = cluster_id; w < work_total && ok; w += n_clusters) {
+                int base[4], n0;
+                decode(w, base, n0);
+                int kb = 0;
+                for (int t = 0; t < p.n_taps && ok; ++t) {
+                    const CUtensorMap* amap = &p.a_map[p.tap_src[t]];
+                    const int c1 = base[0] + p.tap_off[t][0], c2 = base[1] + p.tap_off[t][1];
+                    const int c3 = base[2] + p.tap_off[t][2], c4 = base[3] + p.tap_off[t][3];
+                    for (int ch = 0; ch < p.tap_chunks[t]; ++ch, ++kb, ++g) {
+                        const int s = g % kStages;
+                        if (!mbar_wait(&empty_bar[s], ((g / kStages) & 1) ^ 1, err_flag, 11)) { ok = false; break; }
+                        if (leader) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);       // both CTAs' bytes
+                        const uint32_t full_addr = cluster_map_shared(smem_u32(&full_bar[s]), 0);
+                        unsigned char* stage = smem + s * S::kStageBytes;
+                        tma_load_5d_pair(stage, amap, full_addr, ch * kBlockK, c1, c2, c3, c4);
+                        tma_load_5d_pair(stage + kABytes, &p.b_map, full_addr, kb * kBlockK, n0 + static_cast<int>(rank) * 128, 0, 0, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            const uint32_t idesc = umma_idesc_bf16(256, kN);
+            int g = 0, j = 0;
+            bool ok = true;
+            for (int w = cluster_id; w < work_total && ok; w += n_clusters, ++j) {
+                const int buf = j & 1;
+                if (!mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1, err_flag, 14)) break;     // both epilogues drained it
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kN);
+                for (int kb = 0; kb < p.k_blocks; ++kb, ++g) {
+                    const int s = g % kStages;
+                    if (!mbar_wait(&full_bar[s], (g / kStages) & 1, err_flag, 12)) { ok = false; break; }
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
+                    const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        umma_bf16_pair(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                    umma_commit_pair(&empty_bar[s], 0x3);
+                }
+                if (ok) umma_commit_pair(&acc_full[buf], 0x3);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        float* s_bias = reinterpret_cast<float*>(smem + S::kBiasOffset);
+        unsigned char* staging = smem + S::kStagingOffset;
+        const uint32_t acc_empty_leader0 = cluster_map_shared(smem_u32(&acc_empty[0]), 0);
+        int j = 0, chunk_no = 0;
+        for (int w = cluster_id; w < work_total; w += n_clusters, ++j) {
+            int base[4], n0;
+            const bool tile_valid = decode(w, base, n0);
+            const int buf = j & 1;
+            for (int i = threadIdx.x - 64; i < kN; i += 128) s_bias[i] = bias != nullptr ? __ldg(bias + n0 + i) : 0.f;
+            named_barrier(2, 128);
+            if (!mbar_wait(&acc_full[buf], (j >> 1) & 1, err_flag, 13)) break;
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < kN; c0 += 64, ++chunk_no) {
+                unsigned char* st = staging + (chunk_no & 1) * 16384;
+                if (warp == 2 && lane == 0) tma_store_wait_read_keep1();       // the store issued from this buffer two chunks ago
+                named_barrier(1, 128);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * kN + c0 + hf * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int jj = 0; jj < 32; jj += 8) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float x = __uint_as_float(v[jj + e]) + s_bias[c0 + hf * 32 + jj + e];
+                            if (p.act == kActLeaky) x = x > 0.f ? x : kLeakySlope * x;
+                            else if (p.act == kActRelu) x = fmaxf(x, 0.f);
+                            f[e] = x;
+                        }
+                        uint4 q;
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]);
+                        __nv_bfloat162 h1 = __floats2bfloat162_rn(f[2], f[3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]);
+                        __nv_bfloat162 h3 = __floats2bfloat162_rn(f[6], f[7]);
+                        q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+                        q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+                        const int chunk = hf * 4 + (jj >> 3);
+                        *reinterpret_cast<uint4*>(st + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
+                    }
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                named_barrier(1, 128);
+                if (warp == 2 && lane == 0) {
+                    if (tile_valid) {
+                        tma_store_5d(&p.c_map, st, n0 + c0, base[0], base[1], base[2], base[3]);
+                        tma_store_commit();
+                    }
+                    // after the last chunk every epilogue thread of this CTA has read its accumulator rows: hand the buffer back
+                    if (c0 + 64 == kN) mbar_arrive_cluster(acc_empty_leader0 + buf * 8);
+                }
+            }
+        }
+        if (warp == 2 && lane == 0) tma_store_wait_read();
+    }
+    tc_fence_before();
+    cluster_sync_all();                               // neither CTA leaves (or frees tensor memory) while the other can still signal it
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// The same CTA-pair tile for layers whose tile list fits one round: one tile per cluster, single accumulator buffer, six
+// ring stages, and the drained ring itself is the epilogue's staging area (measured 2 us per launch faster on the
+// decoder layers than running the persistent kernel for a single round).
+constexpr int kPairSingleSmem = 6 * 2 * kABytes + 128 + 256 * 4 + 1024;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
+conv_gemm_pair_single_kernel(const __grid_constant__ ConvGemmParams p, const float* __restrict__ bias, int* __restrict__ err_flag) {
+    constexpr int kStages = 6;
+    constexpr int kStageBytes = 2 * kABytes;
+    constexpr int kBarOffset = kStages * kStageBytes;
+    constexpr int kBiasOffset = kBarOffset + 128;
+    constexpr int kN = 256;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOffset);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* accum_bar = empty_bar + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n_tiles = p.N / kN;
+    int base[4];
+    bool tile_valid;
+    int n0;
+    {
+        const int w = blockIdx.x >> 1;
+        n0 = (w % n_tiles) * kN;
+        int t = (w / n_tiles) * 2 + static_cast<int>(rank);
+        const int m_tiles = p.tiles[0] * p.tiles[1] * p.tiles[2] * p.tiles[3];
+        tile_valid = t < m_tiles;
+        if (!tile_valid) t = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            base[i] = (t % p.tiles[i]) * p.box[i];
+            t /= p.tiles[i];
+        }
+    }
+    pdl_launch_dependents();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.a_map[0]);
+        tma_prefetch_desc(&p.a_map[1]);
+        tma_prefetch_desc(&p.b_map);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_pair(tmem_slot, kN);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+    if (warp == 0) {
+        if (lane == 0) {
+            int kb = 0;
+            bool ok = true;
+            for (int t = 0; t < p.n_taps && ok; ++t) {
+                const CUtensorMap* amap = &p.a_map[p.tap_src[t]];
+                const int c1 = base[0] + p.tap_off[t][0], c2 = base[1] + p.tap_off[t][1];
+                const int c3 = base[2] + p.tap_off[t][2], c4 = base[3] + p.tap_off[t][3];
+                for (int ch = 0; ch < p.tap_chunks[t]; ++ch, ++kb) {
+                    const int s = kb % kStages;
+                    if (!mbar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1, err_flag, 11)) { ok = false; break; }
+                    if (leader) mbar_expect_tx(&full_bar[s], 2 * kStageBytes);
+                    const uint32_t full_addr = cluster_map_shared(smem_u32(&full_bar[s]), 0);
+                    unsigned char* stage = smem + s * kStageBytes;
+                    tma_load_5d_pair(stage, amap, full_addr, ch * kBlockK, c1, c2, c3, c4);
+                    tma_load_5d_pair(stage + kABytes, &p.b_map, full_addr, kb * kBlockK, n0 + static_cast<int>(rank) * 128, 0, 0, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            const uint32_t idesc = umma_idesc_bf16(256, kN);
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                const int s = kb % kStages;
+                if (!mbar_wait(&full_bar[s], (kb / kStages) & 1, err_flag, 12)) break;
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+                const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                    umma_bf16_pair(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                umma_commit_pair(&empty_bar[s], 0x3);
+            }
+            umma_commit_pair(accum_bar, 0x3);
+        }
+    } else {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        float* s_bias = reinterpret_cast<float*>(smem + kBiasOffset);
+        for (int i = threadIdx.x - 64; i < kN; i += 128)
+            s_bias[i] = (bias != nullptr && n0 + i < p.N) ? __ldg(bias + n0 + i) : 0.f;
+        named_barrier(2, 128);
+        mbar_wait(accum_bar, 0, err_flag, 13);
+        tc_fence_after();
+        tma_prefetch_desc(&p.c_map);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kN; c0 += 64) {
+            unsigned char* st = smem + (c0 >> 6) * 16384;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0 + hf * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float x = __uint_as_float(v[j + e]) + s_bias[c0 + hf * 32 + j + e];
+                        if (p.act == kActLeaky) x = x > 0.f ? x : kLeakySlope * x;
+                        else if (p.act == kActRelu) x = fmaxf(x, 0.f);
+                        f[e] = x;
+                    }
+                    uint4 q;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn(f[2], f[3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]);
+                    __nv_bfloat162 h3 = __floats2bfloat162_rn(f[6], f[7]);
+                    q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+                    q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+                    const int chunk = hf * 4 + (j >> 3);
+                    *reinterpret_cast<uint4*>(st + row * 128 + ((chunk ^ (row & 7)) << 4)) = q;
+                }
+            }
+            fence_proxy_async_smem();
+            named_barrier(1, 128);
+            if (warp == 2 && lane == 0 && tile_valid) {
+                tma_store_5d(&p.c_map, st, n0 + c0, base[0], base[1], base[2], base[3]);
+                tma_store_commit();
+            }
+        }
+        if (warp == 2 && lane == 0) tma_store_wait_read();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, kN);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // weight packing / BatchNorm folding (run once at model load)
 // ---------------------------------------------------------------------------------------------
 struct PackTaps {
@@ -427,7 +770,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, const void* w_packed, const float* bia
     int block_n = 128;
     if (d.N <= 32) block_n = 32;
     else if (d.N <= 64) block_n = 64;
-    else if (d.block_n_hint == 256 && d.N % 256 == 0 && d.out_type == kOutBf16 && d.split_k == 1) block_n = 256;
+    else if (d.block_n_hint >= 256 && d.N % 256 == 0 && d.out_type == kOutBf16 && d.split_k == 1) block_n = 256;
     {
         long long wd[2] = {K, d.N}, ws[2] = {1, K};
         int wb[5] = {kBlockK, block_n > 128 ? 128 : block_n, 1, 1, 1};
@@ -495,11 +838,42 @@ int conv_gemm_plan(const ConvGemmDesc& d, const void* w_packed, const float* bia
     }
     plan->grid = dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>((d.N + block_n - 1) / block_n),
                       static_cast<unsigned>(d.split_k));
+    plan->pair = (d.block_n_hint == 512 && block_n == 256 && p.c_tma && m_tiles >= 2) ? 1 : 0;
+    if (plan->pair) {                                   // persistent: one cluster (CTA pair) per SM pair, or fewer
+        const long long work = (m_tiles + 1) / 2 * (d.N / 256);
+        const long long slots = a2m_num_sms() / 2;
+        // the tile list takes ceil(work / slots) rounds whatever the grid: launch only as many clusters as fill those
+        // rounds evenly (128 tiles -> 64 clusters x 2 rounds, not 74) and leave the other SMs to the kernels of the
+        // second stream lane
+        const long long rounds = (work + slots - 1) / slots;
+        const long long clusters = (work + rounds - 1) / rounds;
+        plan->grid = dim3(static_cast<unsigned>(2 * clusters), 1, 1);
+        if (rounds == 1) plan->pair = 2;                // one tile per cluster
+    }
     plan->flops = 2 * m_valid * d.N * K;
     return A2M_OK;
 }
 
+static int launch_pair(const ConvGemmPlan& plan, int* err_flag, cudaStream_t stream) {
+    if (plan.pair == 2) {
+        static A2mPerDeviceOnce configured;
+        if (configured.first())
+            A2M_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_pair_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSingleSmem));
+        A2M_CUDA_CHECK(a2m_launch_pdl(conv_gemm_pair_single_kernel, plan.grid, dim3(kThreads), kPairSingleSmem, stream, plan.p,
+                                      plan.bias, err_flag));
+    } else {
+        static A2mPerDeviceOnce configured;
+        if (configured.first())
+            A2M_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemPair::kTotal));
+        A2M_CUDA_CHECK(a2m_launch_pdl(conv_gemm_pair_kernel, plan.grid, dim3(kThreads), SmemPair::kTotal, stream, plan.p, plan.bias,
+                                      err_flag));
+    }
+    a2m_count_launch();
+    return A2M_OK;
+}
+
 int conv_gemm_launch(const ConvGemmPlan& plan, int* err_flag, cudaStream_t stream) {
+    if (plan.pair) return launch_pair(plan, err_flag, stream);
     switch (plan.block_n) {
         case 32: return launch_variant<32, 3>(plan, err_flag, stream);
         case 64: return launch_variant<64, 3>(plan, err_flag, stream);
@@ -538,6 +912,7 @@ extern "C" int a2m_gemm_taps(const a2m_gemm_desc* g, const float* w_src, int64_t
         d.taps.push_back(tp);
     }
     d.N = g->N; d.out_base = g->out_base; d.act = g->act; d.out_type = g->out_type;
+    d.block_n_hint = g->tile_hint;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long K = conv_gemm_k(d);
     __nv_bfloat16* wp = nullptr;

@@ -49,7 +49,8 @@ struct ConvGemmDesc {
     long long out_base;
     int act;
     int out_type;
-    int block_n_hint = 0;       // 256: use 128 x 256 tiles if the layer allows it (N % 256 == 0, bf16 output)
+    int block_n_hint = 0;       // 256: use 128 x 256 tiles if the layer allows it (N % 256 == 0, bf16 output);
+                                // 512: 256 x 256 tiles on CTA pairs (same conditions + TMA-storable output)
     int split_k = 1;            // > 1: K blocks split over gridDim.z; split z writes its fp32 partial sums at
     long long split_stride = 0; // out + z * split_stride (act must be none; bias added by split 0); the consumer
                                 // sums the planes in a fixed order (deterministic, batch-invariant)
@@ -85,6 +86,7 @@ struct ConvGemmPlan {
     void* out;
     int block_n;
     int stages;                 // shared-memory ring depth of the 128 x 128 variant (2 or 3)
+    int pair;                   // the CTA-pair kernel (cta_group::2, 256 x 256 tiles): 1 persistent, 2 one tile per cluster
     dim3 grid;
     long long flops;            // 2 * M * N * K of the valid output rows
 };

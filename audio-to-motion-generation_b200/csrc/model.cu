@@ -511,10 +511,12 @@ struct Emit {
         for (int i = 0; i < 4; ++i) { d.box[i] = box[i]; d.m_extent[i] = ext[i]; d.out_stride[i] = ostride[i]; }
         d.taps = std::move(taps);
         d.N = L.N; d.out_base = obase; d.act = act >= 0 ? act : L.act; d.out_type = out_type; d.split_k = split_k; d.split_stride = split_stride;
-        {   // wide layers with enough tiles to fill the SMs run 128 x 256 tiles (one CTA per SM, fewer operand bytes per FLOP)
+        {   // layers whose width is a multiple of 256 run 256 x 256 tiles on CTA pairs (the planner falls back to
+            // 128 x 256 / 128 x 128 tiles where the output cannot be stored by TMA or there is a single M tile)
             long long m_tiles = 1;
             for (int i = 0; i < 4; ++i) m_tiles *= (ext[i] + box[i] - 1) / box[i];
             if (L.N % 256 == 0 && L.N >= 512 && m_tiles * (L.N / 256) >= 120) d.block_n_hint = 256;
+            if (L.N % 256 == 0 && m_tiles >= 2) d.block_n_hint = 512;
         }
         auto plan = std::make_shared<ConvGemmPlan>();
         rc = conv_gemm_plan(d, L.w, L.bias, out, plan.get());

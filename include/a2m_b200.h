@@ -236,7 +236,8 @@ typedef struct a2m_gemm_desc {
     int32_t N;
     int32_t act;
     int32_t out_type;
-    int32_t reserved;
+    int32_t tile_hint;                   /* 0: the planner's default tile; 256: 128 x 256 tiles; 512: 256 x 256 tiles on CTA pairs
+                                            (cta_group::2) -- both only where the layer allows it (N % 256 == 0, bf16 output) */
     int64_t out_stride[4];               /* elements */
     int64_t out_base;
 } a2m_gemm_desc;

@@ -62,6 +62,7 @@ def run(desc_kw, w, w_stride_n, w_stride_c, scale, bias, out):
     d.act = ACT[desc_kw.get("act", "none")]
     d.out_type = 1 if out.dtype == torch.float32 else 0
     d.out_base = desc_kw.get("out_base", 0)
+    d.tile_hint = desc_kw.get("tile_hint", 0)
     c.check(c.lib().a2m_gemm_taps(ctypes.byref(d), c.ptr(w), w_stride_n, w_stride_c, c.ptr(scale), c.ptr(bias),
                                   c.ptr(out), c.stream_ptr()))
     torch.cuda.synchronize()

@@ -195,3 +195,41 @@ def test_full_size_layer_and_linearity():
     kw["sources"] = [(a * 2, [C, T, B], [1, C, T * C]), (s * 2, [C, T, B], [1, C, T * C])]
     gc.run(kw, w, 2 * C * 3, 3, None, None, out2)
     assert torch.equal(out2.float(), 2 * out.float())
+
+
+@pytest.mark.parametrize("hint", [256, 512])
+@pytest.mark.parametrize("B,T,C,N,act", [(8, 64, 256, 256, "leaky"), (5, 64, 128, 512, "none"), (3, 32, 320, 768, "relu"),
+                                          (1, 128, 64, 256, "leaky")])
+def test_wide_tiles_conv1d_k3(B, T, C, N, act, hint):
+    """The 128 x 256 variant (hint 256) and the CTA-pair variant (hint 512: two neighbouring M tiles and 256 output
+    channels are one cta_group::2 MMA tile; B = 5, 3 give odd M-tile counts, i.e. a pair whose second half is idle)."""
+    x = gc.bf16_round(gc.gen((B, C, T), 40))
+    w = gc.gen((N, C, 3), 41, (3 * C) ** -0.5)
+    b = gc.gen((N,), 42, 0.1)
+    ref = gc.act_ref(F.conv1d(x, gc.bf16_round(w), b, padding=1), act).permute(0, 2, 1).contiguous()
+    xd = x.permute(0, 2, 1).contiguous().to(torch.bfloat16).cuda()
+    out = torch.full((B, T, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    kw = dict(sources=[(xd, [C, T, B], [1, C, T * C])], box=gc.rows_box(T, B), m_extent=[T, B, 1, 1],
+              out_stride=[N, T * N, 0, 0], taps=[(0, (j - 1, 0, 0, 0), C, j) for j in range(3)], N=N, act=act, tile_hint=hint)
+    gc.run(kw, w.cuda(), C * 3, 3, None, b.cuda(), out)
+    check(out, gc.bf16_round(ref))
+
+
+def test_pair_tiles_match_single_cta_tiles_bit_for_bit():
+    """Same K order, same fp32 accumulation per output element: the CTA-pair kernel must reproduce the 128 x 256 kernel
+    exactly (a large-K two-source layer, the shape of unet.up1)."""
+    B, T, C0, C1, N = 6, 32, 256, 256, 512
+    a = gc.gen((B, T, C0), 50).to(torch.bfloat16).cuda()
+    s = gc.gen((B, T, C1), 51).to(torch.bfloat16).cuda()
+    w = gc.gen((N, C0 + C1, 3), 52, (3 * (C0 + C1)) ** -0.5).cuda()
+    b = gc.gen((N,), 53, 0.1).cuda()
+    outs = []
+    for hint in (256, 512):
+        out = torch.full((B, T, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+        taps = [(0, (j - 1, 0, 0, 0), C0, j) for j in range(3)] + [(1, (j - 1, 0, 0, 0), C1, C0 * 3 + j) for j in range(3)]
+        kw = dict(sources=[(a, [C0, T, B], [1, C0, T * C0]), (s, [C1, T, B], [1, C1, T * C1])], box=gc.rows_box(T, B),
+                  m_extent=[T, B, 1, 1], out_stride=[N, T * N, 0, 0], taps=taps, N=N, act="leaky", tile_hint=hint)
+        gc.run(kw, w, (C0 + C1) * 3, 3, None, b, out)
+        outs.append(out)
+    assert not torch.isnan(outs[0].float()).any()
+    assert torch.equal(outs[0], outs[1])
