@@ -16,6 +16,9 @@ def label(full):
     m = re.search(r"conv_gemm_kernel<(?:\(int\))?(\d+)", full)
     if m:
         return "conv_gemm_kernel<%s>" % m.group(1)
+    m = re.search(r"logmel512_kernel<(\w+)", full)
+    if m:
+        return "logmel512_kernel<%s>" % m.group(1)
     m = re.search(r"([A-Za-z_0-9]+_kernel)", full)
     if m:
         return m.group(1)
@@ -24,9 +27,12 @@ def label(full):
 
 
 def main():
-    rows = load(sys.argv[1])
+    rows = [r for r in load(sys.argv[1]) if r.get("Metric Name", "gpu__time_duration.sum") == "gpu__time_duration.sum"]
+    scale = {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3}
+    for r in rows:
+        r["Metric Value"] = str(float(r["Metric Value"].replace(",", "")) * scale.get(r.get("Metric Unit", "ns"), 1e-3) * 1000.0)
     ks = [(label(r["Kernel Name"]), float(r["Metric Value"]) / 1000.0, r["Grid Size"], r["Kernel Name"]) for r in rows]
-    starts = [i for i, k in enumerate(ks) if "logmel_kernel" in k[3]]
+    starts = [i for i, k in enumerate(ks) if "logmel" in k[3]]
     step = ks[starts[-1]:]
     total = sum(t for _, t, _, _ in step)
     agg = collections.OrderedDict()

@@ -1,6 +1,6 @@
 """Sum DRAM traffic per kernel class over the LAST step of an ncu launch list captured with
---metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum  ->  profiles/r1_traffic.json
-    python tools/traffic_summary.py gpurun_out/traffic.csv profiles/r1_traffic.json"""
+--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum  ->  profiles/r2_traffic.json
+    python tools/traffic_summary.py gpurun_out/traffic.csv profiles/r2_traffic.json"""
 import collections
 import csv
 import json
@@ -17,7 +17,7 @@ for r in rows:
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "usecond": 1, "ms": 1e3, "nsecond": 1e-3}.get(unit, 1)
     d[r["Metric Name"]] = v * scale
 ks = list(by_id.values())
-starts = [i for i, k in enumerate(ks) if "logmel_kernel" in k["name"]]
+starts = [i for i, k in enumerate(ks) if "logmel" in k["name"]]
 step = ks[starts[-1]:]
 agg = collections.OrderedDict()
 for k in step:
@@ -29,8 +29,8 @@ for k in step:
     a["dram_bytes"] += k.get("dram__bytes_read.sum", 0.0) + k.get("dram__bytes_write.sum", 0.0)
 out = {"note": "ncu --clock-control none, tools/profile_step.py (B=256), --cache-control none (warm L2), last of 2 steps; launches serialised by ncu",
        "per_kernel": agg,
-       "conv_gemm_bytes_per_step": agg.get("conv_gemm_kernel", {}).get("dram_bytes"),
-       "logmel_bytes_per_launch": agg.get("logmel_kernel", {}).get("dram_bytes"),
+       "conv_gemm_bytes_per_step": sum(a["dram_bytes"] for n, a in agg.items() if n.startswith("conv_gemm")),
+       "logmel_bytes_per_launch": sum(a["dram_bytes"] for n, a in agg.items() if n.startswith("logmel")),
        "eval_bytes_per_launch": agg.get("eval_l1_pck_kernel", {}).get("dram_bytes")}
 json.dump(out, open(sys.argv[2], "w"), indent=1)
 for n, a in agg.items():
