@@ -256,6 +256,31 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, const float* __restri
     }
 }
 
+// LayerNorm statistics of one accumulator row (256 fp32 columns of my tensor-memory lane, + bias): two passes, thread-local,
+// so a row's result never depends on which rows share its tile or its launch.
+__device__ __forceinline__ void ln256_row_stats(uint32_t tmem_row, const float* s_bias, float& mean, float& rstd) {
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 256; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_row + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += __uint_as_float(v[j]) + s_bias[c + j];
+    }
+    mean = sum * (1.f / 256.f);
+    float sq = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 256; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_row + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const float dlt = __uint_as_float(v[j]) + s_bias[c + j] - mean; sq = fmaf(dlt, dlt, sq); }
+    }
+    rstd = rsqrtf(sq * (1.f / 256.f) + 1e-5f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2), persistent: two neighbouring M tiles and a 256-wide N tile are ONE 256 x 256 MMA tile.
 // Each CTA stages its own 128 activation rows and its own half of the weight tile (128 of the 256 rows): 32 KB per K
@@ -276,7 +301,7 @@ struct SmemPair {
     static constexpr int kStagingOffset = kStages * kStageBytes;            // 2 x [128 rows][64 cols] bf16, 128B-swizzled
     static constexpr int kBarOffset = kStagingOffset + 2 * 16384;
     static constexpr int kBiasOffset = kBarOffset + 256;
-    static constexpr int kTotal = kBiasOffset + 256 * 4 + 1024;
+    static constexpr int kTotal = kBiasOffset + 3 * 256 * 4 + 1024;        // bias | LN gamma | LN beta
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
@@ -387,6 +412,9 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p, const float* __r
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         float* s_bias = reinterpret_cast<float*>(smem + S::kBiasOffset);
+        float* s_gamma = s_bias + kN;
+        float* s_beta = s_gamma + kN;
+        const bool ln = p.ln_gamma != nullptr;          // LayerNorm over the row's 256 channels (N = 256: the whole row is mine)
         unsigned char* staging = smem + S::kStagingOffset;
         const uint32_t acc_empty_leader0 = cluster_map_shared(smem_u32(&acc_empty[0]), 0);
         int j = 0, chunk_no = 0;
@@ -394,10 +422,15 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p, const float* __r
             int base[4], n0;
             const bool tile_valid = decode(w, base, n0);
             const int buf = j & 1;
-            for (int i = threadIdx.x - 64; i < kN; i += 128) s_bias[i] = bias != nullptr ? __ldg(bias + n0 + i) : 0.f;
+            for (int i = threadIdx.x - 64; i < kN; i += 128) {
+                s_bias[i] = bias != nullptr ? __ldg(bias + n0 + i) : 0.f;
+                if (ln) { s_gamma[i] = __ldg(p.ln_gamma + i); s_beta[i] = __ldg(p.ln_beta + i); }
+            }
             named_barrier(2, 128);
             if (!mbar_wait(&acc_full[buf], (j >> 1) & 1, err_flag, 13)) break;
             tc_fence_after();
+            float mean = 0.f, rstd = 1.f;
+            if (ln) ln256_row_stats(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * kN, s_bias, mean, rstd);
 #pragma unroll 1
             for (int c0 = 0; c0 < kN; c0 += 64, ++chunk_no) {
                 unsigned char* st = staging + (chunk_no & 1) * 16384;
@@ -414,6 +447,7 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p, const float* __r
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             float x = __uint_as_float(v[jj + e]) + s_bias[c0 + hf * 32 + jj + e];
+                            if (ln) x = (x - mean) * rstd * s_gamma[c0 + hf * 32 + jj + e] + s_beta[c0 + hf * 32 + jj + e];
                             if (p.act == kActLeaky) x = x > 0.f ? x : kLeakySlope * x;
                             else if (p.act == kActRelu) x = fmaxf(x, 0.f);
                             f[e] = x;
@@ -455,7 +489,7 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p, const float* __r
 // The same CTA-pair tile for layers whose tile list fits one round: one tile per cluster, single accumulator buffer, six
 // ring stages, and the drained ring itself is the epilogue's staging area (measured 2 us per launch faster on the
 // decoder layers than running the persistent kernel for a single round).
-constexpr int kPairSingleSmem = 6 * 2 * kABytes + 128 + 256 * 4 + 1024;
+constexpr int kPairSingleSmem = 6 * 2 * kABytes + 128 + 3 * 256 * 4 + 1024;      // ring, barriers, bias | LN gamma | LN beta, slack
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
 conv_gemm_pair_single_kernel(const __grid_constant__ ConvGemmParams p, const float* __restrict__ bias, int* __restrict__ err_flag) {
     constexpr int kStages = 6;
@@ -547,12 +581,19 @@ conv_gemm_pair_single_kernel(const __grid_constant__ ConvGemmParams p, const flo
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         float* s_bias = reinterpret_cast<float*>(smem + kBiasOffset);
-        for (int i = threadIdx.x - 64; i < kN; i += 128)
+        float* s_gamma = s_bias + kN;
+        float* s_beta = s_gamma + kN;
+        const bool ln = p.ln_gamma != nullptr;          // LayerNorm over the row's 256 channels (one N tile: the whole row is mine)
+        for (int i = threadIdx.x - 64; i < kN; i += 128) {
             s_bias[i] = (bias != nullptr && n0 + i < p.N) ? __ldg(bias + n0 + i) : 0.f;
+            if (ln) { s_gamma[i] = __ldg(p.ln_gamma + i); s_beta[i] = __ldg(p.ln_beta + i); }
+        }
         named_barrier(2, 128);
         mbar_wait(accum_bar, 0, err_flag, 13);
         tc_fence_after();
         tma_prefetch_desc(&p.c_map);
+        float mean = 0.f, rstd = 1.f;
+        if (ln) ln256_row_stats(tmem_base + (static_cast<uint32_t>(quad * 32) << 16), s_bias, mean, rstd);
 #pragma unroll 1
         for (int c0 = 0; c0 < kN; c0 += 64) {
             unsigned char* st = smem + (c0 >> 6) * 16384;
@@ -567,6 +608,7 @@ conv_gemm_pair_single_kernel(const __grid_constant__ ConvGemmParams p, const flo
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         float x = __uint_as_float(v[j + e]) + s_bias[c0 + hf * 32 + j + e];
+                        if (ln) x = (x - mean) * rstd * s_gamma[c0 + hf * 32 + j + e] + s_beta[c0 + hf * 32 + j + e];
                         if (p.act == kActLeaky) x = x > 0.f ? x : kLeakySlope * x;
                         else if (p.act == kActRelu) x = fmaxf(x, 0.f);
                         f[e] = x;
@@ -838,7 +880,10 @@ int conv_gemm_plan(const ConvGemmDesc& d, const void* w_packed, const float* bia
     }
     plan->grid = dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>((d.N + block_n - 1) / block_n),
                       static_cast<unsigned>(d.split_k));
-    plan->pair = (d.block_n_hint == 512 && block_n == 256 && p.c_tma && m_tiles >= 2) ? 1 : 0;
+    const bool want_ln = d.ln_gamma != nullptr && d.ln_beta != nullptr && d.N == 256;
+    // (a layer with a fused LayerNorm takes the pair kernel even for a single M tile -- half the pair idles -- so that a
+    // row's arithmetic is the same for every batch size)
+    plan->pair = (d.block_n_hint == 512 && block_n == 256 && p.c_tma && (m_tiles >= 2 || want_ln)) ? 1 : 0;
     if (plan->pair) {                                   // persistent: one cluster (CTA pair) per SM pair, or fewer
         const long long work = (m_tiles + 1) / 2 * (d.N / 256);
         const long long slots = a2m_num_sms() / 2;
@@ -850,6 +895,9 @@ int conv_gemm_plan(const ConvGemmDesc& d, const void* w_packed, const float* bia
         plan->grid = dim3(static_cast<unsigned>(2 * clusters), 1, 1);
         if (rounds == 1) plan->pair = 2;                // one tile per cluster
     }
+    plan->ln_fused = (want_ln && plan->pair != 0) ? 1 : 0;
+    p.ln_gamma = plan->ln_fused ? d.ln_gamma : nullptr;
+    p.ln_beta = plan->ln_fused ? d.ln_beta : nullptr;
     plan->flops = 2 * m_valid * d.N * K;
     return A2M_OK;
 }

@@ -51,6 +51,9 @@ struct ConvGemmDesc {
     int out_type;
     int block_n_hint = 0;       // 256: use 128 x 256 tiles if the layer allows it (N % 256 == 0, bf16 output);
                                 // 512: 256 x 256 tiles on CTA pairs (same conditions + TMA-storable output)
+    const float* ln_gamma = nullptr;    // LayerNorm over the N = 256 output channels of a row, applied to the fp32 accumulator + bias
+    const float* ln_beta = nullptr;     // in the epilogue (real_motion_model.py:205,257 after proj_out); the planner reports in
+                                        // ConvGemmPlan::ln_fused whether this layer's tiling can do it (one 256-wide tile per row)
     int split_k = 1;            // > 1: K blocks split over gridDim.z; split z writes its fp32 partial sums at
     long long split_stride = 0; // out + z * split_stride (act must be none; bias added by split 0); the consumer
                                 // sums the planes in a fixed order (deterministic, batch-invariant)
@@ -77,6 +80,8 @@ struct ConvGemmParams {
     int out_type;
     int split_k;
     long long split_stride;
+    const float* ln_gamma;      // non-null: LayerNorm(256) fused into the epilogue (pair kernel, one tile per cluster)
+    const float* ln_beta;
 };
 
 struct ConvGemmPlan {
@@ -86,6 +91,7 @@ struct ConvGemmPlan {
     void* out;
     int block_n;
     int stages;                 // shared-memory ring depth of the 128 x 128 variant (2 or 3)
+    int ln_fused;               // 1: the requested LayerNorm runs in this launch's epilogue
     int pair;                   // the CTA-pair kernel (cta_group::2, 256 x 256 tiles): 1 persistent, 2 one tile per cluster
     dim3 grid;
     long long flops;            // 2 * M * N * K of the valid output rows

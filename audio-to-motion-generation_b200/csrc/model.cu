@@ -501,10 +501,11 @@ struct Emit {
     int rc = A2M_OK;
     std::string tag;                            // label of the ops emitted next (per-op profile)
 
-    void gemm(const LayerW& L, std::vector<Tap> taps, const AView* views, int n_src, const int box[4], const int ext[4],
+    // ln: LayerNorm(256) that follows this layer; fused into the epilogue where the tiling allows it (the return value says so)
+    bool gemm(const LayerW& L, std::vector<Tap> taps, const AView* views, int n_src, const int box[4], const int ext[4],
               void* out, const long long ostride[4], long long obase, int out_type, int act = -1, int split_k = 1,
-              long long split_stride = 0) {
-        if (dry || rc != A2M_OK) return;
+              long long split_stride = 0, const LnW* ln = nullptr) {
+        if (dry || rc != A2M_OK) return false;
         ConvGemmDesc d;
         d.n_src = n_src;
         for (int s = 0; s < n_src; ++s) d.a[s] = views[s];
@@ -516,17 +517,19 @@ struct Emit {
             long long m_tiles = 1;
             for (int i = 0; i < 4; ++i) m_tiles *= (ext[i] + box[i] - 1) / box[i];
             if (L.N % 256 == 0 && L.N >= 512 && m_tiles * (L.N / 256) >= 120) d.block_n_hint = 256;
-            if (L.N % 256 == 0 && m_tiles >= 2) d.block_n_hint = 512;
+            if (L.N % 256 == 0 && (m_tiles >= 2 || ln != nullptr)) d.block_n_hint = 512;
         }
+        if (ln) { d.ln_gamma = ln->w; d.ln_beta = ln->b; }
         auto plan = std::make_shared<ConvGemmPlan>();
         rc = conv_gemm_plan(d, L.w, L.bias, out, plan.get());
-        if (rc != A2M_OK) return;
+        if (rc != A2M_OK) return false;
         P->gemm_flops += plan->flops;
         int* flag = m->err_flag;
         P->ops.push_back([plan, flag](cudaStream_t s) { return conv_gemm_launch(*plan, flag, s); });
         P->op_is_gemm.push_back(1);
         P->op_name.push_back(tag + ".gemm");
         P->op_flops.push_back(plan->flops);
+        return plan->ln_fused != 0;
     }
     // rows = (L, B) of a [B, L, C] tensor; taps shift along L
     void conv_rows(const LayerW& L, const __nv_bfloat16* a0, int c0, const __nv_bfloat16* a1, int c1, int len, int B,
@@ -582,14 +585,14 @@ struct Emit {
         conv_rows(even, a, C, nullptr, 0, len, B, out, 2LL * N, 2LL * len * N, 0, kOutBf16);
         conv_rows(odd, a, C, nullptr, 0, len, B, out, 2LL * N, 2LL * len * N, N, kOutBf16);
     }
-    void linear_rows(const LayerW& L, const __nv_bfloat16* a0, const __nv_bfloat16* a1, int C, long long rows, void* out,
-                     long long ldc, long long col, int out_type) {
+    bool linear_rows(const LayerW& L, const __nv_bfloat16* a0, const __nv_bfloat16* a1, int C, long long rows, void* out,
+                     long long ldc, long long col, int out_type, const LnW* ln = nullptr) {
         AView v[2];
         v[0].ptr = a0; v[0].rank = 2; v[0].dims[0] = C; v[0].dims[1] = rows; v[0].strides[0] = 1; v[0].strides[1] = C;
         if (a1) { v[1] = v[0]; v[1].ptr = a1; }
         const int box[4] = {128, 1, 1, 1}, ext[4] = {static_cast<int>(rows), 1, 1, 1};
         const long long os[4] = {ldc, 0, 0, 0};
-        gemm(L, L.taps, v, a1 ? 2 : 1, box, ext, out, os, col, out_type);
+        return gemm(L, L.taps, v, a1 ? 2 : 1, box, ext, out, os, col, out_type, -1, 1, 0, ln);
     }
     void op(std::function<int(cudaStream_t)> f) {
         if (!dry && rc == A2M_OK) {
@@ -828,11 +831,10 @@ int build_plan(a2m_model* m, ForwardPlan* P) {
             }
             __nv_bfloat16* cur = xb;
             E.tag = dn + ".proj_out";
-            E.linear_rows(D.proj_out, cur, nullptr, J * 64, static_cast<long long>(BT), t1, 256, 0, kOutBf16);
-            {
+            const LnW nw = D.norm;                       // LayerNorm(256) in proj_out's epilogue where its tiling holds whole rows
+            if (!E.linear_rows(D.proj_out, cur, nullptr, J * 64, static_cast<long long>(BT), t2, 256, 0, kOutBf16, &nw)) {
                 E.tag = dn + ".norm";
-                const LnW nw = D.norm;
-                E.op([=](cudaStream_t s) { return launch_layernorm(t1, static_cast<long long>(BT), 256, nw.w, nw.b, t2, s); });
+                E.op([=](cudaStream_t s) { return launch_layernorm(t2, static_cast<long long>(BT), 256, nw.w, nw.b, t2, s); });
             }
             E.tag = dn + ".post_res";
             E.resblock(D.post_res, t2, T, B, t1, t3, qkv, t4);
