@@ -13,6 +13,7 @@
 #include <vector>
 #include <cstring>
 #include "a2m_common.cuh"
+#include "fft_math.cuh"
 
 void a2m_count_launch();
 
@@ -183,6 +184,220 @@ melspec_wide_kernel(const float* __restrict__ wav, WideTables tab, WideGeom g, f
     }
 }
 
+
+// =====================================================================================================
+// melspec2048_kernel: the same transform on the register-radix / packed-f32x2 scheme of the 512-point kernel (logmel.cu).
+//   * 64 threads own a PAIR of consecutive frames (A, B): every register holds the same quantity of both frames, every
+//     butterfly is one FADD2 / FMUL2 / FFMA2, every twiddle / window / untangle constant serves two frames.
+//   * 1024-point complex FFT of the even/odd-packed frame = 16 x 16 x 4: n = t + 64 m, k = k1 + 16 (q + 16 r)
+//       pass A  thread t:        DFT16 over m, twiddle W1024^(t k1)                      -> exchange 1 (shared memory)
+//       pass B  thread (k1, v):  DFT16 over u (t = 4 u + v), twiddle W64^(v q)           -> exchange 2
+//       pass C  thread (k1, v'): DFT4 over v for q = 4 v' .. 4 v' + 3                    -> Z[k1 + 16 q + 256 r]
+//     two exchanges through one padded 17 KB region per group (16-byte units, layouts chosen so that every quarter
+//     warp hits eight different bank groups both ways) instead of five Stockham passes; group-level named barriers only.
+//   * untangle of the bin pairs (j, 1024 - j), j = t + 64 i, from Z in the same region; |2 X|^2 (or |2 X|) goes back as
+//     (A, B) pairs and each thread projects two mel bands (b and n_mel - 1 - b: the wide and the narrow triangles
+//     balance), the factor 1/4 (1/2) folded into the weights.
+// Four groups per CTA, two CTAs per SM; any hop, all padding modes.
+// =====================================================================================================
+namespace fast {
+
+using a2m_fft::pair_t;
+using a2m_fft::cpx;
+
+constexpr int kGroupThreads = 64;
+constexpr int kGroups = 4;
+constexpr int kThreadsF = kGroupThreads * kGroups;
+constexpr int kRow = 68;                                 // 16-byte units per exchange row (64 + 4: rows 4 bank groups apart)
+constexpr int kRegionBytes = 16 * kRow * 16;             // 17 408 B per group
+constexpr int kPwEntries = 1028;                         // bins 0..1024 + 3 zeros (the 4-bin groups of the mel runs)
+static_assert(kPwEntries * 8 <= kRegionBytes && (1024 + 32) * 16 <= kRegionBytes, "Z and the powers alias the exchange region");
+
+struct FastTab {
+    const float2* win2;       // [1024] (w[2 n], w[2 n + 1])
+    const float2* tw1;        // [16][64] exp(-2 pi i t k1 / 1024) at [k1][t]
+    const float2* tw2;        // [16][4]  exp(-2 pi i v q / 64) at [q][v]
+    const float2* unt;        // [516]    (-sin, -cos)(2 pi j / 2048), j = 0..512
+    const float2* uv;         // [kPwPadded] per bin (padded index): weight into band g(k) ("rising"), into band g(k) - 1 ("falling"),
+                              // x 1/4 (power) or 1/2 (magnitude): the kernel keeps |2 X|
+    const int* seg;           // [n_mel + 2] first bin of segment g; band c = rising over segment c + falling over segment c + 1
+};
+constexpr int kPwPadded = 1028 + 1028 / 16 + 2;          // powers / weights are stored at k + (k >> 4): band starts 16 or 32 bins
+__device__ __forceinline__ int pw_idx(int k) { return k + (k >> 4); }      // apart no longer share a bank
+
+constexpr int kSmemFast = 1024 * 8 + 1024 * 8 + 520 * 8 + kPwPadded * 8 + 132 * 4 + kGroups * kRegionBytes;
+static_assert(((1024 + 1024 + 520 + kPwPadded) * 8 + 132 * 4) % 16 == 0, "the exchange regions are accessed in 16-byte units");
+
+__device__ __forceinline__ void group_sync(int grp) { a2m::named_barrier(1 + grp, kGroupThreads); }
+__device__ __forceinline__ void st_cpx(unsigned char* base, int unit, cpx v) {
+    *reinterpret_cast<ulonglong2*>(base + unit * 16) = make_ulonglong2(v.re, v.im);
+}
+__device__ __forceinline__ cpx ld_cpx(const unsigned char* base, int unit) {
+    const ulonglong2 u = *reinterpret_cast<const ulonglong2*>(base + unit * 16);
+    return a2m_fft::make(u.x, u.y);
+}
+__device__ __forceinline__ int z_unit(int k) { return k + 2 * (k >> 6); }      // Z[k]: two pad units per 64
+
+__global__ void __launch_bounds__(kThreadsF, 2)
+melspec2048_kernel(const float* __restrict__ wav, FastTab tab, WideGeom g, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_f[];
+    float2* s_win = reinterpret_cast<float2*>(smem_f);
+    float2* s_tw1 = s_win + 1024;
+    float2* s_unt = s_tw1 + 1024;
+    float2* s_uv = s_unt + 520;
+    int* s_seg = reinterpret_cast<int*>(s_uv + kPwPadded);
+    const int tid = threadIdx.x, grp = tid >> 6, t = tid & 63;
+    unsigned char* region = smem_f + (1024 + 1024 + 520 + kPwPadded) * 8 + 132 * 4 + grp * kRegionBytes;
+    for (int i = tid; i < 1024; i += kThreadsF) { s_win[i] = tab.win2[i]; s_tw1[i] = tab.tw1[i]; }
+    for (int i = tid; i < 516; i += kThreadsF) s_unt[i] = tab.unt[i];
+    for (int i = tid; i < kPwPadded; i += kThreadsF) s_uv[i] = tab.uv[i];
+    for (int i = tid; i < g.n_mel + 2; i += kThreadsF) s_seg[i] = tab.seg[i];
+    __syncthreads();
+
+    const long long N = g.n_samples;
+    const int lead = g.pad_mode ? kC : 0;
+    const long long pairs_per_clip = (g.frames + 1) >> 1;
+    const long long n_items = pairs_per_clip * (g.n_items / g.chunks_per_clip);      // clips x frame pairs
+    const int k1b = t >> 2, vb = t & 3;                  // my (k1, v) of passes B and C
+
+    for (long long item = static_cast<long long>(blockIdx.x) * kGroups + grp; item < n_items;
+         item += static_cast<long long>(gridDim.x) * kGroups) {
+        const long long clip = item / pairs_per_clip;
+        const long long fa = (item - clip * pairs_per_clip) * 2, fb = fa + 1;
+        const bool has_b = fb < g.frames;
+        const float* y = wav + clip * g.wav_stride;
+        auto sample = [&](long long sidx) {
+            if (g.pad_mode == 1) { if (sidx < 0) sidx = -sidx; if (sidx >= N) sidx = 2 * (N - 1) - sidx; }      // np.pad mode='reflect'
+            return (sidx >= 0 && sidx < N) ? __ldg(y + sidx) : 0.f;
+        };
+        // ---- load both frames x window, even/odd packed: z[n] = x[2 n] + i x[2 n + 1], n = t + 64 m
+        cpx z[16];
+        {
+            const long long sa = fa * g.hop - lead, sb = fb * g.hop - lead;
+            const bool interior = sa >= 0 && has_b && sb + kNfftW <= N;      // both frames inside the clip: no padding logic,
+            if (interior) {                                                  // 64 independent loads in flight
+                const float* pa = y + sa + 2 * t;
+                const float* pb = y + sb + 2 * t;
+                float ax[16], ay[16], bx[16], by[16];
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    ax[m] = __ldg(pa + 128 * m); ay[m] = __ldg(pa + 128 * m + 1);
+                    bx[m] = __ldg(pb + 128 * m); by[m] = __ldg(pb + 128 * m + 1);
+                }
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const float2 w = s_win[t + 64 * m];
+                    z[m] = a2m_fft::make(a2m_fft::mul2(a2m_fft::pack(ax[m], bx[m]), a2m_fft::bcast(w.x)),
+                                         a2m_fft::mul2(a2m_fft::pack(ay[m], by[m]), a2m_fft::bcast(w.y)));
+                }
+            } else {                                     // frames that touch the padding (two at each end of a clip)
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int n = t + 64 * m;
+                    const float ax = sample(sa + 2 * n), ay = sample(sa + 2 * n + 1);
+                    const float bx = has_b ? sample(sb + 2 * n) : 0.f, by = has_b ? sample(sb + 2 * n + 1) : 0.f;
+                    const float2 w = s_win[n];
+                    z[m] = a2m_fft::make(a2m_fft::mul2(a2m_fft::pack(ax, bx), a2m_fft::bcast(w.x)),
+                                         a2m_fft::mul2(a2m_fft::pack(ay, by), a2m_fft::bcast(w.y)));
+                }
+            }
+        }
+        // ---- pass A: DFT16 over m, twiddle W1024^(t k1)
+        a2m_fft::dft16(z);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) {
+            const float2 w = s_tw1[k1 * 64 + t];
+            z[k1] = a2m_fft::mul_scalar(z[k1], w.x, w.y);
+        }
+        group_sync(grp);                                 // the previous pair's mel projection has read the region
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) st_cpx(region, k1 * kRow + t, z[k1]);
+        group_sync(grp);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) z[u] = ld_cpx(region, k1b * kRow + 4 * u + vb);
+        // ---- pass B: DFT16 over u, twiddle W64^(v q)
+        a2m_fft::dft16(z);
+        if (vb != 0) {
+#pragma unroll
+            for (int q = 1; q < 16; ++q) {
+                const float2 w = __ldg(tab.tw2 + q * 4 + vb);
+                z[q] = a2m_fft::mul_scalar(z[q], w.x, w.y);
+            }
+        }
+        group_sync(grp);                                 // every exchange-1 read is done
+#pragma unroll
+        for (int q = 0; q < 16; ++q) st_cpx(region, k1b * kRow + (q >> 2) * 17 + (q & 3) * 4 + vb, z[q]);
+        group_sync(grp);
+        // ---- pass C: for q = 4 v' + qi, DFT4 over v -> Z[k1 + 16 q + 256 r] in z[4 qi + r]
+#pragma unroll
+        for (int qi = 0; qi < 4; ++qi) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) z[4 * qi + v] = ld_cpx(region, k1b * kRow + vb * 17 + qi * 4 + v);
+            a2m_fft::dft4(z[4 * qi], z[4 * qi + 1], z[4 * qi + 2], z[4 * qi + 3]);
+        }
+        group_sync(grp);                                 // every exchange-2 read is done
+#pragma unroll
+        for (int qi = 0; qi < 4; ++qi)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) st_cpx(region, z_unit(k1b + 16 * (4 * vb + qi) + 256 * r), z[4 * qi + r]);
+        group_sync(grp);
+        // ---- untangle the bin pairs (j, 1024 - j), j = t + 64 i (i = 0..7) and j = 512 (thread 0)
+        pair_t sq_lo[9], sq_hi[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int j = i < 8 ? t + 64 * i : 512;
+            sq_lo[i] = sq_hi[i] = a2m_fft::pack(0.f, 0.f);
+            if (i < 8 || t == 0) {
+                const cpx zk = ld_cpx(region, z_unit(j)), zp = ld_cpx(region, z_unit((kC - j) & (kC - 1)));
+                const float2 tu = s_unt[j];
+                a2m_fft::untangle_pair_sq(zk, zp, tu.x, tu.y, sq_lo[i], sq_hi[i]);
+            }
+        }
+        group_sync(grp);                                 // every Z read is done: the region becomes the (A, B) powers per bin
+        {
+            float2* s_pw = reinterpret_cast<float2*>(region);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const int j = i < 8 ? t + 64 * i : 512;
+                if (i < 8 || t == 0) {
+                    float2 a = make_float2(a2m_fft::lo(sq_lo[i]), a2m_fft::hi(sq_lo[i]));
+                    float2 b = make_float2(a2m_fft::lo(sq_hi[i]), a2m_fft::hi(sq_hi[i]));
+                    if (g.power != 2) { a.x = sqrtf(a.x); a.y = sqrtf(a.y); b.x = sqrtf(b.x); b.y = sqrtf(b.y); }
+                    s_pw[pw_idx(j)] = a;
+                    s_pw[pw_idx(kC - j)] = b;
+                }
+            }
+        }
+        group_sync(grp);
+        // ---- mel bands: bands 0..63 by index, bands >= 64 from the top down (wide and narrow triangles balance)
+        {
+            const float2* s_pw = reinterpret_cast<const float2*>(region);
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const int c = side == 0 ? t : g.n_mel - 1 - t;
+                if (side == 0 ? c >= g.n_mel : c < 64) continue;
+                const int k0 = s_seg[c], k1 = s_seg[c + 1], k2 = s_seg[c + 2];
+                pair_t acc = a2m_fft::pack(0.f, 0.f);
+                for (int k = k0; k < k1; ++k) {         // rising edge: segment c
+                    const float2 pw = s_pw[pw_idx(k)];
+                    acc = a2m_fft::fma2(a2m_fft::pack(pw.x, pw.y), a2m_fft::bcast(s_uv[pw_idx(k)].x), acc);
+                }
+                for (int k = k1; k < k2; ++k) {         // falling edge: segment c + 1
+                    const float2 pw = s_pw[pw_idx(k)];
+                    acc = a2m_fft::fma2(a2m_fft::pack(pw.x, pw.y), a2m_fft::bcast(s_uv[pw_idx(k)].y), acc);
+                }
+                const float va = a2m_fft::lo(acc), vbv = a2m_fft::hi(acc);
+                const float la = g.log_mode ? (va == 0.f ? g.log_offset : va) : va + g.log_offset;
+                const float lb = g.log_mode ? (vbv == 0.f ? g.log_offset : vbv) : vbv + g.log_offset;
+                out[(clip * g.frames + fa) * g.n_mel + c] = logf(la);
+                if (has_b) out[(clip * g.frames + fb) * g.n_mel + c] = logf(lb);
+            }
+        }
+    }
+}
+
+}  // namespace fast
+
 constexpr int kSmemFixedWide = (2 * kCPad) * 8 + kNfftW * 4 + kC * 8 + 1028 * 4;      // + 4 * nnz mel weights
 
 }  // namespace
@@ -192,6 +407,8 @@ struct a2m_melspec_plan {
     float log_offset;
     void* blob;
     WideTables tab;
+    fast::FastTab ftab;
+    int fast_ok;              // the filterbank has the segment structure melspec2048_kernel projects with
 };
 
 extern "C" int a2m_melspec_plan_create(int nfft, int hop, int n_mel, int power, int pad_mode, const double* window_host,
@@ -245,6 +462,68 @@ extern "C" int a2m_melspec_plan_create(int nfft, int hop, int n_mel, int power, 
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
     const size_t o_win = carve(kNfftW * 4), o_tw = carve(kC * 8), o_unt = carve(kC * 8), o_cm = carve(kMaxMelW * 16),
                  o_wt = carve((nnz + 4) * 4);
+    // tables of the register-radix kernel
+    const size_t o_tw1 = carve(1024 * 8), o_tw2 = carve(64 * 8), o_unt2 = carve(516 * 8), o_uv = carve(fast::kPwPadded * 8),
+                 o_seg = carve(132 * 4);
+    std::vector<float2> tw1(1024), tw2(64), unt2(516, make_float2(0.f, 0.f));
+    for (int k1 = 0; k1 < 16; ++k1)
+        for (int t = 0; t < 64; ++t) {
+            const double a = two_pi * ((t * k1) % 1024) / 1024.0;
+            tw1[k1 * 64 + t] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(-std::sin(a)));
+        }
+    for (int q = 0; q < 16; ++q)
+        for (int v = 0; v < 4; ++v) {
+            const double a = two_pi * ((v * q) % 64) / 64.0;
+            tw2[q * 4 + v] = make_float2(static_cast<float>(std::cos(a)), static_cast<float>(-std::sin(a)));
+        }
+    for (int j = 0; j <= 512; ++j) {
+        const double a = two_pi * j / 2048.0;
+        unt2[j] = make_float2(static_cast<float>(-std::sin(a)), static_cast<float>(-std::cos(a)));
+    }
+    // the filterbank as segments: bin k of segment g feeds band g ("rising", weight u) and band g - 1 ("falling", weight v).
+    // True of every triangular bank (Slaney, HTK); a matrix that is not of that shape runs the generic kernel.
+    std::vector<float2> uv(fast::kPwPadded, make_float2(0.f, 0.f));
+    std::vector<int> seg(132, kBinsW);
+    bool fast_ok = true;
+    {
+        const float fold = power == 2 ? 0.25f : 0.5f;       // the kernel keeps |2 X|
+        std::vector<int> peak(n_mel, -1);
+        for (int c = 0; c < n_mel; ++c) {
+            double best = 0.0;
+            for (int k = 0; k < kBinsW; ++k) {
+                const double w = mel_weights_host[static_cast<size_t>(k) * n_mel + c];
+                if (w > best) { best = w; peak[c] = k; }
+            }
+        }
+        std::vector<int> gk(kBinsW, 0);
+        int prev = 0;
+        for (int k = 0; k < kBinsW && fast_ok; ++k) {
+            int first = -1, count = 0;
+            for (int c = 0; c < n_mel; ++c)
+                if (mel_weights_host[static_cast<size_t>(k) * n_mel + c] != 0.0) { if (first < 0) first = c; ++count; }
+            int gseg = prev;
+            if (count == 2) {
+                if (mel_weights_host[static_cast<size_t>(k) * n_mel + first + 1] == 0.0) fast_ok = false;     // not adjacent
+                gseg = first + 1;
+            } else if (count == 1) {
+                gseg = k <= peak[first] ? first : first + 1;
+            } else if (count > 2) {
+                fast_ok = false;
+            }
+            if (gseg < prev) fast_ok = false;
+            gk[k] = gseg;
+            prev = gseg;
+            const int e = k + (k >> 4);
+            const double u = gseg < n_mel ? mel_weights_host[static_cast<size_t>(k) * n_mel + gseg] : 0.0;
+            const double v = gseg >= 1 ? mel_weights_host[static_cast<size_t>(k) * n_mel + gseg - 1] : 0.0;
+            uv[e] = make_float2(static_cast<float>(u) * fold, static_cast<float>(v) * fold);
+        }
+        for (int gi = 0; gi <= n_mel + 1; ++gi) {           // first bin with g(k) >= gi
+            int k = 0;
+            while (k < kBinsW && gk[k] < gi) ++k;
+            seg[gi] = k;
+        }
+    }
     unsigned char* blob = nullptr;
     A2M_CUDA_CHECK(cudaMalloc(&blob, off));
     std::vector<unsigned char> host(off, 0);
@@ -253,6 +532,11 @@ extern "C" int a2m_melspec_plan_create(int nfft, int hop, int n_mel, int power, 
     memcpy(host.data() + o_unt, unt.data(), kC * 8);
     memcpy(host.data() + o_cm, meta.data(), kMaxMelW * 16);
     if (nnz) memcpy(host.data() + o_wt, weights.data(), nnz * 4);
+    memcpy(host.data() + o_tw1, tw1.data(), 1024 * 8);
+    memcpy(host.data() + o_tw2, tw2.data(), 64 * 8);
+    memcpy(host.data() + o_unt2, unt2.data(), 516 * 8);
+    memcpy(host.data() + o_uv, uv.data(), fast::kPwPadded * 8);
+    memcpy(host.data() + o_seg, seg.data(), 132 * 4);
     cudaError_t e = cudaMemcpy(blob, host.data(), off, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(blob); a2m_set_error("a2m_melspec_plan_create: upload failed: %s", cudaGetErrorString(e)); return (int)e; }
     a2m_melspec_plan* p = new a2m_melspec_plan();
@@ -263,6 +547,13 @@ extern "C" int a2m_melspec_plan_create(int nfft, int hop, int n_mel, int power, 
     p->tab.unt = reinterpret_cast<const float2*>(blob + o_unt);
     p->tab.col_meta = reinterpret_cast<const int4*>(blob + o_cm);
     p->tab.weights = reinterpret_cast<const float*>(blob + o_wt);
+    p->ftab.win2 = reinterpret_cast<const float2*>(blob + o_win);         // (w[2 n], w[2 n + 1]) = the window read as float2
+    p->ftab.tw1 = reinterpret_cast<const float2*>(blob + o_tw1);
+    p->ftab.tw2 = reinterpret_cast<const float2*>(blob + o_tw2);
+    p->ftab.unt = reinterpret_cast<const float2*>(blob + o_unt2);
+    p->ftab.uv = reinterpret_cast<const float2*>(blob + o_uv);
+    p->ftab.seg = reinterpret_cast<const int*>(blob + o_seg);
+    p->fast_ok = fast_ok ? 1 : 0;
     *out = p;
     return A2M_OK;
 }
@@ -298,15 +589,28 @@ extern "C" int a2m_melspec_f32(const a2m_melspec_plan* plan, const float* wav, i
     g.n_samples = n_samples; g.wav_stride = wav_stride; g.frames = frames;
     g.chunks_per_clip = static_cast<int>((frames + kChunk - 1) / kChunk);
     g.n_items = static_cast<long long>(g.chunks_per_clip) * n_clips;
-    const int smem = kSmemFixedWide + 4 * ((plan->nnz + 3) & ~3);
-    A2M_ARG_CHECK(smem <= 100 * 1024, "a2m_melspec_f32: %d bytes of shared memory", smem);
+    if (!plan->fast_ok) {                                  // a filterbank that is not made of adjacent triangles: generic kernel
+        const int smem = kSmemFixedWide + 4 * ((plan->nnz + 3) & ~3);
+        A2M_ARG_CHECK(smem <= 100 * 1024, "a2m_melspec_f32: %d bytes of shared memory", smem);
+        static A2mPerDeviceOnce wide_attr_set;
+        if (wide_attr_set.first())
+            A2M_CUDA_CHECK(cudaFuncSetAttribute(melspec_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        long long wgrid = 4LL * a2m_num_sms();
+        if (wgrid > g.n_items) wgrid = g.n_items;
+        melspec_wide_kernel<<<static_cast<unsigned>(wgrid), kThreadsW, smem, static_cast<cudaStream_t>(stream)>>>(
+            wav, plan->tab, g, out);
+        a2m_count_launch();
+        A2M_LAUNCH_CHECK();
+        return A2M_OK;
+    }
     static A2mPerDeviceOnce attr_set;
-    if (attr_set.first())                                  // the cap of the argument check above: covers every plan
-        A2M_CUDA_CHECK(cudaFuncSetAttribute(melspec_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    long long grid = 4LL * a2m_num_sms();
-    if (grid > g.n_items) grid = g.n_items;
-    melspec_wide_kernel<<<static_cast<unsigned>(grid), kThreadsW, smem, static_cast<cudaStream_t>(stream)>>>(
-        wav, plan->tab, g, out);
+    if (attr_set.first())
+        A2M_CUDA_CHECK(cudaFuncSetAttribute(fast::melspec2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fast::kSmemFast));
+    const long long pairs = (frames + 1) / 2 * n_clips;
+    long long grid = 2LL * a2m_num_sms();                   // two CTAs per SM, four frame pairs per CTA and turn
+    if (grid * fast::kGroups > pairs) grid = (pairs + fast::kGroups - 1) / fast::kGroups;
+    fast::melspec2048_kernel<<<static_cast<unsigned>(grid), fast::kThreadsF, fast::kSmemFast, static_cast<cudaStream_t>(stream)>>>(
+        wav, plan->ftab, g, out);
     a2m_count_launch();
     A2M_LAUNCH_CHECK();
     return A2M_OK;

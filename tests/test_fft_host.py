@@ -40,3 +40,16 @@ def test_host_fft_matches_oracle(harness, tmp_path, kind, n):
     lm_ref = np.log(ref @ w + 0.01)
     lm_got = np.log(got.astype(np.float64) @ w + 0.01)
     assert np.all(np.abs(lm_got - lm_ref) <= 1e-4 * np.maximum(1.0, np.abs(lm_ref)))
+
+
+def test_host_fft2048_index_algebra(tmp_path):
+    """melspec2048_kernel's 16 x 16 x 4 split, exchange layouts and untangle (tests/host/fft2048_host_test.cu emulates
+    the kernel's data flow with the same fft_math.cuh functions) against a direct fp64 DFT."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "fft2048_host_test")
+    subprocess.run([nvcc, "-O1", "-o", exe, os.path.join(ROOT, "tests", "host", "fft2048_host_test.cu")], check=True,
+                   capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout
