@@ -221,12 +221,19 @@ struct FastTab {
     const float2* uv;         // [kPwPadded] per bin (padded index): weight into band g(k) ("rising"), into band g(k) - 1 ("falling"),
                               // x 1/4 (power) or 1/2 (magnitude): the kernel keeps |2 X|
     const int* seg;           // [n_mel + 2] first bin of segment g; band c = rising over segment c + falling over segment c + 1
+    const int2* chunk;        // [kMaxChunks] {first bin, end bin}: the segments cut into pieces of <= 8 bins, in bin order
+    const int* seg_chunk;     // [n_mel + 2] first chunk of segment g
+    int n_chunks;
 };
-constexpr int kPwPadded = 1028 + 1028 / 16 + 2;          // powers / weights are stored at k + (k >> 4): band starts 16 or 32 bins
-__device__ __forceinline__ int pw_idx(int k) { return k + (k >> 4); }      // apart no longer share a bank
+constexpr int kMaxChunks = 320;
+constexpr int kChunkBins = 8;
+constexpr int kPwPadded = 1030;                          // bins 0..1024 (+ slack: the projection reads pairs of bins)
+__device__ __forceinline__ int pw_idx(int k) { return k; }
 
-constexpr int kSmemFast = 1024 * 8 + 1024 * 8 + 520 * 8 + kPwPadded * 8 + 132 * 4 + kGroups * kRegionBytes;
-static_assert(((1024 + 1024 + 520 + kPwPadded) * 8 + 132 * 4) % 16 == 0, "the exchange regions are accessed in 16-byte units");
+constexpr int kTablesBytes = (1024 + 1024 + 520 + kPwPadded + kMaxChunks) * 8 + 132 * 4;
+constexpr int kSmemFast = kTablesBytes + kGroups * kRegionBytes;
+static_assert(kTablesBytes % 16 == 0, "the exchange regions are accessed in 16-byte units");
+static_assert(kPwPadded * 8 % 16 == 0 && kPwPadded * 8 + kMaxChunks * 16 <= kRegionBytes, "powers + chunk partials alias the exchange region");
 
 __device__ __forceinline__ void group_sync(int grp) { a2m::named_barrier(1 + grp, kGroupThreads); }
 __device__ __forceinline__ void st_cpx(unsigned char* base, int unit, cpx v) {
@@ -237,6 +244,12 @@ __device__ __forceinline__ cpx ld_cpx(const unsigned char* base, int unit) {
     return a2m_fft::make(u.x, u.y);
 }
 __device__ __forceinline__ int z_unit(int k) { return k + 2 * (k >> 6); }      // Z[k]: two pad units per 64
+// natural log of a positive normal number (the caller adds an offset or floors zeros first): one MUFU + one multiply
+__device__ __forceinline__ float fast_log(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * 0.69314718055994530942f;
+}
 
 __global__ void __launch_bounds__(kThreadsF, 2)
 melspec2048_kernel(const float* __restrict__ wav, FastTab tab, WideGeom g, float* __restrict__ out) {
@@ -245,13 +258,15 @@ melspec2048_kernel(const float* __restrict__ wav, FastTab tab, WideGeom g, float
     float2* s_tw1 = s_win + 1024;
     float2* s_unt = s_tw1 + 1024;
     float2* s_uv = s_unt + 520;
-    int* s_seg = reinterpret_cast<int*>(s_uv + kPwPadded);
+    int2* s_chunk = reinterpret_cast<int2*>(s_uv + kPwPadded);
+    int* s_seg = reinterpret_cast<int*>(s_chunk + kMaxChunks);           // first chunk of each segment
     const int tid = threadIdx.x, grp = tid >> 6, t = tid & 63;
-    unsigned char* region = smem_f + (1024 + 1024 + 520 + kPwPadded) * 8 + 132 * 4 + grp * kRegionBytes;
+    unsigned char* region = smem_f + kTablesBytes + grp * kRegionBytes;
     for (int i = tid; i < 1024; i += kThreadsF) { s_win[i] = tab.win2[i]; s_tw1[i] = tab.tw1[i]; }
     for (int i = tid; i < 516; i += kThreadsF) s_unt[i] = tab.unt[i];
     for (int i = tid; i < kPwPadded; i += kThreadsF) s_uv[i] = tab.uv[i];
-    for (int i = tid; i < g.n_mel + 2; i += kThreadsF) s_seg[i] = tab.seg[i];
+    for (int i = tid; i < kMaxChunks; i += kThreadsF) s_chunk[i] = tab.chunk[i];
+    for (int i = tid; i < g.n_mel + 2; i += kThreadsF) s_seg[i] = tab.seg_chunk[i];
     __syncthreads();
 
     const long long N = g.n_samples;
@@ -369,28 +384,51 @@ melspec2048_kernel(const float* __restrict__ wav, FastTab tab, WideGeom g, float
             }
         }
         group_sync(grp);
-        // ---- mel bands: bands 0..63 by index, bands >= 64 from the top down (wide and narrow triangles balance)
+        // ---- mel projection in two steps.  (1) every thread takes chunks t, t + 64, ... of <= 8 consecutive bins of one
+        // segment and sums both edges: R = sum u P (into band g), F = sum v P (into band g - 1); consecutive lanes read
+        // consecutive bins, every thread has the same three or four chunks of work.  (2) band c = the R partials of
+        // segment c + the F partials of segment c + 1, summed in chunk order (deterministic).
         {
             const float2* s_pw = reinterpret_cast<const float2*>(region);
+            float4* s_part = reinterpret_cast<float4*>(region + kPwPadded * 8);
+            for (int ci = t; ci < tab.n_chunks; ci += kGroupThreads) {
+                const int2 ch = s_chunk[ci];
+                pair_t r = a2m_fft::pack(0.f, 0.f), f = a2m_fft::pack(0.f, 0.f);
+#pragma unroll
+                for (int ii = 0; ii < kChunkBins; ++ii) {
+                    const int k = ch.x + ((ii + t) & (kChunkBins - 1));       // rotated per lane: lanes 64 B apart spread over the banks
+                    if (k < ch.y) {
+                        const float2 pw = s_pw[k], uv = s_uv[k];
+                        const pair_t pp = a2m_fft::pack(pw.x, pw.y);
+                        r = a2m_fft::fma2(pp, a2m_fft::bcast(uv.x), r);
+                        f = a2m_fft::fma2(pp, a2m_fft::bcast(uv.y), f);
+                    }
+                }
+                s_part[ci] = make_float4(a2m_fft::lo(r), a2m_fft::hi(r), a2m_fft::lo(f), a2m_fft::hi(f));
+            }
+            group_sync(grp);
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
-                const int c = side == 0 ? t : g.n_mel - 1 - t;
-                if (side == 0 ? c >= g.n_mel : c < 64) continue;
-                const int k0 = s_seg[c], k1 = s_seg[c + 1], k2 = s_seg[c + 2];
-                pair_t acc = a2m_fft::pack(0.f, 0.f);
-                for (int k = k0; k < k1; ++k) {         // rising edge: segment c
-                    const float2 pw = s_pw[pw_idx(k)];
-                    acc = a2m_fft::fma2(a2m_fft::pack(pw.x, pw.y), a2m_fft::bcast(s_uv[pw_idx(k)].x), acc);
+                const int c = t + 64 * side;
+                if (c >= g.n_mel) continue;
+                float va = 0.f, vbv = 0.f;
+                const int c0 = s_seg[c], c1 = s_seg[c + 1], c2 = s_seg[c + 2];
+                float va2 = 0.f, vb2 = 0.f;              // two chains: the wide bands have up to 14 partials per edge
+                for (int ci = c0; ci + 1 < c1; ci += 2) {
+                    const float4 p0 = s_part[ci], p1 = s_part[ci + 1];
+                    va += p0.x; vbv += p0.y; va2 += p1.x; vb2 += p1.y;
                 }
-                for (int k = k1; k < k2; ++k) {         // falling edge: segment c + 1
-                    const float2 pw = s_pw[pw_idx(k)];
-                    acc = a2m_fft::fma2(a2m_fft::pack(pw.x, pw.y), a2m_fft::bcast(s_uv[pw_idx(k)].y), acc);
+                if ((c1 - c0) & 1) { const float4 pp = s_part[c1 - 1]; va += pp.x; vbv += pp.y; }
+                for (int ci = c1; ci + 1 < c2; ci += 2) {
+                    const float4 p0 = s_part[ci], p1 = s_part[ci + 1];
+                    va += p0.z; vbv += p0.w; va2 += p1.z; vb2 += p1.w;
                 }
-                const float va = a2m_fft::lo(acc), vbv = a2m_fft::hi(acc);
+                if ((c2 - c1) & 1) { const float4 pp = s_part[c2 - 1]; va += pp.z; vbv += pp.w; }
+                va += va2; vbv += vb2;
                 const float la = g.log_mode ? (va == 0.f ? g.log_offset : va) : va + g.log_offset;
                 const float lb = g.log_mode ? (vbv == 0.f ? g.log_offset : vbv) : vbv + g.log_offset;
-                out[(clip * g.frames + fa) * g.n_mel + c] = logf(la);
-                if (has_b) out[(clip * g.frames + fb) * g.n_mel + c] = logf(lb);
+                out[(clip * g.frames + fa) * g.n_mel + c] = fast_log(la);
+                if (has_b) out[(clip * g.frames + fb) * g.n_mel + c] = fast_log(lb);
             }
         }
     }
@@ -464,7 +502,7 @@ extern "C" int a2m_melspec_plan_create(int nfft, int hop, int n_mel, int power, 
                  o_wt = carve((nnz + 4) * 4);
     // tables of the register-radix kernel
     const size_t o_tw1 = carve(1024 * 8), o_tw2 = carve(64 * 8), o_unt2 = carve(516 * 8), o_uv = carve(fast::kPwPadded * 8),
-                 o_seg = carve(132 * 4);
+                 o_seg = carve(132 * 4), o_chunk = carve(fast::kMaxChunks * 8), o_sc = carve(132 * 4);
     std::vector<float2> tw1(1024), tw2(64), unt2(516, make_float2(0.f, 0.f));
     for (int k1 = 0; k1 < 16; ++k1)
         for (int t = 0; t < 64; ++t) {
@@ -513,7 +551,7 @@ extern "C" int a2m_melspec_plan_create(int nfft, int hop, int n_mel, int power, 
             if (gseg < prev) fast_ok = false;
             gk[k] = gseg;
             prev = gseg;
-            const int e = k + (k >> 4);
+            const int e = k;
             const double u = gseg < n_mel ? mel_weights_host[static_cast<size_t>(k) * n_mel + gseg] : 0.0;
             const double v = gseg >= 1 ? mel_weights_host[static_cast<size_t>(k) * n_mel + gseg - 1] : 0.0;
             uv[e] = make_float2(static_cast<float>(u) * fold, static_cast<float>(v) * fold);
@@ -524,6 +562,19 @@ extern "C" int a2m_melspec_plan_create(int nfft, int hop, int n_mel, int power, 
             seg[gi] = k;
         }
     }
+    std::vector<int2> chunks;
+    std::vector<int> seg_chunk(132, 0);
+    if (fast_ok) {
+        for (int gi = 0; gi <= n_mel; ++gi) {
+            seg_chunk[gi] = static_cast<int>(chunks.size());
+            for (int k = seg[gi]; k < seg[gi + 1]; k += fast::kChunkBins)
+                chunks.push_back(make_int2(k, k + fast::kChunkBins < seg[gi + 1] ? k + fast::kChunkBins : seg[gi + 1]));
+        }
+        for (int gi = n_mel + 1; gi < 132; ++gi) seg_chunk[gi] = static_cast<int>(chunks.size());
+        if (chunks.size() > static_cast<size_t>(fast::kMaxChunks)) fast_ok = false;
+    }
+    const int n_chunks = static_cast<int>(chunks.size());
+    chunks.resize(fast::kMaxChunks, make_int2(0, 0));
     unsigned char* blob = nullptr;
     A2M_CUDA_CHECK(cudaMalloc(&blob, off));
     std::vector<unsigned char> host(off, 0);
@@ -537,6 +588,8 @@ extern "C" int a2m_melspec_plan_create(int nfft, int hop, int n_mel, int power, 
     memcpy(host.data() + o_unt2, unt2.data(), 516 * 8);
     memcpy(host.data() + o_uv, uv.data(), fast::kPwPadded * 8);
     memcpy(host.data() + o_seg, seg.data(), 132 * 4);
+    memcpy(host.data() + o_chunk, chunks.data(), fast::kMaxChunks * 8);
+    memcpy(host.data() + o_sc, seg_chunk.data(), 132 * 4);
     cudaError_t e = cudaMemcpy(blob, host.data(), off, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(blob); a2m_set_error("a2m_melspec_plan_create: upload failed: %s", cudaGetErrorString(e)); return (int)e; }
     a2m_melspec_plan* p = new a2m_melspec_plan();
@@ -553,6 +606,9 @@ extern "C" int a2m_melspec_plan_create(int nfft, int hop, int n_mel, int power, 
     p->ftab.unt = reinterpret_cast<const float2*>(blob + o_unt2);
     p->ftab.uv = reinterpret_cast<const float2*>(blob + o_uv);
     p->ftab.seg = reinterpret_cast<const int*>(blob + o_seg);
+    p->ftab.chunk = reinterpret_cast<const int2*>(blob + o_chunk);
+    p->ftab.seg_chunk = reinterpret_cast<const int*>(blob + o_sc);
+    p->ftab.n_chunks = n_chunks;
     p->fast_ok = fast_ok ? 1 : 0;
     *out = p;
     return A2M_OK;
