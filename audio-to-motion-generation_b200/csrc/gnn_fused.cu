@@ -22,6 +22,7 @@
 #include <cstring>
 #include "conv_gemm.cuh"
 #include "layers.cuh"
+#include "fft_math.cuh"        // packed fp32 pairs (add / mul / fma .f32x2) for the row epilogue
 
 void a2m_count_launch();
 
@@ -249,18 +250,19 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
         GNN_TILE_STAMP(0);
         mbar_wait(x_bar, static_cast<uint32_t>(it & 1), err_flag, 40);
         GNN_TILE_STAMP(1);
-        float x[32];                                   // residual stream: this thread's 32 features in fp32
+        using a2m_fft::pair_t;
+        pair_t x[16];                                  // residual stream: this thread's 32 features in fp32, as 16 packed pairs
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const uint4 u = *reinterpret_cast<const uint4*>(s_x + sw128_off(r, half * 4 + c));
             const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { x[c * 8 + 2 * e] = bf_lo(w4[e]); x[c * 8 + 2 * e + 1] = bf_hi(w4[e]); }
+            for (int e = 0; e < 4; ++e) x[c * 4 + e] = a2m_fft::pack(bf_lo(w4[e]), bf_hi(w4[e]));
         }
 
 #pragma unroll 1
         for (int layer = 0; layer < 5; ++layer) {
-            float v[32];
+            pair_t v[16];
             if (tid < 192) {                            // this layer's bias | ln_w | ln_b (read after several barriers)
                 const float* src = tid < 64 ? ((layer & 1) ? p.gc_bias[layer >> 1] : p.gat_bias[layer >> 1])
                                             : tid < 128 ? p.ln_w[layer] : p.ln_b[layer];
@@ -418,20 +420,23 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 tmem_ld_32x32(tmem_lane + kColOut4 + half * 32, t);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(t[i]);
+                for (int i = 0; i < 16; ++i) v[i] = a2m_fft::pack(__uint_as_float(t[2 * i]), __uint_as_float(t[2 * i + 1]));
             }
-            // ---- + bias, LayerNorm(64) over the two 32-feature halves of the node -> LeakyReLU -> + residual
+            // ---- + bias, LayerNorm(64) over the two 32-feature halves of the node -> LeakyReLU -> + residual; every step on
+            // packed pairs (FADD2 / FMUL2 / FFMA2: half the issue slots of this phase, the longest of the layer)
             {
+                using namespace a2m_fft;
                 const float4* par = reinterpret_cast<const float4*>(s_par + half * 32);
 #pragma unroll
                 for (int i4 = 0; i4 < 8; ++i4) {
                     const float4 b4 = par[i4];
-                    v[i4 * 4] += b4.x; v[i4 * 4 + 1] += b4.y; v[i4 * 4 + 2] += b4.z; v[i4 * 4 + 3] += b4.w;
+                    v[2 * i4] = add2(v[2 * i4], pack(b4.x, b4.y));
+                    v[2 * i4 + 1] = add2(v[2 * i4 + 1], pack(b4.z, b4.w));
                 }
-                float s = 0.f, sq = 0.f;
+                pair_t s2 = pack(0.f, 0.f), q2 = pack(0.f, 0.f);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { s += v[i]; sq = fmaf(v[i], v[i], sq); }
-                *reinterpret_cast<float2*>(s_ln + (r * 2 + half) * 2) = make_float2(s, sq);
+                for (int i = 0; i < 16; ++i) { s2 = add2(s2, v[i]); q2 = fma2(v[i], v[i], q2); }
+                *reinterpret_cast<float2*>(s_ln + (r * 2 + half) * 2) = make_float2(lo(s2) + hi(s2), lo(q2) + hi(q2));
                 switch (quad) {                            // only the two warps that share these 32 rows (warp, warp + 4);
                     case 0: named_barrier(1, 64); break;   // literal ids keep the kernel at five hardware barriers
                     case 1: named_barrier(2, 64); break;
@@ -441,24 +446,28 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 const float4 a = *reinterpret_cast<const float4*>(s_ln + r * 4);
                 const float mean = (a.x + a.z) * (1.f / 64.f);
                 const float rstd = rsqrtf(fmaxf((a.y + a.w) * (1.f / 64.f) - mean * mean, 0.f) + 1e-5f);
+                const pair_t nmean = bcast(-mean), rs = bcast(rstd), slope = bcast(kLeakySlope);
 #pragma unroll
                 for (int i4 = 0; i4 < 8; ++i4) {
                     const float4 w4 = par[16 + i4], b4 = par[32 + i4];
-                    x[i4 * 4] += leaky((v[i4 * 4] - mean) * rstd * w4.x + b4.x);
-                    x[i4 * 4 + 1] += leaky((v[i4 * 4 + 1] - mean) * rstd * w4.y + b4.y);
-                    x[i4 * 4 + 2] += leaky((v[i4 * 4 + 2] - mean) * rstd * w4.z + b4.z);
-                    x[i4 * 4 + 3] += leaky((v[i4 * 4 + 3] - mean) * rstd * w4.w + b4.w);
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const pair_t w = h2 ? pack(w4.z, w4.w) : pack(w4.x, w4.y), b = h2 ? pack(b4.z, b4.w) : pack(b4.x, b4.y);
+                        const pair_t y = fma2(add2(v[2 * i4 + h2], nmean), mul2(w, rs), b);
+                        const pair_t z = mul2(y, slope);                           // LeakyReLU(0.2) = max(y, 0.2 y)
+                        x[2 * i4 + h2] = add2(x[2 * i4 + h2], pack(fmaxf(lo(y), lo(z)), fmaxf(hi(y), hi(z))));
+                    }
                 }
             }
             if (!live) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) x[i] = 0.f;
+                for (int i = 0; i < 16; ++i) x[i] = a2m_fft::pack(0.f, 0.f);
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint4 o;
-                o.x = pack_bf16(x[c * 8], x[c * 8 + 1]); o.y = pack_bf16(x[c * 8 + 2], x[c * 8 + 3]);
-                o.z = pack_bf16(x[c * 8 + 4], x[c * 8 + 5]); o.w = pack_bf16(x[c * 8 + 6], x[c * 8 + 7]);
+                o.x = pack_bf16(a2m_fft::lo(x[c * 4]), a2m_fft::hi(x[c * 4])); o.y = pack_bf16(a2m_fft::lo(x[c * 4 + 1]), a2m_fft::hi(x[c * 4 + 1]));
+                o.z = pack_bf16(a2m_fft::lo(x[c * 4 + 2]), a2m_fft::hi(x[c * 4 + 2])); o.w = pack_bf16(a2m_fft::lo(x[c * 4 + 3]), a2m_fft::hi(x[c * 4 + 3]));
                 *reinterpret_cast<uint4*>(s_x + sw128_off(r, half * 4 + c)) = o;
             }
             tc_fence_before();
