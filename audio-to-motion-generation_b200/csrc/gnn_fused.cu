@@ -232,6 +232,20 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
         tmem_st_32x16(tmem_lane + kColZb + cb, o);
     };
 
+    // the same for 64 columns (one head): both loads in flight before the single wait
+    auto convert2 = [&](uint32_t c0, uint32_t cb) {
+        uint32_t ta[32], tb[32], o[16];
+        tmem_ld_32x32(tmem_lane + kColZf + c0, ta);
+        tmem_ld_32x32(tmem_lane + kColZf + c0 + 32, tb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = pack_bf16(__uint_as_float(ta[2 * i]), __uint_as_float(ta[2 * i + 1]));
+        tmem_st_32x16(tmem_lane + kColZb + cb, o);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = pack_bf16(__uint_as_float(tb[2 * i]), __uint_as_float(tb[2 * i + 1]));
+        tmem_st_32x16(tmem_lane + kColZb + cb + 16, o);
+    };
+
     uint32_t wpar[3] = {0, 0, 0}, upar = 0;             // thread 0 only
     uint32_t spar = 0, zpar = 0, opar = 0;
     long long item = 0;                                // first weight slice of the current layer (thread 0's view)
@@ -319,8 +333,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 tc_fence_after();
                 GNN_STAMP(layer * 12 + 4);
                 write_p(half + 2, sd1);                 // round 2: heads 2 and 3 (the MMAs that read round 1 are done)
-                convert(half * 64, half * 32);
-                convert(half * 64 + 32, half * 32 + 16);
+                convert2(half * 64, half * 32);
                 tmem_st_wait();
                 tc_fence_before();
                 fence_proxy_async_smem();
@@ -355,8 +368,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                     for (int k = 1; k <= kMaxDeg; ++k)
                         if (k <= dg) *reinterpret_cast<__nv_bfloat16*>(s_p + pofs[k]) = one;
                 }
-                convert(half * 64, half * 32);
-                convert(half * 64 + 32, half * 32 + 16);
+                convert2(half * 64, half * 32);
                 tmem_st_wait();
                 tc_fence_before();
                 fence_proxy_async_smem();
