@@ -437,7 +437,7 @@ def main():
         achieved = flops / (out_ms[1] * 1e-3) / 1e12
         # a2m_model_profile times every launch between its own pair of events on an otherwise idle GPU: each kernel is
         # timed ALONE, so the burst peak is the denominator; the sustained one is given beside it
-        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, %d launches/step)" % n_gemm.value,
+        roof = {"bound": "tensor", "kernel": "conv_gemm_pair_kernel / conv_gemm_pair_single_kernel / conv_gemm_kernel (tcgen05 implicit GEMM; cta_group::2 tiles where N %% 256 == 0; %d launches/step)" % n_gemm.value,
                 "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
                 "peak_kind": pk["src"] + " burst (every launch timed alone between its own events)",
                 "frac_of_sustained_peak": achieved / pk["tf_sustained"], "sustained_peak": pk["tf_sustained"],
