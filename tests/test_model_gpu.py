@@ -135,6 +135,19 @@ def test_batch_invariance_and_config2_size(stress_model):
     assert torch.equal(again, pose)
 
 
+def test_batch_invariance_beyond_one_round_of_tiles(stress_model):
+    """B = 320 puts more than one round of 256-row tiles on the SM pairs: the persistent CTA-pair GEMM (double-buffered
+    accumulator, LayerNorm fused into proj_out's epilogue) must give every clip the pose it gets in a batch of 8, where
+    the one-tile-per-cluster kernel runs."""
+    x = model_input(12, 8, 64, 64).cuda().repeat(40, 1, 1)
+    pose, _ = stress_model(x)
+    stress_model.check_device_status()
+    assert pose.shape == (320, 64, 104)
+    small, _ = stress_model(x[:8])
+    assert torch.equal(pose[:8], small)
+    assert torch.equal(pose[312:], small)
+
+
 def test_error_behaviour(mods, stress_model):
     with pytest.raises(ValueError):
         stress_model(torch.zeros(1, 62, 64, device="cuda"))            # T % 4 != 0 (reference: opaque cat error)
