@@ -2,6 +2,7 @@
 // channel attention, LayerNorm, the static-graph GAT / GraphConv tails and the pose losses.
 // See layers.cuh for the contracts and the reference lines each kernel restates.
 #include "layers.cuh"
+#include "fft_math.cuh"
 
 void a2m_count_launch();
 
@@ -53,20 +54,21 @@ conv0_kernel(const float* __restrict__ mel, long long stride_b, long long stride
         s_rows[i] = v;
     }
     const int cp = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float w0[16], w1[16];
+    using a2m_fft::pair_t;                            // my two channels ride one packed register: FFMA2, half the issue slots
+    pair_t wp[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {                    // w is tap-major [16][64]: one coalesced 256-byte row per tap
         const float2 ww = __ldg(reinterpret_cast<const float2*>(w + i * 64) + cp);
-        w0[i] = ww.x; w1[i] = ww.y;
+        wp[i] = a2m_fft::pack(ww.x, ww.y);
     }
-    const float b0 = __ldg(bias + 2 * cp), b1 = __ldg(bias + 2 * cp + 1);
+    const pair_t bp = a2m_fft::pack(__ldg(bias + 2 * cp), __ldg(bias + 2 * cp + 1));
     __syncthreads();
     const int groups = (Wo + 3) / 4;
     for (int item = warp; item < kConv0Rows * groups; item += 8) {
         const int r = item / groups, wo0 = (item - r * groups) * 4;
         const int ho = ho0 + r;
         if (ho >= Ho) break;
-        float a0[4] = {b0, b0, b0, b0}, a1[4] = {b1, b1, b1, b1};
+        pair_t acc[4] = {bp, bp, bp, bp};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float* row = s_rows + (2 * r + i) * stride + 2 * wo0;       // 16-byte aligned: stride and 2*wo0 are multiples of 4
@@ -77,16 +79,14 @@ conv0_kernel(const float* __restrict__ mel, long long stride_b, long long stride
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    a0[u] = fmaf(xs[2 * u + j], w0[i * 4 + j], a0[u]);
-                    a1[u] = fmaf(xs[2 * u + j], w1[i * 4 + j], a1[u]);
-                }
+                for (int j = 0; j < 4; ++j) acc[u] = a2m_fft::fma2(a2m_fft::bcast(xs[2 * u + j]), wp[i * 4 + j], acc[u]);
         }
         __nv_bfloat16* o = out + ((b * Ho + ho) * Wo + wo0) * 64 + 2 * cp;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
             if (wo0 + u < Wo)
-                *reinterpret_cast<__nv_bfloat162*>(o + u * 64) = __floats2bfloat162_rn(leaky(a0[u]), leaky(a1[u]));
+                *reinterpret_cast<__nv_bfloat162*>(o + u * 64) =
+                    __floats2bfloat162_rn(leaky(a2m_fft::lo(acc[u])), leaky(a2m_fft::hi(acc[u])));
     }
 }
 
