@@ -17,6 +17,7 @@ same for every N.  `--config 3` runs BASELINE config 3 instead: the 100 000-clip
 takes clips [r * ceil(n / N), (r + 1) * ceil(n / N))), one all-reduce at the end.
 """
 import argparse
+import faulthandler
 import importlib
 import json
 import os
@@ -253,9 +254,11 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     numa = bind_to_gpu_cpus(local) if world > 1 else None      # pinned host batches on the GPU's own NUMA node
+    faulthandler.dump_traceback_later(600, exit=True)          # watchdog (re-armed per phase below): never hang the node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+        print("[bench rank %d] process group up" % rank, file=sys.stderr, flush=True)
 
     a2m = importlib.import_module("audio-to-motion-generation_b200")
     cabi = importlib.import_module("audio-to-motion-generation_b200._cabi")
@@ -277,6 +280,8 @@ def main():
                 p.copy_(0.1 * torch.randn(p.shape, generator=g))
     model = model.to(device).eval()
     comm = pipeline.Communicator(rank, world, device) if world > 1 else None
+    if world > 1:
+        print("[bench rank %d] communicator up" % rank, file=sys.stderr, flush=True)
     pipe = pipeline.AudioToPosePipeline(model, comm=comm, lanes=args.lanes, graphs=bool(args.graphs),
                                         adapter_frames_only=bool(args.adapter_frames_only))
 
@@ -286,6 +291,14 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    t_start = time.perf_counter()
+
+    def phase(name):
+        """progress marker on stderr (stdout carries only the JSON line) + watchdog: a phase that makes no progress for
+        five minutes dumps every thread's stack and ends the process instead of hanging the node"""
+        print("[bench rank %d +%.1fs] %s" % (rank, time.perf_counter() - t_start, name), file=sys.stderr, flush=True)
+        faulthandler.dump_traceback_later(300, exit=True)
 
     def max_over_ranks(ms):
         if world > 1:
@@ -336,6 +349,7 @@ def main():
                     "clocks": clocks, "gpu_launches": int(lib.a2m_launch_count()),
                     "result": {k: res[k] for k in ("pck_hits", "n_keypoints", "pck", "l1_pose", "l1_motion", "n_frames")}}
             print(json.dumps(line), file=out, flush=True)
+        faulthandler.cancel_dump_traceback_later()
         if comm is not None:
             comm.close()
         if world > 1:
@@ -361,6 +375,7 @@ def main():
         return max_over_ranks(e0.elapsed_time(e1)), res
 
     # ---- device-resident arm -------------------------------------------------------------------------
+    phase("inputs ready")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                          # nvidia-smi needs ~0.1 s to produce its first line: start it before the warm-up
@@ -373,7 +388,9 @@ def main():
         sampler.mark()                           # samples from here on are "under load"
     lib.a2m_launch_count_reset()
     pipe.replayed_launches = 0
+    phase("warm-up done")
     ms_total, result = timed_steps(args.steps)
+    phase("timed steps done")
     launches = int(lib.a2m_launch_count()) + int(pipe.replayed_launches)
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms_total / 1e3)
@@ -390,6 +407,7 @@ def main():
             time.sleep(0.2)
             sampler2.mark()
         ms_sus, _ = timed_steps(n_sus)
+        phase("sustained leg done (%d steps)" % n_sus)
         clocks2 = sampler2.stop() if rank == 0 else None
         sustained = {"value": world * B * n_sus / (ms_sus / 1e3), "unit": UNIT, "steps": n_sus, "seconds": ms_sus / 1e3,
                      "ms_per_step": ms_sus / n_sus, "clocks": clocks2}
@@ -411,14 +429,17 @@ def main():
         return ms, time.perf_counter() - t0, res
 
     ms_e2e, wall_e2e, result_e2e = e2e_run(wav_host)
+    phase("e2e fp32 done")
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     h2d = wav_host[0].numel() * 4 + gt_host[0].numel() * 4
     ms_e2e16, wall_e2e16, result_e2e16 = e2e_run(pcm_host)
+    phase("e2e int16 done")
     h2d16 = pcm_host[0].numel() * 2 + gt_host[0].numel() * 4
 
     # ---- the same fixed evaluation set for every N (per-clip seeds): integer hit counts must not depend on N ----
     check_clips = 2048
     _, check = sharded_eval(check_clips)
+    phase("sharded check done")
 
     # ---- roofline of the dominant kernel (tcgen05 conv GEMM) and of the two HBM-bound kernels ----------
     pk = peaks()
@@ -524,6 +545,7 @@ def main():
                                   "l1_pose": check["l1_pose"]}}
         line.update(extra)
         print(json.dumps(line), file=out, flush=True)
+    faulthandler.cancel_dump_traceback_later()
     if comm is not None:
         comm.close()
     if world > 1:
