@@ -254,7 +254,7 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     numa = bind_to_gpu_cpus(local) if world > 1 else None      # pinned host batches on the GPU's own NUMA node
-    faulthandler.dump_traceback_later(600, exit=True)          # watchdog (re-armed per phase below): never hang the node
+    faulthandler.dump_traceback_later(300, exit=True)          # watchdog (re-armed per phase below): never hang the node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
