@@ -206,6 +206,26 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
     for (int k = 0; k <= kMaxDeg; ++k) pofs[k] = half * 32768 + p_off(r, idx[k]);     // my P buffer is buffer `half`
 
     // softmax over {self} + neighbours for head h (the head mean 1/4 folded in) -> my P buffer
+    // the same in two steps: the coefficients first (registers), the stores once the P buffer is free again
+    auto softmax_p = [&](int h, float sd, float (&alpha)[kMaxDeg + 1]) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k <= kMaxDeg; ++k) {
+            alpha[k] = k <= dg ? leaky(s_src[idx[k] * 4 + h] + sd) : -INFINITY;
+            m = fmaxf(m, alpha[k]);
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int k = 0; k <= kMaxDeg; ++k) { alpha[k] = k <= dg ? __expf(alpha[k] - m) : 0.f; den += alpha[k]; }
+        const float inv = 0.25f / den;
+#pragma unroll
+        for (int k = 0; k <= kMaxDeg; ++k) alpha[k] *= inv;
+    };
+    auto store_p = [&](const float (&alpha)[kMaxDeg + 1]) {
+#pragma unroll
+        for (int k = 0; k <= kMaxDeg; ++k)
+            if (k <= dg) *reinterpret_cast<__nv_bfloat16*>(s_p + pofs[k]) = __float2bfloat16_rn(alpha[k]);
+    };
     auto write_p = [&](int h, float sd) {
         float alpha[kMaxDeg + 1];
         float m = -INFINITY;
@@ -328,11 +348,13 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                                       desc_add(x_desc, kk * 2048), idesc_agg, kk != 0);
                     umma_commit(z_bar);
                 }
+                float alpha2[kMaxDeg + 1];
+                softmax_p(half + 2, sd1, alpha2);       // round 2's coefficients while round 1's MMAs run
                 mbar_wait(z_bar, zpar, err_flag, 44);
                 zpar ^= 1;
                 tc_fence_after();
                 GNN_STAMP(layer * 12 + 4);
-                write_p(half + 2, sd1);                 // round 2: heads 2 and 3 (the MMAs that read round 1 are done)
+                store_p(alpha2);                        // round 2: heads 2 and 3 (the MMAs that read round 1 are done)
                 convert2(half * 64, half * 32);
                 tmem_st_wait();
                 tc_fence_before();
