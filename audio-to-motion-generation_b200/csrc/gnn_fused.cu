@@ -182,6 +182,12 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    // bounded waits (a2m_common.cuh); after a thread's first time-out the rest of its waits are skipped, so that one lost
+    // signal ends this launch within seconds -- with the error code in *err_flag -- instead of costing two seconds per wait
+    bool dead = false;
+    auto wait = [&](uint64_t* bar, uint32_t parity, int code) {
+        if (!dead && !mbar_wait(bar, parity, err_flag, code)) dead = true;
+    };
     pdl_wait();                                        // node features come from the previous kernel (proj_in)
     auto load_tile = [&](long long tile) {             // thread 0 only
         const int group = static_cast<int>(tile / p.tiles_per_group);
@@ -271,7 +277,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
     long long item = 0;                                // first weight slice of the current layer (thread 0's view)
     auto wait_item = [&](long long it_) {              // thread 0 only
         const int slot = static_cast<int>(it_ % 3);
-        mbar_wait(&w_bar[slot], wpar[slot], err_flag, 41);
+        wait(&w_bar[slot], wpar[slot], 41);
         wpar[slot] ^= 1;
         return desc_add(w_desc, static_cast<uint32_t>(slot) * 8192u);
     };
@@ -282,7 +288,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
         const int row0 = static_cast<int>(tile - static_cast<long long>(group) * p.tiles_per_group) * rows_per_tile;
         const bool live = valid_row && row0 + r < group_rows;
         GNN_TILE_STAMP(0);
-        mbar_wait(x_bar, static_cast<uint32_t>(it & 1), err_flag, 40);
+        wait(x_bar, static_cast<uint32_t>(it & 1), 40);
         GNN_TILE_STAMP(1);
         using a2m_fft::pair_t;
         pair_t x[16];                                  // residual stream: this thread's 32 features in fp32, as 16 packed pairs
@@ -307,13 +313,13 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 // ================= GATConv =================
                 if (tid == 0) {
                     tc_fence_after();
-                    mbar_wait(u_bar, upar, err_flag, 42); upar ^= 1;
+                    wait(u_bar, upar, 42); upar ^= 1;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_bf16(tmem_base + kColS4, desc_add(x_desc, k * 32), desc_add(u_desc, k * 32), idesc_s, k != 0);
                     umma_commit(s_bar);
                 }
-                mbar_wait(s_bar, spar, err_flag, 43);
+                wait(s_bar, spar, 43);
                 spar ^= 1;
                 tc_fence_after();
                 GNN_STAMP(layer * 12 + 1);
@@ -350,7 +356,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                 }
                 float alpha2[kMaxDeg + 1];
                 softmax_p(half + 2, sd1, alpha2);       // round 2's coefficients while round 1's MMAs run
-                mbar_wait(z_bar, zpar, err_flag, 44);
+                wait(z_bar, zpar, 44);
                 zpar ^= 1;
                 tc_fence_after();
                 GNN_STAMP(layer * 12 + 4);
@@ -378,7 +384,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                                       desc_add(x_desc, kk * 2048), idesc_agg, kk != 0);
                     umma_commit(z_bar);
                 }
-                mbar_wait(z_bar, zpar, err_flag, 45);
+                wait(z_bar, zpar, 45);
                 zpar ^= 1;
                 tc_fence_after();
                 GNN_STAMP(layer * 12 + 6);
@@ -407,7 +413,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                     }
                     umma_commit(o_bar);
                 }
-                mbar_wait(o_bar, opar, err_flag, 46);
+                wait(o_bar, opar, 46);
                 opar ^= 1;
                 tc_fence_after();
                 GNN_STAMP(layer * 12 + 8);
@@ -423,7 +429,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                                   desc_add(x_desc, kk * 2048), idesc_agg, kk != 0);
                     umma_commit(z_bar);
                 }
-                mbar_wait(z_bar, zpar, err_flag, 47);
+                wait(z_bar, zpar, 47);
                 zpar ^= 1;
                 tc_fence_after();
                 GNN_STAMP(layer * 12 + 4);
@@ -443,7 +449,7 @@ gnn4_kernel(const __grid_constant__ GnnParams p, int* __restrict__ err_flag) {
                         umma_bf16(tmem_base + kColOut4, desc_add(x_desc, k * 32), desc_add(wroot, k * 32), idesc_h, 1);
                     umma_commit(o_bar);
                 }
-                mbar_wait(o_bar, opar, err_flag, 48);
+                wait(o_bar, opar, 48);
                 opar ^= 1;
                 tc_fence_after();
                 GNN_STAMP(layer * 12 + 8);

@@ -168,6 +168,7 @@ class AudioToPosePipeline:
         self.smooth = motion_evaluation.new_smoothness(self.device) if smoothness else None
         self._copy_stream = torch.cuda.Stream(self.device)
         self._staging = {}                      # (wav shape, gt shape, depth) -> ring of [wav_dev, gt_dev, last-use event]
+        self._readback = None                   # pinned ring for the per-step read-back of the running metrics
         self._n_lanes = max(1, int(lanes))
         self._lane_streams = [torch.cuda.Stream(self.device) for _ in range(self._n_lanes)]
         self._turn = 0
@@ -224,7 +225,7 @@ class AudioToPosePipeline:
                for b in range(0, logmel.shape[0], per_call)]
         return out[0] if len(out) == 1 else torch.cat(out)
 
-    def step(self, wav, gt_pose, done_event=None):
+    def step(self, wav, gt_pose, done_event=None, readback=None):
         """One batch, inputs already on the device: enqueues mel -> generator -> evaluation on the next lane and
         accumulates the metric partials.  Returns the poses; they (and the metrics) are complete once
         ``sync_lanes()`` / ``finish()`` has been called on the consuming stream."""
@@ -240,6 +241,8 @@ class AudioToPosePipeline:
                 motion_evaluation.evaluate_poses(pose, gt_pose, self.alpha, accum=self.accum)
             if self.smooth is not None:
                 motion_evaluation.evaluate_smoothness(pose, accum=self.smooth, from_pose=True)
+            if readback is not None:                                # running metric partials of this step, 64 bytes D2H
+                readback.copy_(self.accum, non_blocking=True)
             if done_event is not None:
                 done_event.record(st)                               # the lane no longer reads wav / gt_pose after this
         wav.record_stream(st)
@@ -283,11 +286,12 @@ class AudioToPosePipeline:
         self.replayed_launches += n_kernels
         return s_pose
 
-    def run_host_batches(self, batches, depth=3):
+    def run_host_batches(self, batches, depth=3, per_step_readback=True):
         """End-to-end over HOST batches [(wav_pinned [B,N], gt_pinned [B,64,104]), ...]: batch i+1 is copied to the
         device on a side stream while the kernels of batch i run.  The copies land in a ring of `depth` preallocated
         device buffers per input shape (no allocation inside the loop); a slot is rewritten only after the lane that
-        consumed it has finished with it.  Returns the number of clips processed."""
+        consumed it has finished with it; after every step the running 64-byte metric accumulator is read back into a
+        pinned host ring (asynchronously: `finish()` is what waits).  Returns the number of clips processed."""
         main = torch.cuda.current_stream(self.device)
         clips = 0
         it = iter(batches)
@@ -321,7 +325,12 @@ class AudioToPosePipeline:
             staged = stage(nxt) if nxt is not None else None
             main.wait_event(ev)
             done = torch.cuda.Event()
-            self.step(slot[0], slot[1], done_event=done)
+            rb = None
+            if per_step_readback:
+                if self._readback is None:
+                    self._readback = [torch.empty(self.accum.shape, dtype=self.accum.dtype).pin_memory() for _ in range(4)]
+                rb = self._readback[turn % 4]
+            self.step(slot[0], slot[1], done_event=done, readback=rb)
             slot[2] = done
             clips += slot[0].shape[0]
         return clips

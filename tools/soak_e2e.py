@@ -5,6 +5,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 6000
+readback = (sys.argv[2] != "0") if len(sys.argv) > 2 else True
 pipeline = importlib.import_module("audio-to-motion-generation_b200.pipeline")
 rmm = importlib.import_module("audio-to-motion-generation_b200.real_motion_model")
 torch.manual_seed(0)
@@ -17,7 +18,8 @@ gt = [(50 * torch.randn(B, 64, 104)).pin_memory() for _ in range(4)]
 for name, src in (("fp32", wav), ("int16", pcm)):
     pipe.reset()
     t0 = time.perf_counter()
-    n = pipe.run_host_batches((src[i % 4], gt[i % 4]) for i in range(steps))
+    n = pipe.run_host_batches(((src[i % 4], gt[i % 4]) for i in range(steps)), per_step_readback=readback)
     res = pipe.finish()
     dt = time.perf_counter() - t0
+    print("readback %s " % readback, end="")
     print("%s: %d clips in %.2f s = %.0f clips/s, pck %.4f" % (name, n, dt, n / dt, res["pck"]), flush=True)
