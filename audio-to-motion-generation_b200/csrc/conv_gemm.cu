@@ -11,6 +11,14 @@
 //               + folded bias, LeakyReLU(0.2) / ReLU, bf16 (or fp32) vector stores, strided so
 //               ConvTranspose parities and the [B,T,104] pose layout are written in place
 // Two CTAs fit per SM (3 stages x 32 KB), so one CTA's epilogue overlaps the other's main loop.
+//
+// Three kernels share that structure (the planner picks, conv_gemm_plan):
+//   conv_gemm_kernel<BLOCK_N, STAGES>  one 128 x {32, 64, 128, 256} tile per CTA (cta_group::1): narrow / ragged widths,
+//                                      fp32 and split-K outputs
+//   conv_gemm_pair_single_kernel       one 256 x 256 tile per 2-CTA cluster (cta_group::2), layers with one round of tiles
+//   conv_gemm_pair_kernel              the same tile, persistent over a tile list, accumulator double-buffered in tensor
+//                                      memory so that a tile's epilogue runs under the next tile's MMAs
+// The two pair kernels can also apply LayerNorm(256) to the accumulator rows in their epilogue (proj_out).
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
