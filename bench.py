@@ -203,9 +203,10 @@ def bind_to_gpu_cpus(index):
         cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
         allowed = os.sched_getaffinity(0)
         cpus = [c for c in cpus if c in allowed]
-        if cpus:
+        if len(cpus) >= 8:                        # never squeeze a rank (main thread + NCCL proxy threads) onto a few cores
             os.sched_setaffinity(0, cpus)
             return "%d cores local to GPU %d" % (len(cpus), index)
+        return "unbound (%d local cores allowed)" % len(cpus)
     except Exception as exc:                      # no NVML, restricted container, ...: keep the default placement
         return "unbound (%s)" % type(exc).__name__
     return "unbound"
